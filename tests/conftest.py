@@ -1,0 +1,37 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+for p in (ROOT, GOLD):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    """(arrays, meta) of the fixtures generated from the real reference (tests/golden/make_golden.py)."""
+    arrays = np.load(os.path.join(GOLD, "ref_cpu.npz"))
+    with open(os.path.join(GOLD, "ref_cpu_meta.json")) as f:
+        meta = json.load(f)
+    return arrays, meta
+
+
+def fq_mismatch(y, y_ref, step=None):
+    """Return (fraction of elements that differ beyond 1e-5 relative, max |diff| in units of `step`)."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    r = np.asarray(y_ref, dtype=np.float64).reshape(-1)
+    tol = 1e-5 * np.maximum(np.abs(r), np.abs(y)) + 1e-9
+    bad = np.abs(y - r) > tol
+    frac = float(bad.mean()) if y.size else 0.0
+    if step is None or not bad.any():
+        return frac, 0.0
+    return frac, float((np.abs(y - r)[bad] / step).max())
