@@ -1,0 +1,1161 @@
+// fqb200: fused fake-quantization kernels for B200 (sm_100a) + the C ABI of include/fqb200.h.
+//
+// One hooked tensor = one launch of fq_fused_kernel, a persistent cooperative kernel:
+//
+//   phase S1  read x          per-item min / max / sum            -> grid barrier, leader: per-group finalize
+//   phase S2  read x          per-item sum|x-mu|, sum (x-mu)^2    -> grid barrier, leader: bit allocation,
+//             (only when b or std is needed)                         ACIQ alpha, (delta, offset), scale/zero-point
+//   phase A   read x, write y quantize - clip - dequantize with the per-group parameters
+//   phase C   (weights only)  mean / variance correction of y
+//
+// Work item = (group g, part p): a contiguous share of the N*H*W elements of channel g, walked with 128-bit
+// loads directly on the NCHW layout (no transposes).  Items are assigned round-robin to the resident CTAs and
+// walked in opposite directions in consecutive phases so the tail of one phase is still in L2 for the next.
+//
+// Reference semantics (file:line in /root/reference) are cited at each device function; the CPU restatement
+// they are tested against lives in oracle/fq_oracle.py.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/fqb200.h"
+#include "fq_device.cuh"
+
+namespace fqb {
+
+// ACIQ multipliers, int_quantizer.py:81-85.  Index = bit width (0..8).
+__constant__ float kGaus[9] = {0.f, 1.24f, 1.71f, 2.15f, 2.55f, 2.93f, 3.28f, 3.61f, 3.92f};
+__constant__ float kGausPos[9] = {0.f, 1.71f, 2.15f, 2.55f, 2.93f, 3.28f, 3.61f, 3.92f, 4.2f};
+__constant__ float kLaplace[9] = {1.05f, 1.86f, 2.83f, 3.89f, 5.03f, 6.2f, 7.41f, 8.64f, 9.89f};
+__constant__ float kLaplacePos[9] = {1.86f, 2.83f, 3.89f, 5.02f, 6.2f, 7.41f, 8.64f, 9.89f, 11.16f};
+// mid-tread: optimal Laplace clipping multiplier vs number of bins, int_quantizer.py:41-51 (filled by the host)
+constexpr int kTable = 101;
+__constant__ double kOmegaTable[kTable];
+__constant__ double kAlphaTable[kTable];
+
+enum : int { FLAG_PASSTHROUGH = 1, FLAG_TRUE_ZERO = 2 };
+
+// Per-group (or per-tensor) leaf parameters as the apply phase consumes them.
+//   torch leaf:     a = scale, b = zero_point,            c = qmax
+//   compiled leaf:  a = scale, b = shift (zp or -offset),  c = qmax, flags
+//   mid-tread leaf: a = Delta, b = c_min,                  c = c_max
+struct alignas(16) LeafParam {
+  float a, b, c;
+  int flags;
+};
+
+struct FusedArgs {
+  Geometry geo;
+  const float* in;
+  float* out;
+  const float* noise;  // standalone a1 only
+  float* grid_out;     // optional integer grid (quantize1)
+  // configuration (mirrors fqb200_desc)
+  int scope, range_mode, leaf, num_bits, positive, solve_f64;
+  float clip_k;
+  int bit_alloc, prior, ba_round;
+  float ba_target;
+  float mt_target;
+  int mt_clip;
+  int bias_corr, var_corr, stats_only;
+  int need_dev;      // phase S2 required (b and/or std)
+  const float *g_delta, *g_offset, *g_bits;
+  int given_per_group;
+  double n_per_group;  // outer * inner
+  float* out_stats;
+  // workspace
+  GridSync* sync;
+  float *pmin, *pmax;                   // [items]
+  double *psum, *pabs, *psq;            // [items]
+  float *gmin, *gmax, *gmean, *gb, *gstd, *gbits, *gprior;  // [G]
+  double* gmean_d;                      // [G]
+  float *gdelta, *goffset;              // [G]
+  LeafParam* lp;                        // [G] (entry 0 when the parameters are per tensor)
+  float *cq, *co, *ck;                  // [G] weight correction: mean(w_q), mean(w), variance factor
+};
+
+// ------------------------------------------------------------------------------------------------
+// leader-section helpers (run by ONE CTA between phases)
+// ------------------------------------------------------------------------------------------------
+struct LeaderSmem {
+  double d[kWarps];
+  float f[kWarps];
+  int i[kWarps];
+  int flag;
+};
+
+// Reduce the P per-item partials of every group in a fixed order.  L = min(32, pow2 >= P) lanes cooperate on
+// one group; kThreads / L groups are finished per sweep.
+template <typename T, typename Op>
+__device__ __forceinline__ void reduce_partials(const T* part, T* out, const Geometry& geo, T identity, Op op) {
+  unsigned L = 1;
+  while (L < geo.parts && L < 32) L <<= 1;
+  const unsigned sub = threadIdx.x % L;
+  const unsigned per_sweep = kThreads / L;
+  for (unsigned g0 = 0; g0 < geo.groups; g0 += per_sweep) {
+    const unsigned g = g0 + threadIdx.x / L;
+    T acc = identity;
+    if (g < geo.groups)
+      for (unsigned p = sub; p < geo.parts; p += L) acc = op(acc, ld_ws(part + static_cast<size_t>(p) * geo.groups + g));
+    for (unsigned o = L >> 1; o > 0; o >>= 1) acc = op(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+    if (g < geo.groups && sub == 0) out[g] = acc;
+  }
+}
+
+// per-group bit allocation, int_quantizer.py:381-407 (get_bits_alloc_fixed_target).  All threads of the CTA.
+__device__ void solve_bit_alloc(const FusedArgs& A, LeaderSmem& sm) {
+  const unsigned G = A.geo.groups;
+  const float* prior = (A.prior == FQB200_PRIOR_STD) ? A.gstd : A.gb;
+  // p = alpha^(2/3)  (torch.pow with a python-float exponent -> fp32 powf)
+  double local = 0.0;
+  for (unsigned g = threadIdx.x; g < G; g += kThreads) {
+    float p = powf(prior[g], 0.6666666666666666f);
+    A.gprior[g] = p;
+    local += static_cast<double>(p);
+  }
+  const float psum = static_cast<float>(block_reduce(local, OpAdd(), sm.d));
+  const float goal = A.ba_target;
+  double m = static_cast<double>(A.ba_target);
+  float half_gap = 1.0f;
+  const float inv_g = 1.0f / static_cast<float>(G);  // torch's CUDA mean multiplies by fl(1/N)
+  int it = 0;
+  while (fabsf(2.0f * half_gap) > 0.01f && it < 10) {
+    ++it;
+    const float budget = static_cast<float>(static_cast<double>(G) * exp2(m));
+    int sum_bits = 0;
+    for (unsigned g = threadIdx.x; g < G; g += kThreads) {
+      const float bins = __fdiv_rn(__fmul_rn(budget, A.gprior[g]), psum);
+      const float lg = log2f(bins);
+      float bits = A.ba_round ? rintf(lg) : ceilf(lg);
+      if (!(bits >= 0.f)) bits = 0.f;
+      if (bits > 8.f) bits = 8.f;
+      A.gbits[g] = bits;
+      sum_bits += static_cast<int>(bits);
+    }
+    const int total = block_reduce(sum_bits, OpAdd(), sm.i);
+    const float mean = __fmul_rn(static_cast<float>(total), inv_g);
+    half_gap = __fmul_rn(__fsub_rn(goal, mean), 0.5f);
+    m += static_cast<double>(half_gap);
+  }
+  __syncthreads();
+}
+
+// (delta, offset) of one group/tensor from its statistics: int_quantizer.py:284-300 (alpha2DeltaOffset),
+// :227-275 (alpha), :348-352 / :354-357 (fp32 per-channel vs float64 per-tensor arithmetic), :361-379, :409-424.
+__device__ __forceinline__ void solve_range(const FusedArgs& A, float mn, float mx, float mean, float b, float sd,
+                                            float bits, float& delta, float& offset) {
+  if (A.range_mode == FQB200_RANGE_MINMAX) {
+    offset = A.positive ? 0.f : mn;
+    delta = __fsub_rn(mx, offset);
+    return;
+  }
+  float alpha;
+  const int bi = static_cast<int>(bits);
+  if (A.range_mode == FQB200_RANGE_LAPLACE) {
+    alpha = __fmul_rn(b, A.positive ? kLaplacePos[bi] : kLaplace[bi]);
+  } else if (A.range_mode == FQB200_RANGE_GAUS) {
+    alpha = __fmul_rn(sd, A.positive ? kGausPos[A.num_bits] : kGaus[A.num_bits]);
+  } else {
+    alpha = __fmul_rn(A.clip_k, sd);
+  }
+  if (A.solve_f64) {
+    const double al = alpha, me = mean;
+    double dl, of;
+    if (A.positive) {
+      dl = fmax(me, 0.0) + al;
+      of = 0.0;
+    } else {
+      dl = 2.0 * al;
+      of = fmax(static_cast<double>(mn), me - al);
+    }
+    delta = static_cast<float>(dl);
+    offset = static_cast<float>(of);
+  } else {
+    if (A.positive) {
+      delta = __fadd_rn(fmaxf(mean, 0.f), alpha);
+      offset = 0.f;
+    } else {
+      const float rng = __fmul_rn(2.f, alpha);
+      offset = fmaxf(mn, __fsub_rn(mean, alpha));
+      // the reference forms max_ = offset + range and later max_ - offset (:351, :447)
+      delta = __fsub_rn(__fadd_rn(offset, rng), offset);
+    }
+  }
+}
+
+// leaf parameters from (delta, offset, bits)
+__device__ __forceinline__ LeafParam make_leaf_param(int leaf, float delta, float offset, float bits) {
+  LeafParam q;
+  q.flags = 0;
+  if (leaf == FQB200_LEAF_TORCH) {
+    // int_quantizer.py:557-572
+    const float qmax = static_cast<float>((1 << static_cast<int>(bits)) - 1);
+    float scale = (qmax > 0.f) ? __fdiv_rn(delta, qmax) : 0.f;
+    scale = fmaxf(scale, 1e-8f);
+    q.a = scale;
+    q.b = rintf(__fsub_rn(0.f, __fdiv_rn(offset, scale)));
+    q.c = qmax;
+    q.flags = FLAG_TRUE_ZERO;
+  } else {
+    // gemmlowp.cu:30-41 with int_quantizer.py:613 (preserve_zero)
+    if (!(delta > 0.f)) {
+      q.a = 1.f;
+      q.b = 0.f;
+      q.c = 0.f;
+      q.flags = FLAG_PASSTHROUGH;
+      return q;
+    }
+    const float qmax = static_cast<float>((1 << static_cast<int>(bits)) - 1);
+    const float scale = __fdiv_rn(delta, qmax);
+    const bool tz = (__fadd_rn(offset, delta) > 0.f) && (offset < 0.f);
+    q.a = scale;
+    q.b = tz ? roundf(__fdiv_rn(-offset, scale)) : -offset;
+    q.c = qmax;
+    q.flags = tz ? FLAG_TRUE_ZERO : 0;
+  }
+  return q;
+}
+
+__device__ __forceinline__ void export_stats(const FusedArgs& A, unsigned g, float mn, float mx, float mean, float b,
+                                             float sd, float delta, float offset, float bits, const LeafParam& q) {
+  if (!A.out_stats) return;
+  float* o = A.out_stats + static_cast<size_t>(g) * FQB200_STATS_STRIDE;
+  o[0] = mn; o[1] = mx; o[2] = mean; o[3] = b; o[4] = sd; o[5] = delta; o[6] = offset; o[7] = bits;
+  o[8] = q.a; o[9] = q.b; o[10] = q.c; o[11] = static_cast<float>(q.flags);
+}
+
+// mid-tread parameters, int_quantizer.py:185-214 (+ :128-145)
+__device__ void solve_mid_tread(const FusedArgs& A, LeaderSmem& sm) {
+  const unsigned G = A.geo.groups;
+  double local = 0.0;
+  for (unsigned g = threadIdx.x; g < G; g += kThreads) {
+    float p = powf(A.gstd[g], 0.6666666666666666f);
+    A.gprior[g] = p;
+    local += static_cast<double>(p);
+  }
+  const float psum = static_cast<float>(block_reduce(local, OpAdd(), sm.d));
+  const float budget = static_cast<float>(static_cast<double>(G) * exp2(static_cast<double>(A.mt_target)));
+  const bool sym = !A.positive;
+  for (unsigned g = threadIdx.x; g < G; g += kThreads) {
+    const float omega = rintf(__fdiv_rn(__fmul_rn(budget, A.gprior[g]), psum));
+    const float mn = A.gmin[g], mx = A.gmax[g], mu = A.gmean[g], b = A.gb[g];
+    float rng;
+    if (A.mt_clip) {
+      // alpha multiplier: linear interpolation in the (omega, alpha) table, float64, one-sided uses 2*omega
+      double om = sym ? static_cast<double>(omega) : 2.0 * static_cast<double>(omega);
+      int i = 0;
+      while (i < kTable - 1 && kOmegaTable[i] < om) ++i;  // searchsorted(side='left'), clamped to the table
+      double am;
+      if (i == 0) {
+        am = kAlphaTable[0];
+      } else {
+        const double inc = (kAlphaTable[i] - kAlphaTable[i - 1]) / (kOmegaTable[i] - kOmegaTable[i - 1]);
+        am = kAlphaTable[i] - inc * (kOmegaTable[i] - om);
+      }
+      const float amf = static_cast<float>(am);
+      rng = sym ? __fmul_rn(__fmul_rn(2.f, amf), b) : __fadd_rn(fmaxf(mu, 0.f), __fmul_rn(amf, b));
+    } else {
+      rng = sym ? __fsub_rn(mx, mn) : mx;
+    }
+    const float step = (omega > 0.f) ? __fdiv_rn(rng, omega) : 3.402823466e+38f;
+    LeafParam q;
+    q.a = step;
+    q.flags = 0;
+    if (A.mt_clip) {
+      const float mu_q = sym ? __fdiv_rn(mu, step) : __fdiv_rn(fmaxf(mu, 0.f), step);
+      q.c = __fadd_rn(mu_q, sym ? __fmul_rn(omega, 0.5f) : omega);
+      q.b = sym ? __fsub_rn(mu_q, __fmul_rn(omega, 0.5f)) : 0.f;
+    } else {
+      q.b = -INFINITY;
+      q.c = INFINITY;
+    }
+    A.lp[g] = q;
+    export_stats(A, g, mn, mx, mu, b, A.gstd[g], rng, 0.f, omega, q);
+  }
+}
+
+// The parameter solve: runs once per launch, after the last statistics phase.
+__device__ void solve_params(const FusedArgs& A, LeaderSmem& sm) {
+  const unsigned G = A.geo.groups;
+  if (A.leaf == FQB200_LEAF_MIDTREAD) {
+    solve_mid_tread(A, sm);
+    return;
+  }
+  const bool alloc = A.bit_alloc && A.num_bits <= 4 && A.scope == FQB200_SCOPE_GROUP;
+  if (alloc) solve_bit_alloc(A, sm);
+  if (A.scope != FQB200_SCOPE_GROUP) {
+    // GROUP_MEAN: batch average of the per-sample min / max (int_quantizer.py:372, :525-526);
+    // TENSOR: global min / max assembled from the per-row ones.  Either way ONE parameter set.
+    float mn, mx;
+    if (A.scope == FQB200_SCOPE_GROUP_MEAN) {
+      double smin = 0.0, smax = 0.0;
+      for (unsigned g = threadIdx.x; g < G; g += kThreads) {
+        smin += static_cast<double>(A.gmin[g]);
+        smax += static_cast<double>(A.gmax[g]);
+      }
+      smin = block_reduce(smin, OpAdd(), sm.d);
+      smax = block_reduce(smax, OpAdd(), sm.d);
+      mn = static_cast<float>(smin / G);
+      mx = static_cast<float>(smax / G);
+    } else {
+      float lmin = INFINITY, lmax = -INFINITY;
+      for (unsigned g = threadIdx.x; g < G; g += kThreads) {
+        lmin = fminf(lmin, A.gmin[g]);
+        lmax = fmaxf(lmax, A.gmax[g]);
+      }
+      mn = block_reduce(lmin, OpMin(), sm.f);
+      mx = block_reduce(lmax, OpMax(), sm.f);
+    }
+    if (threadIdx.x == 0) {
+      float delta, offset;
+      solve_range(A, mn, mx, 0.f, 0.f, 0.f, static_cast<float>(A.num_bits), delta, offset);
+      const LeafParam q = make_leaf_param(A.leaf, delta, offset, static_cast<float>(A.num_bits));
+      A.lp[0] = q;
+      A.gdelta[0] = delta;
+      A.goffset[0] = offset;
+      export_stats(A, 0, mn, mx, 0.f, 0.f, 0.f, delta, offset, static_cast<float>(A.num_bits), q);
+    }
+    return;
+  }
+  for (unsigned g = threadIdx.x; g < G; g += kThreads) {
+    const float bits = alloc ? A.gbits[g] : static_cast<float>(A.num_bits);
+    const float mn = A.gmin[g], mx = A.gmax[g], mean = A.gmean[g];
+    const float b = A.need_dev ? A.gb[g] : 0.f, sd = A.need_dev ? A.gstd[g] : 0.f;
+    float delta, offset;
+    solve_range(A, mn, mx, mean, b, sd, bits, delta, offset);
+    const LeafParam q = make_leaf_param(A.leaf, delta, offset, bits);
+    A.lp[g] = q;
+    A.gdelta[g] = delta;
+    A.goffset[g] = offset;
+    export_stats(A, g, mn, mx, mean, b, sd, delta, offset, bits, q);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming phases
+// ------------------------------------------------------------------------------------------------
+struct PhaseSmem {
+  float f0[kWarps], f1[kWarps];
+  double d0[kWarps], d1[kWarps];
+};
+
+// item order: forward in even phases, backward in odd ones (L2 reuse between phases)
+__device__ __forceinline__ bool next_item(const Geometry& geo, unsigned long long& it, bool reverse, bool first) {
+  const unsigned long long per = (geo.items + gridDim.x - 1) / gridDim.x;  // max items per CTA
+  // k-th item of this CTA is blockIdx.x + k*gridDim.x; walk k upward or downward
+  if (first) {
+    if (!reverse) {
+      it = blockIdx.x;
+    } else {
+      unsigned long long k = per;  // one past the last candidate
+      it = blockIdx.x + (k - 1) * gridDim.x;
+      if (it >= geo.items) {
+        if (k < 2) return false;
+        it -= gridDim.x;
+      }
+    }
+    return it < geo.items;
+  }
+  if (!reverse) {
+    it += gridDim.x;
+    return it < geo.items;
+  }
+  if (it < gridDim.x) return false;
+  it -= gridDim.x;
+  return true;
+}
+
+// S1: min / max / sum per item  (int_quantizer.py:541-546)
+template <int VEC>
+__device__ void phase_stats1(const FusedArgs& A, PhaseSmem& sm, bool reverse) {
+  unsigned long long it;
+  for (bool ok = next_item(A.geo, it, reverse, true); ok; ok = next_item(A.geo, it, reverse, false)) {
+    float mn = INFINITY, mx = -INFINITY;
+    double s = 0.0;
+    if constexpr (VEC == 4) {
+      walk_item<4>(A.geo, A.in, it, [&](const float4& x, unsigned long long) {
+        mn = fminf(mn, fminf(fminf(x.x, x.y), fminf(x.z, x.w)));
+        mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+        s += static_cast<double>(__fadd_rn(__fadd_rn(x.x, x.y), __fadd_rn(x.z, x.w)));
+      });
+    } else {
+      walk_item<1>(A.geo, A.in, it, [&](float x, unsigned long long) {
+        mn = fminf(mn, x);
+        mx = fmaxf(mx, x);
+        s += static_cast<double>(x);
+      });
+    }
+    mn = warp_reduce(mn, OpMin());
+    mx = warp_reduce(mx, OpMax());
+    s = warp_reduce(s, OpAdd());
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+      sm.f0[threadIdx.x >> 5] = mn;
+      sm.f1[threadIdx.x >> 5] = mx;
+      sm.d0[threadIdx.x >> 5] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kWarps; ++w) {
+        mn = fminf(mn, sm.f0[w]);
+        mx = fmaxf(mx, sm.f1[w]);
+        s += sm.d0[w];
+      }
+      // partial layout [p][g] so that the leader's per-group reads are coalesced over g
+      const size_t slot = static_cast<size_t>(it);  // it = p * G + g: the leader reads [p][g]
+      st_ws(A.pmin + slot, mn);
+      st_ws(A.pmax + slot, mx);
+      st_ws(A.psum + slot, s);
+    }
+  }
+}
+
+// S2: sum |x - mu| and sum (x - mu)^2 per item, mu = fp32 group mean  (int_quantizer.py:547-550)
+template <int VEC>
+__device__ void phase_stats2(const FusedArgs& A, PhaseSmem& sm, bool reverse) {
+  unsigned long long it;
+  for (bool ok = next_item(A.geo, it, reverse, true); ok; ok = next_item(A.geo, it, reverse, false)) {
+    const float mu = ld_ws(A.gmean + (it % A.geo.groups));
+    double sa = 0.0, sq = 0.0;
+    if constexpr (VEC == 4) {
+      walk_item<4>(A.geo, A.in, it, [&](const float4& x, unsigned long long) {
+        const float d0 = __fsub_rn(x.x, mu), d1 = __fsub_rn(x.y, mu), d2 = __fsub_rn(x.z, mu), d3 = __fsub_rn(x.w, mu);
+        sa += static_cast<double>(__fadd_rn(__fadd_rn(fabsf(d0), fabsf(d1)), __fadd_rn(fabsf(d2), fabsf(d3))));
+        sq += static_cast<double>(__fmaf_rn(d3, d3, __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)))));
+      });
+    } else {
+      walk_item<1>(A.geo, A.in, it, [&](float x, unsigned long long) {
+        const float d = __fsub_rn(x, mu);
+        sa += static_cast<double>(fabsf(d));
+        sq += static_cast<double>(__fmul_rn(d, d));
+      });
+    }
+    sa = warp_reduce(sa, OpAdd());
+    sq = warp_reduce(sq, OpAdd());
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+      sm.d0[threadIdx.x >> 5] = sa;
+      sm.d1[threadIdx.x >> 5] = sq;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kWarps; ++w) {
+        sa += sm.d0[w];
+        sq += sm.d1[w];
+      }
+      const size_t slot = static_cast<size_t>(it);  // it = p * G + g: the leader reads [p][g]
+      st_ws(A.pabs + slot, sa);
+      st_ws(A.psq + slot, sq);
+    }
+  }
+}
+
+// one element through the leaf
+template <int LEAF>
+__device__ __forceinline__ float leaf_apply(float x, const LeafParam& q, const Divisor& dv, float noise, float& grid) {
+  if constexpr (LEAF == FQB200_LEAF_TORCH) {
+    // int_quantizer.py:573-592: o = x/scale + zp; clamp [0, qmax]; round-half-even; (o - zp) * scale
+    float t = __fadd_rn(div_exact(x, dv), q.b);
+    t = max_nan(min_nan(t, q.c), 0.f);
+    t = rint_small_nonneg(t);
+    grid = t;
+    return __fmul_rn(__fsub_rn(t, q.b), q.a);
+  } else if constexpr (LEAF == FQB200_LEAF_COMPILED) {
+    // gemmlowp.cu:10-24
+    if (q.flags & FLAG_PASSTHROUGH) {
+      grid = x;
+      return x;
+    }
+    float t;
+    if (q.flags & FLAG_TRUE_ZERO)
+      t = __fadd_rn(div_exact(x, dv), q.b);
+    else
+      t = div_exact(__fadd_rn(x, q.b), dv);
+    t = __fadd_rn(t, noise);
+    t = fmaxf(fminf(t, q.c), 0.f);
+    t = roundf(t);
+    grid = t;
+    if (q.flags & FLAG_TRUE_ZERO) return __fmul_rn(__fsub_rn(t, q.b), q.a);
+    return __fmaf_rn(t, q.a, -q.b);  // single FFMA in the reference's nvcc build ("a1 contraction")
+  } else {
+    // int_quantizer.py:202-224: round(x/Delta), clamp to [c_min, c_max], * Delta
+    float t = rintf(div_exact(x, dv));
+    t = max_nan(min_nan(t, q.c), q.b);
+    grid = t;
+    return __fmul_rn(t, q.a);
+  }
+}
+
+// A: quantize - clip - dequantize.  ACC: also accumulate sum(y) per item (weight bias correction).
+template <int VEC, int LEAF, bool ACC>
+__device__ void phase_apply(const FusedArgs& A, PhaseSmem& sm, bool reverse) {
+  unsigned long long it;
+  const bool per_group = (A.scope == FQB200_SCOPE_GROUP);
+  for (bool ok = next_item(A.geo, it, reverse, true); ok; ok = next_item(A.geo, it, reverse, false)) {
+    const unsigned g = static_cast<unsigned>(it % A.geo.groups);
+    const float4 raw = ld_ws(reinterpret_cast<const float4*>(A.lp) + (per_group ? g : 0u));
+    LeafParam q;
+    q.a = raw.x;
+    q.b = raw.y;
+    q.c = raw.z;
+    q.flags = __float_as_int(raw.w);
+    const Divisor dv = make_divisor(q.a);
+    double sy = 0.0;
+    float* out = A.out;
+    float* grid_out = A.grid_out;
+    const float* noise = A.noise;
+    if constexpr (VEC == 4) {
+      walk_item<4>(A.geo, A.in, it, [&](const float4& x, unsigned long long off) {
+        float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (LEAF == FQB200_LEAF_COMPILED && noise) nz = ld_tensor(reinterpret_cast<const float4*>(noise) + off);
+        float4 y, gq;
+        y.x = leaf_apply<LEAF>(x.x, q, dv, nz.x, gq.x);
+        y.y = leaf_apply<LEAF>(x.y, q, dv, nz.y, gq.y);
+        y.z = leaf_apply<LEAF>(x.z, q, dv, nz.z, gq.z);
+        y.w = leaf_apply<LEAF>(x.w, q, dv, nz.w, gq.w);
+        st_tensor(reinterpret_cast<float4*>(out) + off, y);
+        if (grid_out) st_tensor(reinterpret_cast<float4*>(grid_out) + off, gq);
+        if (ACC) sy += static_cast<double>(__fadd_rn(__fadd_rn(y.x, y.y), __fadd_rn(y.z, y.w)));
+      });
+    } else {
+      walk_item<1>(A.geo, A.in, it, [&](float x, unsigned long long off) {
+        float nz = 0.f;
+        if (LEAF == FQB200_LEAF_COMPILED && noise) nz = ld_tensor(noise + off);
+        float gq;
+        const float y = leaf_apply<LEAF>(x, q, dv, nz, gq);
+        st_tensor(out + off, y);
+        if (grid_out) st_tensor(grid_out + off, gq);
+        if (ACC) sy += static_cast<double>(y);
+      });
+    }
+    if (ACC) {
+      sy = warp_reduce(sy, OpAdd());
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) sm.d0[threadIdx.x >> 5] = sy;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < kWarps; ++w) sy += sm.d0[w];
+        const size_t slot = static_cast<size_t>(it);  // it = p * G + g: the leader reads [p][g]
+        st_ws(A.psum + slot, sy);
+      }
+    }
+  }
+}
+
+// C0: sum (y - mean_q)^2 per item (variance correction needs std(w_q))
+template <int VEC>
+__device__ void phase_corr_var(const FusedArgs& A, PhaseSmem& sm, bool reverse) {
+  unsigned long long it;
+  for (bool ok = next_item(A.geo, it, reverse, true); ok; ok = next_item(A.geo, it, reverse, false)) {
+    const float mu = ld_ws(A.cq + (it % A.geo.groups));
+    double sq = 0.0;
+    if constexpr (VEC == 4) {
+      walk_item<4>(A.geo, A.out, it, [&](const float4& y, unsigned long long) {
+        const float d0 = __fsub_rn(y.x, mu), d1 = __fsub_rn(y.y, mu), d2 = __fsub_rn(y.z, mu), d3 = __fsub_rn(y.w, mu);
+        sq += static_cast<double>(__fmaf_rn(d3, d3, __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)))));
+      });
+    } else {
+      walk_item<1>(A.geo, A.out, it, [&](float y, unsigned long long) {
+        const float d = __fsub_rn(y, mu);
+        sq += static_cast<double>(__fmul_rn(d, d));
+      });
+    }
+    sq = warp_reduce(sq, OpAdd());
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm.d0[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kWarps; ++w) sq += sm.d0[w];
+      const size_t slot = static_cast<size_t>(it);  // it = p * G + g: the leader reads [p][g]
+      st_ws(A.psq + slot, sq);
+    }
+  }
+}
+
+// C1: y <- (y - m_q) * k + m_q  (variance), then y <- y - m_q + m_o  (mean); inference_quantization_manager.py:386-391
+template <int VEC>
+__device__ void phase_corr_apply(const FusedArgs& A, bool reverse) {
+  unsigned long long it;
+  for (bool ok = next_item(A.geo, it, reverse, true); ok; ok = next_item(A.geo, it, reverse, false)) {
+    const unsigned g = static_cast<unsigned>(it % A.geo.groups);
+    const float mq = ld_ws(A.cq + g), mo = ld_ws(A.co + g);
+    const float kv = A.var_corr ? ld_ws(A.ck + g) : 1.f;
+    const bool vc = A.var_corr != 0, bc = A.bias_corr != 0;
+    float* out = A.out;
+    auto fix = [&](float y) {
+      if (vc) y = __fadd_rn(__fmul_rn(__fsub_rn(y, mq), kv), mq);
+      if (bc) y = __fadd_rn(__fsub_rn(y, mq), mo);
+      return y;
+    };
+    if constexpr (VEC == 4) {
+      walk_item<4>(A.geo, A.out, it, [&](const float4& y, unsigned long long off) {
+        st_tensor(reinterpret_cast<float4*>(out) + off, make_float4(fix(y.x), fix(y.y), fix(y.z), fix(y.w)));
+      });
+    } else {
+      walk_item<1>(A.geo, A.out, it, [&](float y, unsigned long long off) { st_tensor(out + off, fix(y)); });
+    }
+  }
+}
+
+template <int VEC, bool ACC>
+__device__ __forceinline__ void dispatch_apply(const FusedArgs& A, PhaseSmem& sm, bool reverse) {
+  switch (A.leaf) {
+    case FQB200_LEAF_TORCH: phase_apply<VEC, FQB200_LEAF_TORCH, ACC>(A, sm, reverse); break;
+    case FQB200_LEAF_COMPILED: phase_apply<VEC, FQB200_LEAF_COMPILED, ACC>(A, sm, reverse); break;
+    default: phase_apply<VEC, FQB200_LEAF_MIDTREAD, ACC>(A, sm, reverse); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused persistent kernel (cooperative launch: every CTA is resident)
+// ------------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __grid_constant__ FusedArgs A) {
+  __shared__ PhaseSmem psm;
+  __shared__ LeaderSmem lsm;
+  unsigned epoch = 0;
+  const Geometry& geo = A.geo;
+  const double n = A.n_per_group;
+  bool rev = false;
+
+  // ---- S1
+  phase_stats1<VEC>(A, psm, rev);
+  rev = !rev;
+  if (grid_arrive(A.sync, epoch, &lsm.flag)) {
+    reduce_partials(A.pmin, A.gmin, geo, INFINITY, OpMin());
+    reduce_partials(A.pmax, A.gmax, geo, -INFINITY, OpMax());
+    reduce_partials(A.psum, A.gmean_d, geo, 0.0, OpAdd());
+    __syncthreads();
+    for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) {
+      const double m = A.gmean_d[g] / n;
+      A.gmean_d[g] = m;
+      A.gmean[g] = static_cast<float>(m);
+    }
+    __syncthreads();
+    if (!A.need_dev) solve_params(A, lsm);
+    grid_release(A.sync, epoch);
+  }
+
+  // ---- S2
+  if (A.need_dev) {
+    phase_stats2<VEC>(A, psm, rev);
+    rev = !rev;
+    if (grid_arrive(A.sync, epoch, &lsm.flag)) {
+      // reuse gb / gstd as fp32 results; accumulate through double temporaries in cq/co-free space: psum is free now
+      double* tmp = A.psum;  // [items] >= [G]
+      reduce_partials(A.pabs, tmp, geo, 0.0, OpAdd());
+      __syncthreads();
+      for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) A.gb[g] = static_cast<float>(tmp[g] / n);
+      __syncthreads();
+      reduce_partials(A.psq, tmp, geo, 0.0, OpAdd());
+      __syncthreads();
+      for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) {
+        // sum (x - mu32)^2 -> sum (x - mu)^2 with the exact mean; unbiased (torch.std default)
+        const double dm = A.gmean_d[g] - static_cast<double>(A.gmean[g]);
+        double ss = tmp[g] - n * dm * dm;
+        if (ss < 0.0) ss = 0.0;
+        A.gstd[g] = static_cast<float>(sqrt(ss / (n - 1.0)));
+      }
+      __syncthreads();
+      solve_params(A, lsm);
+      grid_release(A.sync, epoch);
+    }
+  }
+
+  // ---- A (+ C)
+  if (!A.stats_only) {
+    const bool corr = (A.bias_corr || A.var_corr);
+    if (corr)
+      dispatch_apply<VEC, true>(A, psm, rev);
+    else
+      dispatch_apply<VEC, false>(A, psm, rev);
+    rev = !rev;
+    if (corr) {
+      if (grid_arrive(A.sync, epoch, &lsm.flag)) {
+        double* tmp = A.pabs;
+        reduce_partials(A.psum, tmp, geo, 0.0, OpAdd());
+        __syncthreads();
+        for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) {
+          A.cq[g] = static_cast<float>(tmp[g] / n);
+          A.co[g] = A.gmean[g];
+        }
+        grid_release(A.sync, epoch);
+      }
+      if (A.var_corr) {
+        phase_corr_var<VEC>(A, psm, rev);
+        rev = !rev;
+        if (grid_arrive(A.sync, epoch, &lsm.flag)) {
+          double* tmp = A.pabs;
+          reduce_partials(A.psq, tmp, geo, 0.0, OpAdd());
+          __syncthreads();
+          for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) {
+            // tmp = sum (y - fl32(mean_q))^2 ; treat fl32(mean_q) as the mean (error O(ulp^2))
+            const float sdq = static_cast<float>(sqrt(tmp[g] / (n - 1.0)));
+            A.ck[g] = __fdiv_rn(A.gstd[g], __fadd_rn(sdq, 1e-8f));
+          }
+          grid_release(A.sync, epoch);
+        }
+      }
+      phase_corr_apply<VEC>(A, rev);
+    }
+  }
+  grid_exit(A.sync);
+}
+
+// Standalone a1 with host-side scalars (gemmlowp.cu:30-45): flat grid-stride, parameters by value.
+template <int VEC>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+    fq_leaf_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ noise,
+                   unsigned long long nvec, LeafParam q) {
+  using V = typename VecT<VEC>::type;
+  const Divisor dv = make_divisor(q.a);
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kThreads;
+  for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * kThreads + threadIdx.x; i < nvec; i += stride) {
+    float gq;
+    if constexpr (VEC == 4) {
+      const float4 x = ld_tensor(reinterpret_cast<const float4*>(in) + i);
+      float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (noise) nz = ld_tensor(reinterpret_cast<const float4*>(noise) + i);
+      float4 y;
+      y.x = leaf_apply<FQB200_LEAF_COMPILED>(x.x, q, dv, nz.x, gq);
+      y.y = leaf_apply<FQB200_LEAF_COMPILED>(x.y, q, dv, nz.y, gq);
+      y.z = leaf_apply<FQB200_LEAF_COMPILED>(x.z, q, dv, nz.z, gq);
+      y.w = leaf_apply<FQB200_LEAF_COMPILED>(x.w, q, dv, nz.w, gq);
+      st_tensor(reinterpret_cast<float4*>(out) + i, y);
+    } else {
+      const float x = ld_tensor(in + i);
+      const float nz = noise ? ld_tensor(noise + i) : 0.f;
+      st_tensor(out + i, leaf_apply<FQB200_LEAF_COMPILED>(x, q, dv, nz, gq));
+    }
+  }
+}
+
+// Mode A (parameters given by the caller, int_quantizer.py:557-603 called directly): no statistics, no grid
+// barrier, ordinary launch.  Leaf parameters are derived per item from the device-resident delta/offset/bits
+// (a few CTA-uniform flops), so nothing is synchronised with the host.
+template <int VEC, int LEAF>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_given_kernel(const __grid_constant__ FusedArgs A) {
+  unsigned long long it;
+  for (bool ok = next_item(A.geo, it, false, true); ok; ok = next_item(A.geo, it, false, false)) {
+    const unsigned g = static_cast<unsigned>(it % A.geo.groups);
+    const unsigned pi = A.given_per_group ? g : 0u;
+    const float bits = A.g_bits ? __ldg(A.g_bits + g) : static_cast<float>(A.num_bits);
+    const LeafParam q = make_leaf_param(LEAF, __ldg(A.g_delta + pi), __ldg(A.g_offset + pi), bits);
+    const Divisor dv = make_divisor(q.a);
+    float* out = A.out;
+    float* grid_out = A.grid_out;
+    if constexpr (VEC == 4) {
+      walk_item<4>(A.geo, A.in, it, [&](const float4& x, unsigned long long off) {
+        float4 y, gq;
+        y.x = leaf_apply<LEAF>(x.x, q, dv, 0.f, gq.x);
+        y.y = leaf_apply<LEAF>(x.y, q, dv, 0.f, gq.y);
+        y.z = leaf_apply<LEAF>(x.z, q, dv, 0.f, gq.z);
+        y.w = leaf_apply<LEAF>(x.w, q, dv, 0.f, gq.w);
+        st_tensor(reinterpret_cast<float4*>(out) + off, y);
+        if (grid_out) st_tensor(reinterpret_cast<float4*>(grid_out) + off, gq);
+      });
+    } else {
+      walk_item<1>(A.geo, A.in, it, [&](float x, unsigned long long off) {
+        float gq;
+        const float y = leaf_apply<LEAF>(x, q, dv, 0.f, gq);
+        st_tensor(out + off, y);
+        if (grid_out) st_tensor(grid_out + off, gq);
+      });
+    }
+  }
+}
+
+// test hook: q[i] = div_exact(a[i], b[i]) next to IEEE a[i]/b[i]
+__global__ void fq_divtest_kernel(const float* a, const float* b, float* fast, float* ieee, unsigned long long n) {
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const Divisor dv = make_divisor(b[i]);
+    fast[i] = div_exact(a[i], dv);
+    ieee[i] = __fdiv_rn(a[i], b[i]);
+  }
+}
+
+}  // namespace fqb
+
+// ================================================================================================
+// host side: geometry, workspace carving, launches, C ABI
+// ================================================================================================
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+
+struct DeviceInfo {
+  int device = -1;
+  int sms = 0;
+  int resident = 0;  // CTAs of fq_fused_kernel<4> that fit at once
+  bool tables = false;
+};
+DeviceInfo g_dev[64];
+
+// optimum of 2*exp(-a) + a^2/(3 w^2): a*exp(a) = 3 w^2 (Lambert W), Newton in float64.  The reference gets the
+// same numbers from scipy's Brent minimiser (int_quantizer.py:48) to ~1e-8.
+double laplace_opt_alpha(double w) {
+  const double c = 3.0 * w * w;
+  double a = (c < 1.0) ? c : log(c);
+  if (a <= 0) a = 1e-3;
+  for (int i = 0; i < 100; ++i) {
+    const double e = exp(a), f = a * e - c, fp = e * (a + 1.0);
+    const double na = a - f / fp;
+    if (fabs(na - a) <= 1e-16 * fabs(na)) {
+      a = na;
+      break;
+    }
+    a = na;
+  }
+  return a;
+}
+
+int get_device(DeviceInfo** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+  if (dev < 0 || dev >= 64) return fail(FQB200_ERR_UNSUPPORTED, "device index out of range%s");
+  DeviceInfo& d = g_dev[dev];
+  if (d.device != dev) {
+    int sms = 0, per_sm = 0;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fqb::fq_fused_kernel<4>, fqb::kThreads, 0);
+    if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+    int per_sm1 = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, fqb::fq_fused_kernel<1>, fqb::kThreads, 0);
+    if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+    if (per_sm1 < per_sm) per_sm = per_sm1;
+    if (per_sm < 1) return fail(FQB200_ERR_CUDA, "fused kernel does not fit on an SM%s");
+    // mid-tread table (int_quantizer.py:41-51): omega grid = 5 decades x 20 steps, leading 0
+    double om[fqb::kTable], al[fqb::kTable];
+    om[0] = 0.0;
+    al[0] = 0.0;
+    const double lo[5] = {0.01, 0.1, 1, 10, 100}, hi[5] = {0.1, 1, 10, 100, 1000};
+    for (int dcd = 0; dcd < 5; ++dcd)
+      for (int k = 0; k < 20; ++k) {
+        const double w = lo[dcd] + (hi[dcd] - lo[dcd]) * k / 20.0;
+        om[1 + dcd * 20 + k] = w;
+        al[1 + dcd * 20 + k] = laplace_opt_alpha(w);
+      }
+    e = cudaMemcpyToSymbol(fqb::kOmegaTable, om, sizeof(om));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(fqb::kAlphaTable, al, sizeof(al));
+    if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "table upload: %s", cudaGetErrorString(e));
+    d.sms = sms;
+    d.resident = sms * per_sm;
+    d.device = dev;
+  }
+  *out = &d;
+  return FQB200_OK;
+}
+
+struct Plan {
+  fqb::Geometry geo;
+  int vec;
+  int grid;
+};
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Choose vector width, parts per group and grid size.
+int make_plan(int64_t outer, int64_t groups, int64_t inner, bool can_vec, int resident, Plan* pl) {
+  if (outer <= 0 || groups <= 0 || inner <= 0) return fail(FQB200_ERR_INVALID, "non-positive tensor extent%s");
+  if (groups > 0x7fffffffLL || outer > 0x7fffffffLL || inner > 0x7fffffffLL * 4LL)
+    return fail(FQB200_ERR_UNSUPPORTED, "tensor extent exceeds 2^31%s");
+  const int vec = (can_vec && inner % 4 == 0) ? 4 : 1;
+  const uint64_t inner_v = static_cast<uint64_t>(inner / vec);
+  if (inner_v > 0xffffffffULL) return fail(FQB200_ERR_UNSUPPORTED, "row too long%s");
+  const uint64_t group_v = static_cast<uint64_t>(outer) * inner_v;
+  const uint64_t total_v = group_v * static_cast<uint64_t>(groups);
+  // item size target: >= ~64 KB per item when the tensor allows, ~8 items per CTA for balance
+  const uint64_t min_item_v = (64u * 1024u) / (4u * vec) * 1u;  // vectors
+  uint64_t want_items = static_cast<uint64_t>(resident) * 8u;
+  uint64_t max_items = total_v / min_item_v;
+  if (max_items < 1) max_items = 1;
+  if (want_items > max_items) want_items = max_items;
+  uint64_t parts = (want_items + groups - 1) / static_cast<uint64_t>(groups);
+  if (parts < 1) parts = 1;
+  // never split finer than one CTA sweep per item, and keep item length < 2^31
+  uint64_t max_parts = group_v / static_cast<uint64_t>(fqb::kThreads);
+  if (max_parts < 1) max_parts = 1;
+  if (parts > max_parts) parts = max_parts;
+  // balance: prefer a part count that makes groups*parts a near multiple of the resident CTA count
+  uint64_t best = parts;
+  double best_eff = 0.0;
+  for (uint64_t p = parts; p <= parts * 2 && p <= max_parts; ++p) {
+    const uint64_t items = p * static_cast<uint64_t>(groups);
+    const uint64_t waves = (items + resident - 1) / resident;
+    const double eff = static_cast<double>(items) / static_cast<double>(waves * resident);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = p;
+    }
+    if (items < static_cast<uint64_t>(resident)) break;
+  }
+  parts = best;
+  while ((group_v + parts - 1) / parts >= 0x7fffffffULL) ++parts;
+  fqb::Geometry& g = pl->geo;
+  g.groups = static_cast<unsigned>(groups);
+  g.parts = static_cast<unsigned>(parts);
+  g.inner_v = static_cast<unsigned>(inner_v);
+  g.step_q = static_cast<unsigned>(fqb::kThreads / inner_v);
+  g.step_r = static_cast<unsigned>(fqb::kThreads % inner_v);
+  g.group_v = group_v;
+  g.row_pitch = static_cast<uint64_t>(groups) * inner_v;
+  g.items = parts * static_cast<uint64_t>(groups);
+  pl->vec = vec;
+  pl->grid = static_cast<int>(g.items < static_cast<uint64_t>(resident) ? g.items : static_cast<uint64_t>(resident));
+  return FQB200_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// workspace layout; returns total bytes, fills pointers when base != nullptr
+size_t carve(char* base, uint64_t items, uint64_t groups, fqb::FusedArgs* A) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off = align_up(off + bytes, 256);
+    return p;
+  };
+  char* sync = take(sizeof(fqb::GridSync));
+  char* pmin = take(items * sizeof(float));
+  char* pmax = take(items * sizeof(float));
+  const uint64_t dn = items > groups ? items : groups;
+  char* psum = take(dn * sizeof(double));
+  char* pabs = take(dn * sizeof(double));
+  char* psq = take(dn * sizeof(double));
+  char* gf = take(groups * sizeof(float) * 12);
+  char* gd = take(groups * sizeof(double));
+  char* lp = take(groups * sizeof(fqb::LeafParam));
+  if (A) {
+    A->sync = reinterpret_cast<fqb::GridSync*>(sync);
+    A->pmin = reinterpret_cast<float*>(pmin);
+    A->pmax = reinterpret_cast<float*>(pmax);
+    A->psum = reinterpret_cast<double*>(psum);
+    A->pabs = reinterpret_cast<double*>(pabs);
+    A->psq = reinterpret_cast<double*>(psq);
+    float* f = reinterpret_cast<float*>(gf);
+    A->gmin = f + 0 * groups;
+    A->gmax = f + 1 * groups;
+    A->gmean = f + 2 * groups;
+    A->gb = f + 3 * groups;
+    A->gstd = f + 4 * groups;
+    A->gbits = f + 5 * groups;
+    A->gprior = f + 6 * groups;
+    A->gdelta = f + 7 * groups;
+    A->goffset = f + 8 * groups;
+    A->cq = f + 9 * groups;
+    A->co = f + 10 * groups;
+    A->ck = f + 11 * groups;
+    A->gmean_d = reinterpret_cast<double*>(gd);
+    A->lp = reinterpret_cast<fqb::LeafParam*>(lp);
+  }
+  return off;
+}
+
+int check_desc(const fqb200_desc* d) {
+  if (!d) return fail(FQB200_ERR_INVALID, "null descriptor%s");
+  if (d->scope < FQB200_SCOPE_GROUP || d->scope > FQB200_SCOPE_TENSOR) return fail(FQB200_ERR_INVALID, "bad scope%s");
+  if (d->range_mode < FQB200_RANGE_MINMAX || d->range_mode > FQB200_RANGE_KSTD) return fail(FQB200_ERR_INVALID, "bad range_mode%s");
+  if (d->leaf < FQB200_LEAF_TORCH || d->leaf > FQB200_LEAF_MIDTREAD) return fail(FQB200_ERR_INVALID, "bad leaf%s");
+  if (d->leaf != FQB200_LEAF_MIDTREAD && (d->num_bits < 1 || d->num_bits > 8))
+    return fail(FQB200_ERR_INVALID, "num_bits must be in 1..8%s");
+  if (d->scope != FQB200_SCOPE_GROUP && (d->range_mode != FQB200_RANGE_MINMAX || d->leaf == FQB200_LEAF_MIDTREAD))
+    return fail(FQB200_ERR_UNSUPPORTED, "group-mean / tensor scopes are defined for min/max ranges only%s");
+  if (d->bit_alloc && !(d->bit_alloc_target > 0.f)) return fail(FQB200_ERR_INVALID, "bit_alloc_target must be > 0%s");
+  if ((d->bias_corr || d->var_corr) && d->scope == FQB200_SCOPE_GROUP_MEAN)
+    return fail(FQB200_ERR_UNSUPPORTED, "weight correction is per row (scope GROUP or TENSOR)%s");
+  return FQB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fqb200_abi_version(void) { return FQB200_ABI_VERSION; }
+
+const char* fqb200_last_error(void) { return g_err; }
+
+int fqb200_resident_ctas(void) {
+  DeviceInfo* di = nullptr;
+  if (get_device(&di) != FQB200_OK) return -1;
+  return di->resident;
+}
+
+size_t fqb200_workspace_bytes(const fqb200_desc* d) {
+  if (check_desc(d) != FQB200_OK) return 0;
+  // plan-independent upper bound: items <= resident*16 + groups
+  int resident = 148 * fqb::kCtasPerSm;
+  DeviceInfo* di = nullptr;
+  if (get_device(&di) == FQB200_OK) resident = di->resident;
+  Plan pl;
+  if (make_plan(d->outer, d->groups, d->inner, true, resident, &pl) != FQB200_OK) return 0;
+  Plan pl1;
+  if (make_plan(d->outer, d->groups, d->inner, false, resident, &pl1) != FQB200_OK) return 0;
+  const uint64_t items = pl.geo.items > pl1.geo.items ? pl.geo.items : pl1.geo.items;
+  return carve(nullptr, items, static_cast<uint64_t>(d->groups), nullptr);
+}
+
+int fqb200_workspace_init(void* workspace, size_t bytes, void* stream) {
+  if (!workspace || bytes < sizeof(fqb::GridSync)) return fail(FQB200_ERR_WORKSPACE, "workspace too small%s");
+  cudaError_t e = cudaMemsetAsync(workspace, 0, 256 < bytes ? 256 : bytes, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  return FQB200_OK;
+}
+
+int fqb200_float2gemmlowp(const float* in, float* out, int64_t n, float range, float offset, int num_bits, int int_exp,
+                          int enforce_true_zero, const float* noise, void* stream) {
+  g_err[0] = 0;
+  if (n < 0 || num_bits < 1 || num_bits > 30) return fail(FQB200_ERR_INVALID, "bad n / num_bits%s");
+  if (n == 0) return FQB200_OK;
+  if (!in || !out) return fail(FQB200_ERR_INVALID, "null tensor pointer%s");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (range <= 0) {  // gemmlowp.cu:31-32: the reference hands back its input
+    if (in != out) {
+      cudaError_t e = cudaMemcpyAsync(out, in, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+    }
+    return FQB200_OK;
+  }
+  DeviceInfo* di = nullptr;
+  int rc = get_device(&di);
+  if (rc != FQB200_OK) return rc;
+  // host wrapper arithmetic, gemmlowp.cu:36-41 (fp32, one rounding per operator)
+  const long long qmax_i = (1ll << num_bits) - 1;
+  volatile float scale = range / static_cast<float>(qmax_i);
+  if (int_exp) scale = powf(2.f, static_cast<float>(static_cast<int>(ceilf(log2f(scale)))));
+  volatile float zr = -offset / scale;
+  const float zero_point = roundf(zr);
+  fqb::LeafParam q;
+  q.a = scale;
+  q.b = enforce_true_zero ? zero_point : -offset;
+  q.c = static_cast<float>(qmax_i);
+  q.flags = enforce_true_zero ? fqb::FLAG_TRUE_ZERO : 0;
+  const bool vec = (n % 4 == 0) && aligned16(in) && aligned16(out) && (!noise || aligned16(noise));
+  const unsigned long long nvec = vec ? static_cast<unsigned long long>(n / 4) : static_cast<unsigned long long>(n);
+  unsigned long long want = (nvec + fqb::kThreads - 1) / fqb::kThreads;
+  const unsigned long long cap = static_cast<unsigned long long>(di->resident) * 4ull;
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  if (vec)
+    fqb::fq_leaf_kernel<4><<<grid, fqb::kThreads, 0, st>>>(in, out, noise, nvec, q);
+  else
+    fqb::fq_leaf_kernel<1><<<grid, fqb::kThreads, 0, st>>>(in, out, noise, nvec, q);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "launch fq_leaf_kernel: %s", cudaGetErrorString(e));
+  return FQB200_OK;
+}
+
+int fqb200_quantize1(const float* in, float* out, float* grid, int64_t outer, int64_t groups, int64_t inner,
+                     const float* delta, const float* offset, const float* bits, int per_group, int num_bits,
+                     void* stream) {
+  g_err[0] = 0;
+  if (outer == 0 || groups == 0 || inner == 0) return FQB200_OK;
+  if (!in || !out || !delta || !offset) return fail(FQB200_ERR_INVALID, "null pointer%s");
+  if (num_bits < 1 || num_bits > 8) {
+    if (!bits) return fail(FQB200_ERR_INVALID, "num_bits must be in 1..8%s");
+  }
+  if (bits && !per_group) return fail(FQB200_ERR_INVALID, "per-row bit widths need per-group parameters%s");
+  DeviceInfo* di = nullptr;
+  int rc = get_device(&di);
+  if (rc != FQB200_OK) return rc;
+  Plan pl;
+  const bool can_vec = aligned16(in) && aligned16(out) && (!grid || aligned16(grid));
+  rc = make_plan(outer, groups, inner, can_vec, di->resident * 4, &pl);
+  if (rc != FQB200_OK) return rc;
+  fqb::FusedArgs A;
+  memset(&A, 0, sizeof(A));
+  A.geo = pl.geo;
+  A.in = in;
+  A.out = out;
+  A.grid_out = grid;
+  A.leaf = FQB200_LEAF_TORCH;
+  A.num_bits = num_bits;
+  A.g_delta = delta;
+  A.g_offset = offset;
+  A.g_bits = bits;
+  A.given_per_group = per_group;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pl.vec == 4)
+    fqb::fq_given_kernel<4, FQB200_LEAF_TORCH><<<pl.grid, fqb::kThreads, 0, st>>>(A);
+  else
+    fqb::fq_given_kernel<1, FQB200_LEAF_TORCH><<<pl.grid, fqb::kThreads, 0, st>>>(A);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "launch fq_given_kernel: %s", cudaGetErrorString(e));
+  return FQB200_OK;
+}
+
+int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  g_err[0] = 0;
+  int rc = check_desc(d);
+  if (rc != FQB200_OK) return rc;
+  if (d->outer == 0 || d->groups == 0 || d->inner == 0) return FQB200_OK;
+  if (!in) return fail(FQB200_ERR_INVALID, "null input%s");
+  if (!out && !d->stats_only) return fail(FQB200_ERR_INVALID, "null output%s");
+  if (d->stats_only && !d->out_stats) return fail(FQB200_ERR_INVALID, "stats_only needs out_stats%s");
+  DeviceInfo* di = nullptr;
+  rc = get_device(&di);
+  if (rc != FQB200_OK) return rc;
+  Plan pl;
+  const bool can_vec = aligned16(in) && (d->stats_only || aligned16(out));
+  rc = make_plan(d->outer, d->groups, d->inner, can_vec, di->resident, &pl);
+  if (rc != FQB200_OK) return rc;
+  fqb::FusedArgs A;
+  memset(&A, 0, sizeof(A));
+  const size_t need = carve(nullptr, pl.geo.items, pl.geo.groups, nullptr);
+  if (!workspace || workspace_bytes < need) return fail(FQB200_ERR_WORKSPACE, "workspace smaller than fqb200_workspace_bytes()%s");
+  if (!aligned16(workspace)) return fail(FQB200_ERR_WORKSPACE, "workspace must be 16-byte aligned%s");
+  carve(static_cast<char*>(workspace), pl.geo.items, pl.geo.groups, &A);
+  A.geo = pl.geo;
+  A.in = in;
+  A.out = out;
+  A.scope = d->scope;
+  A.range_mode = d->range_mode;
+  A.leaf = d->leaf;
+  A.num_bits = d->num_bits;
+  A.positive = d->positive;
+  A.solve_f64 = d->solve_f64;
+  A.clip_k = d->clip_k;
+  A.bit_alloc = d->bit_alloc;
+  A.prior = d->bit_alloc_prior;
+  A.ba_round = d->bit_alloc_round;
+  A.ba_target = d->bit_alloc_target;
+  A.mt_target = d->mt_target;
+  A.mt_clip = d->mt_clip;
+  A.bias_corr = d->bias_corr;
+  A.var_corr = d->var_corr;
+  A.stats_only = d->stats_only;
+  A.out_stats = d->out_stats;
+  A.n_per_group = static_cast<double>(d->outer) * static_cast<double>(d->inner);
+  const bool alloc = d->bit_alloc && d->num_bits <= 4 && d->scope == FQB200_SCOPE_GROUP && d->leaf != FQB200_LEAF_MIDTREAD;
+  A.need_dev = (d->range_mode != FQB200_RANGE_MINMAX) || alloc || d->var_corr || d->leaf == FQB200_LEAF_MIDTREAD ||
+               (d->stats_only ? 1 : 0);
+  void* args[] = {&A};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if (pl.vec == 4)
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fqb::fq_fused_kernel<4>), dim3(pl.grid), dim3(fqb::kThreads), args, 0, st);
+  else
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fqb::fq_fused_kernel<1>), dim3(pl.grid), dim3(fqb::kThreads), args, 0, st);
+  if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cooperative launch fq_fused_kernel: %s", cudaGetErrorString(e));
+  return FQB200_OK;
+}
+
+// test hook (not part of the drop-in surface): compares div_exact with IEEE division on the device
+int fqb200_test_division(const float* a, const float* b, float* fast, float* ieee, int64_t n, void* stream) {
+  if (n <= 0) return FQB200_OK;
+  fqb::fq_divtest_kernel<<<296, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, fast, ieee, static_cast<unsigned long long>(n));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "launch: %s", cudaGetErrorString(e));
+  return FQB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,410 @@
+"""Drop-in ``IntQuantizer`` for the reference's
+``pytorch_quantizer/quantization/qtypes/int_quantizer.py`` (same constructor dict, same ``__call__``,
+same mutable attributes, same method names), routed to the fused sm_100a kernels in ``libfqb200.so``.
+
+Where the reference runs ~10 elementwise kernels, several reductions, up to 6 transposed copies and O(C)
+host synchronisations per hooked tensor, every dispatch target below is ONE cooperative kernel launch on the
+native NCHW layout and never reads anything back to the host.
+
+Scope: on-the-fly statistics (``stat_id is None``).  Offline statistics (``-sm use``),
+KLD thresholds and entropy measurement are the "next" rows and raise ``NotImplementedError`` here.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import int_quantization
+from . import ops
+
+__all__ = ["IntQuantizer", "int_quantizer"]
+
+
+def _laplace_opt_alpha(w):
+    """argmin_a 2*exp(-a) + a^2/(3 w^2)  <=>  a*exp(a) = 3 w^2 (Newton on the Lambert-W equation)."""
+    c = 3.0 * w * w
+    a = c if c < 1.0 else math.log(c)
+    a = max(a, 1e-3)
+    for _ in range(100):
+        e = math.exp(a)
+        na = a - (a * e - c) / (e * (a + 1.0))
+        if abs(na - a) <= 1e-16 * abs(na):
+            a = na
+            break
+        a = na
+    return a
+
+
+def _build_tables():
+    # int_quantizer.py:41-51: omega grid of 5 decades x 20 steps with a leading 0; alpha = optimal Laplace clip
+    res = 20
+    omega = np.concatenate([np.linspace(lo, hi, res, endpoint=False)
+                            for lo, hi in ((0.01, 0.1), (0.1, 1), (1, 10), (10, 100), (100, 1000))])
+    alpha = np.array([_laplace_opt_alpha(w) for w in omega])
+    return np.concatenate([[0], omega]), np.concatenate([[0], alpha])
+
+
+omega_table, alpha_table = _build_tables()
+
+
+def _to_dev(t, device):
+    if isinstance(t, torch.Tensor):
+        return t.to(device)
+    return torch.tensor(t, dtype=torch.float32).to(device)
+
+
+class IntQuantizer(object):
+    """Mirror of the reference class (int_quantizer.py:56-122).  ``params`` keys as in the reference:
+    clipping, stats_kind, kld (optional) and pcq_weights, pcq_act, bit_alloc_act, bit_alloc_weight, bcorr_act,
+    bcorr_weight, vcorr_weight, bit_alloc_rmode, bit_alloc_prior, bit_alloc_target_act,
+    bit_alloc_target_weight, measure_entropy, logger, mtd_quant (required)."""
+
+    def __init__(self, size, params):
+        self.num_bits = size
+        self.stochastic = False
+        self.int_exp = False
+        self.enforce_true_zero = True
+        self.clipping = params["clipping"] if "clipping" in params else "no"
+        self.stats_kind = params["stats_kind"] if "stats_kind" in params else "mean"
+        self.kld = params["kld"] if "kld" in params else False
+        self.pcq_w = params["pcq_weights"]
+        self.pcq_a = params["pcq_act"]
+        self.bit_alloc_act = params["bit_alloc_act"]
+        self.bit_alloc_weight = params["bit_alloc_weight"]
+        self.bcorr_act = params["bcorr_act"]
+        self.bcorr_weight = params["bcorr_weight"]
+        self.vcorr_weight = params["vcorr_weight"]
+        self.bit_alloc_round = params["bit_alloc_rmode"] == "round"
+        self.bit_alloc_prior = params["bit_alloc_prior"]
+        ta, tw = params["bit_alloc_target_act"], params["bit_alloc_target_weight"]
+        self.bit_alloc_target_act = ta if ta is not None else self.num_bits
+        self.bit_alloc_target_weight = tw if tw is not None else self.num_bits
+        self.measure_entropy = params["measure_entropy"]
+        self.logger = params["logger"]
+        self.mtd_quant = params["mtd_quant"]
+        self.alpha_gaus = {1: 1.24, 2: 1.71, 3: 2.15, 4: 2.55, 5: 2.93, 6: 3.28, 7: 3.61, 8: 3.92}
+        self.alpha_gaus_positive = {1: 1.71, 2: 2.15, 3: 2.55, 4: 2.93, 5: 3.28, 6: 3.61, 7: 3.92, 8: 4.2}
+        self.alpha_laplace = {0: 1.05, 1: 1.86, 2: 2.83, 3: 3.89, 4: 5.03, 5: 6.2, 6: 7.41, 7: 8.64, 8: 9.89}
+        self.alpha_laplace_positive = {0: 1.86, 1: 2.83, 2: 3.89, 3: 5.02, 4: 6.2, 5: 7.41, 6: 8.64, 7: 9.89, 8: 11.16}
+        self.sm = None  # statistics manager class (offline statistics: not built yet)
+        self.force_positive = False
+        self.half_range = False
+
+    # ------------------------------------------------------------------------------------------
+    # dispatch (int_quantizer.py:92-122)
+    # ------------------------------------------------------------------------------------------
+    def __call__(self, tensor, id, tag="", stat_id=None, override_att=None, weight_correction=None):
+        """``weight_correction=(bias_corr, var_corr)`` is an extension used by this package's manager: the
+        per-output-channel mean / variance correction of inference_quantization_manager.py:374-391 is applied
+        inside the same kernel launch that quantizes the weight."""
+        if override_att is not None:
+            orig_att = getattr(self, override_att[0])
+            setattr(self, override_att[0], override_att[1])
+        try:
+            self._unsupported(stat_id)
+            if self.clipping != "no":
+                if self.mtd_quant:
+                    res = self.mid_tread_quantize_activation(tensor, id)
+                else:
+                    res = self.gemmlowpClippingQuantize(tensor, id, tag, stat_id=stat_id, clip_type=self.clipping)
+            elif self.pcq_w:
+                if self.mtd_quant:
+                    res = self.mid_tread_quantize_weights_per_channel(tensor, id, weight_correction)
+                else:
+                    res = self.gemmlowpQuantizeWeightsPerChannel(tensor, id, weight_correction=weight_correction)
+            elif self._pc_act(tensor):
+                if self.mtd_quant:
+                    res = self.mid_tread_quantize_activation_per_channel(tensor, id)
+                else:
+                    res = self.gemmlowpQuantizeActivationPerChannel(tensor, id, tag, stat_id=stat_id)
+            else:
+                res = self.gemmlowpMinMaxQuantize(tensor, tag, stat_id=stat_id, weight_correction=weight_correction)
+        finally:
+            if override_att is not None:
+                setattr(self, override_att[0], orig_att)
+        return res
+
+    def __repr__(self):
+        return ("IntQuantizer - [bits: {}, clipping: {}, bit_alloc_act: {}, bit_alloc_weight: {}, bit_alloc_round: {}, "
+                "pcq_w: {}, pcq_a: {}, bcorr_act: {}, bcorr_weight: {}, vcorr_weight: {}, kind: {}]").format(
+            self.num_bits, self.clipping, self.bit_alloc_act, self.bit_alloc_weight, self.bit_alloc_round, self.pcq_w,
+            self.pcq_a, self.bcorr_act, self.bcorr_weight, self.vcorr_weight, self.stats_kind)
+
+    # ------------------------------------------------------------------------------------------
+    # helpers
+    # ------------------------------------------------------------------------------------------
+    def _unsupported(self, stat_id):
+        if self.kld:
+            raise NotImplementedError("KLD thresholds need offline statistics (SURVEY.md 8f: next)")
+        if stat_id is not None:
+            raise NotImplementedError("offline statistics (-sm use) are the next scope row (SURVEY.md 8f)")
+        if self.measure_entropy:
+            raise NotImplementedError("entropy measurement (-me) is the next scope row (SURVEY.md 8f)")
+
+    def _pc_act(self, tensor):
+        return bool(self.pcq_a and len(tensor.shape) > 3 and (tensor.shape[2] > 1 or tensor.shape[3] > 1))
+
+    def _positive(self):
+        return bool(self.force_positive or self.half_range)
+
+    @staticmethod
+    def _nchw_layout(tensor):
+        n, c = tensor.shape[0], tensor.shape[1]
+        return (n, c, tensor.numel() // (n * c))
+
+    def _range_mode(self, clip_type):
+        if clip_type == "laplace":
+            return L.RANGE_LAPLACE, 0.0
+        if clip_type == "gaus":
+            return L.RANGE_GAUS, 0.0
+        if "std" in clip_type:
+            return L.RANGE_KSTD, float(clip_type.replace("std", ""))
+        raise NotImplementedError("clipping %r needs offline statistics or is undefined in the reference" % clip_type)
+
+    def _prior(self):
+        return L.PRIOR_STD if self.bit_alloc_prior == "gaus" else L.PRIOR_B
+
+    # ------------------------------------------------------------------------------------------
+    # dispatch targets
+    # ------------------------------------------------------------------------------------------
+    def gemmlowpClippingQuantize(self, tensor, id, tag="", stat_id=None, clip_type="laplace"):
+        """ACIQ clipping, int_quantizer.py:327-359: per channel (pcq_a, 4-D, HW>1, C>1; fp32 parameter math,
+        optional bit allocation) or per tensor (float64 parameter math)."""
+        self._unsupported(stat_id)
+        mode, k = self._range_mode(clip_type)
+        if self._pc_act(tensor) and tensor.shape[1] > 1:
+            return ops.fused(tensor, self._nchw_layout(tensor), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
+                             leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(),
+                             bit_alloc=self.bit_alloc_act, bit_alloc_prior=self._prior(),
+                             bit_alloc_round=self.bit_alloc_round, bit_alloc_target=self.bit_alloc_target_act)
+        return ops.fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
+                         leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(), solve_f64=True)
+
+    def gemmlowpMinMaxQuantize(self, tensor, tag="", stat_id=None, weight_correction=None):
+        """Per-tensor min/max range through the compiled-leaf arithmetic, int_quantizer.py:361-379 + :605-614.
+        Activations (tag contains 'activation', not 'classifier') use the batch average of per-sample min/max."""
+        self._unsupported(stat_id)
+        avg = ("activation" in tag and "classifier" not in tag)
+        kw = dict(range_mode=L.RANGE_MINMAX, leaf=L.LEAF_COMPILED, num_bits=self.num_bits, positive=self._positive())
+        if weight_correction is not None and any(weight_correction):
+            rows = tensor.shape[0]
+            return ops.fused(tensor, (1, rows, tensor.numel() // rows), scope=L.SCOPE_TENSOR,
+                             bias_corr=weight_correction[0], var_corr=weight_correction[1], **kw)
+        if avg:
+            n = tensor.shape[0]
+            return ops.fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_GROUP_MEAN, **kw)
+        return ops.fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, **kw)
+
+    def gemmlowpQuantizeActivationPerChannel(self, tensor, id, tag="", stat_id=None, min_=None, max_=None):
+        """Per-channel min/max (0 lower bound when positive) with optional bit allocation, int_quantizer.py:409-451."""
+        self._unsupported(stat_id)
+        layout = self._nchw_layout(tensor)
+        if min_ is None and max_ is None:
+            return ops.fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
+                             num_bits=self.num_bits, positive=self._positive(), bit_alloc=self.bit_alloc_act,
+                             bit_alloc_prior=self._prior(), bit_alloc_round=self.bit_alloc_round,
+                             bit_alloc_target=self.bit_alloc_target_act)
+        # explicit bounds (API compatibility): statistics pass for what is missing, then the given-parameter leaf
+        st = ops.fused(tensor, layout, num_bits=min(self.num_bits, 8), bit_alloc=self.bit_alloc_act,
+                       bit_alloc_prior=self._prior(), bit_alloc_round=self.bit_alloc_round,
+                       bit_alloc_target=self.bit_alloc_target_act, stats_only=True)
+        c = layout[1]
+        if min_ is None:
+            min_ = torch.zeros(c, device=tensor.device) if self._positive() else st[:, 0]
+        if max_ is None:
+            max_ = st[:, 1]
+        min_ = _to_dev(min_, tensor.device).reshape(-1)
+        max_ = _to_dev(max_, tensor.device).reshape(-1)
+        if min_.numel() == 1:
+            min_ = min_.expand(c)
+        if max_.numel() == 1:
+            max_ = max_.expand(c)
+        bits = st[:, 7].contiguous() if (self.bit_alloc_act and self.num_bits <= 4) else None
+        return ops.quantize1(tensor, (max_ - min_).contiguous(), min_.contiguous(), self.num_bits, bits=bits,
+                             layout=layout)
+
+    def gemmlowpQuantizeWeightsPerChannel(self, tensor, id, min_=None, max_=None, weight_correction=None):
+        """Per-output-channel min/max with optional bit allocation from the row std, int_quantizer.py:453-476."""
+        rows = tensor.shape[0]
+        layout = (1, rows, tensor.numel() // rows)
+        if min_ is not None or max_ is not None:
+            t = tensor.reshape(rows, -1)
+            mn = _to_dev(min_, tensor.device) if min_ is not None else t.min(-1)[0]
+            mx = _to_dev(max_, tensor.device) if max_ is not None else t.max(-1)[0]
+            bits = None
+            if self.bit_alloc_weight and self.num_bits <= 4:
+                bits = self.get_bits_alloc_fixed_target(t.std(-1), self.bit_alloc_target_weight, self.bit_alloc_round)
+            return ops.quantize1(tensor, mx - mn, mn, self.num_bits, bits=bits, layout=layout)
+        bc, vc = weight_correction if weight_correction is not None else (False, False)
+        return ops.fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
+                         num_bits=self.num_bits, positive=False, bit_alloc=self.bit_alloc_weight,
+                         bit_alloc_prior=L.PRIOR_STD, bit_alloc_round=self.bit_alloc_round,
+                         bit_alloc_target=self.bit_alloc_target_weight, bias_corr=bc, var_corr=vc)
+
+    # mid-tread "bin allocation" quantizer, int_quantizer.py:147-225
+    def mid_tread_quantize_weights_per_channel(self, tensor, id, weight_correction=None):
+        rows = tensor.shape[0]
+        bc, vc = weight_correction if weight_correction is not None else (False, False)
+        return ops.fused(tensor, (1, rows, tensor.numel() // rows), leaf=L.LEAF_MIDTREAD, positive=False,
+                         mt_target=self.bit_alloc_target_weight, mt_clip=False, bias_corr=bc, var_corr=vc)
+
+    def mid_tread_quantize_activation(self, tensor, id):
+        if self._pc_act(tensor):
+            return self.mid_tread_quantize_activation_per_channel(tensor, id)
+        return ops.fused(tensor, (1, 1, tensor.numel()), leaf=L.LEAF_MIDTREAD, positive=self._positive(),
+                         mt_target=self.bit_alloc_target_act, mt_clip=True)
+
+    def mid_tread_quantize_activation_per_channel(self, tensor, id):
+        return ops.fused(tensor, self._nchw_layout(tensor), leaf=L.LEAF_MIDTREAD, positive=self._positive(),
+                         mt_target=self.bit_alloc_target_act, mt_clip=True)
+
+    def mid_tread_quantization(self, tensor, id, target, clip=False, sym=True):
+        """[R, K] view, int_quantizer.py:185-225.  Returns (quantized, None) like the reference without entropy."""
+        out = ops.fused(tensor, (1, tensor.shape[0], tensor.numel() // tensor.shape[0]), leaf=L.LEAF_MIDTREAD,
+                        positive=not sym, mt_target=target, mt_clip=clip)
+        return out, None
+
+    # ------------------------------------------------------------------------------------------
+    # leaves with caller-provided parameters
+    # ------------------------------------------------------------------------------------------
+    def __gemmlowpQuantize1__(self, tensor, delta, offset, bit_alloc=None, measure_entropy=False):
+        """int_quantizer.py:557-603: [R, K] tensor with [R] parameters, or any shape with 0-d parameters."""
+        if measure_entropy:
+            raise NotImplementedError("entropy measurement is the next scope row (SURVEY.md 8f)")
+        return ops.quantize1(tensor, delta, offset, self.num_bits, bits=bit_alloc)
+
+    def __gemmlowpQuantize__(self, tensor, delta, offset):
+        """int_quantizer.py:605-614.  Tensor arguments are converted to python floats exactly as the reference's
+        pybind call does (a host synchronisation); the dispatch targets above never come through here."""
+        preserve_zero = bool(self.enforce_true_zero and (offset + delta) > 0 and offset < 0)
+        return int_quantization.float2gemmlowp(tensor.contiguous(), float(delta), float(offset), self.num_bits,
+                                               self.int_exp, preserve_zero, None)
+
+    # ------------------------------------------------------------------------------------------
+    # statistics / parameter helpers kept for API compatibility (small torch ops on [C]-sized tensors)
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _stats_cols(tensor, layout):
+        return ops.fused(tensor, layout, stats_only=True)
+
+    @staticmethod
+    def __act_stats__(tensor, stats, avg_over_batch=False):
+        """int_quantizer.py:507-528 through one statistics-only launch."""
+        cols = {"min": 0, "max": 1, "mean": 2, "b": 3, "std": 4}
+        if avg_over_batch:
+            n = tensor.shape[0]
+            st = IntQuantizer._stats_cols(tensor, (1, n, tensor.numel() // n))
+            return {s: st[:, cols[s]].mean(dim=0) for s in stats}
+        st = IntQuantizer._stats_cols(tensor, (1, 1, tensor.numel()))
+        return {s: st[0, cols[s]] for s in stats}
+
+    @staticmethod
+    def __act_stats_perchannel__(tensor, stats, avg_over_batch=False):
+        """int_quantizer.py:530-555 without the transposed copy."""
+        cols = {"min": 0, "max": 1, "mean": 2, "b": 3, "std": 4}
+        n, c = tensor.shape[0], tensor.shape[1]
+        hw = tensor.numel() // (n * c)
+        if avg_over_batch:
+            st = IntQuantizer._stats_cols(tensor, (1, n * c, hw)).view(n, c, -1)
+            return {s: st[:, :, cols[s]].mean(dim=0) for s in stats}
+        st = IntQuantizer._stats_cols(tensor, (n, c, hw))
+        return {s: st[:, cols[s]].contiguous() for s in stats}
+
+    @staticmethod
+    def get_bits_alloc(alpha, num_bits, round=False):
+        """int_quantizer.py:381-391."""
+        budget = len(alpha) * 2 ** num_bits
+        p = alpha ** (2.0 / 3)
+        bins = (budget * p) / p.sum()
+        bits = torch.round(torch.log2(bins)) if round else torch.ceil(torch.log2(bins))
+        return bits.clamp_(0, 8)
+
+    @staticmethod
+    def get_bits_alloc_fixed_target(alpha, num_bits, round=False):
+        """int_quantizer.py:393-407."""
+        goal = num_bits
+        m = goal
+        half_gap = 1.0
+        it = 0
+        bits = None
+        while abs(2 * half_gap) > 0.01 and it < 10:
+            it += 1
+            bits = IntQuantizer.get_bits_alloc(alpha, num_bits=m, round=round)
+            half_gap = (goal - bits.mean()) / 2
+            m += half_gap.item()
+        return bits
+
+    @staticmethod
+    def get_omega(sigma, target_bins):
+        """int_quantizer.py:128-135."""
+        p = sigma ** (2.0 / 3)
+        return (len(sigma) * target_bins * p) / p.sum()
+
+    @staticmethod
+    def get_alpha_mult(omega, sym=True):
+        """int_quantizer.py:137-145 (the caller's omega is left untouched, as on CUDA tensors in the reference)."""
+        om = omega.detach().cpu().numpy().astype(np.float64)
+        if not sym:
+            om = om * 2
+        i = np.minimum(omega_table.searchsorted(om), len(omega_table) - 1)
+        inc = (alpha_table[i] - alpha_table[i - 1]) / (omega_table[i] - omega_table[i - 1])
+        return alpha_table[i] - inc * (omega_table[i] - om)
+
+    def get_alpha_laplace(self, tensor, stat_id=None, kind="mean", per_channel=False):
+        """int_quantizer.py:227-253."""
+        self._unsupported(stat_id)
+        stats = self.__act_stats_perchannel__ if per_channel else self.__act_stats__
+        b = stats(tensor, ["b"])["b"]
+        table = self.alpha_laplace_positive if self._positive() else self.alpha_laplace
+        if self.bit_alloc_act and per_channel and self.num_bits <= 4:
+            prior = "std" if self.bit_alloc_prior == "gaus" else "b"
+            pr = stats(tensor, [prior])[prior]
+            bits = self.get_bits_alloc_fixed_target(pr, self.bit_alloc_target_act, self.bit_alloc_round)
+            factor = torch.tensor([table[int(v)] for v in bits.tolist()], dtype=torch.float32, device=tensor.device)
+            return b * factor
+        return b * table[self.num_bits]
+
+    def get_alpha_gaus(self, tensor, tag, stat_id=None, per_channel=False):
+        """int_quantizer.py:255-264."""
+        self._unsupported(stat_id)
+        stats = self.__act_stats_perchannel__ if per_channel else self.__act_stats__
+        std = stats(tensor, ["std"])["std"]
+        return std * (self.alpha_gaus_positive if self._positive() else self.alpha_gaus)[self.num_bits]
+
+    def get_alpha_pstd(self, tensor, p, tag, stat_id=None, per_channel=False):
+        """int_quantizer.py:266-275."""
+        self._unsupported(stat_id)
+        stats = self.__act_stats_perchannel__ if per_channel else self.__act_stats__
+        return p * stats(tensor, ["std"])["std"]
+
+    def get_alpha(self, tensor, tag="", stat_id=None, clip_type="laplace", per_channel=False):
+        """int_quantizer.py:302-325."""
+        if clip_type == "laplace":
+            return self.get_alpha_laplace(tensor, stat_id, per_channel=per_channel)
+        if clip_type == "gaus":
+            return self.get_alpha_gaus(tensor, tag, stat_id, per_channel=per_channel)
+        if "std" in clip_type:
+            return self.get_alpha_pstd(tensor, float(clip_type.replace("std", "")), tag, stat_id, per_channel=per_channel)
+        raise NotImplementedError("clipping %r needs offline statistics" % clip_type)
+
+    def alpha2DeltaOffset(self, alpha, max_value, min_value, mean, clip2max=False):
+        """int_quantizer.py:284-300 (numpy arithmetic, host side)."""
+        def _np(v):
+            return v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v
+        alpha, max_value, min_value, mean = map(_np, (alpha, max_value, min_value, mean))
+        if self._positive():
+            delta = np.maximum(np.array(mean), 0) + alpha
+            if clip2max:
+                delta = np.minimum(delta, max_value)
+            return delta, 0
+        delta = 2 * alpha
+        if clip2max:
+            delta = np.minimum(delta, max_value - min_value)
+        return delta, np.maximum(min_value, mean - alpha)
+
+
+def int_quantizer(qtype, quant_params):
+    """Factory with the reference's naming rule (int_quantizer.py:626-632): 'intN' -> N bits."""
+    size = int(qtype[len("int"):]) if len(qtype) > len("int") else 32
+    return IntQuantizer(size, quant_params)

@@ -1,0 +1,145 @@
+"""Tensor-level wrappers over the C ABI: device pointers and the current stream come from torch, the
+arithmetic all happens in libfqb200.so.  Nothing here synchronises with the host."""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+_workspaces = {}  # (device index, stream handle) -> uint8 tensor
+
+
+def _stream_handle(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda_f32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise L.FqError("%s must live on a CUDA device: the fake-quantization path has no CPU implementation" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+
+
+def _workspace(device, stream, nbytes):
+    key = (device.index, stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        size = max(int(nbytes), 1 << 20)
+        ws = torch.empty(size, dtype=torch.uint8, device=device)
+        L.check(L.load().fqb200_workspace_init(ws.data_ptr(), ws.numel(), stream))
+        _workspaces[key] = ws
+    return ws
+
+
+def resident_ctas():
+    return L.load().fqb200_resident_ctas()
+
+
+def float2gemmlowp(x, range_, offset, num_bits, int_exp, enforce_true_zero, noise=None, out=None):
+    """C ABI fqb200_float2gemmlowp on torch tensors (scalars by value, like the reference's pybind call)."""
+    _require_cuda_f32(x, "in")
+    lib = L.load()
+    x = x.contiguous()
+    if noise is not None:
+        _require_cuda_f32(noise, "noise")
+        noise = noise.contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        L.check(lib.fqb200_float2gemmlowp(x.data_ptr(), out.data_ptr(), x.numel(), float(range_), float(offset),
+                                          int(num_bits), int(bool(int_exp)), int(bool(enforce_true_zero)),
+                                          noise.data_ptr() if noise is not None else None, _stream_handle(x.device)))
+    return out
+
+
+def quantize1(x, delta, offset, num_bits, bits=None, layout=None, want_grid=False):
+    """C ABI fqb200_quantize1.  ``layout`` = (outer, groups, inner); default: [R, K] rows with per-row
+    parameters when ``delta`` has R elements, else one parameter set for the whole tensor."""
+    _require_cuda_f32(x, "tensor")
+    lib = L.load()
+    x = x.contiguous()
+    dev = x.device
+    delta = torch.as_tensor(delta, dtype=torch.float32, device=dev).contiguous()
+    offset = torch.as_tensor(offset, dtype=torch.float32, device=dev).contiguous()
+    per_group = delta.numel() > 1 or (bits is not None)
+    if layout is None:
+        layout = (1, x.shape[0], x.numel() // x.shape[0]) if per_group else (1, 1, x.numel())
+    outer, groups, inner = layout
+    if per_group:
+        if delta.numel() == 1:
+            delta = delta.reshape(1).expand(groups).contiguous()
+        if offset.numel() == 1:
+            offset = offset.reshape(1).expand(groups).contiguous()
+        if delta.numel() != groups or offset.numel() != groups:
+            raise ValueError("per-group parameters must have %d elements" % groups)
+    if bits is not None:
+        bits = torch.as_tensor(bits, dtype=torch.float32, device=dev).contiguous()
+        if bits.numel() != groups:
+            raise ValueError("bit_alloc must have %d elements" % groups)
+    out = torch.empty_like(x)
+    grid = torch.empty_like(x) if want_grid else None
+    with torch.cuda.device(dev):
+        L.check(lib.fqb200_quantize1(x.data_ptr(), out.data_ptr(), grid.data_ptr() if want_grid else None,
+                                     outer, groups, inner, delta.data_ptr(), offset.data_ptr(),
+                                     bits.data_ptr() if bits is not None else None, int(per_group), int(num_bits),
+                                     _stream_handle(dev)))
+    return (out, grid) if want_grid else out
+
+
+def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH, num_bits=8,
+          positive=False, solve_f64=False, clip_k=0.0, bit_alloc=False, bit_alloc_prior=L.PRIOR_STD,
+          bit_alloc_round=True, bit_alloc_target=None, mt_target=0.0, mt_clip=False, bias_corr=False,
+          var_corr=False, stats_only=False, want_stats=False, out=None):
+    """C ABI fqb200_fused: statistics -> parameters -> quantize/dequantize in one launch.
+
+    Returns ``out`` (or ``(out, stats)`` with ``want_stats``; ``stats`` alone with ``stats_only``), where
+    ``stats`` is a [groups, 12] tensor with columns ``_lib.STAT_COLUMNS``."""
+    _require_cuda_f32(x, "tensor")
+    lib = L.load()
+    x = x.contiguous()
+    dev = x.device
+    outer, groups, inner = (int(v) for v in layout)
+    if outer * groups * inner != x.numel():
+        raise ValueError("layout %r does not cover %d elements" % (layout, x.numel()))
+    d = L.Desc()
+    d.outer, d.groups, d.inner = outer, groups, inner
+    d.scope, d.range_mode, d.leaf = scope, range_mode, leaf
+    d.num_bits, d.positive, d.solve_f64 = int(num_bits), int(bool(positive)), int(bool(solve_f64))
+    d.clip_k = float(clip_k)
+    d.bit_alloc, d.bit_alloc_prior, d.bit_alloc_round = int(bool(bit_alloc)), bit_alloc_prior, int(bool(bit_alloc_round))
+    d.bit_alloc_target = float(bit_alloc_target if bit_alloc_target is not None else num_bits)
+    d.mt_target, d.mt_clip = float(mt_target), int(bool(mt_clip))
+    d.bias_corr, d.var_corr, d.stats_only = int(bool(bias_corr)), int(bool(var_corr)), int(bool(stats_only))
+    stats = None
+    if want_stats or stats_only:
+        stats = torch.zeros((groups, L.STATS_STRIDE), dtype=torch.float32, device=dev)
+        d.out_stats = stats.data_ptr()
+    else:
+        d.out_stats = None
+    if x.numel() == 0:
+        return stats if stats_only else ((x.clone(), stats) if want_stats else x.clone())
+    if out is None and not stats_only:
+        out = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        stream = _stream_handle(dev)
+        need = lib.fqb200_workspace_bytes(ctypes.byref(d))
+        if need == 0:
+            L.check(L.ERR_INVALID if not lib.fqb200_last_error() else L.ERR_INVALID)
+        ws = _workspace(dev, stream, need)
+        L.check(lib.fqb200_fused(ctypes.byref(d), x.data_ptr(), out.data_ptr() if out is not None else None,
+                                 ws.data_ptr(), ws.numel(), stream))
+    if stats_only:
+        return stats
+    return (out, stats) if want_stats else out
+
+
+def _test_division(a, b):
+    """(fast, ieee) quotients from the device: the 3-instruction exact division next to __fdiv_rn."""
+    lib = L.load()
+    fast, ieee = torch.empty_like(a), torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        L.check(lib.fqb200_test_division(a.data_ptr(), b.data_ptr(), fast.data_ptr(), ieee.data_ptr(), a.numel(),
+                                         _stream_handle(a.device)))
+    return fast, ieee

@@ -1,0 +1,142 @@
+/*
+ * fqb200 - B200-native (sm_100a) fake-quantization library: C ABI.
+ *
+ * Drop-in boundary for the fake-quantization hot path of submission2019/cnn-quantization
+ * (SURVEY.md section 8).  Plain C: device pointers, sizes, a stream handle; no torch types.
+ * Every entry point returns 0 (FQB200_OK) or an FQB200_ERR_* code; nothing throws, nothing
+ * keeps global state besides the cached device properties.  All tensors are fp32, contiguous,
+ * resident on the current CUDA device.  `stream` is a cudaStream_t passed as void*.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   fqb200_float2gemmlowp   <- kernels/int_quantization.cpp:6-12 + kernels/gemmlowp.cu:8-45
+ *                              (`int_quantization.float2gemmlowp`, the only compiled symbol)
+ *   fqb200_quantize1        <- pytorch_quantizer/quantization/qtypes/int_quantizer.py:557-603
+ *                              (`IntQuantizer.__gemmlowpQuantize1__`, parameters given)
+ *   fqb200_fused            <- int_quantizer.py:327-359 (gemmlowpClippingQuantize), :409-451
+ *                              (gemmlowpQuantizeActivationPerChannel), :453-476
+ *                              (gemmlowpQuantizeWeightsPerChannel), :361-379 + :605-614
+ *                              (gemmlowpMinMaxQuantize -> __gemmlowpQuantize__), :147-225 (mid-tread),
+ *                              with :507-555 (statistics), :227-325 (ACIQ alpha), :381-407 (bit
+ *                              allocation) and inference_quantization_manager.py:374-391 (weight
+ *                              bias / variance correction) fused into ONE kernel launch.
+ */
+#ifndef FQB200_H_
+#define FQB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQB200_ABI_VERSION 1
+
+/* ---- return codes ------------------------------------------------------------------------- */
+#define FQB200_OK 0
+#define FQB200_ERR_INVALID 1     /* bad argument (null pointer, non-positive size, bad enum) */
+#define FQB200_ERR_WORKSPACE 2   /* workspace missing or smaller than fqb200_workspace_bytes() */
+#define FQB200_ERR_CUDA 3        /* CUDA runtime error; text via fqb200_last_error() */
+#define FQB200_ERR_UNSUPPORTED 4 /* valid request this build does not implement */
+
+/* ---- enums (plain ints in the struct) ------------------------------------------------------- */
+/* how statistics map to quantization parameters */
+#define FQB200_SCOPE_GROUP 0      /* one parameter set per group (per channel / per output row) */
+#define FQB200_SCOPE_GROUP_MEAN 1 /* statistics per group, averaged over groups -> ONE parameter set
+                                     (the reference's avg_over_batch min/max, int_quantizer.py:372,:525-526) */
+#define FQB200_SCOPE_TENSOR 2     /* min of the group minima / max of the group maxima -> ONE parameter set, while
+                                     `groups` keeps its meaning for the per-row weight correction (per-tensor
+                                     weight quantization + -bcw, inference_quantization_manager.py:374-391) */
+/* where (delta, offset) come from */
+#define FQB200_RANGE_MINMAX 0  /* delta = max - min, offset = min (0 if positive) */
+#define FQB200_RANGE_LAPLACE 1 /* ACIQ Laplace: alpha = F[bits] * b          (int_quantizer.py:227-253) */
+#define FQB200_RANGE_GAUS 2    /* ACIQ Gauss:   alpha = F[bits] * std        (:255-264) */
+#define FQB200_RANGE_KSTD 3    /* alpha = clip_k * std ('2std')              (:266-275) */
+/* which leaf arithmetic */
+#define FQB200_LEAF_TORCH 0    /* __gemmlowpQuantize1__: round-half-even, scale floor 1e-8, true zero */
+#define FQB200_LEAF_COMPILED 1 /* float2gemmlowp: roundf (half away), no floor, preserve_zero rule */
+#define FQB200_LEAF_MIDTREAD 2 /* mid_tread_quantization (bin allocation), int_quantizer.py:185-225 */
+/* bit-allocation prior */
+#define FQB200_PRIOR_STD 0
+#define FQB200_PRIOR_B 1
+
+/* number of floats written per group into fqb200_desc.out_stats */
+#define FQB200_STATS_STRIDE 12
+/* out_stats[g*12 + k]: 0 min, 1 max, 2 mean, 3 b, 4 std, 5 delta, 6 offset, 7 bits, 8 scale, 9 zero_point,
+ * 10 qmax, 11 flags (bit0: passthrough, bit1: true-zero form) */
+
+/*
+ * One hooked tensor = one descriptor = one kernel launch.
+ * The tensor is viewed as [outer][groups][inner], contiguous fp32:
+ *   per-channel activation [N,C,H,W]      outer=N  groups=C    inner=H*W
+ *   per-output-channel weight [O,I,k,k]   outer=1  groups=O    inner=I*k*k
+ *   per-tensor                            outer=1  groups=1    inner=numel
+ *   per-sample averaged min/max           outer=1  groups=N    inner=C*H*W, scope=GROUP_MEAN
+ */
+typedef struct fqb200_desc {
+  int64_t outer, groups, inner;
+  int32_t scope;      /* FQB200_SCOPE_* */
+  int32_t range_mode; /* FQB200_RANGE_* */
+  int32_t leaf;       /* FQB200_LEAF_* */
+  int32_t num_bits;   /* 1..8 (ignored by the mid-tread leaf) */
+  int32_t positive;   /* force_positive or half_range: range starts at 0, one-sided ACIQ tables */
+  int32_t solve_f64;  /* parameter arithmetic in float64, rounded to fp32 at the end: the reference's
+                         per-tensor clipping branch (int_quantizer.py:354-357) */
+  float clip_k;       /* FQB200_RANGE_KSTD multiplier */
+  /* per-group bit allocation (int_quantizer.py:381-407); only honoured when num_bits <= 4, like the reference */
+  int32_t bit_alloc;
+  int32_t bit_alloc_prior; /* FQB200_PRIOR_* */
+  int32_t bit_alloc_round; /* 1: round, 0: ceil */
+  float bit_alloc_target;  /* mean bits per group to hit (the reference defaults it to num_bits) */
+  /* mid-tread leaf */
+  float mt_target; /* log2 of the mean number of bins per group */
+  int32_t mt_clip; /* 1: Laplace clipping around the mean (activations), 0: min/max range (weights) */
+  /* weight post-processing (inference_quantization_manager.py:374-391) */
+  int32_t bias_corr; /* w_q <- w_q - mean(w_q) + mean(w) per group */
+  int32_t var_corr;  /* w_q <- (w_q - mean(w_q)) * std(w)/(std(w_q)+1e-8) + mean(w_q), before bias_corr */
+  int32_t stats_only; /* 1: compute statistics/parameters into out_stats, do not touch `out` */
+  float* out_stats;   /* optional device buffer, groups * FQB200_STATS_STRIDE floats (one row when the
+                         parameters are per tensor is NOT assumed: always `groups` rows) */
+} fqb200_desc;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int fqb200_abi_version(void);
+/* text of the last error on the calling thread ("" if none) */
+const char* fqb200_last_error(void);
+/* number of CTAs the fused kernel keeps resident on the current device (148 SMs x 2 on a B200) */
+int fqb200_resident_ctas(void);
+
+/* Scratch the fused kernel needs for `d` (partials, per-group results, grid-barrier words). */
+size_t fqb200_workspace_bytes(const fqb200_desc* d);
+/* Zero the barrier words once after allocating a workspace (kernels leave them zeroed). */
+int fqb200_workspace_init(void* workspace, size_t bytes, void* stream);
+
+/*
+ * a1 - `int_quantization.float2gemmlowp(in, range, offset, num_bits, int_exp, enforce_true_zero, noise)`.
+ * range <= 0 copies `in` to `out` (the reference returns its input).  `noise` may be NULL (= zeros).
+ * `out` may alias `in`.
+ */
+int fqb200_float2gemmlowp(const float* in, float* out, int64_t n, float range, float offset, int num_bits,
+                          int int_exp, int enforce_true_zero, const float* noise, void* stream);
+
+/*
+ * a3 - `IntQuantizer.__gemmlowpQuantize1__(tensor, delta, offset, bit_alloc)`, parameters on the device:
+ * `delta`/`offset` hold `groups` floats (per_group=1) or one float (per_group=0); `bits` is NULL or
+ * `groups` floats (per-row bit widths).  Tensor viewed [outer][groups][inner] (a [R,K] matrix is
+ * outer=1, groups=R, inner=K).  Optional `grid` receives the integer grid q (fp32 integers).
+ */
+int fqb200_quantize1(const float* in, float* out, float* grid, int64_t outer, int64_t groups, int64_t inner,
+                     const float* delta, const float* offset, const float* bits, int per_group, int num_bits,
+                     void* stream);
+
+/*
+ * a4/a5/a6/a11/a12(+a7-a10, a13) - statistics -> parameters -> quantize-dequantize (-> weight
+ * correction) in ONE cooperative kernel launch.  `out` may alias `in`.
+ */
+int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FQB200_H_ */
