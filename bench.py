@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py - ResNet-50 W4A4 (ACIQ Laplace + per-channel bit allocation + weight bias correction) inference
+throughput through the fused sm_100a fake-quantization path.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's pure-PyTorch algorithm on host CPU cores
+
+A step = one forward of the hooked model over one synthetic 512x3x224x224 batch per GPU (55 hooked activation
+tensors, 5.79 G elements; BASELINE.json config "ResNet-50 W4A4 -pcq_w -pcq_a -c laplace -baa -baw -bcw, batch 512").
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "resnet50_w4a4_images_per_s"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="fqb200", choices=["fqb200", "reference"])
+    ap.add_argument("--config", default="resnet50_w4a4")
+    ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
+    ap.add_argument("--cpu-batch", type=int, default=16, help="images per step of the CPU reference arm / cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's algorithm (oracle port) on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_pipeline_images_per_s(config, batch, steps, warmup):
+    import torch
+    from cnn_quantization_b200 import pipeline
+    from oracle import fq_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model, qm = pipeline.build_quantized_model(config, "cpu", quantizer_factory=fq_oracle.oracle_int_quantizer)
+    x, t = pipeline.synthetic_batch(batch, seed=1)
+    with torch.no_grad():
+        for _ in range(warmup):
+            pipeline.accuracy_counts(model(x), t)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pipeline.accuracy_counts(model(x), t)
+        dt = time.perf_counter() - t0
+    qm.detach()
+    return batch * steps / dt, dt / steps, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    ips, sec, cores = cpu_pipeline_images_per_s(args.config, args.cpu_batch, steps, warm)
+    sample = "%d steps of %d images (of the %d-image batch) through the oracle port of int_quantizer.py, %d host threads" % (
+        steps, args.cpu_batch, args.batch, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: %s, batch %d/GPU, 224x224" % (args.config, args.batch),
+                       "cpu_sample_batch": args.cpu_batch},
+            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# this framework
+# ---------------------------------------------------------------------------------------------------
+def run_fqb200(args):
+    import torch
+    import torch.distributed as dist
+    import cnn_quantization_b200 as fq
+    from cnn_quantization_b200 import ops, pipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the fake-quantization path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    fq._lib.load()
+    torch.backends.cudnn.benchmark = True  # inference_sim.py:205
+
+    model, qm = pipeline.build_quantized_model(args.config, dev)
+    x_host, t_host = pipeline.synthetic_batch(args.batch, seed=1000 + rank, pin=True)
+    x_dev, t_dev = x_host.to(dev), t_host.to(dev)
+    total = torch.zeros(4, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        with torch.no_grad():
+            total.add_(pipeline.accuracy_counts(model(x_dev), t_dev))
+
+    host_metrics = torch.zeros(4).pin_memory()
+
+    def step_e2e():
+        with torch.no_grad():
+            x = x_host.to(dev, non_blocking=True)
+            t = t_host.to(dev, non_blocking=True)
+            host_metrics.copy_(pipeline.accuracy_counts(model(x), t), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the step's metrics
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ---------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.profile_reset(enable=True)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    prof = ops.profile_collect()
+    ops.profile_reset(enable=False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region 2: end to end from pinned host memory --------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    t_ms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t_ms.tolist()
+    loss, top1, top5, n_img = pipeline.reduce_metrics(total)  # the path's one collective
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        images = world * args.batch * args.steps
+        value = images / (ms / 1e3)
+        e2e = images / (ms_e2e / 1e3)
+        # dominant kernel: fq_fused_kernel in mode D (3 reads + 1 write = 16 B/element), per-launch CUDA events
+        dom = prof["modes"].get("D", {"launches": 0, "elems": 0, "ms": 0.0, "bytes": 0})
+        achieved = (dom["bytes"] / 1e9) / (dom["ms"] / 1e3) if dom["ms"] > 0 else 0.0
+        quant_ms = sum(m["ms"] for m in prof["modes"].values())
+        quant_elems = sum(m["elems"] for m in prof["modes"].values())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: %s (-pcq_w -pcq_a -c laplace -baa -baw -bcw), batch %d per GPU, "
+                                   "3x224x224, random-init torchvision weights" % (args.config, args.batch),
+                       "parallelism": "dp%d (batch sharded per rank, one all-reduce of 4 metrics)" % world,
+                       "l2": "inputs larger than L2 (308 MB input, every hooked tensor 51 MB - 1.6 GB)",
+                       "conv": "cuDNN fp32 NCHW via torch (third party in the reference too)"},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": x_host.numel() * 4 + t_host.numel() * 8, "d2h_bytes_per_step": 16},
+            "gpu_launches": prof["launches"],
+            "roofline": {"bound": "hbm", "kernel": "fq_fused_kernel<4> mode D (stats, deviations, apply)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "peak_source": peak_src, "traffic": None, "launches": dom["launches"],
+                         "algorithmic_bytes_per_elem": 16, "avg_launch_ms": dom["ms"] / max(dom["launches"], 1)},
+            "quant": {"gelem_per_s": quant_elems / (quant_ms / 1e3) / 1e9 if quant_ms else None,
+                      "ms_per_step": quant_ms / args.steps, "share_of_step": quant_ms / ms,
+                      "modes": {k: {"launches": v["launches"], "ms": v["ms"], "GBps": (v["bytes"] / 1e9) / (v["ms"] / 1e3) if v["ms"] else None}
+                                for k, v in prof["modes"].items()}},
+            "clocks": clocks,
+            "check": {"loss": loss, "top1": top1, "top5": top5, "images": n_img},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            ips, sec, cores = cpu_pipeline_images_per_s(args.config, args.cpu_batch, 1, 1)
+            line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "1 step of %d images through the oracle port of int_quantizer.py + torch CPU convs" % args.cpu_batch}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_fqb200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,379 @@
+"""Host-side mirror of the reference's quantization manager for the inference path
+(pytorch_quantizer/quantization/inference/inference_quantization_manager.py): same tag -> quantizer table, same
+call sites, same ``quantize_instant`` / ``quantize_model`` semantics, but
+
+* call sites are PyTorch *forward hooks* on the stock ``nn.Conv2d / nn.Linear / nn.MaxPool2d / nn.AvgPool2d /
+  nn.BatchNorm2d`` modules instead of the reference's class swap (``nn.Conv2d = Conv2dWithId`` ..., :518-533).
+  While the manager is enabled the stock classes' ``__init__`` is wrapped only to stamp the construction-order
+  id the reference's ``*WithId`` counters would have produced (:29,51,77,153,221,255);
+* the quantizers are this package's ``IntQuantizer`` (one fused sm_100a launch per hooked tensor), and the
+  weight bias / variance correction of ``quantize_model`` (:374-391) happens inside the weight's launch;
+* nothing is a process-wide singleton: several managers can exist (one per rank / model).
+
+Scope: ``-sm no`` (on-the-fly statistics), the mode every BASELINE config runs.  ``collect`` / ``use`` raise.
+"""
+import argparse
+from itertools import count
+
+import torch
+import torch.nn as nn
+
+from .dummy_quantizer import DummyQuantizer
+from . import int_quantizer as _iq
+
+__all__ = ["QuantizationManagerInference", "make_args", "get_params", "absorb_bn", "search_absorbe_bn",
+           "resnet_mark_before_relu", "set_node_names"]
+
+FUSED_RELU_ARCHS = ("alexnet", "vgg16", "vgg16_bn", "inception_v3")
+
+
+def make_args(**over):
+    """An ``args`` namespace with the reference CLI's defaults (inference/inference_sim.py:52-112) for the fields the
+    manager and the quantizers read."""
+    d = dict(arch="resnet18", qtype=None, qweight="int8", q_off=False, clipping="no", stats_mode="no", stats_kind="mean",
+             stats_folder=None, stats_batch_avg=False, kld_threshold=False, measure_stats=False,
+             per_channel_quant_weights=False, per_channel_quant_act=False, bit_alloc_act=False, bit_alloc_weight=False,
+             bit_alloc_rmode="round", bit_alloc_prior="gaus", bit_alloc_target_act=None, bit_alloc_target_weight=None,
+             bias_corr_act=False, bias_corr_weight=False, var_corr_weight=False, measure_entropy=False,
+             mid_thread_quant=False, rho_act=None, rho_weight=None, preserve_zero=False)
+    d.update(over)
+    return argparse.Namespace(**d)
+
+
+def get_params(args, logger=None):
+    """The ``qparams`` dict the reference builds in inference_sim.py:345-372."""
+    return {
+        "int": {
+            "clipping": args.clipping, "stats_kind": args.stats_kind, "true_zero": args.preserve_zero,
+            "kld": args.kld_threshold, "pcq_weights": args.per_channel_quant_weights,
+            "pcq_act": args.per_channel_quant_act, "bit_alloc_act": args.bit_alloc_act,
+            "bit_alloc_weight": args.bit_alloc_weight, "bit_alloc_rmode": args.bit_alloc_rmode,
+            "bit_alloc_prior": args.bit_alloc_prior, "bit_alloc_target_act": args.bit_alloc_target_act,
+            "bit_alloc_target_weight": args.bit_alloc_target_weight, "bcorr_act": args.bias_corr_act,
+            "bcorr_weight": args.bias_corr_weight, "vcorr_weight": args.var_corr_weight, "logger": logger,
+            "measure_entropy": args.measure_entropy, "mtd_quant": args.mid_thread_quant,
+        },
+        "qmanager": {"rho_act": args.rho_act, "rho_weight": args.rho_weight},
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+# model preparation utilities (reference: utils/absorb_bn.py, utils/mark_relu.py, utils/model_naming.py)
+# ---------------------------------------------------------------------------------------------------
+def absorb_bn(module, bn):
+    """Fold an eval-mode BatchNorm into the preceding conv / linear: w *= gamma/sigma, b = (b - mu)/sigma*gamma + beta
+    (utils/absorb_bn.py:5-23; buffers stay on the module's device instead of a hard-coded .cuda())."""
+    with torch.no_grad():
+        w = module.weight.data
+        if module.bias is None:
+            module.bias = nn.Parameter(torch.zeros(w.size(0), dtype=w.dtype, device=w.device))
+        b = module.bias.data
+        invstd = bn.running_var.clone().add_(bn.eps).pow_(-0.5)
+        shape = (w.size(0),) + (1,) * (w.dim() - 1)
+        w.mul_(invstd.view(shape))
+        b.add_(-bn.running_mean).mul_(invstd)
+        if bn.affine:
+            w.mul_(bn.weight.data.view(shape))
+            b.mul_(bn.weight.data).add_(bn.bias.data)
+        bn.register_buffer("running_mean", torch.zeros_like(bn.running_mean))
+        bn.register_buffer("running_var", torch.ones_like(bn.running_var))
+        bn.register_parameter("weight", None)
+        bn.register_parameter("bias", None)
+        bn.affine = False
+
+
+def search_absorbe_bn(model):
+    """Fold every BN that directly follows a (groups==1) conv or a linear among its siblings, mark it ``absorbed``
+    (utils/absorb_bn.py:26-41)."""
+    prev = None
+    for m in model.children():
+        is_bn = isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d))
+        absorbing = (isinstance(prev, nn.Conv2d) and prev.groups == 1) or isinstance(prev, nn.Linear)
+        if is_bn and absorbing:
+            m.absorbed = True
+            absorb_bn(prev, m)
+        search_absorbe_bn(m)
+        prev = m
+
+
+def resnet_mark_before_relu(model):
+    """Tag the convs whose output feeds a ReLU (``before_relu`` -> half_range), utils/mark_relu.py:4-29."""
+    from torchvision.models.resnet import BasicBlock, Bottleneck
+    root = model.module if isinstance(model, nn.DataParallel) else model
+    root.conv1.before_relu = True
+
+    def walk(m):
+        for ch in m.children():
+            if isinstance(ch, Bottleneck):
+                for name in ("conv1", "bn1", "conv2", "bn2"):
+                    getattr(ch, name).before_relu = True
+            elif isinstance(ch, BasicBlock):
+                ch.conv1.before_relu = True
+                ch.bn1.before_relu = True
+            else:
+                walk(ch)
+
+    walk(model)
+
+
+def set_node_names(model):
+    """``internal_name`` on every leaf module, tensorboard style (utils/model_naming.py:4-28)."""
+    def type_name(m):
+        return type(m).__name__.replace("WithId", "")
+
+    def rec(parent, name):
+        kids = list(parent.named_children())
+        for k, m in kids:
+            rec(m, name + "/" + type_name(m) + "[" + k + "]")
+        if not kids:
+            parent.internal_name = name
+
+    rec(model, type_name(model))
+
+
+# ---------------------------------------------------------------------------------------------------
+# the manager
+# ---------------------------------------------------------------------------------------------------
+_STAMPED = (nn.Linear, nn.Conv2d, nn.BatchNorm2d, nn.MaxPool2d, nn.AvgPool2d)
+
+
+def _identity_forward(x):
+    return x
+
+
+class QuantizationManagerInference(object):
+    """``with QuantizationManagerInference(args, qparams) as qm: model = build(); qm.attach(model); qm.quantize_model(model)``.
+
+    ``quantizer_factory(qtype, quant_params)`` defaults to this package's CUDA ``int_quantizer``; tests and the CPU
+    baseline inject the oracle's factory to run the very same call sites on CPU."""
+
+    def __init__(self, args, qparams, quantizer_factory=None):
+        self.args = args
+        self.verbose = False
+        self.quantize = args.qtype is not None
+        self.disable_quantization = args.q_off
+        self.enabled = False
+        self.bn_folding = False
+        self.bcorr_act = args.bias_corr_act
+        self.bcorr_weight = args.bias_corr_weight
+        self.vcorr_weight = args.var_corr_weight
+        if args.stats_mode != "no":
+            raise NotImplementedError("stats_mode %r: offline statistics are the next scope row (SURVEY.md 8f)" % args.stats_mode)
+        self._factory = quantizer_factory or _iq.int_quantizer
+        self._fuse_weight_correction = quantizer_factory is None
+        self.fused_relu = args.arch is not None and (args.arch in FUSED_RELU_ARCHS or "squeezenet" in args.arch)
+        self.ignore_ids = []
+        self.quantizers = {}
+        self.quantizer_default = None
+        self.calls = []          # (id, tag, half_range, shape) of every quantize_instant while `record` is set
+        self.record = False
+        self._hooks = []
+        self._patched = []
+        self._orig_init = {}
+        self._counters = {}
+        if self.quantize:
+            self.__fill_quantizers__(args.qtype, qparams, args.arch, args.qweight)
+            self.quantizer_default = self._load("int8", qparams)
+            if args.qtype == "int4":
+                self.set_8bit_list(["conv%d_activation" % i for i in [0]])  # createTruncationManager, :334-340
+
+    # -- quantizer table (TruncationOpManagerInference.__fill_quantizers__, :407-476) ----------------
+    def _load(self, qtype, qparams):
+        name = qtype.rstrip("1234567890")
+        if name != "int":
+            raise NotImplementedError("qtype %r: only the int quantizer is on the hot path" % qtype)
+        return self._factory(qtype, qparams[name] if name in qparams else {})
+
+    def __fill_quantizers__(self, qtype, qparams, arch=None, qweight="int8"):
+        q = self._load("int8", qparams)
+        q.clipping, q.kld, q.pcq_w, q.pcq_a, q.stats_kind, q.measure_entropy = "no", False, False, False, "max", False
+        self.quantizers["activation_classifier"] = q
+
+        if qweight == "f32":
+            q = DummyQuantizer()
+        else:
+            q = self._load(qweight, qparams)
+            q.pcq_a, q.clipping, q.kld, q.stats_kind = False, "no", False, "max"
+        self.quantizers["weight"] = q
+
+        q = self._load("int8", qparams)
+        q.pcq_a, q.clipping, q.kld, q.stats_kind, q.measure_entropy = False, "no", False, "max", False
+        self.quantizers["weight_classifier"] = q
+
+        self.quantizers["bias"] = DummyQuantizer()
+
+        q = self._load("int8", qparams)
+        q.pcq_w, q.pcq_a, q.clipping, q.kld = False, False, "no", False
+        self.quantizers["ignored"] = q
+
+        q = self._load(qtype, qparams)
+        q.force_positive, q.pcq_w = self.fused_relu, False
+        self.quantizers["activation"] = q
+
+        q = self._load(qtype, qparams)
+        q.force_positive, q.pcq_w, q.pcq_a = self.fused_relu, False, False
+        self.quantizers["activation_linear"] = q
+
+        q = self._load("int8", qparams)
+        q.pcq_w, q.pcq_a, q.clipping, q.kld, q.measure_entropy = False, False, "no", False, False
+        self.quantizers["activation_pooling"] = q
+
+    def get_quantizer(self, tag, tensor=None):
+        return self.quantizers[tag] if tag in self.quantizers else self.quantizer_default
+
+    def set_8bit_list(self, ignore_ids):
+        self.ignore_ids = ignore_ids
+
+    def reset_counters(self):
+        pass
+
+    # -- enable / disable: stamp construction order like the reference's class-level counters --------------
+    def enable(self):
+        if not self.quantize:
+            return
+        self.enabled = not self.disable_quantization
+        if self._orig_init:
+            return
+        self._counters = {cls: count(0) for cls in _STAMPED}
+        for cls in _STAMPED:
+            orig = cls.__init__
+            self._orig_init[cls] = orig
+
+            def stamped(mod, *a, __orig=orig, __cls=cls, **k):
+                __orig(mod, *a, **k)
+                if type(mod) is __cls or not hasattr(mod, "_fq_id"):
+                    mod._fq_id = next(self._counters[__cls])
+
+            cls.__init__ = stamped
+
+    def stop_stamping(self):
+        """Restore the stock constructors (ids already stamped stay); quantization stays enabled."""
+        for cls, orig in self._orig_init.items():
+            cls.__init__ = orig
+        self._orig_init = {}
+
+    def disable(self):
+        self.enabled = False
+        self.stop_stamping()
+
+    def __enter__(self):
+        self.enable()
+        return self
+
+    def __exit__(self, *exc):
+        self.disable()
+        self.detach()
+
+    # -- call sites: forward hooks reproducing the *WithId.forward bodies (:58-74, :84-101, :162-217, :227-250, :262-283)
+    def attach(self, model):
+        """Register the forward hooks.  Modules built outside ``enable()`` get ids in ``model.modules()`` order."""
+        fallback = {cls: count(0) for cls in _STAMPED}
+        for m in model.modules():
+            cls = next((c for c in _STAMPED if type(m) is c), None)
+            if cls is None:
+                continue
+            if not hasattr(m, "_fq_id"):
+                m._fq_id = next(fallback[cls])
+            if cls is nn.BatchNorm2d and self.bn_folding and hasattr(m, "absorbed"):
+                # :264-265: an absorbed BN returns its input untouched; do not even run the (identity) normalisation
+                m.forward = _identity_forward
+                self._patched.append(m)
+                continue
+            hook = {nn.Conv2d: self._conv_hook, nn.Linear: self._linear_hook, nn.MaxPool2d: self._maxpool_hook,
+                    nn.AvgPool2d: self._avgpool_hook, nn.BatchNorm2d: self._bn_hook}[cls]
+            self._hooks.append(m.register_forward_hook(hook))
+        return model
+
+    def detach(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        for m in self._patched:
+            m.__dict__.pop("forward", None)
+        self._patched = []
+
+    def _conv_hook(self, m, inputs, out):
+        if not self.enabled:
+            return None
+        tag = "activation_classifier" if out.shape[1] == 1000 else "activation"
+        return self.quantize_instant(out, "conv%d_activation" % m._fq_id, tag, half_range=hasattr(m, "before_relu"),
+                                     verbose=self.verbose)
+
+    def _linear_hook(self, m, inputs, out):
+        if not self.enabled:
+            return None
+        classifier = m.weight.shape[0] == 1000
+        tag = "activation_classifier" if classifier else "activation_linear"
+        half_range = hasattr(m, "before_relu") if not classifier else False
+        return self.quantize_instant(out, "linear%d_activation" % m._fq_id, tag, half_range=half_range, verbose=self.verbose)
+
+    def _maxpool_hook(self, m, inputs, out):
+        if not self.enabled:
+            return None
+        return self.quantize_instant(out, "maxpool%d_out" % m._fq_id, "activation_pooling", verbose=self.verbose)
+
+    def _avgpool_hook(self, m, inputs, out):
+        if not self.enabled:
+            return None
+        # the reference passes the tag in the id slot here (:99): the tensor goes through the DEFAULT quantizer
+        tag_act = "activation_classifier" if out.shape[1] == 1000 else "activation_pooling"
+        return self.quantize_instant(out, tag_act, verbose=self.verbose)
+
+    def _bn_hook(self, m, inputs, out):
+        if self.bn_folding and hasattr(m, "absorbed"):
+            return inputs[0]  # :264-265: an absorbed BN is the identity
+        if not self.enabled:
+            return None
+        # same argument-order slip as the reference (:278): id="activation", tag="" -> default quantizer
+        return self.quantize_instant(out, "activation", half_range=hasattr(m, "before_relu"), verbose=self.verbose)
+
+    # -- quantize_instant (:549-562) ------------------------------------------------------------------------
+    def quantize_instant(self, tensor, id, tag="", stat_id=None, half_range=False, override_att=None, verbose=False,
+                         **extra):
+        ignore = stat_id is not None and any(l == stat_id for l in self.ignore_ids)
+        qtag = "ignored" if ignore else tag
+        q = self.get_quantizer(qtag)
+        q.half_range = half_range
+        if verbose:
+            print("Quantize {0:21} | Id - {1:18} | {2:} | {3:}".format(tag, str(stat_id), str(q), str(tensor.device)))
+        if self.record:
+            self.calls.append((id, tag, bool(half_range), tuple(tensor.shape)))
+        if isinstance(q, DummyQuantizer):
+            return q(tensor, id, tag, stat_id, override_att)
+        return q(tensor, id, tag, stat_id, override_att, **extra)
+
+    # -- quantize_model (:352-393) ---------------------------------------------------------------------------
+    def quantize_model(self, model):
+        import torchvision
+        inception = isinstance(model, torchvision.models.Inception3)
+        corr = (bool(self.bcorr_weight), bool(self.vcorr_weight))
+        for n, m in model.named_modules():
+            weight_q = None
+            extra = {"weight_correction": corr} if (self._fuse_weight_correction and any(corr)) else {}
+            if isinstance(m, nn.Conv2d):
+                first8 = (inception and n in ("Conv2d_1a_3x3.conv", "Conv2d_2a_3x3.conv")) or m.weight.shape[1] == 3
+                weight_q = self.quantize_instant(m.weight.data, n + ".weight", "weight",
+                                                 override_att=("num_bits", 8) if first8 else None, verbose=self.verbose,
+                                                 **extra)
+            elif isinstance(m, nn.Linear):
+                tag = "weight_classifier" if m.weight.shape[0] == 1000 else "weight"
+                weight_q = self.quantize_instant(m.weight.data, n + ".weight", tag, verbose=self.verbose, **extra)
+            if weight_q is None:
+                continue
+            if any(corr) and not extra:
+                weight_q = self._weight_correction_torch(m.weight.data, weight_q, *corr)
+            m.weight.data = weight_q
+
+    @staticmethod
+    def _weight_correction_torch(w, w_q, bias_corr, var_corr):
+        """:374-391 as stock torch ops: only used when a foreign quantizer factory (the CPU oracle) is injected."""
+        bshape = (-1, 1, 1, 1) if w_q.dim() == 4 else (-1, 1)
+        m_q = w_q.view(w_q.shape[0], -1).mean(-1).view(bshape)
+        m_o = w.view(w.shape[0], -1).mean(-1).view(bshape)
+        if var_corr:
+            eps = torch.tensor([1e-8]).to(w_q.device)
+            k = w.view(w.shape[0], -1).std(dim=-1) / (w_q.view(w_q.shape[0], -1).std(dim=-1) + eps)
+            w_q = (w_q - m_q) * k.view(bshape) + m_q
+        if bias_corr:
+            w_q = w_q - m_q + m_o
+        return w_q

@@ -8,6 +8,48 @@ from . import _lib as L
 
 _workspaces = {}  # (device index, stream handle) -> uint8 tensor
 
+# ---- optional per-launch timing (bench.py): CUDA events recorded on the launching stream around each call --------
+_prof = {"on": False, "records": [], "launches": 0}
+
+
+def profile_reset(enable):
+    _prof["on"] = bool(enable)
+    _prof["records"] = []
+    _prof["launches"] = 0
+
+
+def profile_collect():
+    """Synchronise and return {'launches': n, 'modes': {mode: {launches, elems, bytes, ms}}}.  Modes by algorithmic
+    traffic: 'D' two statistics passes + apply (16 B/elem), 'B' one statistics pass + apply (12), 'A' apply only (8),
+    'S' statistics only."""
+    torch.cuda.synchronize()
+    modes = {}
+    for mode, elems, nbytes, e0, e1 in _prof["records"]:
+        m = modes.setdefault(mode, {"launches": 0, "elems": 0, "bytes": 0, "ms": 0.0})
+        m["launches"] += 1
+        m["elems"] += elems
+        m["bytes"] += nbytes
+        m["ms"] += e0.elapsed_time(e1)
+    return {"launches": _prof["launches"], "modes": modes}
+
+
+class _Timed(object):
+    def __init__(self, mode, elems, bytes_per_elem):
+        self.args = (mode, elems, elems * bytes_per_elem)
+
+    def __enter__(self):
+        _prof["launches"] += 1
+        if _prof["on"]:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _prof["on"]:
+            self.e1.record()
+            _prof["records"].append(self.args + (self.e0, self.e1))
+
 
 def _stream_handle(device):
     return torch.cuda.current_stream(device).cuda_stream
@@ -47,7 +89,7 @@ def float2gemmlowp(x, range_, offset, num_bits, int_exp, enforce_true_zero, nois
         noise = noise.contiguous()
     if out is None:
         out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _Timed("A", x.numel(), 8):
         L.check(lib.fqb200_float2gemmlowp(x.data_ptr(), out.data_ptr(), x.numel(), float(range_), float(offset),
                                           int(num_bits), int(bool(int_exp)), int(bool(enforce_true_zero)),
                                           noise.data_ptr() if noise is not None else None, _stream_handle(x.device)))
@@ -80,7 +122,7 @@ def quantize1(x, delta, offset, num_bits, bits=None, layout=None, want_grid=Fals
             raise ValueError("bit_alloc must have %d elements" % groups)
     out = torch.empty_like(x)
     grid = torch.empty_like(x) if want_grid else None
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _Timed("A", x.numel(), 8):
         L.check(lib.fqb200_quantize1(x.data_ptr(), out.data_ptr(), grid.data_ptr() if want_grid else None,
                                      outer, groups, inner, delta.data_ptr(), offset.data_ptr(),
                                      bits.data_ptr() if bits is not None else None, int(per_group), int(num_bits),
@@ -128,8 +170,13 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
         if need == 0:
             L.check(L.ERR_INVALID if not lib.fqb200_last_error() else L.ERR_INVALID)
         ws = _workspace(dev, stream, need)
-        L.check(lib.fqb200_fused(ctypes.byref(d), x.data_ptr(), out.data_ptr() if out is not None else None,
-                                 ws.data_ptr(), ws.numel(), stream))
+        two_pass = (range_mode != L.RANGE_MINMAX or leaf == L.LEAF_MIDTREAD or var_corr or stats_only or
+                    (bit_alloc and num_bits <= 4 and scope == L.SCOPE_GROUP))
+        mode = "S" if stats_only else ("D" if two_pass else "B")
+        bpe = (8 if two_pass else 4) + (0 if stats_only else 8)
+        with _Timed(mode, x.numel(), bpe):
+            L.check(lib.fqb200_fused(ctypes.byref(d), x.data_ptr(), out.data_ptr() if out is not None else None,
+                                     ws.data_ptr(), ws.numel(), stream))
     if stats_only:
         return stats
     return (out, stats) if want_stats else out

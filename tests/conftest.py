@@ -25,11 +25,11 @@ def golden():
     return arrays, meta
 
 
-def fq_mismatch(y, y_ref, step=None):
-    """Return (fraction of elements that differ beyond 1e-5 relative, max |diff| in units of `step`)."""
+def fq_mismatch(y, y_ref, step=None, atol=1e-9):
+    """Return (fraction of elements that differ beyond 1e-5 relative (+atol), max |diff| in units of `step`)."""
     y = np.asarray(y, dtype=np.float64).reshape(-1)
     r = np.asarray(y_ref, dtype=np.float64).reshape(-1)
-    tol = 1e-5 * np.maximum(np.abs(r), np.abs(y)) + 1e-9
+    tol = 1e-5 * np.maximum(np.abs(r), np.abs(y)) + atol
     bad = np.abs(y - r) > tol
     frac = float(bad.mean()) if y.size else 0.0
     if step is None or not bad.any():

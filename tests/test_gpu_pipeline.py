@@ -1,0 +1,72 @@
+"""GPU pipeline: the hook manager with the CUDA quantizers on the same seeded models / inputs the real reference ran
+(tests/golden/make_census.py), plus multi-batch validation bookkeeping."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def census():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    with open(os.path.join(GOLD, "ref_census.json")) as f:
+        return json.load(f), np.load(os.path.join(GOLD, "ref_pipeline.npz"))
+
+
+@pytest.mark.parametrize("name", ["resnet18_w4a4", "resnet50_w4a4", "resnet50_w8a8", "vgg16_w4a4"])
+def test_cuda_pipeline_call_sites_and_logits(census, name):
+    from cnn_quantization_b200 import pipeline
+    meta, logits = census
+    info = meta[name]
+    torch.backends.cudnn.allow_tf32 = False  # compare against fp32 CPU convolutions
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model, qm = pipeline.build_quantized_model(dict(arch=info["arch"], **info["flags"]), "cuda")
+    qm.record = True
+    rs = np.random.RandomState(12345)
+    x = torch.from_numpy(rs.standard_normal((info["batch"], 3, info["hw"], info["hw"])).astype(np.float32)).cuda()
+    with torch.no_grad():
+        y = model(x).cpu().numpy()
+    qm.detach()
+    calls = [[c[0], c[1], c[2], list(c[3])] for c in qm.calls]
+    assert calls == info["act_calls"]
+    ref = logits[name]
+    # 4-bit grids amplify last-ulp differences of cuDNN vs CPU convolutions into occasional one-step flips that then
+    # propagate, so logits are compared as a whole: same direction, same scale
+    cos = float((y * ref).sum() / (np.linalg.norm(y) * np.linalg.norm(ref)))
+    assert cos > 0.98, cos
+    assert abs(np.linalg.norm(y) / np.linalg.norm(ref) - 1) < 0.1
+
+
+def test_weights_match_reference_quantize_model(census):
+    """quantize_model with the fused CUDA weight launch (quantize + bias correction) == the oracle manager on CPU."""
+    from cnn_quantization_b200 import pipeline
+    from oracle import fq_oracle as O
+    meta, _ = census
+    info = meta["resnet18_w4a4"]
+    flags = dict(arch=info["arch"], **info["flags"])
+    m_gpu, q1 = pipeline.build_quantized_model(flags, "cuda")
+    m_cpu, q2 = pipeline.build_quantized_model(flags, "cpu", quantizer_factory=O.oracle_int_quantizer)
+    q1.detach()
+    q2.detach()
+    for (n1, p1), (n2, p2) in zip(m_gpu.named_parameters(), m_cpu.named_parameters()):
+        assert n1 == n2
+        a, b = p1.detach().cpu().numpy(), p2.detach().numpy()
+        scale = float(np.abs(b).max()) + 1e-12
+        bad = np.abs(a - b) > 1e-5 * scale
+        assert bad.mean() <= 2e-3, (n1, float(bad.mean()))
+
+
+def test_validate_accumulates_like_average_meters():
+    from cnn_quantization_b200 import pipeline
+    model, qm = pipeline.build_quantized_model("resnet18_w4a4", "cuda")
+    batches = [pipeline.synthetic_batch(4, seed=s, hw=64) for s in (1, 2, 3)]
+    total = pipeline.validate(model, batches, "cuda")
+    loss, top1, top5, n = pipeline.reduce_metrics(total)
+    qm.detach()
+    assert n == 12 and 0 <= top1 <= top5 <= 100 and np.isfinite(loss)
