@@ -33,7 +33,7 @@ def parse():
     ap.add_argument("--impl", default="fqb200", choices=["fqb200", "reference"])
     ap.add_argument("--config", default="resnet50_w4a4")
     ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
-    ap.add_argument("--cpu-batch", type=int, default=16, help="images per step of the CPU reference arm / cpu_baseline")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="images per step of the CPU reference arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -48,50 +48,53 @@ def peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons sampled through NVML every 100 ms while the timed region runs."""
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.rows, self.stop_flag, self.thread, self.err = index, [], threading.Event(), None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.rows.append((sm, pw, rs))
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                return
+            time.sleep(0.1)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [v.strip() for v in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        seen = set()
+        for _, _, rs in self.rows:
+            for k, bit in names.items():
+                if rs & bit:
+                    seen.add(k)
+        busy = sorted(sm for sm, pw, _ in self.rows if pw > 250.0) or sorted(sm for sm, _, _ in self.rows)
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": self.max_sm, "samples": len(self.rows),
+                "power_w_max": max((pw for _, pw, _ in self.rows), default=None), "reasons": sorted(seen)}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -120,7 +123,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 2))
     warm = 1 if args.warmup > 0 else 0
     ips, sec, cores = cpu_pipeline_images_per_s(args.config, args.cpu_batch, steps, warm)
     sample = "%d steps of %d images (of the %d-image batch) through the oracle port of int_quantizer.py, %d host threads" % (
@@ -191,12 +194,16 @@ def run_fqb200(args):
         sampler.start()
     ops.profile_reset(enable=True)
     barrier()
+    if os.environ.get("FQB_CUDA_PROFILER"):  # ncu --profile-from-start off: capture the timed region only
+        torch.cuda.profiler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         step_resident()
     ev1.record()
     barrier()
+    if os.environ.get("FQB_CUDA_PROFILER"):
+        torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1)
     prof = ops.profile_collect()
     ops.profile_reset(enable=False)
@@ -254,7 +261,7 @@ def run_fqb200(args):
             "check": {"loss": loss, "top1": top1, "top5": top5, "images": n_img},
         }
         if world == 1 and not args.no_cpu_baseline:
-            ips, sec, cores = cpu_pipeline_images_per_s(args.config, args.cpu_batch, 1, 1)
+            ips, sec, cores = cpu_pipeline_images_per_s(args.config, args.cpu_batch, 1, 0)
             line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "1 step of %d images through the oracle port of int_quantizer.py + torch CPU convs" % args.cpu_batch}
         print(json.dumps(line))

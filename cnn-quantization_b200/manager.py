@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from .dummy_quantizer import DummyQuantizer
-from . import int_quantizer as _iq
+from .int_quantizer import int_quantizer as _default_factory
 
 __all__ = ["QuantizationManagerInference", "make_args", "get_params", "absorb_bn", "search_absorbe_bn",
            "resnet_mark_before_relu", "set_node_names"]
@@ -159,7 +159,7 @@ class QuantizationManagerInference(object):
         self.vcorr_weight = args.var_corr_weight
         if args.stats_mode != "no":
             raise NotImplementedError("stats_mode %r: offline statistics are the next scope row (SURVEY.md 8f)" % args.stats_mode)
-        self._factory = quantizer_factory or _iq.int_quantizer
+        self._factory = quantizer_factory or _default_factory
         self._fuse_weight_correction = quantizer_factory is None
         self.fused_relu = args.arch is not None and (args.arch in FUSED_RELU_ARCHS or "squeezenet" in args.arch)
         self.ignore_ids = []
