@@ -6,7 +6,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfqb200.so")
+LIB_PATH = os.environ.get("FQB200_LIB") or os.path.join(HERE, "libfqb200.so")  # env override: A/B builds in development
 
 OK, ERR_INVALID, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 SCOPE_GROUP, SCOPE_GROUP_MEAN, SCOPE_TENSOR = 0, 1, 2
@@ -33,6 +33,7 @@ class Desc(ctypes.Structure):
         ("mt_target", ctypes.c_float), ("mt_clip", ctypes.c_int32),
         ("bias_corr", ctypes.c_int32), ("var_corr", ctypes.c_int32), ("stats_only", ctypes.c_int32),
         ("out_stats", ctypes.c_void_p),
+        ("bias", ctypes.c_void_p),
     ]
 
 

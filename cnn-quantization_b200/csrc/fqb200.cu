@@ -18,6 +18,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/fqb200.h"
@@ -50,7 +51,7 @@ struct FusedArgs {
   Geometry geo;
   const float* in;
   float* out;
-  const float* noise;  // standalone a1 only
+  const float* bias;   // optional per-group addend applied to x before everything else (folded-BN conv bias)
   float* grid_out;     // optional integer grid (quantize1)
   // configuration (mirrors fqb200_desc)
   int scope, range_mode, leaf, num_bits, positive, solve_f64;
@@ -65,6 +66,7 @@ struct FusedArgs {
   int given_per_group;
   double n_per_group;  // outer * inner
   float* out_stats;
+  unsigned long long* dbg;  // development: globaltimer stamps of the phase boundaries (NULL in production)
   // workspace
   GridSync* sync;
   float *pmin, *pmax;                   // [items]
@@ -86,26 +88,50 @@ struct LeaderSmem {
   int flag;
 };
 
-// Reduce the P per-item partials of every group in a fixed order.  L = min(32, pow2 >= P) lanes cooperate on
-// one group; kThreads / L groups are finished per sweep.
-template <typename T, typename Op>
-__device__ __forceinline__ void reduce_partials(const T* part, T* out, const Geometry& geo, T identity, Op op) {
-  unsigned L = 1;
-  while (L < geo.parts && L < 32) L <<= 1;
+// Reduce the per-segment partials of every group in a fixed order.  In slab p group g was touched by the CTAs
+// cta_of(first vector) .. cta_of(last vector) (usually one or two); CTA c left its partial at partial_slot(p, c, g).
+// `red_lanes` lanes cooperate on one group; kThreads / red_lanes groups are finished per sweep.  Up to three arrays
+// are reduced in one sweep so their (independent) L2 round trips overlap.
+template <typename T0, typename Op0, typename T1, typename Op1, typename T2, typename Op2>
+__device__ __forceinline__ void reduce_partials3(const Geometry& geo, const T0* p0, T0* o0, T0 id0, Op0 op0, const T1* p1,
+                                                 T1* o1, T1 id1, Op1 op1, const T2* p2, T2* o2, T2 id2, Op2 op2) {
+  const unsigned L = geo.red_lanes;
   const unsigned sub = threadIdx.x % L;
   const unsigned per_sweep = kThreads / L;
   for (unsigned g0 = 0; g0 < geo.groups; g0 += per_sweep) {
     const unsigned g = g0 + threadIdx.x / L;
-    T acc = identity;
-    if (g < geo.groups)
-      for (unsigned p = sub; p < geo.parts; p += L) acc = op(acc, ld_ws(part + static_cast<size_t>(p) * geo.groups + g));
-    for (unsigned o = L >> 1; o > 0; o >>= 1) acc = op(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-    if (g < geo.groups && sub == 0) out[g] = acc;
+    T0 a0 = id0;
+    T1 a1 = id1;
+    T2 a2 = id2;
+    if (g < geo.groups) {
+      for (unsigned p = 0; p < geo.slabs; ++p) {
+        const Slab s = slab_of(geo, p);
+        if (s.len == 0) continue;
+        const unsigned long long first = static_cast<unsigned long long>(g) * s.len;
+        const unsigned c_lo = cta_of(s, first), c_hi = cta_of(s, first + s.len - 1ull);
+        for (unsigned c = c_lo + sub; c <= c_hi; c += L) {
+          const size_t slot = partial_slot(geo, p, c, g);
+          if (p0) a0 = op0(a0, ld_ws(p0 + slot));
+          if (p1) a1 = op1(a1, ld_ws(p1 + slot));
+          if (p2) a2 = op2(a2, ld_ws(p2 + slot));
+        }
+      }
+    }
+    for (unsigned o = L >> 1; o > 0; o >>= 1) {
+      a0 = op0(a0, __shfl_xor_sync(0xffffffffu, a0, o));
+      a1 = op1(a1, __shfl_xor_sync(0xffffffffu, a1, o));
+      a2 = op2(a2, __shfl_xor_sync(0xffffffffu, a2, o));
+    }
+    if (g < geo.groups && sub == 0) {
+      if (p0) o0[g] = a0;
+      if (p1) o1[g] = a1;
+      if (p2) o2[g] = a2;
+    }
   }
 }
 
 // per-group bit allocation, int_quantizer.py:381-407 (get_bits_alloc_fixed_target).  All threads of the CTA.
-__device__ void solve_bit_alloc(const FusedArgs& A, LeaderSmem& sm) {
+__device__ __noinline__ void solve_bit_alloc(const FusedArgs& A, LeaderSmem& sm) {
   const unsigned G = A.geo.groups;
   const float* prior = (A.prior == FQB200_PRIOR_STD) ? A.gstd : A.gb;
   // p = alpha^(2/3)  (torch.pow with a python-float exponent -> fp32 powf)
@@ -227,7 +253,7 @@ __device__ __forceinline__ void export_stats(const FusedArgs& A, unsigned g, flo
 }
 
 // mid-tread parameters, int_quantizer.py:185-214 (+ :128-145)
-__device__ void solve_mid_tread(const FusedArgs& A, LeaderSmem& sm) {
+__device__ __noinline__ void solve_mid_tread(const FusedArgs& A, LeaderSmem& sm) {
   const unsigned G = A.geo.groups;
   double local = 0.0;
   for (unsigned g = threadIdx.x; g < G; g += kThreads) {
@@ -277,7 +303,7 @@ __device__ void solve_mid_tread(const FusedArgs& A, LeaderSmem& sm) {
 }
 
 // The parameter solve: runs once per launch, after the last statistics phase.
-__device__ void solve_params(const FusedArgs& A, LeaderSmem& sm) {
+__device__ __noinline__ void solve_params(const FusedArgs& A, LeaderSmem& sm) {
   const unsigned G = A.geo.groups;
   if (A.leaf == FQB200_LEAF_MIDTREAD) {
     solve_mid_tread(A, sm);
@@ -336,128 +362,153 @@ __device__ void solve_params(const FusedArgs& A, LeaderSmem& sm) {
 // ------------------------------------------------------------------------------------------------
 // streaming phases
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stamp(const FusedArgs& A, int slot) {
+  if (A.dbg && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    A.dbg[slot] = t;
+  }
+}
+
 struct PhaseSmem {
   float f0[kWarps], f1[kWarps];
   double d0[kWarps], d1[kWarps];
 };
 
-// item order: forward in even phases, backward in odd ones (L2 reuse between phases)
-__device__ __forceinline__ bool next_item(const Geometry& geo, unsigned long long& it, bool reverse, bool first) {
-  const unsigned long long per = (geo.items + gridDim.x - 1) / gridDim.x;  // max items per CTA
-  // k-th item of this CTA is blockIdx.x + k*gridDim.x; walk k upward or downward
-  if (first) {
-    if (!reverse) {
-      it = blockIdx.x;
-    } else {
-      unsigned long long k = per;  // one past the last candidate
-      it = blockIdx.x + (k - 1) * gridDim.x;
-      if (it >= geo.items) {
-        if (k < 2) return false;
-        it -= gridDim.x;
-      }
-    }
-    return it < geo.items;
-  }
-  if (!reverse) {
-    it += gridDim.x;
-    return it < geo.items;
-  }
-  if (it < gridDim.x) return false;
-  it -= gridDim.x;
-  return true;
+#ifndef FQB_USTATS
+#define FQB_USTATS 4
+#endif
+#ifndef FQB_UAPPLY
+#define FQB_UAPPLY 4
+#endif
+#ifndef FQB_ASYNC
+#define FQB_ASYNC 1
+#endif
+// 128-bit path: cp.async ring (FQB_ASYNC=1) or register batches; scalar path: register batches
+extern __shared__ __align__(16) unsigned char fq_dyn_smem[];
+__device__ __forceinline__ unsigned ring_base() {
+  return static_cast<unsigned>(__cvta_generic_to_shared(fq_dyn_smem)) + threadIdx.x * 16u;
+}
+template <int U, bool REV, typename Body>
+__device__ __forceinline__ void walk4(const Geometry& geo, const float* base, unsigned g, unsigned long long vb, unsigned len,
+                                      Body&& body) {
+#if FQB_ASYNC
+  walk_segment_async<REV>(geo, base, g, vb, len, ring_base(), body);
+#else
+  walk_segment<4, U, REV>(geo, base, g, vb, len, body);
+#endif
 }
 
-// S1: min / max / sum per item  (int_quantizer.py:541-546)
-template <int VEC>
-__device__ void phase_stats1(const FusedArgs& A, PhaseSmem& sm, bool reverse) {
-  unsigned long long it;
-  for (bool ok = next_item(A.geo, it, reverse, true); ok; ok = next_item(A.geo, it, reverse, false)) {
+constexpr int kUnrollStats = FQB_USTATS;  // statistics phases: independent 128-bit loads in flight per thread
+constexpr int kUnrollApply = FQB_UAPPLY;  // apply phase: loads (+ as many stores) in flight per thread
+
+// CTA-wide sums of up to two doubles and min/max of two floats, result valid in thread 0
+__device__ __forceinline__ void block_combine(PhaseSmem& sm, float& mn, float& mx, double& s0, double& s1, bool use_f,
+                                              bool use_d1) {
+  if (use_f) {
+    mn = warp_reduce(mn, OpMin());
+    mx = warp_reduce(mx, OpMax());
+  }
+  s0 = warp_reduce(s0, OpAdd());
+  if (use_d1) s1 = warp_reduce(s1, OpAdd());
+  __syncthreads();
+  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    sm.f0[w] = mn;
+    sm.f1[w] = mx;
+    sm.d0[w] = s0;
+    sm.d1[w] = s1;
+  }
+  __syncthreads();
+  if (w == 0) {
+    float a = (l < kWarps) ? sm.f0[l] : INFINITY, b = (l < kWarps) ? sm.f1[l] : -INFINITY;
+    double c = (l < kWarps) ? sm.d0[l] : 0.0, d = (l < kWarps) ? sm.d1[l] : 0.0;
+#pragma unroll
+    for (int o = kWarps / 2; o > 0; o >>= 1) {
+      a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+      b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    mn = a;
+    mx = b;
+    s0 = c;
+    s1 = d;
+  }
+}
+
+// S1: min / max / sum per segment  (int_quantizer.py:541-546)
+template <int VEC, bool REV>
+__device__ void phase_stats1(const FusedArgs& A, PhaseSmem& sm) {
+  for_each_segment(A.geo, REV, [&](unsigned g, unsigned p, unsigned long long vb, unsigned len) {
     float mn = INFINITY, mx = -INFINITY;
-    double s = 0.0;
+    double s = 0.0, unused = 0.0;
+    const float bias = A.bias ? __ldg(A.bias + g) : 0.f;  // x + 0 when there is none
     if constexpr (VEC == 4) {
-      walk_item<4>(A.geo, A.in, it, [&](const float4& x, unsigned long long) {
+      walk4<kUnrollStats, REV>(A.geo, A.in, g, vb, len, [&](float4 x, unsigned) {
+        x = make_float4(__fadd_rn(x.x, bias), __fadd_rn(x.y, bias), __fadd_rn(x.z, bias), __fadd_rn(x.w, bias));
         mn = fminf(mn, fminf(fminf(x.x, x.y), fminf(x.z, x.w)));
         mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
         s += static_cast<double>(__fadd_rn(__fadd_rn(x.x, x.y), __fadd_rn(x.z, x.w)));
       });
     } else {
-      walk_item<1>(A.geo, A.in, it, [&](float x, unsigned long long) {
+      walk_segment<1, kUnrollStats, REV>(A.geo, A.in, g, vb, len, [&](float x, unsigned) {
+        x = __fadd_rn(x, bias);
         mn = fminf(mn, x);
         mx = fmaxf(mx, x);
         s += static_cast<double>(x);
       });
     }
-    mn = warp_reduce(mn, OpMin());
-    mx = warp_reduce(mx, OpMax());
-    s = warp_reduce(s, OpAdd());
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) {
-      sm.f0[threadIdx.x >> 5] = mn;
-      sm.f1[threadIdx.x >> 5] = mx;
-      sm.d0[threadIdx.x >> 5] = s;
-    }
-    __syncthreads();
+    block_combine(sm, mn, mx, s, unused, true, false);
     if (threadIdx.x == 0) {
-      for (int w = 1; w < kWarps; ++w) {
-        mn = fminf(mn, sm.f0[w]);
-        mx = fmaxf(mx, sm.f1[w]);
-        s += sm.d0[w];
-      }
-      // partial layout [p][g] so that the leader's per-group reads are coalesced over g
-      const size_t slot = static_cast<size_t>(it);  // it = p * G + g: the leader reads [p][g]
+      const size_t slot = partial_slot(A.geo, p, blockIdx.x, g);
       st_ws(A.pmin + slot, mn);
       st_ws(A.pmax + slot, mx);
       st_ws(A.psum + slot, s);
     }
-  }
+  });
 }
 
-// S2: sum |x - mu| and sum (x - mu)^2 per item, mu = fp32 group mean  (int_quantizer.py:547-550)
-template <int VEC>
-__device__ void phase_stats2(const FusedArgs& A, PhaseSmem& sm, bool reverse) {
-  unsigned long long it;
-  for (bool ok = next_item(A.geo, it, reverse, true); ok; ok = next_item(A.geo, it, reverse, false)) {
-    const float mu = ld_ws(A.gmean + (it % A.geo.groups));
+// S2: sum |x - mu| and sum (x - mu)^2 per segment, mu = fp32 group mean  (int_quantizer.py:547-550)
+// `src` is the input (activations, weights) or the output (variance correction of quantized weights).
+template <int VEC, bool REV>
+__device__ void phase_stats2(const FusedArgs& A, PhaseSmem& sm, const float* src, const float* mean, bool with_bias,
+                             double* out_abs, double* out_sq) {
+  for_each_segment(A.geo, REV, [&](unsigned g, unsigned p, unsigned long long vb, unsigned len) {
+    const float mu = ld_ws(mean + g);
+    const float bias = (with_bias && A.bias != nullptr) ? __ldg(A.bias + g) : 0.f;
+    float fu0 = 0.f, fu1 = 0.f;
     double sa = 0.0, sq = 0.0;
     if constexpr (VEC == 4) {
-      walk_item<4>(A.geo, A.in, it, [&](const float4& x, unsigned long long) {
+      walk4<kUnrollStats, REV>(A.geo, src, g, vb, len, [&](float4 x, unsigned) {
+        x = make_float4(__fadd_rn(x.x, bias), __fadd_rn(x.y, bias), __fadd_rn(x.z, bias), __fadd_rn(x.w, bias));
         const float d0 = __fsub_rn(x.x, mu), d1 = __fsub_rn(x.y, mu), d2 = __fsub_rn(x.z, mu), d3 = __fsub_rn(x.w, mu);
         sa += static_cast<double>(__fadd_rn(__fadd_rn(fabsf(d0), fabsf(d1)), __fadd_rn(fabsf(d2), fabsf(d3))));
         sq += static_cast<double>(__fmaf_rn(d3, d3, __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)))));
       });
     } else {
-      walk_item<1>(A.geo, A.in, it, [&](float x, unsigned long long) {
+      walk_segment<1, kUnrollStats, REV>(A.geo, src, g, vb, len, [&](float x, unsigned) {
+        x = __fadd_rn(x, bias);
         const float d = __fsub_rn(x, mu);
         sa += static_cast<double>(fabsf(d));
         sq += static_cast<double>(__fmul_rn(d, d));
       });
     }
-    sa = warp_reduce(sa, OpAdd());
-    sq = warp_reduce(sq, OpAdd());
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) {
-      sm.d0[threadIdx.x >> 5] = sa;
-      sm.d1[threadIdx.x >> 5] = sq;
-    }
-    __syncthreads();
+    block_combine(sm, fu0, fu1, sa, sq, false, true);
     if (threadIdx.x == 0) {
-      for (int w = 1; w < kWarps; ++w) {
-        sa += sm.d0[w];
-        sq += sm.d1[w];
-      }
-      const size_t slot = static_cast<size_t>(it);  // it = p * G + g: the leader reads [p][g]
-      st_ws(A.pabs + slot, sa);
-      st_ws(A.psq + slot, sq);
+      const size_t slot = partial_slot(A.geo, p, blockIdx.x, g);
+      if (out_abs) st_ws(out_abs + slot, sa);
+      st_ws(out_sq + slot, sq);
     }
-  }
+  });
 }
 
 // one element through the leaf
-template <int LEAF>
+template <int LEAF, bool FAST, bool NOISE = false>
 __device__ __forceinline__ float leaf_apply(float x, const LeafParam& q, const Divisor& dv, float noise, float& grid) {
   if constexpr (LEAF == FQB200_LEAF_TORCH) {
     // int_quantizer.py:573-592: o = x/scale + zp; clamp [0, qmax]; round-half-even; (o - zp) * scale
-    float t = __fadd_rn(div_exact(x, dv), q.b);
+    float t = __fadd_rn(div_exact<FAST>(x, dv), q.b);
     t = max_nan(min_nan(t, q.c), 0.f);
     t = rint_small_nonneg(t);
     grid = t;
@@ -470,10 +521,10 @@ __device__ __forceinline__ float leaf_apply(float x, const LeafParam& q, const D
     }
     float t;
     if (q.flags & FLAG_TRUE_ZERO)
-      t = __fadd_rn(div_exact(x, dv), q.b);
+      t = __fadd_rn(div_exact<FAST>(x, dv), q.b);
     else
-      t = div_exact(__fadd_rn(x, q.b), dv);
-    t = __fadd_rn(t, noise);
+      t = div_exact<FAST>(__fadd_rn(x, q.b), dv);
+    if (NOISE) t = __fadd_rn(t, noise);
     t = fmaxf(fminf(t, q.c), 0.f);
     t = roundf(t);
     grid = t;
@@ -481,105 +532,83 @@ __device__ __forceinline__ float leaf_apply(float x, const LeafParam& q, const D
     return __fmaf_rn(t, q.a, -q.b);  // single FFMA in the reference's nvcc build ("a1 contraction")
   } else {
     // int_quantizer.py:202-224: round(x/Delta), clamp to [c_min, c_max], * Delta
-    float t = rintf(div_exact(x, dv));
+    float t = rintf(div_exact<FAST>(x, dv));
     t = max_nan(min_nan(t, q.c), q.b);
     grid = t;
     return __fmul_rn(t, q.a);
   }
 }
 
-// A: quantize - clip - dequantize.  ACC: also accumulate sum(y) per item (weight bias correction).
-template <int VEC, int LEAF, bool ACC>
-__device__ void phase_apply(const FusedArgs& A, PhaseSmem& sm, bool reverse) {
-  unsigned long long it;
-  const bool per_group = (A.scope == FQB200_SCOPE_GROUP);
-  for (bool ok = next_item(A.geo, it, reverse, true); ok; ok = next_item(A.geo, it, reverse, false)) {
-    const unsigned g = static_cast<unsigned>(it % A.geo.groups);
-    const float4 raw = ld_ws(reinterpret_cast<const float4*>(A.lp) + (per_group ? g : 0u));
-    LeafParam q;
-    q.a = raw.x;
-    q.b = raw.y;
-    q.c = raw.z;
-    q.flags = __float_as_int(raw.w);
-    const Divisor dv = make_divisor(q.a);
-    double sy = 0.0;
-    float* out = A.out;
-    float* grid_out = A.grid_out;
-    const float* noise = A.noise;
-    if constexpr (VEC == 4) {
-      walk_item<4>(A.geo, A.in, it, [&](const float4& x, unsigned long long off) {
-        float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (LEAF == FQB200_LEAF_COMPILED && noise) nz = ld_tensor(reinterpret_cast<const float4*>(noise) + off);
-        float4 y, gq;
-        y.x = leaf_apply<LEAF>(x.x, q, dv, nz.x, gq.x);
-        y.y = leaf_apply<LEAF>(x.y, q, dv, nz.y, gq.y);
-        y.z = leaf_apply<LEAF>(x.z, q, dv, nz.z, gq.z);
-        y.w = leaf_apply<LEAF>(x.w, q, dv, nz.w, gq.w);
-        st_tensor(reinterpret_cast<float4*>(out) + off, y);
-        if (grid_out) st_tensor(reinterpret_cast<float4*>(grid_out) + off, gq);
-        if (ACC) sy += static_cast<double>(__fadd_rn(__fadd_rn(y.x, y.y), __fadd_rn(y.z, y.w)));
-      });
-    } else {
-      walk_item<1>(A.geo, A.in, it, [&](float x, unsigned long long off) {
-        float nz = 0.f;
-        if (LEAF == FQB200_LEAF_COMPILED && noise) nz = ld_tensor(noise + off);
-        float gq;
-        const float y = leaf_apply<LEAF>(x, q, dv, nz, gq);
-        st_tensor(out + off, y);
-        if (grid_out) st_tensor(grid_out + off, gq);
-        if (ACC) sy += static_cast<double>(y);
-      });
-    }
-    if (ACC) {
-      sy = warp_reduce(sy, OpAdd());
-      __syncthreads();
-      if ((threadIdx.x & 31) == 0) sm.d0[threadIdx.x >> 5] = sy;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        for (int w = 1; w < kWarps; ++w) sy += sm.d0[w];
-        const size_t slot = static_cast<size_t>(it);  // it = p * G + g: the leader reads [p][g]
-        st_ws(A.psum + slot, sy);
-      }
-    }
+__device__ __forceinline__ LeafParam load_leaf_param(const LeafParam* lp, unsigned idx) {
+  const float4 raw = ld_ws(reinterpret_cast<const float4*>(lp) + idx);
+  LeafParam q;
+  q.a = raw.x;
+  q.b = raw.y;
+  q.c = raw.z;
+  q.flags = __float_as_int(raw.w);
+  return q;
+}
+
+// the apply loop over one segment; ACC: also accumulate sum(y) (weight bias correction); GRID: also store the
+// integer grid.  `bias` is 0 when there is none (x + 0 only turns -0 into +0, which quantizes identically).
+template <int VEC, int LEAF, bool ACC, bool REV, bool FAST, bool GRID>
+__device__ __forceinline__ void apply_segment_v(const FusedArgs& A, unsigned g, unsigned long long vb, unsigned len,
+                                                const LeafParam& q, const Divisor& dv, float bias, double& sy) {
+  float* out = A.out;
+  float* grid_out = A.grid_out;
+  if constexpr (VEC == 4) {
+    walk4<kUnrollApply, REV>(A.geo, A.in, g, vb, len, [&](float4 x, unsigned off) {
+      float4 y, gq;
+      y.x = leaf_apply<LEAF, FAST>(__fadd_rn(x.x, bias), q, dv, 0.f, gq.x);
+      y.y = leaf_apply<LEAF, FAST>(__fadd_rn(x.y, bias), q, dv, 0.f, gq.y);
+      y.z = leaf_apply<LEAF, FAST>(__fadd_rn(x.z, bias), q, dv, 0.f, gq.z);
+      y.w = leaf_apply<LEAF, FAST>(__fadd_rn(x.w, bias), q, dv, 0.f, gq.w);
+      st_tensor(reinterpret_cast<float4*>(out) + off, y);
+      if (GRID) st_tensor(reinterpret_cast<float4*>(grid_out) + off, gq);
+      if (ACC) sy += static_cast<double>(__fadd_rn(__fadd_rn(y.x, y.y), __fadd_rn(y.z, y.w)));
+    });
+  } else {
+    walk_segment<1, kUnrollApply, REV>(A.geo, A.in, g, vb, len, [&](float x, unsigned off) {
+      float gq;
+      const float y = leaf_apply<LEAF, FAST>(__fadd_rn(x, bias), q, dv, 0.f, gq);
+      st_tensor(out + off, y);
+      if (GRID) st_tensor(grid_out + off, gq);
+      if (ACC) sy += static_cast<double>(y);
+    });
   }
 }
 
-// C0: sum (y - mean_q)^2 per item (variance correction needs std(w_q))
-template <int VEC>
-__device__ void phase_corr_var(const FusedArgs& A, PhaseSmem& sm, bool reverse) {
-  unsigned long long it;
-  for (bool ok = next_item(A.geo, it, reverse, true); ok; ok = next_item(A.geo, it, reverse, false)) {
-    const float mu = ld_ws(A.cq + (it % A.geo.groups));
-    double sq = 0.0;
-    if constexpr (VEC == 4) {
-      walk_item<4>(A.geo, A.out, it, [&](const float4& y, unsigned long long) {
-        const float d0 = __fsub_rn(y.x, mu), d1 = __fsub_rn(y.y, mu), d2 = __fsub_rn(y.z, mu), d3 = __fsub_rn(y.w, mu);
-        sq += static_cast<double>(__fmaf_rn(d3, d3, __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)))));
-      });
-    } else {
-      walk_item<1>(A.geo, A.out, it, [&](float y, unsigned long long) {
-        const float d = __fsub_rn(y, mu);
-        sq += static_cast<double>(__fmul_rn(d, d));
-      });
+template <int VEC, int LEAF, bool ACC, bool REV, bool GRID>
+__device__ __forceinline__ void apply_segment(const FusedArgs& A, unsigned g, unsigned long long vb, unsigned len,
+                                              const LeafParam& q, double& sy) {
+  const Divisor dv = make_divisor(q.a);
+  const float bias = A.bias ? __ldg(A.bias + g) : 0.f;
+  if (dv.fast)
+    apply_segment_v<VEC, LEAF, ACC, REV, true, GRID>(A, g, vb, len, q, dv, bias, sy);
+  else
+    apply_segment_v<VEC, LEAF, ACC, REV, false, GRID>(A, g, vb, len, q, dv, bias, sy);
+}
+
+// A: quantize - clip - dequantize with the solved per-group (or per-tensor) parameters.
+template <int VEC, int LEAF, bool ACC, bool REV>
+__device__ void phase_apply(const FusedArgs& A, PhaseSmem& sm) {
+  const bool per_group = (A.scope == FQB200_SCOPE_GROUP);
+  for_each_segment(A.geo, REV, [&](unsigned g, unsigned p, unsigned long long vb, unsigned len) {
+    const LeafParam q = load_leaf_param(A.lp, per_group ? g : 0u);
+    double sy = 0.0, unused = 0.0;
+    apply_segment<VEC, LEAF, ACC, REV, false>(A, g, vb, len, q, sy);
+    if (ACC) {
+      float f0 = 0.f, f1 = 0.f;
+      block_combine(sm, f0, f1, sy, unused, false, false);
+      if (threadIdx.x == 0) st_ws(A.psum + partial_slot(A.geo, p, blockIdx.x, g), sy);
     }
-    sq = warp_reduce(sq, OpAdd());
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sm.d0[threadIdx.x >> 5] = sq;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < kWarps; ++w) sq += sm.d0[w];
-      const size_t slot = static_cast<size_t>(it);  // it = p * G + g: the leader reads [p][g]
-      st_ws(A.psq + slot, sq);
-    }
-  }
+  });
 }
 
 // C1: y <- (y - m_q) * k + m_q  (variance), then y <- y - m_q + m_o  (mean); inference_quantization_manager.py:386-391
-template <int VEC>
-__device__ void phase_corr_apply(const FusedArgs& A, bool reverse) {
-  unsigned long long it;
-  for (bool ok = next_item(A.geo, it, reverse, true); ok; ok = next_item(A.geo, it, reverse, false)) {
-    const unsigned g = static_cast<unsigned>(it % A.geo.groups);
+template <int VEC, bool REV>
+__device__ void phase_corr_apply(const FusedArgs& A) {
+  for_each_segment(A.geo, REV, [&](unsigned g, unsigned p, unsigned long long vb, unsigned len) {
     const float mq = ld_ws(A.cq + g), mo = ld_ws(A.co + g);
     const float kv = A.var_corr ? ld_ws(A.ck + g) : 1.f;
     const bool vc = A.var_corr != 0, bc = A.bias_corr != 0;
@@ -590,43 +619,42 @@ __device__ void phase_corr_apply(const FusedArgs& A, bool reverse) {
       return y;
     };
     if constexpr (VEC == 4) {
-      walk_item<4>(A.geo, A.out, it, [&](const float4& y, unsigned long long off) {
+      walk4<kUnrollApply, REV>(A.geo, A.out, g, vb, len, [&](float4 y, unsigned off) {
         st_tensor(reinterpret_cast<float4*>(out) + off, make_float4(fix(y.x), fix(y.y), fix(y.z), fix(y.w)));
       });
     } else {
-      walk_item<1>(A.geo, A.out, it, [&](float y, unsigned long long off) { st_tensor(out + off, fix(y)); });
+      walk_segment<1, kUnrollApply, REV>(A.geo, A.out, g, vb, len, [&](float y, unsigned off) { st_tensor(out + off, fix(y)); });
     }
-  }
-}
-
-template <int VEC, bool ACC>
-__device__ __forceinline__ void dispatch_apply(const FusedArgs& A, PhaseSmem& sm, bool reverse) {
-  switch (A.leaf) {
-    case FQB200_LEAF_TORCH: phase_apply<VEC, FQB200_LEAF_TORCH, ACC>(A, sm, reverse); break;
-    case FQB200_LEAF_COMPILED: phase_apply<VEC, FQB200_LEAF_COMPILED, ACC>(A, sm, reverse); break;
-    default: phase_apply<VEC, FQB200_LEAF_MIDTREAD, ACC>(A, sm, reverse); break;
-  }
+  });
 }
 
 // ------------------------------------------------------------------------------------------------
 // the fused persistent kernel (cooperative launch: every CTA is resident)
 // ------------------------------------------------------------------------------------------------
-template <int VEC>
+// One instantiation per (vector width, leaf, second statistics pass?, weight correction?) so that each kernel holds
+// only the loops it runs.  Phase directions: S1 forward, S2 backward, A forward again (backward when there is no S2):
+// each phase starts on the bytes the previous one touched last, which are still in L2.
+template <int VEC, int LEAF, bool DEV, bool CORR>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __grid_constant__ FusedArgs A) {
   __shared__ PhaseSmem psm;
   __shared__ LeaderSmem lsm;
   unsigned epoch = 0;
   const Geometry& geo = A.geo;
   const double n = A.n_per_group;
-  bool rev = false;
 
   // ---- S1
-  phase_stats1<VEC>(A, psm, rev);
-  rev = !rev;
+  if (blockIdx.x == 0) stamp(A, 0);
+  phase_stats1<VEC, false>(A, psm);
+  if (blockIdx.x == 0) stamp(A, 1);
+  stamp(A, 16 + 4 * blockIdx.x);
+  if (A.dbg && threadIdx.x == 0) {
+    unsigned sm;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    A.dbg[16 + 4 * blockIdx.x + 3] = sm;
+  }
   if (grid_arrive(A.sync, epoch, &lsm.flag)) {
-    reduce_partials(A.pmin, A.gmin, geo, INFINITY, OpMin());
-    reduce_partials(A.pmax, A.gmax, geo, -INFINITY, OpMax());
-    reduce_partials(A.psum, A.gmean_d, geo, 0.0, OpAdd());
+    stamp(A, 2);
+    reduce_partials3(geo, A.pmin, A.gmin, INFINITY, OpMin(), A.pmax, A.gmax, -INFINITY, OpMax(), A.psum, A.gmean_d, 0.0, OpAdd());
     __syncthreads();
     for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) {
       const double m = A.gmean_d[g] / n;
@@ -634,48 +662,50 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
       A.gmean[g] = static_cast<float>(m);
     }
     __syncthreads();
-    if (!A.need_dev) solve_params(A, lsm);
+    if (!DEV) solve_params(A, lsm);
+    stamp(A, 3);
     grid_release(A.sync, epoch);
   }
+  if (blockIdx.x == 0) stamp(A, 4);
 
   // ---- S2
-  if (A.need_dev) {
-    phase_stats2<VEC>(A, psm, rev);
-    rev = !rev;
+  if constexpr (DEV) {
+    phase_stats2<VEC, true>(A, psm, A.in, A.gmean, true, A.pabs, A.psq);
+    if (blockIdx.x == 0) stamp(A, 5);
+    stamp(A, 16 + 4 * blockIdx.x + 1);
     if (grid_arrive(A.sync, epoch, &lsm.flag)) {
-      // reuse gb / gstd as fp32 results; accumulate through double temporaries in cq/co-free space: psum is free now
-      double* tmp = A.psum;  // [items] >= [G]
-      reduce_partials(A.pabs, tmp, geo, 0.0, OpAdd());
-      __syncthreads();
-      for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) A.gb[g] = static_cast<float>(tmp[g] / n);
-      __syncthreads();
-      reduce_partials(A.psq, tmp, geo, 0.0, OpAdd());
+      stamp(A, 6);
+      double* tabs = A.psum;              // [>= G] free now
+      double* tsq = A.psum + geo.groups;  // psum holds slots + 2G doubles
+      reduce_partials3(geo, A.pabs, tabs, 0.0, OpAdd(), A.psq, tsq, 0.0, OpAdd(), static_cast<const double*>(nullptr),
+                       static_cast<double*>(nullptr), 0.0, OpAdd());
       __syncthreads();
       for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) {
+        A.gb[g] = static_cast<float>(tabs[g] / n);
         // sum (x - mu32)^2 -> sum (x - mu)^2 with the exact mean; unbiased (torch.std default)
         const double dm = A.gmean_d[g] - static_cast<double>(A.gmean[g]);
-        double ss = tmp[g] - n * dm * dm;
+        double ss = tsq[g] - n * dm * dm;
         if (ss < 0.0) ss = 0.0;
         A.gstd[g] = static_cast<float>(sqrt(ss / (n - 1.0)));
       }
       __syncthreads();
       solve_params(A, lsm);
+      stamp(A, 7);
       grid_release(A.sync, epoch);
     }
+    if (blockIdx.x == 0) stamp(A, 8);
   }
 
   // ---- A (+ C)
   if (!A.stats_only) {
-    const bool corr = (A.bias_corr || A.var_corr);
-    if (corr)
-      dispatch_apply<VEC, true>(A, psm, rev);
-    else
-      dispatch_apply<VEC, false>(A, psm, rev);
-    rev = !rev;
-    if (corr) {
+    phase_apply<VEC, LEAF, CORR, !DEV>(A, psm);
+    if (blockIdx.x == 0) stamp(A, 9);
+    stamp(A, 16 + 4 * blockIdx.x + 2);
+    if constexpr (CORR) {
       if (grid_arrive(A.sync, epoch, &lsm.flag)) {
         double* tmp = A.pabs;
-        reduce_partials(A.psum, tmp, geo, 0.0, OpAdd());
+        reduce_partials3(geo, A.psum, tmp, 0.0, OpAdd(), static_cast<const double*>(nullptr), static_cast<double*>(nullptr), 0.0,
+                         OpAdd(), static_cast<const double*>(nullptr), static_cast<double*>(nullptr), 0.0, OpAdd());
         __syncthreads();
         for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) {
           A.cq[g] = static_cast<float>(tmp[g] / n);
@@ -684,50 +714,61 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
         grid_release(A.sync, epoch);
       }
       if (A.var_corr) {
-        phase_corr_var<VEC>(A, psm, rev);
-        rev = !rev;
+        phase_stats2<VEC, false>(A, psm, A.out, A.cq, false, nullptr, A.psq);
         if (grid_arrive(A.sync, epoch, &lsm.flag)) {
           double* tmp = A.pabs;
-          reduce_partials(A.psq, tmp, geo, 0.0, OpAdd());
+          reduce_partials3(geo, A.psq, tmp, 0.0, OpAdd(), static_cast<const double*>(nullptr), static_cast<double*>(nullptr), 0.0,
+                           OpAdd(), static_cast<const double*>(nullptr), static_cast<double*>(nullptr), 0.0, OpAdd());
           __syncthreads();
           for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) {
-            // tmp = sum (y - fl32(mean_q))^2 ; treat fl32(mean_q) as the mean (error O(ulp^2))
+            // tmp = sum (y - fl32(mean_q))^2 ; fl32(mean_q) stands in for the mean (error O(ulp^2))
             const float sdq = static_cast<float>(sqrt(tmp[g] / (n - 1.0)));
             A.ck[g] = __fdiv_rn(A.gstd[g], __fadd_rn(sdq, 1e-8f));
           }
           grid_release(A.sync, epoch);
         }
       }
-      phase_corr_apply<VEC>(A, rev);
+      phase_corr_apply<VEC, false>(A);
     }
   }
   grid_exit(A.sync);
 }
 
 // Standalone a1 with host-side scalars (gemmlowp.cu:30-45): flat grid-stride, parameters by value.
-template <int VEC>
+template <int VEC, bool NOISE, bool FAST>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     fq_leaf_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ noise,
                    unsigned long long nvec, LeafParam q) {
   using V = typename VecT<VEC>::type;
   const Divisor dv = make_divisor(q.a);
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kThreads;
-  for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * kThreads + threadIdx.x; i < nvec; i += stride) {
-    float gq;
-    if constexpr (VEC == 4) {
-      const float4 x = ld_tensor(reinterpret_cast<const float4*>(in) + i);
-      float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (noise) nz = ld_tensor(reinterpret_cast<const float4*>(noise) + i);
-      float4 y;
-      y.x = leaf_apply<FQB200_LEAF_COMPILED>(x.x, q, dv, nz.x, gq);
-      y.y = leaf_apply<FQB200_LEAF_COMPILED>(x.y, q, dv, nz.y, gq);
-      y.z = leaf_apply<FQB200_LEAF_COMPILED>(x.z, q, dv, nz.z, gq);
-      y.w = leaf_apply<FQB200_LEAF_COMPILED>(x.w, q, dv, nz.w, gq);
-      st_tensor(reinterpret_cast<float4*>(out) + i, y);
-    } else {
-      const float x = ld_tensor(in + i);
-      const float nz = noise ? ld_tensor(noise + i) : 0.f;
-      st_tensor(out + i, leaf_apply<FQB200_LEAF_COMPILED>(x, q, dv, nz, gq));
+  unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * kThreads + threadIdx.x;
+  constexpr int U = 4;
+  for (; i < nvec; i += U * stride) {
+    V x[U], nz[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      ok[u] = i + u * stride < nvec;
+      if (ok[u]) {
+        x[u] = ld_tensor(reinterpret_cast<const V*>(in) + i + u * stride);
+        if (NOISE) nz[u] = ld_tensor(reinterpret_cast<const V*>(noise) + i + u * stride);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      float gq;
+      if constexpr (VEC == 4) {
+        float4 y;
+        y.x = leaf_apply<FQB200_LEAF_COMPILED, FAST, NOISE>(x[u].x, q, dv, NOISE ? nz[u].x : 0.f, gq);
+        y.y = leaf_apply<FQB200_LEAF_COMPILED, FAST, NOISE>(x[u].y, q, dv, NOISE ? nz[u].y : 0.f, gq);
+        y.z = leaf_apply<FQB200_LEAF_COMPILED, FAST, NOISE>(x[u].z, q, dv, NOISE ? nz[u].z : 0.f, gq);
+        y.w = leaf_apply<FQB200_LEAF_COMPILED, FAST, NOISE>(x[u].w, q, dv, NOISE ? nz[u].w : 0.f, gq);
+        st_tensor(reinterpret_cast<float4*>(out) + i + u * stride, y);
+      } else {
+        st_tensor(out + i + u * stride, leaf_apply<FQB200_LEAF_COMPILED, FAST, NOISE>(x[u], q, dv, NOISE ? nz[u] : 0.f, gq));
+      }
     }
   }
 }
@@ -737,34 +778,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 // (a few CTA-uniform flops), so nothing is synchronised with the host.
 template <int VEC, int LEAF>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_given_kernel(const __grid_constant__ FusedArgs A) {
-  unsigned long long it;
-  for (bool ok = next_item(A.geo, it, false, true); ok; ok = next_item(A.geo, it, false, false)) {
-    const unsigned g = static_cast<unsigned>(it % A.geo.groups);
+  for_each_segment(A.geo, false, [&](unsigned g, unsigned p, unsigned long long vb, unsigned len) {
+    (void)p;
     const unsigned pi = A.given_per_group ? g : 0u;
     const float bits = A.g_bits ? __ldg(A.g_bits + g) : static_cast<float>(A.num_bits);
     const LeafParam q = make_leaf_param(LEAF, __ldg(A.g_delta + pi), __ldg(A.g_offset + pi), bits);
-    const Divisor dv = make_divisor(q.a);
-    float* out = A.out;
-    float* grid_out = A.grid_out;
-    if constexpr (VEC == 4) {
-      walk_item<4>(A.geo, A.in, it, [&](const float4& x, unsigned long long off) {
-        float4 y, gq;
-        y.x = leaf_apply<LEAF>(x.x, q, dv, 0.f, gq.x);
-        y.y = leaf_apply<LEAF>(x.y, q, dv, 0.f, gq.y);
-        y.z = leaf_apply<LEAF>(x.z, q, dv, 0.f, gq.z);
-        y.w = leaf_apply<LEAF>(x.w, q, dv, 0.f, gq.w);
-        st_tensor(reinterpret_cast<float4*>(out) + off, y);
-        if (grid_out) st_tensor(reinterpret_cast<float4*>(grid_out) + off, gq);
-      });
-    } else {
-      walk_item<1>(A.geo, A.in, it, [&](float x, unsigned long long off) {
-        float gq;
-        const float y = leaf_apply<LEAF>(x, q, dv, 0.f, gq);
-        st_tensor(out + off, y);
-        if (grid_out) st_tensor(grid_out + off, gq);
-      });
-    }
-  }
+    double sy = 0.0;
+    if (A.grid_out)
+      apply_segment<VEC, LEAF, false, false, true>(A, g, vb, len, q, sy);
+    else
+      apply_segment<VEC, LEAF, false, false, false>(A, g, vb, len, q, sy);
+  });
 }
 
 // test hook: q[i] = div_exact(a[i], b[i]) next to IEEE a[i]/b[i]
@@ -772,7 +796,7 @@ __global__ void fq_divtest_kernel(const float* a, const float* b, float* fast, f
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
   for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const Divisor dv = make_divisor(b[i]);
-    fast[i] = div_exact(a[i], dv);
+    fast[i] = dv.fast ? div_exact<true>(a[i], dv) : div_exact<false>(a[i], dv);
     ieee[i] = __fdiv_rn(a[i], b[i]);
   }
 }
@@ -785,6 +809,7 @@ __global__ void fq_divtest_kernel(const float* a, const float* b, float* fast, f
 namespace {
 
 thread_local char g_err[512] = "";
+unsigned long long* g_dbg_timing = nullptr;  // development: see fqb200_debug_timing
 
 int fail(int code, const char* fmt, const char* detail = "") {
   snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -798,6 +823,28 @@ struct DeviceInfo {
   bool tables = false;
 };
 DeviceInfo g_dev[64];
+
+// dynamic shared memory of a launch: the cp.async ring of the 128-bit path
+size_t dyn_smem(int vec) { return (FQB_ASYNC && vec == 4) ? static_cast<size_t>(fqb::kRingBytes) : 0; }
+
+// the 24 instantiations of the fused kernel: (VEC 4|1) x (leaf 0..2) x (second statistics pass) x (weight correction)
+template <int VEC, int LEAF>
+const void* fused_ptr2(bool dev, bool corr) {
+  if (dev) return corr ? reinterpret_cast<const void*>(fqb::fq_fused_kernel<VEC, LEAF, true, true>)
+                       : reinterpret_cast<const void*>(fqb::fq_fused_kernel<VEC, LEAF, true, false>);
+  return corr ? reinterpret_cast<const void*>(fqb::fq_fused_kernel<VEC, LEAF, false, true>)
+              : reinterpret_cast<const void*>(fqb::fq_fused_kernel<VEC, LEAF, false, false>);
+}
+const void* fused_kernel_ptr(int vec, int leaf, bool dev, bool corr) {
+  if (vec == 4) {
+    if (leaf == FQB200_LEAF_TORCH) return fused_ptr2<4, FQB200_LEAF_TORCH>(dev, corr);
+    if (leaf == FQB200_LEAF_COMPILED) return fused_ptr2<4, FQB200_LEAF_COMPILED>(dev, corr);
+    return fused_ptr2<4, FQB200_LEAF_MIDTREAD>(dev, corr);
+  }
+  if (leaf == FQB200_LEAF_TORCH) return fused_ptr2<1, FQB200_LEAF_TORCH>(dev, corr);
+  if (leaf == FQB200_LEAF_COMPILED) return fused_ptr2<1, FQB200_LEAF_COMPILED>(dev, corr);
+  return fused_ptr2<1, FQB200_LEAF_MIDTREAD>(dev, corr);
+}
 
 // optimum of 2*exp(-a) + a^2/(3 w^2): a*exp(a) = 3 w^2 (Lambert W), Newton in float64.  The reference gets the
 // same numbers from scipy's Brent minimiser (int_quantizer.py:48) to ~1e-8.
@@ -827,13 +874,23 @@ int get_device(DeviceInfo** out) {
     int sms = 0, per_sm = 0;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fqb::fq_fused_kernel<4>, fqb::kThreads, 0);
-    if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
-    int per_sm1 = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, fqb::fq_fused_kernel<1>, fqb::kThreads, 0);
-    if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
-    if (per_sm1 < per_sm) per_sm = per_sm1;
+    per_sm = 1 << 20;
+    for (int v = 0; v < 24; ++v) {
+      int n = 0;
+      const int vw = (v & 1) ? 1 : 4;
+      const void* fn = fused_kernel_ptr(vw, (v >> 1) % 3, (v / 6) & 1, v / 12);
+      if (vw == 4) {
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem(4));
+        if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      }
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kThreads, dyn_smem(vw));
+      if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+      if (n < per_sm) per_sm = n;
+    }
     if (per_sm < 1) return fail(FQB200_ERR_CUDA, "fused kernel does not fit on an SM%s");
+    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH>),
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem(4));
+    if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     // mid-tread table (int_quantizer.py:41-51): omega grid = 5 decades x 20 steps, leading 0
     double om[fqb::kTable], al[fqb::kTable];
     om[0] = 0.0;
@@ -864,74 +921,68 @@ struct Plan {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// Choose vector width, parts per group and grid size.
-int make_plan(int64_t outer, int64_t groups, int64_t inner, bool can_vec, int resident, Plan* pl) {
+// Choose vector width, slab count and grid size; fill the geometry.
+int make_plan(int64_t outer, int64_t groups, int64_t inner, bool can_vec, int max_ctas, Plan* pl) {
   if (outer <= 0 || groups <= 0 || inner <= 0) return fail(FQB200_ERR_INVALID, "non-positive tensor extent%s");
-  if (groups > 0x7fffffffLL || outer > 0x7fffffffLL || inner > 0x7fffffffLL * 4LL)
+  if (groups > 0x3fffffffLL || outer > 0x7fffffffLL || inner > 0x7fffffffLL * 4LL)
     return fail(FQB200_ERR_UNSUPPORTED, "tensor extent exceeds 2^31%s");
   const int vec = (can_vec && inner % 4 == 0) ? 4 : 1;
   const uint64_t inner_v = static_cast<uint64_t>(inner / vec);
   if (inner_v > 0xffffffffULL) return fail(FQB200_ERR_UNSUPPORTED, "row too long%s");
+  const uint64_t G = static_cast<uint64_t>(groups);
   const uint64_t group_v = static_cast<uint64_t>(outer) * inner_v;
-  const uint64_t total_v = group_v * static_cast<uint64_t>(groups);
-  // item size target: >= ~64 KB per item when the tensor allows, ~8 items per CTA for balance
-  const uint64_t min_item_v = (64u * 1024u) / (4u * vec) * 1u;  // vectors
-  uint64_t want_items = static_cast<uint64_t>(resident) * 8u;
-  uint64_t max_items = total_v / min_item_v;
-  if (max_items < 1) max_items = 1;
-  if (want_items > max_items) want_items = max_items;
-  uint64_t parts = (want_items + groups - 1) / static_cast<uint64_t>(groups);
-  if (parts < 1) parts = 1;
-  // never split finer than one CTA sweep per item, and keep item length < 2^31
-  uint64_t max_parts = group_v / static_cast<uint64_t>(fqb::kThreads);
-  if (max_parts < 1) max_parts = 1;
-  if (parts > max_parts) parts = max_parts;
-  // balance: prefer a part count that makes groups*parts a near multiple of the resident CTA count
-  uint64_t best = parts;
-  double best_eff = 0.0;
-  for (uint64_t p = parts; p <= parts * 2 && p <= max_parts; ++p) {
-    const uint64_t items = p * static_cast<uint64_t>(groups);
-    const uint64_t waves = (items + resident - 1) / resident;
-    const double eff = static_cast<double>(items) / static_cast<double>(waves * resident);
-    if (eff > best_eff + 1e-9) {
-      best_eff = eff;
-      best = p;
-    }
-    if (items < static_cast<uint64_t>(resident)) break;
-  }
-  parts = best;
-  while ((group_v + parts - 1) / parts >= 0x7fffffffULL) ++parts;
+  const uint64_t total_v = group_v * G;
+  if (total_v >= (1ULL << 32)) return fail(FQB200_ERR_UNSUPPORTED, "tensors of 2^32 vectors (64 GB) and more are not supported%s");
+  // every CTA gets the same share; at least ~32 KB each so small tensors use fewer CTAs (cheaper barriers)
+  const uint64_t min_chunk_v = (32u * 1024u) / (4u * vec);
+  uint64_t grid = (total_v + min_chunk_v - 1) / min_chunk_v;
+  if (grid > static_cast<uint64_t>(max_ctas)) grid = static_cast<uint64_t>(max_ctas);
+  if (grid < 1) grid = 1;
+  // slabs: keep what the CTAs touch concurrently inside ~slab_mb of memory; a slab is a range of `outer`
+  static const uint64_t slab_mb = getenv("FQB_SLAB_MB") ? strtoull(getenv("FQB_SLAB_MB"), nullptr, 10) : 256;  // development knob
+  const uint64_t bytes = total_v * 4u * vec;
+  uint64_t slabs = (bytes + (slab_mb << 20) - 1) / (slab_mb << 20);
+  if (slabs < 1) slabs = 1;
+  if (slabs > static_cast<uint64_t>(outer)) slabs = static_cast<uint64_t>(outer);
+  if (slabs > 64) slabs = 64;
+  while ((total_v / slabs + grid - 1) / grid >= 0x7fffffffULL) ++slabs;  // segment lengths are 32-bit
+  // how many CTAs can overlap one group inside a slab: ceil(slab_len / chunk) + 1
+  const uint64_t slab_len = (group_v + slabs - 1) / slabs;
+  const uint64_t chunk = (slab_len * G) / grid > 0 ? (slab_len * G) / grid : 1;
+  const uint64_t overlap = ((slab_len + chunk - 1) / chunk + 1) * 1;
+  unsigned lanes = 1;
+  while (lanes < overlap && lanes < 32) lanes <<= 1;
   fqb::Geometry& g = pl->geo;
   g.groups = static_cast<unsigned>(groups);
-  g.parts = static_cast<unsigned>(parts);
+  g.slabs = static_cast<unsigned>(slabs);
   g.inner_v = static_cast<unsigned>(inner_v);
   g.step_q = static_cast<unsigned>(fqb::kThreads / inner_v);
   g.step_r = static_cast<unsigned>(fqb::kThreads % inner_v);
+  g.red_lanes = lanes;
   g.group_v = group_v;
-  g.row_pitch = static_cast<uint64_t>(groups) * inner_v;
-  g.items = parts * static_cast<uint64_t>(groups);
+  g.row_pitch = G * inner_v;
   pl->vec = vec;
-  pl->grid = static_cast<int>(g.items < static_cast<uint64_t>(resident) ? g.items : static_cast<uint64_t>(resident));
+  pl->grid = static_cast<int>(grid);
   return FQB200_OK;
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// workspace layout; returns total bytes, fills pointers when base != nullptr
-size_t carve(char* base, uint64_t items, uint64_t groups, fqb::FusedArgs* A) {
+// workspace layout; returns total bytes, fills pointers when base != nullptr.  Partials: slabs * (ctas + groups) slots.
+size_t carve(char* base, uint64_t slabs_x_ctas, uint64_t slabs, uint64_t groups, fqb::FusedArgs* A) {
   size_t off = 0;
   auto take = [&](size_t bytes) {
     char* p = base ? base + off : nullptr;
     off = align_up(off + bytes, 256);
     return p;
   };
+  const uint64_t slots = slabs_x_ctas + slabs * groups;
   char* sync = take(sizeof(fqb::GridSync));
-  char* pmin = take(items * sizeof(float));
-  char* pmax = take(items * sizeof(float));
-  const uint64_t dn = items > groups ? items : groups;
-  char* psum = take(dn * sizeof(double));
-  char* pabs = take(dn * sizeof(double));
-  char* psq = take(dn * sizeof(double));
+  char* pmin = take(slots * sizeof(float));
+  char* pmax = take(slots * sizeof(float));
+  char* psum = take((slots + 2 * groups) * sizeof(double));
+  char* pabs = take((slots + 2 * groups) * sizeof(double));
+  char* psq = take((slots + 2 * groups) * sizeof(double));
   char* gf = take(groups * sizeof(float) * 12);
   char* gd = take(groups * sizeof(double));
   char* lp = take(groups * sizeof(fqb::LeafParam));
@@ -992,16 +1043,15 @@ int fqb200_resident_ctas(void) {
 
 size_t fqb200_workspace_bytes(const fqb200_desc* d) {
   if (check_desc(d) != FQB200_OK) return 0;
-  // plan-independent upper bound: items <= resident*16 + groups
-  int resident = 148 * fqb::kCtasPerSm;
+  if (d->outer <= 0 || d->groups <= 0 || d->inner <= 0) return 256;
+  int resident = 148 * fqb::kCtasPerSm;  // without a device (build container) assume a B200
   DeviceInfo* di = nullptr;
   if (get_device(&di) == FQB200_OK) resident = di->resident;
-  Plan pl;
-  if (make_plan(d->outer, d->groups, d->inner, true, resident, &pl) != FQB200_OK) return 0;
-  Plan pl1;
-  if (make_plan(d->outer, d->groups, d->inner, false, resident, &pl1) != FQB200_OK) return 0;
-  const uint64_t items = pl.geo.items > pl1.geo.items ? pl.geo.items : pl1.geo.items;
-  return carve(nullptr, items, static_cast<uint64_t>(d->groups), nullptr);
+  Plan a, b;
+  if (make_plan(d->outer, d->groups, d->inner, true, resident, &a) != FQB200_OK) return 0;
+  if (make_plan(d->outer, d->groups, d->inner, false, resident, &b) != FQB200_OK) return 0;
+  const uint64_t slabs = a.geo.slabs > b.geo.slabs ? a.geo.slabs : b.geo.slabs;
+  return carve(nullptr, slabs * static_cast<uint64_t>(resident), slabs, static_cast<uint64_t>(d->groups), nullptr);
 }
 
 int fqb200_workspace_init(void* workspace, size_t bytes, void* stream) {
@@ -1041,13 +1091,20 @@ int fqb200_float2gemmlowp(const float* in, float* out, int64_t n, float range, f
   q.flags = enforce_true_zero ? fqb::FLAG_TRUE_ZERO : 0;
   const bool vec = (n % 4 == 0) && aligned16(in) && aligned16(out) && (!noise || aligned16(noise));
   const unsigned long long nvec = vec ? static_cast<unsigned long long>(n / 4) : static_cast<unsigned long long>(n);
-  unsigned long long want = (nvec + fqb::kThreads - 1) / fqb::kThreads;
-  const unsigned long long cap = static_cast<unsigned long long>(di->resident) * 4ull;
+  unsigned long long want = (nvec + fqb::kThreads * 4ull - 1) / (fqb::kThreads * 4ull);
+  const unsigned long long cap = static_cast<unsigned long long>(di->resident) * 2ull;
   const int grid = static_cast<int>(want < cap ? want : cap);
-  if (vec)
-    fqb::fq_leaf_kernel<4><<<grid, fqb::kThreads, 0, st>>>(in, out, noise, nvec, q);
-  else
-    fqb::fq_leaf_kernel<1><<<grid, fqb::kThreads, 0, st>>>(in, out, noise, nvec, q);
+  const float as = fabsf(q.a);
+  const bool fast = (as > 1e-30f) && (as < 1e30f);
+#define FQB_LAUNCH_LEAF(V, N, F) fqb::fq_leaf_kernel<V, N, F><<<grid, fqb::kThreads, 0, st>>>(in, out, noise, nvec, q)
+  if (vec) {
+    if (noise) { if (fast) FQB_LAUNCH_LEAF(4, true, true); else FQB_LAUNCH_LEAF(4, true, false); }
+    else       { if (fast) FQB_LAUNCH_LEAF(4, false, true); else FQB_LAUNCH_LEAF(4, false, false); }
+  } else {
+    if (noise) { if (fast) FQB_LAUNCH_LEAF(1, true, true); else FQB_LAUNCH_LEAF(1, true, false); }
+    else       { if (fast) FQB_LAUNCH_LEAF(1, false, true); else FQB_LAUNCH_LEAF(1, false, false); }
+  }
+#undef FQB_LAUNCH_LEAF
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "launch fq_leaf_kernel: %s", cudaGetErrorString(e));
   return FQB200_OK;
@@ -1068,7 +1125,7 @@ int fqb200_quantize1(const float* in, float* out, float* grid, int64_t outer, in
   if (rc != FQB200_OK) return rc;
   Plan pl;
   const bool can_vec = aligned16(in) && aligned16(out) && (!grid || aligned16(grid));
-  rc = make_plan(outer, groups, inner, can_vec, di->resident * 4, &pl);
+  rc = make_plan(outer, groups, inner, can_vec, di->resident * 2, &pl);
   if (rc != FQB200_OK) return rc;
   fqb::FusedArgs A;
   memset(&A, 0, sizeof(A));
@@ -1084,7 +1141,7 @@ int fqb200_quantize1(const float* in, float* out, float* grid, int64_t outer, in
   A.given_per_group = per_group;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pl.vec == 4)
-    fqb::fq_given_kernel<4, FQB200_LEAF_TORCH><<<pl.grid, fqb::kThreads, 0, st>>>(A);
+    fqb::fq_given_kernel<4, FQB200_LEAF_TORCH><<<pl.grid, fqb::kThreads, dyn_smem(4), st>>>(A);
   else
     fqb::fq_given_kernel<1, FQB200_LEAF_TORCH><<<pl.grid, fqb::kThreads, 0, st>>>(A);
   cudaError_t e = cudaGetLastError();
@@ -1105,15 +1162,17 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   rc = get_device(&di);
   if (rc != FQB200_OK) return rc;
   Plan pl;
+  if (d->bias && d->scope == FQB200_SCOPE_GROUP_MEAN)
+    return fail(FQB200_ERR_UNSUPPORTED, "a per-group bias needs groups = channels (scope GROUP or TENSOR)%s");
   const bool can_vec = aligned16(in) && (d->stats_only || aligned16(out));
   rc = make_plan(d->outer, d->groups, d->inner, can_vec, di->resident, &pl);
   if (rc != FQB200_OK) return rc;
   fqb::FusedArgs A;
   memset(&A, 0, sizeof(A));
-  const size_t need = carve(nullptr, pl.geo.items, pl.geo.groups, nullptr);
+  const size_t need = carve(nullptr, static_cast<uint64_t>(pl.geo.slabs) * pl.grid, pl.geo.slabs, pl.geo.groups, nullptr);
   if (!workspace || workspace_bytes < need) return fail(FQB200_ERR_WORKSPACE, "workspace smaller than fqb200_workspace_bytes()%s");
   if (!aligned16(workspace)) return fail(FQB200_ERR_WORKSPACE, "workspace must be 16-byte aligned%s");
-  carve(static_cast<char*>(workspace), pl.geo.items, pl.geo.groups, &A);
+  carve(static_cast<char*>(workspace), static_cast<uint64_t>(pl.geo.slabs) * pl.grid, pl.geo.slabs, pl.geo.groups, &A);
   A.geo = pl.geo;
   A.in = in;
   A.out = out;
@@ -1134,6 +1193,8 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   A.var_corr = d->var_corr;
   A.stats_only = d->stats_only;
   A.out_stats = d->out_stats;
+  A.bias = d->bias;
+  A.dbg = g_dbg_timing;
   A.n_per_group = static_cast<double>(d->outer) * static_cast<double>(d->inner);
   const bool alloc = d->bit_alloc && d->num_bits <= 4 && d->scope == FQB200_SCOPE_GROUP && d->leaf != FQB200_LEAF_MIDTREAD;
   A.need_dev = (d->range_mode != FQB200_RANGE_MINMAX) || alloc || d->var_corr || d->leaf == FQB200_LEAF_MIDTREAD ||
@@ -1141,11 +1202,25 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   void* args[] = {&A};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-  if (pl.vec == 4)
-    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fqb::fq_fused_kernel<4>), dim3(pl.grid), dim3(fqb::kThreads), args, 0, st);
-  else
-    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fqb::fq_fused_kernel<1>), dim3(pl.grid), dim3(fqb::kThreads), args, 0, st);
+  e = cudaLaunchCooperativeKernel(fused_kernel_ptr(pl.vec, d->leaf, A.need_dev != 0, d->bias_corr || d->var_corr), dim3(pl.grid),
+                                  dim3(fqb::kThreads), args, dyn_smem(pl.vec), st);
   if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cooperative launch fq_fused_kernel: %s", cudaGetErrorString(e));
+  return FQB200_OK;
+}
+
+// development hook: device buffer of 16 u64 that the next fused launches stamp with %globaltimer at phase boundaries
+int fqb200_debug_timing(unsigned long long* dev_buf) {
+  g_dbg_timing = dev_buf;
+  return FQB200_OK;
+}
+
+// development hook (not part of the drop-in surface): the item shape make_plan picks for a layout
+int fqb200_debug_plan(int64_t outer, int64_t groups, int64_t inner, int max_ctas, int64_t* out6) {
+  Plan pl;
+  int rc = make_plan(outer, groups, inner, true, max_ctas, &pl);
+  if (rc != FQB200_OK) return rc;
+  out6[0] = pl.vec; out6[1] = pl.grid; out6[2] = pl.geo.slabs; out6[3] = pl.geo.red_lanes; out6[4] = 0;
+  out6[5] = 0;
   return FQB200_OK;
 }
 

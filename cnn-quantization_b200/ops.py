@@ -133,7 +133,7 @@ def quantize1(x, delta, offset, num_bits, bits=None, layout=None, want_grid=Fals
 def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH, num_bits=8,
           positive=False, solve_f64=False, clip_k=0.0, bit_alloc=False, bit_alloc_prior=L.PRIOR_STD,
           bit_alloc_round=True, bit_alloc_target=None, mt_target=0.0, mt_clip=False, bias_corr=False,
-          var_corr=False, stats_only=False, want_stats=False, out=None):
+          var_corr=False, stats_only=False, want_stats=False, out=None, bias=None):
     """C ABI fqb200_fused: statistics -> parameters -> quantize/dequantize in one launch.
 
     Returns ``out`` (or ``(out, stats)`` with ``want_stats``; ``stats`` alone with ``stats_only``), where
@@ -154,6 +154,14 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
     d.bit_alloc_target = float(bit_alloc_target if bit_alloc_target is not None else num_bits)
     d.mt_target, d.mt_clip = float(mt_target), int(bool(mt_clip))
     d.bias_corr, d.var_corr, d.stats_only = int(bool(bias_corr)), int(bool(var_corr)), int(bool(stats_only))
+    if bias is not None:
+        _require_cuda_f32(bias, "bias")
+        bias = bias.contiguous()
+        if bias.numel() != groups:
+            raise ValueError("bias must have one element per group (%d)" % groups)
+        d.bias = bias.data_ptr()
+    else:
+        d.bias = None
     stats = None
     if want_stats or stats_only:
         stats = torch.zeros((groups, L.STATS_STRIDE), dtype=torch.float32, device=dev)

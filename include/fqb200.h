@@ -95,8 +95,12 @@ typedef struct fqb200_desc {
   int32_t bias_corr; /* w_q <- w_q - mean(w_q) + mean(w) per group */
   int32_t var_corr;  /* w_q <- (w_q - mean(w_q)) * std(w)/(std(w_q)+1e-8) + mean(w_q), before bias_corr */
   int32_t stats_only; /* 1: compute statistics/parameters into out_stats, do not touch `out` */
-  float* out_stats;   /* optional device buffer, groups * FQB200_STATS_STRIDE floats (one row when the
-                         parameters are per tensor is NOT assumed: always `groups` rows) */
+  float* out_stats;   /* optional device buffer, groups * FQB200_STATS_STRIDE floats (rows beyond the first are
+                         left untouched when the parameters are per tensor) */
+  const float* bias;  /* optional device vector of `groups` floats added to every element of its group before
+                         anything else (x + bias[g], one fp32 rounding): the folded-BN convolution bias, so the
+                         caller can run its convolution bias-free and skip a full read+write pass over the
+                         activation.  NULL = none.  Not available with scope GROUP_MEAN. */
 } fqb200_desc;
 
 /* ---- library ---------------------------------------------------------------------------------- */
