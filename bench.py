@@ -256,7 +256,10 @@ def run_fqb200(args):
             "quant": {"gelem_per_s": quant_elems / (quant_ms / 1e3) / 1e9 if quant_ms else None,
                       "ms_per_step": quant_ms / args.steps, "share_of_step": quant_ms / ms,
                       "modes": {k: {"launches": v["launches"], "ms": v["ms"], "GBps": (v["bytes"] / 1e9) / (v["ms"] / 1e3) if v["ms"] else None}
-                                for k, v in prof["modes"].items()}},
+                                for k, v in prof["modes"].items()},
+                      "by_layout": {k: {"launches": v["launches"], "ms_avg": v["ms"] / v["launches"],
+                                        "frac": (v["bytes"] / 1e9) / (v["ms"] / 1e3) / peak if v["ms"] else None}
+                                    for k, v in sorted(prof["shapes"].items(), key=lambda kv: -kv[1]["ms"])}},
             "clocks": clocks,
             "check": {"loss": loss, "top1": top1, "top5": top5, "images": n_img},
         }

@@ -152,6 +152,7 @@ struct GridSync {
   unsigned release;
   unsigned exited;
   unsigned pad;
+  unsigned unit_counter[8];  // one dynamic work counter per streaming phase
 };
 
 // All threads of all CTAs call this.  Returns true in exactly one CTA (the last to arrive) WITHOUT
@@ -192,6 +193,7 @@ __device__ __forceinline__ void grid_exit(GridSync* gs) {
     if (prev + 1u == gridDim.x) {  // everyone is past the last wait: safe to re-arm
       gs->arrive = 0u;
       gs->release = 0u;
+      for (int i = 0; i < 8; ++i) gs->unit_counter[i] = 0u;
       __threadfence();
       gs->exited = 0u;
     }
@@ -199,23 +201,25 @@ __device__ __forceinline__ void grid_exit(GridSync* gs) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// geometry: the tensor as [outer][groups][inner]; slabs x balanced contiguous chunks
+// geometry: the tensor as [outer][groups][inner], cut into work units handed out dynamically
 // ------------------------------------------------------------------------------------------------
-// The vectors of every group are enumerated in (outer, inner) order: v in [0, group_v).  They are cut into P
-// "slabs" (slab p = v in [group_v*p/P, group_v*(p+1)/P), i.e. a range of the batch dimension); a slab is one
-// contiguous region of memory.  Inside slab p the index space (g, v) - group-major - is split into gridDim.x equal
-// contiguous chunks, one per CTA: every CTA streams the same number of bytes whatever C, N, H*W are, in at most a
-// couple of long segments (a chunk is cut only at group boundaries).  All CTAs work on the same slab at the same
-// time, so the union of their accesses stays inside a few hundred MB (DRAM-page / TLB friendly on GB-sized tensors).
-// Each (slab, CTA, group) segment yields one partial at slot p * (grid + G) + c + g (unique: consecutive CTAs share
-// at most one group).
+// The vectors of every group are enumerated in (outer, inner) order: v in [0, group_v).  A work UNIT is the p-th
+// 1/P share of one group: unit u = p * G + g covers v in [group_v*p/P, group_v*(p+1)/P) of group g.  Units are
+// statically defined (so every partial result is reproducible bit for bit) but DYNAMICALLY assigned: CTAs pull the
+// next unit id from an atomic counter.  Measured on B200: with equal static shares the CTAs of a bandwidth-bound
+// phase finish anywhere between 0.65x and 1.3x of the mean (memory arbitration is not fair), and the tail runs at
+// a fraction of the HBM bandwidth; pulling small units instead ends every phase within one unit time.
+// Consecutive ids are neighbouring channels of the same batch slab, so what the CTAs touch concurrently is a
+// nearly contiguous window of memory.  Every unit leaves one partial at slot u.
 struct Geometry {
   unsigned groups;          // G
-  unsigned slabs;           // P
+  unsigned parts;           // P
+  unsigned units;           // P * G
   unsigned inner_v;         // inner / VEC
   unsigned step_q, step_r;  // kThreads / inner_v, kThreads % inner_v
   unsigned red_lanes;       // lanes per group in the leader's partial reductions (power of two <= 32)
-  unsigned long long group_v;    // outer * inner_v: vectors per group
+  unsigned part_v;          // vectors per part: ceil(group_v / P) (the last part of a group may be shorter)
+  unsigned long long group_v;    // outer * inner_v: vectors per group (< 2^32, checked by the host)
   unsigned long long row_pitch;  // groups * inner_v: vectors between consecutive outer slices of a group
 };
 
@@ -223,207 +227,215 @@ template <int VEC> struct VecT;
 template <> struct VecT<4> { using type = float4; };
 template <> struct VecT<1> { using type = float; };
 
-struct Slab {
-  unsigned long long v0;   // first vector (within a group) of the slab
-  unsigned long long len;  // vectors per group in the slab
-  unsigned long long tot;  // groups * len
-};
-__device__ __forceinline__ Slab slab_of(const Geometry& geo, unsigned p) {
-  Slab s;
-  s.v0 = geo.group_v * p / geo.slabs;
-  s.len = geo.group_v * (p + 1ull) / geo.slabs - s.v0;
-  s.tot = s.len * geo.groups;
-  return s;
-}
-// the CTA whose chunk of the slab contains slab-local index w
-__device__ __forceinline__ unsigned cta_of(const Slab& s, unsigned long long w) {
-  return static_cast<unsigned>(((w + 1ull) * gridDim.x - 1ull) / s.tot);
-}
-__device__ __forceinline__ size_t partial_slot(const Geometry& geo, unsigned p, unsigned c, unsigned g) {
-  return static_cast<size_t>(p) * (gridDim.x + geo.groups) + c + g;
-}
-
-// Visit the segments (g, slab p, first vector within the group, length) of this CTA; `reverse` walks the slabs and
-// the segments inside a chunk back to front.
-template <typename Fn>
-__device__ __forceinline__ void for_each_segment(const Geometry& geo, bool reverse, Fn&& fn) {
-  for (unsigned i = 0; i < geo.slabs; ++i) {
-    const unsigned p = reverse ? geo.slabs - 1u - i : i;
-    const Slab s = slab_of(geo, p);
-    const unsigned long long w0 = s.tot * blockIdx.x / gridDim.x, w1 = s.tot * (blockIdx.x + 1ull) / gridDim.x;
-    if (w1 <= w0) continue;
-    const unsigned g_first = static_cast<unsigned>(w0 / s.len);
-    const unsigned g_last = static_cast<unsigned>((w1 - 1ull) / s.len);
-    for (unsigned k = 0; k <= g_last - g_first; ++k) {
-      const unsigned g = reverse ? g_last - k : g_first + k;
-      const unsigned long long gbase = static_cast<unsigned long long>(g) * s.len;
-      const unsigned long long vb = (g == g_first) ? w0 - gbase : 0ull;
-      const unsigned long long ve = (g == g_last) ? w1 - gbase : s.len;
-      fn(g, p, s.v0 + vb, static_cast<unsigned>(ve - vb));
-    }
-  }
-}
-
-// Walk `len` vectors of group g starting at vector vb (REV: from the last one backwards, so that a phase walked in
-// the opposite direction starts on what the previous phase touched last and still finds it in L2).  Thread t visits
-// vectors t, t+S, t+2S, ...; U independent loads are issued (bounds-predicated) before any is consumed.
-// The (row, column) cursor advances by adds only: one 64-bit division per segment.  Offsets are 32-bit vector
-// indices from the tensor base (the host refuses tensors of 2^32 vectors = 64 GB and more): registers are what
-// limits the number of loads in flight.
-template <int VEC, int U, bool REV, typename Body>
-__device__ __forceinline__ void walk_segment(const Geometry& geo, const float* base, unsigned g, unsigned long long vb,
-                                             unsigned len, Body&& body) {
-  using V = typename VecT<VEC>::type;
-  const V* src = reinterpret_cast<const V*>(base);
-  if (threadIdx.x >= len) return;
-  const unsigned long long v0 = REV ? vb + (len - 1u - threadIdx.x) : vb + threadIdx.x;
-  const unsigned long long a0 = v0 / geo.inner_v;
-  unsigned j = static_cast<unsigned>(v0 - a0 * geo.inner_v);
-  unsigned off = static_cast<unsigned>(a0 * geo.row_pitch + static_cast<unsigned long long>(g) * geo.inner_v + j);
-  const unsigned adv = static_cast<unsigned>(geo.step_q * geo.row_pitch + geo.step_r);
-  const unsigned wrap = static_cast<unsigned>(geo.row_pitch - geo.inner_v);
-  const unsigned inner_v = geo.inner_v, step_r = geo.step_r;
-  auto advance = [&]() {
-    if (!REV) {
-      j += step_r;
-      off += adv;
-      if (j >= inner_v) {
-        j -= inner_v;
-        off += wrap;
-      }
-    } else {
-      off -= adv;
-      if (j < step_r) {
-        j += inner_v;
-        off -= wrap;
-      }
-      j -= step_r;
-    }
-  };
-  constexpr unsigned S = kThreads;
-  // vectors left for this thread's lane of the stride-S sequence: ceil((len - tid) / S)
-  unsigned left = (len - threadIdx.x + S - 1u) / S;
-  while (left >= static_cast<unsigned>(U)) {  // full batches: no predicates
-    unsigned o[U];
-    V x[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      o[u] = off;
-      x[u] = ld_tensor(src + off);
-      advance();
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) body(x[u], o[u]);
-    left -= U;
-  }
-  if (left) {  // one predicated batch for the tail
-    unsigned o[U];
-    V x[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      o[u] = off;
-      if (static_cast<unsigned>(u) < left) x[u] = ld_tensor(src + off);
-      advance();
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (static_cast<unsigned>(u) < left) body(x[u], o[u]);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// asynchronous variant of walk_segment for the 128-bit path: a per-thread ring of cp.async (LDGSTS) copies
+// the streaming engine: dynamic units through a per-thread ring of cp.async (LDGSTS) copies
 // ------------------------------------------------------------------------------------------------
 // Registers cap how many loads a thread can keep in flight (64 registers -> 4 x 128 bit).  cp.async writes the
 // loaded vector straight into shared memory, so the ring can be D deep at no register cost: with D = 8 and 32 warps
-// per SM, 128 KB per SM are in flight - enough to cover HBM latency at full bandwidth.  Every thread reads back only
-// its own slots, so no CTA barrier is involved; completion is tracked with cp.async groups (one per vector, in order).
+// per SM, 128 KB per SM are in flight.  Every thread reads back only its own slots, so the ring itself needs no CTA
+// barrier; completion is tracked with cp.async groups (exactly one group per ring step, in order).
+//
+// The ring does not drain at unit boundaries: the issue side runs ahead into the next unit while the consume side
+// finishes the current one, so the only per-unit cost is the CTA-wide combine of the accumulators.  Unit ids are
+// fetched two units ahead by thread 0 (atomicAdd; the reply is only consumed at the end of the unit, so its latency
+// is hidden) and published through shared memory at the per-unit barrier.
 constexpr int kRingDepth = 8;
-constexpr int kRingBytes = kRingDepth * kThreads * 16;  // dynamic shared memory per CTA
+template <int VEC>
+constexpr int ring_bytes() { return kRingDepth * kThreads * 4 * VEC; }  // dynamic shared memory per CTA
 
-__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr) {
+__device__ __forceinline__ void cp_async_vec(unsigned smem_addr, const float4* gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_vec(unsigned smem_addr, const float* gptr) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ float4 lds128(unsigned smem_addr) {
-  float4 v;
+__device__ __forceinline__ void lds_vec(unsigned smem_addr, float4& v) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr) : "memory");
-  return v;
+}
+__device__ __forceinline__ void lds_vec(unsigned smem_addr, float& v) {
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_addr) : "memory");
 }
 
-template <bool REV, typename Body>
-__device__ __forceinline__ void walk_segment_async(const Geometry& geo, const float* base, unsigned g, unsigned long long vb,
-                                                   unsigned len, unsigned ring /* shared-space address of this thread's slot 0 */,
-                                                   Body&& body) {
-  constexpr int D = kRingDepth;
-  constexpr unsigned S = kThreads;
-  const float4* src = reinterpret_cast<const float4*>(base);
-  if (threadIdx.x >= len) return;
-  const unsigned long long v0 = REV ? vb + (len - 1u - threadIdx.x) : vb + threadIdx.x;
-  const unsigned long long a0 = v0 / geo.inner_v;
-  unsigned j = static_cast<unsigned>(v0 - a0 * geo.inner_v);
-  unsigned off = static_cast<unsigned>(a0 * geo.row_pitch + static_cast<unsigned long long>(g) * geo.inner_v + j);
+struct StreamSmem {
+  unsigned ids[4];  // unit-id queue, indexed by (sequence number of the unit within this CTA) % 4
+};
+
+// (row, column) cursor over the vectors thread t visits in a unit: t, t+S, t+2S, ... (REV: from the end backwards)
+struct Cursor {
+  unsigned j, off;
+};
+template <bool REV>
+__device__ __forceinline__ void cursor_step(const Geometry& geo, Cursor& c) {
   const unsigned adv = static_cast<unsigned>(geo.step_q * geo.row_pitch + geo.step_r);
   const unsigned wrap = static_cast<unsigned>(geo.row_pitch - geo.inner_v);
-  const unsigned inner_v = geo.inner_v, step_r = geo.step_r;
-  auto advance = [&]() {
-    if (!REV) {
-      j += step_r;
-      off += adv;
-      if (j >= inner_v) {
-        j -= inner_v;
-        off += wrap;
-      }
-    } else {
-      off -= adv;
-      if (j < step_r) {
-        j += inner_v;
-        off -= wrap;
-      }
-      j -= step_r;
+  if (!REV) {
+    c.j += geo.step_r;
+    c.off += adv;
+    if (c.j >= geo.inner_v) {
+      c.j -= geo.inner_v;
+      c.off += wrap;
     }
+  } else {
+    c.off -= adv;
+    if (c.j < geo.step_r) {
+      c.j += geo.inner_v;
+      c.off -= wrap;
+    }
+    c.j -= geo.step_r;
+  }
+}
+
+struct UnitInfo {
+  unsigned g;      // group
+  unsigned mine;   // vectors this thread visits
+  unsigned trips;  // ring steps of this thread's WARP (= `mine` of its first lane): warp-uniform loop count
+  Cursor start;    // this thread's first vector
+};
+template <bool REV>
+__device__ __forceinline__ UnitInfo unit_info(const Geometry& geo, unsigned u) {
+  UnitInfo ui;
+  const unsigned p = u / geo.groups;
+  ui.g = u - p * geo.groups;
+  const unsigned gv = static_cast<unsigned>(geo.group_v);
+  const unsigned vb = p * geo.part_v;  // 32-bit: group_v < 2^32
+  const unsigned len = min(geo.part_v, gv - vb);
+  constexpr unsigned S = kThreads;
+  const unsigned t = threadIdx.x, t0 = threadIdx.x & ~31u;
+  ui.mine = (t < len) ? (len - t + S - 1u) / S : 0u;
+  ui.trips = (t0 < len) ? (len - t0 + S - 1u) / S : 0u;
+  const unsigned v0 = (ui.mine == 0) ? vb : (REV ? vb + (len - 1u - t) : vb + t);
+  const unsigned a0 = v0 / geo.inner_v;
+  ui.start.j = v0 - a0 * geo.inner_v;
+  ui.start.off = static_cast<unsigned>(a0 * geo.row_pitch) + ui.g * geo.inner_v + ui.start.j;
+  return ui;
+}
+
+// Stream every unit this CTA manages to pull through `acc`:
+//   acc.begin(g)            unit starts (load per-group constants, reset accumulators)
+//   acc.consume(x, off)     one vector (off = its index from the tensor base, in vectors)
+//   acc.end(u, g)           unit done: CTA-wide combine + partial store; MUST contain at least one __syncthreads()
+// `counter` is this phase's unit counter in the workspace (zero at launch), or nullptr for a static round-robin
+// assignment (ticket k of CTA b = b + k * gridDim.x; used by the workspace-free given-parameter kernel).
+// REV walks ids and vectors backwards.
+template <int VEC, bool REV, typename Acc>
+__device__ __forceinline__ void stream_units(const Geometry& geo, const float* base, unsigned* counter, StreamSmem& ss,
+                                             Acc& acc) {
+  using V = typename VecT<VEC>::type;
+  constexpr int D = kRingDepth;
+  constexpr unsigned kSlot = kThreads * 4u * VEC;  // bytes between consecutive ring slots of one thread
+  const V* src = reinterpret_cast<const V*>(base);
+  extern __shared__ __align__(16) unsigned char fq_ring[];
+  const unsigned ring = static_cast<unsigned>(__cvta_generic_to_shared(fq_ring)) + threadIdx.x * (4u * VEC);
+  const unsigned total = geo.units;
+  auto unit_of = [&](unsigned ticket) { return REV ? total - 1u - ticket : ticket; };
+  unsigned fetched = 0;  // thread 0: tickets taken so far (static mode)
+  // the first two tickets of every CTA are static (b, b + grid): no atomic round trips before the first load;
+  // from the third on they come from the phase counter (offset by the 2 * grid tickets dealt statically)
+  auto take_ticket = [&]() -> unsigned {
+    const unsigned k = fetched++;
+    if (counter && k >= 2u) {
+      const unsigned long long t = 2ull * gridDim.x + atomicAdd(counter, 1u);
+      return t < total ? static_cast<unsigned>(t) : 0xffffffffu;
+    }
+    const unsigned long long t = blockIdx.x + static_cast<unsigned long long>(k) * gridDim.x;
+    return t < total ? static_cast<unsigned>(t) : 0xffffffffu;
   };
-  const unsigned left = (len - threadIdx.x + S - 1u) / S;  // vectors this thread visits
-  unsigned o[D];                                            // offsets of the vectors in flight (stores need them)
-  // prologue: fill the ring (always D groups so that the group arithmetic below is uniform)
-#pragma unroll
-  for (int d = 0; d < D; ++d) {
-    o[d] = off;
-    if (static_cast<unsigned>(d) < left) {
-      cp_async16(ring + d * (S * 16u), src + off);
-      advance();
-    }
-    cp_async_commit();
+
+  __syncthreads();  // ss.ids may still be read by stragglers of a previous phase
+  if (threadIdx.x == 0) {
+    ss.ids[0] = take_ticket();
+    ss.ids[1] = take_ticket();
   }
-  unsigned i = 0;
-  // steady state: D vectors per trip; slot d holds vector i + d
-  while (i + D <= left) {
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      cp_async_wait<D - 1>();  // the oldest group (this slot) has landed
-      const float4 x = lds128(ring + d * (S * 16u));
-      const unsigned od = o[d];
-      o[d] = off;
-      if (i + D + d < left) {  // refill the slot with the vector D ahead
-        cp_async16(ring + d * (S * 16u), src + off);
-        advance();
+  __syncthreads();
+  unsigned seq = 0;  // sequence number (within this CTA) of the unit being consumed
+  unsigned ticket = ss.ids[0];
+  if (ticket >= total) return;
+
+  // consume side
+  UnitInfo cu = unit_info<REV>(geo, unit_of(ticket));
+  Cursor cc = cu.start;
+  unsigned cdone = 0;  // ring steps done in the consumed unit
+  acc.begin(cu.g);
+  // issue side (at most one unit ahead: that is as far as ss.ids is guaranteed visible)
+  unsigned iseq = 0;
+  UnitInfo iu = cu;
+  UnitInfo ahead = cu;  // the unit the issue side entered last (handed to the consume side when it gets there)
+  Cursor ic = cu.start;
+  unsigned idone = 0;
+  bool iexhausted = false;
+  unsigned bubbles = 0;  // bit d: ring slot d carries no ring step (the issue side could not advance)
+  unsigned pending = 0;  // thread 0: ticket fetched during this unit, published at its end
+
+  // one ring step into `slot`; returns false when it had to leave a bubble
+  auto issue_step = [&](unsigned slot) -> bool {
+    while (!iexhausted && idone == iu.trips) {
+      if (iseq > seq) break;
+      const unsigned t = ss.ids[(iseq + 1u) & 3u];
+      if (t >= total) {
+        iexhausted = true;
+        break;
       }
-      cp_async_commit();
-      body(x, od);
+      ++iseq;
+      iu = unit_info<REV>(geo, unit_of(t));
+      ahead = iu;
+      ic = iu.start;
+      idone = 0;
     }
-    i += D;
-  }
-  // drain: fewer than D left, all already in flight
-  cp_async_wait<0>();
+    bool real = false;
+    if (!iexhausted && idone < iu.trips) {
+      if (idone < iu.mine) {
+        cp_async_vec(ring + slot * kSlot, src + ic.off);
+        cursor_step<REV>(geo, ic);
+      }
+      ++idone;
+      real = true;
+    }
+    cp_async_commit();  // exactly one group per ring step, empty or not
+    return real;
+  };
+
+  // prologue: fill the ring
 #pragma unroll
-  for (int d = 0; d < D; ++d) {
-    if (i + d < left) {
-      const float4 x = lds128(ring + d * (S * 16u));
-      body(x, o[d]);
+  for (int d = 0; d < D; ++d)
+    if (!issue_step(d)) bubbles |= 1u << d;
+  unsigned head = 0;
+  if (threadIdx.x == 0) pending = take_ticket();
+
+  for (;;) {
+    if (cdone == cu.trips) {
+      // ---- unit boundary
+      if (threadIdx.x == 0) ss.ids[(seq + 2u) & 3u] = pending;  // visible after the barrier inside end()
+      acc.end(unit_of(ticket), cu.g);
+      ++seq;
+      ticket = ss.ids[seq & 3u];
+      if (ticket >= total) break;
+      if (threadIdx.x == 0) pending = take_ticket();
+      cu = (iseq == seq) ? ahead : unit_info<REV>(geo, unit_of(ticket));  // usually the issue side is already there
+      cc = cu.start;
+      cdone = 0;
+      acc.begin(cu.g);
+      continue;
     }
+    cp_async_wait<D - 1>();  // the oldest group (slot `head`) has landed
+    const bool bubble = (bubbles >> head) & 1u;
+    const bool active = !bubble && cdone < cu.mine;
+    V x;
+    if (active) lds_vec(ring + head * kSlot, x);
+    if (issue_step(head))
+      bubbles &= ~(1u << head);
+    else
+      bubbles |= 1u << head;
+    head = (head + 1u) & (D - 1u);
+    if (active) {
+      acc.consume(x, cc.off);
+      cursor_step<REV>(geo, cc);
+    }
+    if (!bubble) ++cdone;
   }
+  cp_async_wait<0>();
 }
 
 }  // namespace fqb

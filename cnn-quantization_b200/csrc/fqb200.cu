@@ -78,6 +78,14 @@ struct FusedArgs {
   float *cq, *co, *ck;                  // [G] weight correction: mean(w_q), mean(w), variance factor
 };
 
+__device__ __forceinline__ void stamp(const FusedArgs& A, int slot) {
+  if (A.dbg && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    A.dbg[slot] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // leader-section helpers (run by ONE CTA between phases)
 // ------------------------------------------------------------------------------------------------
@@ -88,8 +96,7 @@ struct LeaderSmem {
   int flag;
 };
 
-// Reduce the per-segment partials of every group in a fixed order.  In slab p group g was touched by the CTAs
-// cta_of(first vector) .. cta_of(last vector) (usually one or two); CTA c left its partial at partial_slot(p, c, g).
+// Reduce the P per-unit partials of every group in a fixed order (slot p * G + g: coalesced over g).
 // `red_lanes` lanes cooperate on one group; kThreads / red_lanes groups are finished per sweep.  Up to three arrays
 // are reduced in one sweep so their (independent) L2 round trips overlap.
 template <typename T0, typename Op0, typename T1, typename Op1, typename T2, typename Op2>
@@ -104,17 +111,12 @@ __device__ __forceinline__ void reduce_partials3(const Geometry& geo, const T0* 
     T1 a1 = id1;
     T2 a2 = id2;
     if (g < geo.groups) {
-      for (unsigned p = 0; p < geo.slabs; ++p) {
-        const Slab s = slab_of(geo, p);
-        if (s.len == 0) continue;
-        const unsigned long long first = static_cast<unsigned long long>(g) * s.len;
-        const unsigned c_lo = cta_of(s, first), c_hi = cta_of(s, first + s.len - 1ull);
-        for (unsigned c = c_lo + sub; c <= c_hi; c += L) {
-          const size_t slot = partial_slot(geo, p, c, g);
-          if (p0) a0 = op0(a0, ld_ws(p0 + slot));
-          if (p1) a1 = op1(a1, ld_ws(p1 + slot));
-          if (p2) a2 = op2(a2, ld_ws(p2 + slot));
-        }
+#pragma unroll 4
+      for (unsigned p = sub; p < geo.parts; p += L) {
+        const size_t slot = static_cast<size_t>(p) * geo.groups + g;
+        if (p0) a0 = op0(a0, ld_ws(p0 + slot));
+        if (p1) a1 = op1(a1, ld_ws(p1 + slot));
+        if (p2) a2 = op2(a2, ld_ws(p2 + slot));
       }
     }
     for (unsigned o = L >> 1; o > 0; o >>= 1) {
@@ -147,8 +149,8 @@ __device__ __noinline__ void solve_bit_alloc(const FusedArgs& A, LeaderSmem& sm)
   float half_gap = 1.0f;
   const float inv_g = 1.0f / static_cast<float>(G);  // torch's CUDA mean multiplies by fl(1/N)
   int it = 0;
+  __shared__ int warp_bits[2][kWarps];
   while (fabsf(2.0f * half_gap) > 0.01f && it < 10) {
-    ++it;
     const float budget = static_cast<float>(static_cast<double>(G) * exp2(m));
     int sum_bits = 0;
     for (unsigned g = threadIdx.x; g < G; g += kThreads) {
@@ -160,7 +162,14 @@ __device__ __noinline__ void solve_bit_alloc(const FusedArgs& A, LeaderSmem& sm)
       A.gbits[g] = bits;
       sum_bits += static_cast<int>(bits);
     }
-    const int total = block_reduce(sum_bits, OpAdd(), sm.i);
+    // exact integer sum: one REDUX per warp, one barrier per iteration (buffers alternate)
+    sum_bits = __reduce_add_sync(0xffffffffu, sum_bits);
+    if ((threadIdx.x & 31) == 0) warp_bits[it & 1][threadIdx.x >> 5] = sum_bits;
+    __syncthreads();
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) total += warp_bits[it & 1][w];
+    ++it;
     const float mean = __fmul_rn(static_cast<float>(total), inv_g);
     half_gap = __fmul_rn(__fsub_rn(goal, mean), 0.5f);
     m += static_cast<double>(half_gap);
@@ -311,6 +320,7 @@ __device__ __noinline__ void solve_params(const FusedArgs& A, LeaderSmem& sm) {
   }
   const bool alloc = A.bit_alloc && A.num_bits <= 4 && A.scope == FQB200_SCOPE_GROUP;
   if (alloc) solve_bit_alloc(A, sm);
+  stamp(A, 12);
   if (A.scope != FQB200_SCOPE_GROUP) {
     // GROUP_MEAN: batch average of the per-sample min / max (int_quantizer.py:372, :525-526);
     // TENSOR: global min / max assembled from the per-row ones.  Either way ONE parameter set.
@@ -362,14 +372,6 @@ __device__ __noinline__ void solve_params(const FusedArgs& A, LeaderSmem& sm) {
 // ------------------------------------------------------------------------------------------------
 // streaming phases
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stamp(const FusedArgs& A, int slot) {
-  if (A.dbg && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    A.dbg[slot] = t;
-  }
-}
-
 struct PhaseSmem {
   float f0[kWarps], f1[kWarps];
   double d0[kWarps], d1[kWarps];
@@ -381,28 +383,7 @@ struct PhaseSmem {
 #ifndef FQB_UAPPLY
 #define FQB_UAPPLY 4
 #endif
-#ifndef FQB_ASYNC
-#define FQB_ASYNC 1
-#endif
-// 128-bit path: cp.async ring (FQB_ASYNC=1) or register batches; scalar path: register batches
-extern __shared__ __align__(16) unsigned char fq_dyn_smem[];
-__device__ __forceinline__ unsigned ring_base() {
-  return static_cast<unsigned>(__cvta_generic_to_shared(fq_dyn_smem)) + threadIdx.x * 16u;
-}
-template <int U, bool REV, typename Body>
-__device__ __forceinline__ void walk4(const Geometry& geo, const float* base, unsigned g, unsigned long long vb, unsigned len,
-                                      Body&& body) {
-#if FQB_ASYNC
-  walk_segment_async<REV>(geo, base, g, vb, len, ring_base(), body);
-#else
-  walk_segment<4, U, REV>(geo, base, g, vb, len, body);
-#endif
-}
-
-constexpr int kUnrollStats = FQB_USTATS;  // statistics phases: independent 128-bit loads in flight per thread
-constexpr int kUnrollApply = FQB_UAPPLY;  // apply phase: loads (+ as many stores) in flight per thread
-
-// CTA-wide sums of up to two doubles and min/max of two floats, result valid in thread 0
+// CTA-wide sums of up to two doubles and min/max of two floats, result valid in thread 0.  Two barriers.
 __device__ __forceinline__ void block_combine(PhaseSmem& sm, float& mn, float& mx, double& s0, double& s1, bool use_f,
                                               bool use_d1) {
   if (use_f) {
@@ -437,71 +418,80 @@ __device__ __forceinline__ void block_combine(PhaseSmem& sm, float& mn, float& m
   }
 }
 
-// S1: min / max / sum per segment  (int_quantizer.py:541-546)
-template <int VEC, bool REV>
-__device__ void phase_stats1(const FusedArgs& A, PhaseSmem& sm) {
-  for_each_segment(A.geo, REV, [&](unsigned g, unsigned p, unsigned long long vb, unsigned len) {
-    float mn = INFINITY, mx = -INFINITY;
-    double s = 0.0, unused = 0.0;
-    const float bias = A.bias ? __ldg(A.bias + g) : 0.f;  // x + 0 when there is none
-    if constexpr (VEC == 4) {
-      walk4<kUnrollStats, REV>(A.geo, A.in, g, vb, len, [&](float4 x, unsigned) {
-        x = make_float4(__fadd_rn(x.x, bias), __fadd_rn(x.y, bias), __fadd_rn(x.z, bias), __fadd_rn(x.w, bias));
-        mn = fminf(mn, fminf(fminf(x.x, x.y), fminf(x.z, x.w)));
-        mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
-        s += static_cast<double>(__fadd_rn(__fadd_rn(x.x, x.y), __fadd_rn(x.z, x.w)));
-      });
-    } else {
-      walk_segment<1, kUnrollStats, REV>(A.geo, A.in, g, vb, len, [&](float x, unsigned) {
-        x = __fadd_rn(x, bias);
-        mn = fminf(mn, x);
-        mx = fmaxf(mx, x);
-        s += static_cast<double>(x);
-      });
-    }
+// S1: min / max / sum per unit  (int_quantizer.py:541-546)
+template <int VEC>
+struct AccStats1 {
+  const FusedArgs& A;
+  PhaseSmem& sm;
+  float mn, mx, bias;
+  double s;
+  __device__ __forceinline__ void begin(unsigned g) {
+    mn = INFINITY;
+    mx = -INFINITY;
+    s = 0.0;
+    bias = A.bias ? __ldg(A.bias + g) : 0.f;  // x + 0 when there is none
+  }
+  __device__ __forceinline__ void consume(const float4& v, unsigned) {
+    const float x0 = __fadd_rn(v.x, bias), x1 = __fadd_rn(v.y, bias), x2 = __fadd_rn(v.z, bias), x3 = __fadd_rn(v.w, bias);
+    mn = fminf(mn, fminf(fminf(x0, x1), fminf(x2, x3)));
+    mx = fmaxf(mx, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
+    s += static_cast<double>(__fadd_rn(__fadd_rn(x0, x1), __fadd_rn(x2, x3)));
+  }
+  __device__ __forceinline__ void consume(const float& v, unsigned) {
+    const float x = __fadd_rn(v, bias);
+    mn = fminf(mn, x);
+    mx = fmaxf(mx, x);
+    s += static_cast<double>(x);
+  }
+  __device__ __forceinline__ void end(unsigned u, unsigned) {
+    double unused = 0.0;
     block_combine(sm, mn, mx, s, unused, true, false);
     if (threadIdx.x == 0) {
-      const size_t slot = partial_slot(A.geo, p, blockIdx.x, g);
-      st_ws(A.pmin + slot, mn);
-      st_ws(A.pmax + slot, mx);
-      st_ws(A.psum + slot, s);
+      st_ws(A.pmin + u, mn);
+      st_ws(A.pmax + u, mx);
+      st_ws(A.psum + u, s);
     }
-  });
-}
+  }
+};
 
-// S2: sum |x - mu| and sum (x - mu)^2 per segment, mu = fp32 group mean  (int_quantizer.py:547-550)
-// `src` is the input (activations, weights) or the output (variance correction of quantized weights).
-template <int VEC, bool REV>
-__device__ void phase_stats2(const FusedArgs& A, PhaseSmem& sm, const float* src, const float* mean, bool with_bias,
-                             double* out_abs, double* out_sq) {
-  for_each_segment(A.geo, REV, [&](unsigned g, unsigned p, unsigned long long vb, unsigned len) {
-    const float mu = ld_ws(mean + g);
-    const float bias = (with_bias && A.bias != nullptr) ? __ldg(A.bias + g) : 0.f;
-    float fu0 = 0.f, fu1 = 0.f;
-    double sa = 0.0, sq = 0.0;
-    if constexpr (VEC == 4) {
-      walk4<kUnrollStats, REV>(A.geo, src, g, vb, len, [&](float4 x, unsigned) {
-        x = make_float4(__fadd_rn(x.x, bias), __fadd_rn(x.y, bias), __fadd_rn(x.z, bias), __fadd_rn(x.w, bias));
-        const float d0 = __fsub_rn(x.x, mu), d1 = __fsub_rn(x.y, mu), d2 = __fsub_rn(x.z, mu), d3 = __fsub_rn(x.w, mu);
-        sa += static_cast<double>(__fadd_rn(__fadd_rn(fabsf(d0), fabsf(d1)), __fadd_rn(fabsf(d2), fabsf(d3))));
-        sq += static_cast<double>(__fmaf_rn(d3, d3, __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)))));
-      });
-    } else {
-      walk_segment<1, kUnrollStats, REV>(A.geo, src, g, vb, len, [&](float x, unsigned) {
-        x = __fadd_rn(x, bias);
-        const float d = __fsub_rn(x, mu);
-        sa += static_cast<double>(fabsf(d));
-        sq += static_cast<double>(__fmul_rn(d, d));
-      });
-    }
-    block_combine(sm, fu0, fu1, sa, sq, false, true);
+// S2: sum |x - mu| and sum (x - mu)^2 per unit, mu = fp32 group mean  (int_quantizer.py:547-550).
+// Also used on the quantized weights for the variance correction (then without the bias addend).
+template <int VEC>
+struct AccStats2 {
+  const FusedArgs& A;
+  PhaseSmem& sm;
+  const float* mean;
+  bool with_bias;
+  double* out_abs;
+  double* out_sq;
+  float mu, bias;
+  double sa, sq;
+  __device__ __forceinline__ void begin(unsigned g) {
+    mu = ld_ws(mean + g);
+    bias = (with_bias && A.bias) ? __ldg(A.bias + g) : 0.f;
+    sa = 0.0;
+    sq = 0.0;
+  }
+  __device__ __forceinline__ void consume(const float4& v, unsigned) {
+    const float d0 = __fsub_rn(__fadd_rn(v.x, bias), mu), d1 = __fsub_rn(__fadd_rn(v.y, bias), mu);
+    const float d2 = __fsub_rn(__fadd_rn(v.z, bias), mu), d3 = __fsub_rn(__fadd_rn(v.w, bias), mu);
+    sa += static_cast<double>(__fadd_rn(__fadd_rn(fabsf(d0), fabsf(d1)), __fadd_rn(fabsf(d2), fabsf(d3))));
+    sq += static_cast<double>(__fmaf_rn(d3, d3, __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)))));
+  }
+  __device__ __forceinline__ void consume(const float& v, unsigned) {
+    const float d = __fsub_rn(__fadd_rn(v, bias), mu);
+    sa += static_cast<double>(fabsf(d));
+    sq += static_cast<double>(__fmul_rn(d, d));
+  }
+  __device__ __forceinline__ void end(unsigned u, unsigned) {
+    float f0 = 0.f, f1 = 0.f;
+    block_combine(sm, f0, f1, sa, sq, false, true);
     if (threadIdx.x == 0) {
-      const size_t slot = partial_slot(A.geo, p, blockIdx.x, g);
-      if (out_abs) st_ws(out_abs + slot, sa);
-      st_ws(out_sq + slot, sq);
+      if (out_abs) st_ws(out_abs + u, sa);
+      st_ws(out_sq + u, sq);
     }
-  });
-}
+  }
+};
 
 // one element through the leaf
 template <int LEAF, bool FAST, bool NOISE = false>
@@ -549,84 +539,91 @@ __device__ __forceinline__ LeafParam load_leaf_param(const LeafParam* lp, unsign
   return q;
 }
 
-// the apply loop over one segment; ACC: also accumulate sum(y) (weight bias correction); GRID: also store the
-// integer grid.  `bias` is 0 when there is none (x + 0 only turns -0 into +0, which quantizes identically).
-template <int VEC, int LEAF, bool ACC, bool REV, bool FAST, bool GRID>
-__device__ __forceinline__ void apply_segment_v(const FusedArgs& A, unsigned g, unsigned long long vb, unsigned len,
-                                                const LeafParam& q, const Divisor& dv, float bias, double& sy) {
-  float* out = A.out;
-  float* grid_out = A.grid_out;
-  if constexpr (VEC == 4) {
-    walk4<kUnrollApply, REV>(A.geo, A.in, g, vb, len, [&](float4 x, unsigned off) {
-      float4 y, gq;
-      y.x = leaf_apply<LEAF, FAST>(__fadd_rn(x.x, bias), q, dv, 0.f, gq.x);
-      y.y = leaf_apply<LEAF, FAST>(__fadd_rn(x.y, bias), q, dv, 0.f, gq.y);
-      y.z = leaf_apply<LEAF, FAST>(__fadd_rn(x.z, bias), q, dv, 0.f, gq.z);
-      y.w = leaf_apply<LEAF, FAST>(__fadd_rn(x.w, bias), q, dv, 0.f, gq.w);
-      st_tensor(reinterpret_cast<float4*>(out) + off, y);
-      if (GRID) st_tensor(reinterpret_cast<float4*>(grid_out) + off, gq);
-      if (ACC) sy += static_cast<double>(__fadd_rn(__fadd_rn(y.x, y.y), __fadd_rn(y.z, y.w)));
-    });
-  } else {
-    walk_segment<1, kUnrollApply, REV>(A.geo, A.in, g, vb, len, [&](float x, unsigned off) {
-      float gq;
-      const float y = leaf_apply<LEAF, FAST>(__fadd_rn(x, bias), q, dv, 0.f, gq);
-      st_tensor(out + off, y);
-      if (GRID) st_tensor(grid_out + off, gq);
-      if (ACC) sy += static_cast<double>(y);
-    });
+// A: quantize - clip - dequantize one unit with its group's (or the tensor's) parameters held in registers.
+// ACC: also accumulate sum(y) (weight bias correction); GRID: also store the integer grid; GIVEN: derive the leaf
+// parameters from caller-provided delta / offset / bits instead of the solved table.
+template <int VEC, int LEAF, bool ACC, bool GRID, bool GIVEN>
+struct AccApply {
+  const FusedArgs& A;
+  PhaseSmem& sm;
+  LeafParam q;
+  Divisor dv;
+  float bias;
+  double sy;
+  __device__ __forceinline__ void begin(unsigned g) {
+    if (GIVEN) {
+      const unsigned pi = A.given_per_group ? g : 0u;
+      const float bits = A.g_bits ? __ldg(A.g_bits + g) : static_cast<float>(A.num_bits);
+      q = make_leaf_param(LEAF, __ldg(A.g_delta + pi), __ldg(A.g_offset + pi), bits);
+    } else {
+      q = load_leaf_param(A.lp, (A.scope == FQB200_SCOPE_GROUP) ? g : 0u);
+    }
+    dv = make_divisor(q.a);
+    bias = A.bias ? __ldg(A.bias + g) : 0.f;
+    sy = 0.0;
   }
-}
-
-template <int VEC, int LEAF, bool ACC, bool REV, bool GRID>
-__device__ __forceinline__ void apply_segment(const FusedArgs& A, unsigned g, unsigned long long vb, unsigned len,
-                                              const LeafParam& q, double& sy) {
-  const Divisor dv = make_divisor(q.a);
-  const float bias = A.bias ? __ldg(A.bias + g) : 0.f;
-  if (dv.fast)
-    apply_segment_v<VEC, LEAF, ACC, REV, true, GRID>(A, g, vb, len, q, dv, bias, sy);
-  else
-    apply_segment_v<VEC, LEAF, ACC, REV, false, GRID>(A, g, vb, len, q, dv, bias, sy);
-}
-
-// A: quantize - clip - dequantize with the solved per-group (or per-tensor) parameters.
-template <int VEC, int LEAF, bool ACC, bool REV>
-__device__ void phase_apply(const FusedArgs& A, PhaseSmem& sm) {
-  const bool per_group = (A.scope == FQB200_SCOPE_GROUP);
-  for_each_segment(A.geo, REV, [&](unsigned g, unsigned p, unsigned long long vb, unsigned len) {
-    const LeafParam q = load_leaf_param(A.lp, per_group ? g : 0u);
-    double sy = 0.0, unused = 0.0;
-    apply_segment<VEC, LEAF, ACC, REV, false>(A, g, vb, len, q, sy);
+  template <bool FAST>
+  __device__ __forceinline__ void one(const float4& x, unsigned off) {
+    float4 y, gq;
+    y.x = leaf_apply<LEAF, FAST>(__fadd_rn(x.x, bias), q, dv, 0.f, gq.x);
+    y.y = leaf_apply<LEAF, FAST>(__fadd_rn(x.y, bias), q, dv, 0.f, gq.y);
+    y.z = leaf_apply<LEAF, FAST>(__fadd_rn(x.z, bias), q, dv, 0.f, gq.z);
+    y.w = leaf_apply<LEAF, FAST>(__fadd_rn(x.w, bias), q, dv, 0.f, gq.w);
+    st_tensor(reinterpret_cast<float4*>(A.out) + off, y);
+    if (GRID) st_tensor(reinterpret_cast<float4*>(A.grid_out) + off, gq);
+    if (ACC) sy += static_cast<double>(__fadd_rn(__fadd_rn(y.x, y.y), __fadd_rn(y.z, y.w)));
+  }
+  template <bool FAST>
+  __device__ __forceinline__ void one(const float& x, unsigned off) {
+    float gq;
+    const float y = leaf_apply<LEAF, FAST>(__fadd_rn(x, bias), q, dv, 0.f, gq);
+    st_tensor(A.out + off, y);
+    if (GRID) st_tensor(A.grid_out + off, gq);
+    if (ACC) sy += static_cast<double>(y);
+  }
+  template <typename V>
+  __device__ __forceinline__ void consume(const V& x, unsigned off) {
+    if (dv.fast)  // CTA-uniform
+      one<true>(x, off);
+    else
+      one<false>(x, off);
+  }
+  __device__ __forceinline__ void end(unsigned u, unsigned) {
     if (ACC) {
       float f0 = 0.f, f1 = 0.f;
+      double unused = 0.0;
       block_combine(sm, f0, f1, sy, unused, false, false);
-      if (threadIdx.x == 0) st_ws(A.psum + partial_slot(A.geo, p, blockIdx.x, g), sy);
+      if (threadIdx.x == 0) st_ws(A.psum + u, sy);
+    } else {
+      __syncthreads();  // the engine publishes the next unit ids at this barrier
     }
-  });
-}
+  }
+};
 
 // C1: y <- (y - m_q) * k + m_q  (variance), then y <- y - m_q + m_o  (mean); inference_quantization_manager.py:386-391
-template <int VEC, bool REV>
-__device__ void phase_corr_apply(const FusedArgs& A) {
-  for_each_segment(A.geo, REV, [&](unsigned g, unsigned p, unsigned long long vb, unsigned len) {
-    const float mq = ld_ws(A.cq + g), mo = ld_ws(A.co + g);
-    const float kv = A.var_corr ? ld_ws(A.ck + g) : 1.f;
-    const bool vc = A.var_corr != 0, bc = A.bias_corr != 0;
-    float* out = A.out;
-    auto fix = [&](float y) {
-      if (vc) y = __fadd_rn(__fmul_rn(__fsub_rn(y, mq), kv), mq);
-      if (bc) y = __fadd_rn(__fsub_rn(y, mq), mo);
-      return y;
-    };
-    if constexpr (VEC == 4) {
-      walk4<kUnrollApply, REV>(A.geo, A.out, g, vb, len, [&](float4 y, unsigned off) {
-        st_tensor(reinterpret_cast<float4*>(out) + off, make_float4(fix(y.x), fix(y.y), fix(y.z), fix(y.w)));
-      });
-    } else {
-      walk_segment<1, kUnrollApply, REV>(A.geo, A.out, g, vb, len, [&](float y, unsigned off) { st_tensor(out + off, fix(y)); });
-    }
-  });
-}
+template <int VEC>
+struct AccCorr {
+  const FusedArgs& A;
+  float mq, mo, kv;
+  bool vc, bc;
+  __device__ __forceinline__ void begin(unsigned g) {
+    mq = ld_ws(A.cq + g);
+    mo = ld_ws(A.co + g);
+    kv = A.var_corr ? ld_ws(A.ck + g) : 1.f;
+    vc = A.var_corr != 0;
+    bc = A.bias_corr != 0;
+  }
+  __device__ __forceinline__ float fix(float y) const {
+    if (vc) y = __fadd_rn(__fmul_rn(__fsub_rn(y, mq), kv), mq);
+    if (bc) y = __fadd_rn(__fsub_rn(y, mq), mo);
+    return y;
+  }
+  __device__ __forceinline__ void consume(const float4& y, unsigned off) {
+    st_tensor(reinterpret_cast<float4*>(A.out) + off, make_float4(fix(y.x), fix(y.y), fix(y.z), fix(y.w)));
+  }
+  __device__ __forceinline__ void consume(const float& y, unsigned off) { st_tensor(A.out + off, fix(y)); }
+  __device__ __forceinline__ void end(unsigned, unsigned) { __syncthreads(); }
+};
 
 // ------------------------------------------------------------------------------------------------
 // the fused persistent kernel (cooperative launch: every CTA is resident)
@@ -638,20 +635,18 @@ template <int VEC, int LEAF, bool DEV, bool CORR>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __grid_constant__ FusedArgs A) {
   __shared__ PhaseSmem psm;
   __shared__ LeaderSmem lsm;
+  __shared__ StreamSmem ssm;
   unsigned epoch = 0;
   const Geometry& geo = A.geo;
   const double n = A.n_per_group;
 
   // ---- S1
   if (blockIdx.x == 0) stamp(A, 0);
-  phase_stats1<VEC, false>(A, psm);
-  if (blockIdx.x == 0) stamp(A, 1);
-  stamp(A, 16 + 4 * blockIdx.x);
-  if (A.dbg && threadIdx.x == 0) {
-    unsigned sm;
-    asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
-    A.dbg[16 + 4 * blockIdx.x + 3] = sm;
+  {
+    AccStats1<VEC> acc{A, psm};
+    stream_units<VEC, false>(geo, A.in, &A.sync->unit_counter[0], ssm, acc);
   }
+  if (blockIdx.x == 0) stamp(A, 1);
   if (grid_arrive(A.sync, epoch, &lsm.flag)) {
     stamp(A, 2);
     reduce_partials3(geo, A.pmin, A.gmin, INFINITY, OpMin(), A.pmax, A.gmax, -INFINITY, OpMax(), A.psum, A.gmean_d, 0.0, OpAdd());
@@ -670,16 +665,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
 
   // ---- S2
   if constexpr (DEV) {
-    phase_stats2<VEC, true>(A, psm, A.in, A.gmean, true, A.pabs, A.psq);
+    {
+      AccStats2<VEC> acc{A, psm, A.gmean, true, A.pabs, A.psq};
+      stream_units<VEC, true>(geo, A.in, &A.sync->unit_counter[1], ssm, acc);
+    }
     if (blockIdx.x == 0) stamp(A, 5);
-    stamp(A, 16 + 4 * blockIdx.x + 1);
     if (grid_arrive(A.sync, epoch, &lsm.flag)) {
       stamp(A, 6);
       double* tabs = A.psum;              // [>= G] free now
-      double* tsq = A.psum + geo.groups;  // psum holds slots + 2G doubles
+      double* tsq = A.psum + geo.groups;  // psum holds units + 2G doubles
       reduce_partials3(geo, A.pabs, tabs, 0.0, OpAdd(), A.psq, tsq, 0.0, OpAdd(), static_cast<const double*>(nullptr),
                        static_cast<double*>(nullptr), 0.0, OpAdd());
       __syncthreads();
+      stamp(A, 10);
       for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) {
         A.gb[g] = static_cast<float>(tabs[g] / n);
         // sum (x - mu32)^2 -> sum (x - mu)^2 with the exact mean; unbiased (torch.std default)
@@ -689,6 +687,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
         A.gstd[g] = static_cast<float>(sqrt(ss / (n - 1.0)));
       }
       __syncthreads();
+      stamp(A, 11);
       solve_params(A, lsm);
       stamp(A, 7);
       grid_release(A.sync, epoch);
@@ -698,9 +697,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
 
   // ---- A (+ C)
   if (!A.stats_only) {
-    phase_apply<VEC, LEAF, CORR, !DEV>(A, psm);
+    {
+      AccApply<VEC, LEAF, CORR, false, false> acc{A, psm};
+      stream_units<VEC, !DEV>(geo, A.in, &A.sync->unit_counter[2], ssm, acc);
+    }
     if (blockIdx.x == 0) stamp(A, 9);
-    stamp(A, 16 + 4 * blockIdx.x + 2);
     if constexpr (CORR) {
       if (grid_arrive(A.sync, epoch, &lsm.flag)) {
         double* tmp = A.pabs;
@@ -714,7 +715,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
         grid_release(A.sync, epoch);
       }
       if (A.var_corr) {
-        phase_stats2<VEC, false>(A, psm, A.out, A.cq, false, nullptr, A.psq);
+        {
+          AccStats2<VEC> acc{A, psm, A.cq, false, nullptr, A.psq};
+          stream_units<VEC, false>(geo, A.out, &A.sync->unit_counter[3], ssm, acc);
+        }
         if (grid_arrive(A.sync, epoch, &lsm.flag)) {
           double* tmp = A.pabs;
           reduce_partials3(geo, A.psq, tmp, 0.0, OpAdd(), static_cast<const double*>(nullptr), static_cast<double*>(nullptr), 0.0,
@@ -728,7 +732,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
           grid_release(A.sync, epoch);
         }
       }
-      phase_corr_apply<VEC, false>(A);
+      {
+        AccCorr<VEC> acc{A};
+        stream_units<VEC, false>(geo, A.out, &A.sync->unit_counter[4], ssm, acc);
+      }
     }
   }
   grid_exit(A.sync);
@@ -776,19 +783,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 // Mode A (parameters given by the caller, int_quantizer.py:557-603 called directly): no statistics, no grid
 // barrier, ordinary launch.  Leaf parameters are derived per item from the device-resident delta/offset/bits
 // (a few CTA-uniform flops), so nothing is synchronised with the host.
-template <int VEC, int LEAF>
+template <int VEC, int LEAF, bool GRID>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_given_kernel(const __grid_constant__ FusedArgs A) {
-  for_each_segment(A.geo, false, [&](unsigned g, unsigned p, unsigned long long vb, unsigned len) {
-    (void)p;
-    const unsigned pi = A.given_per_group ? g : 0u;
-    const float bits = A.g_bits ? __ldg(A.g_bits + g) : static_cast<float>(A.num_bits);
-    const LeafParam q = make_leaf_param(LEAF, __ldg(A.g_delta + pi), __ldg(A.g_offset + pi), bits);
-    double sy = 0.0;
-    if (A.grid_out)
-      apply_segment<VEC, LEAF, false, false, true>(A, g, vb, len, q, sy);
-    else
-      apply_segment<VEC, LEAF, false, false, false>(A, g, vb, len, q, sy);
-  });
+  __shared__ PhaseSmem psm;
+  __shared__ StreamSmem ssm;
+  AccApply<VEC, LEAF, false, GRID, true> acc{A, psm};
+  stream_units<VEC, false>(A.geo, A.in, nullptr, ssm, acc);
 }
 
 // test hook: q[i] = div_exact(a[i], b[i]) next to IEEE a[i]/b[i]
@@ -825,7 +825,7 @@ struct DeviceInfo {
 DeviceInfo g_dev[64];
 
 // dynamic shared memory of a launch: the cp.async ring of the 128-bit path
-size_t dyn_smem(int vec) { return (FQB_ASYNC && vec == 4) ? static_cast<size_t>(fqb::kRingBytes) : 0; }
+size_t dyn_smem(int vec) { return static_cast<size_t>(vec == 4 ? fqb::ring_bytes<4>() : fqb::ring_bytes<1>()); }
 
 // the 24 instantiations of the fused kernel: (VEC 4|1) x (leaf 0..2) x (second statistics pass) x (weight correction)
 template <int VEC, int LEAF>
@@ -879,17 +879,18 @@ int get_device(DeviceInfo** out) {
       int n = 0;
       const int vw = (v & 1) ? 1 : 4;
       const void* fn = fused_kernel_ptr(vw, (v >> 1) % 3, (v / 6) & 1, v / 12);
-      if (vw == 4) {
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem(4));
-        if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      }
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem(vw)));
+      if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kThreads, dyn_smem(vw));
       if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
       if (n < per_sm) per_sm = n;
     }
     if (per_sm < 1) return fail(FQB200_ERR_CUDA, "fused kernel does not fit on an SM%s");
-    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH>),
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem(4));
+    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, false>),
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem(4)));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, true>),
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem(4)));
     if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     // mid-tread table (int_quantizer.py:41-51): omega grid = 5 decades x 20 steps, leading 0
     double om[fqb::kTable], al[fqb::kTable];
@@ -921,7 +922,7 @@ struct Plan {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// Choose vector width, slab count and grid size; fill the geometry.
+// Choose vector width, the number of parts per group (unit size) and the grid size; fill the geometry.
 int make_plan(int64_t outer, int64_t groups, int64_t inner, bool can_vec, int max_ctas, Plan* pl) {
   if (outer <= 0 || groups <= 0 || inner <= 0) return fail(FQB200_ERR_INVALID, "non-positive tensor extent%s");
   if (groups > 0x3fffffffLL || outer > 0x7fffffffLL || inner > 0x7fffffffLL * 4LL)
@@ -933,50 +934,49 @@ int make_plan(int64_t outer, int64_t groups, int64_t inner, bool can_vec, int ma
   const uint64_t group_v = static_cast<uint64_t>(outer) * inner_v;
   const uint64_t total_v = group_v * G;
   if (total_v >= (1ULL << 32)) return fail(FQB200_ERR_UNSUPPORTED, "tensors of 2^32 vectors (64 GB) and more are not supported%s");
-  // every CTA gets the same share; at least ~32 KB each so small tensors use fewer CTAs (cheaper barriers)
-  const uint64_t min_chunk_v = (32u * 1024u) / (4u * vec);
-  uint64_t grid = (total_v + min_chunk_v - 1) / min_chunk_v;
-  if (grid > static_cast<uint64_t>(max_ctas)) grid = static_cast<uint64_t>(max_ctas);
-  if (grid < 1) grid = 1;
-  // slabs: keep what the CTAs touch concurrently inside ~slab_mb of memory; a slab is a range of `outer`
-  static const uint64_t slab_mb = getenv("FQB_SLAB_MB") ? strtoull(getenv("FQB_SLAB_MB"), nullptr, 10) : 256;  // development knob
-  const uint64_t bytes = total_v * 4u * vec;
-  uint64_t slabs = (bytes + (slab_mb << 20) - 1) / (slab_mb << 20);
-  if (slabs < 1) slabs = 1;
-  if (slabs > static_cast<uint64_t>(outer)) slabs = static_cast<uint64_t>(outer);
-  if (slabs > 64) slabs = 64;
-  while ((total_v / slabs + grid - 1) / grid >= 0x7fffffffULL) ++slabs;  // segment lengths are 32-bit
-  // how many CTAs can overlap one group inside a slab: ceil(slab_len / chunk) + 1
-  const uint64_t slab_len = (group_v + slabs - 1) / slabs;
-  const uint64_t chunk = (slab_len * G) / grid > 0 ? (slab_len * G) / grid : 1;
-  const uint64_t overlap = ((slab_len + chunk - 1) / chunk + 1) * 1;
-  unsigned lanes = 1;
-  while (lanes < overlap && lanes < 32) lanes <<= 1;
+  const uint64_t ctas = static_cast<uint64_t>(max_ctas);
+  // Units: about `per_cta` per CTA so that dynamic assignment can even out the CTAs' unequal speeds, but no
+  // smaller than one full ring (kRingDepth sweeps of the CTA) when the group allows it.
+  static const uint64_t per_cta = getenv("FQB_UNITS_PER_CTA") ? strtoull(getenv("FQB_UNITS_PER_CTA"), nullptr, 10) : 8;  // development knob
+  const uint64_t min_unit_v = static_cast<uint64_t>(fqb::kRingDepth) * fqb::kThreads;
+  uint64_t parts = (per_cta * ctas + G - 1) / G;
+  const uint64_t max_parts = group_v / min_unit_v > 0 ? group_v / min_unit_v : 1;
+  if (parts > max_parts) parts = max_parts;
+  if (parts < 1) parts = 1;
+  while ((group_v + parts - 1) / parts >= 0x7fffffffULL) ++parts;  // unit lengths are 32-bit
+  parts = (group_v + ((group_v + parts - 1) / parts) - 1) / ((group_v + parts - 1) / parts);  // no empty trailing part
+  if (parts * G >= 0xfffffff0ULL) return fail(FQB200_ERR_UNSUPPORTED, "too many work units%s");
+  const uint64_t units = parts * G;
+  // leader reductions: cover all groups in one sweep when possible (kThreads / lanes >= G), never more lanes than parts
+  unsigned lanes = 32;
+  while (lanes > 1 && (static_cast<uint64_t>(fqb::kThreads / lanes) < G || (lanes >> 1) >= parts)) lanes >>= 1;
   fqb::Geometry& g = pl->geo;
   g.groups = static_cast<unsigned>(groups);
-  g.slabs = static_cast<unsigned>(slabs);
+  g.parts = static_cast<unsigned>(parts);
+  g.units = static_cast<unsigned>(units);
   g.inner_v = static_cast<unsigned>(inner_v);
   g.step_q = static_cast<unsigned>(fqb::kThreads / inner_v);
   g.step_r = static_cast<unsigned>(fqb::kThreads % inner_v);
   g.red_lanes = lanes;
+  g.part_v = static_cast<unsigned>((group_v + parts - 1) / parts);
   g.group_v = group_v;
   g.row_pitch = G * inner_v;
   pl->vec = vec;
-  pl->grid = static_cast<int>(grid);
+  pl->grid = static_cast<int>(units < ctas ? units : ctas);
   return FQB200_OK;
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// workspace layout; returns total bytes, fills pointers when base != nullptr.  Partials: slabs * (ctas + groups) slots.
-size_t carve(char* base, uint64_t slabs_x_ctas, uint64_t slabs, uint64_t groups, fqb::FusedArgs* A) {
+// workspace layout; returns total bytes, fills pointers when base != nullptr.  Partials: one slot per unit.
+size_t carve(char* base, uint64_t units, uint64_t groups, fqb::FusedArgs* A) {
   size_t off = 0;
   auto take = [&](size_t bytes) {
     char* p = base ? base + off : nullptr;
     off = align_up(off + bytes, 256);
     return p;
   };
-  const uint64_t slots = slabs_x_ctas + slabs * groups;
+  const uint64_t slots = units;
   char* sync = take(sizeof(fqb::GridSync));
   char* pmin = take(slots * sizeof(float));
   char* pmax = take(slots * sizeof(float));
@@ -1050,13 +1050,13 @@ size_t fqb200_workspace_bytes(const fqb200_desc* d) {
   Plan a, b;
   if (make_plan(d->outer, d->groups, d->inner, true, resident, &a) != FQB200_OK) return 0;
   if (make_plan(d->outer, d->groups, d->inner, false, resident, &b) != FQB200_OK) return 0;
-  const uint64_t slabs = a.geo.slabs > b.geo.slabs ? a.geo.slabs : b.geo.slabs;
-  return carve(nullptr, slabs * static_cast<uint64_t>(resident), slabs, static_cast<uint64_t>(d->groups), nullptr);
+  const uint64_t units = a.geo.units > b.geo.units ? a.geo.units : b.geo.units;
+  return carve(nullptr, units, static_cast<uint64_t>(d->groups), nullptr);
 }
 
 int fqb200_workspace_init(void* workspace, size_t bytes, void* stream) {
   if (!workspace || bytes < sizeof(fqb::GridSync)) return fail(FQB200_ERR_WORKSPACE, "workspace too small%s");
-  cudaError_t e = cudaMemsetAsync(workspace, 0, 256 < bytes ? 256 : bytes, static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(fqb::GridSync), static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
   return FQB200_OK;
 }
@@ -1140,10 +1140,13 @@ int fqb200_quantize1(const float* in, float* out, float* grid, int64_t outer, in
   A.g_bits = bits;
   A.given_per_group = per_group;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (pl.vec == 4)
-    fqb::fq_given_kernel<4, FQB200_LEAF_TORCH><<<pl.grid, fqb::kThreads, dyn_smem(4), st>>>(A);
-  else
-    fqb::fq_given_kernel<1, FQB200_LEAF_TORCH><<<pl.grid, fqb::kThreads, 0, st>>>(A);
+  if (pl.vec == 4) {
+    if (grid) fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, true><<<pl.grid, fqb::kThreads, dyn_smem(4), st>>>(A);
+    else      fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, false><<<pl.grid, fqb::kThreads, dyn_smem(4), st>>>(A);
+  } else {
+    if (grid) fqb::fq_given_kernel<1, FQB200_LEAF_TORCH, true><<<pl.grid, fqb::kThreads, dyn_smem(1), st>>>(A);
+    else      fqb::fq_given_kernel<1, FQB200_LEAF_TORCH, false><<<pl.grid, fqb::kThreads, dyn_smem(1), st>>>(A);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "launch fq_given_kernel: %s", cudaGetErrorString(e));
   return FQB200_OK;
@@ -1169,10 +1172,10 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   if (rc != FQB200_OK) return rc;
   fqb::FusedArgs A;
   memset(&A, 0, sizeof(A));
-  const size_t need = carve(nullptr, static_cast<uint64_t>(pl.geo.slabs) * pl.grid, pl.geo.slabs, pl.geo.groups, nullptr);
+  const size_t need = carve(nullptr, pl.geo.units, pl.geo.groups, nullptr);
   if (!workspace || workspace_bytes < need) return fail(FQB200_ERR_WORKSPACE, "workspace smaller than fqb200_workspace_bytes()%s");
   if (!aligned16(workspace)) return fail(FQB200_ERR_WORKSPACE, "workspace must be 16-byte aligned%s");
-  carve(static_cast<char*>(workspace), static_cast<uint64_t>(pl.geo.slabs) * pl.grid, pl.geo.slabs, pl.geo.groups, &A);
+  carve(static_cast<char*>(workspace), pl.geo.units, pl.geo.groups, &A);
   A.geo = pl.geo;
   A.in = in;
   A.out = out;
@@ -1219,8 +1222,8 @@ int fqb200_debug_plan(int64_t outer, int64_t groups, int64_t inner, int max_ctas
   Plan pl;
   int rc = make_plan(outer, groups, inner, true, max_ctas, &pl);
   if (rc != FQB200_OK) return rc;
-  out6[0] = pl.vec; out6[1] = pl.grid; out6[2] = pl.geo.slabs; out6[3] = pl.geo.red_lanes; out6[4] = 0;
-  out6[5] = 0;
+  out6[0] = pl.vec; out6[1] = pl.grid; out6[2] = pl.geo.parts; out6[3] = pl.geo.red_lanes; out6[4] = pl.geo.units;
+  out6[5] = static_cast<int64_t>((pl.geo.group_v + pl.geo.parts - 1) / pl.geo.parts);
   return FQB200_OK;
 }
 

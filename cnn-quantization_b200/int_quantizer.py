@@ -90,24 +90,34 @@ class IntQuantizer(object):
         self.sm = None  # statistics manager class (offline statistics: not built yet)
         self.force_positive = False
         self.half_range = False
+        # extension (default off = reference behaviour): overwrite the input tensor instead of allocating the result.
+        # The manager switches it on for activation tags, where the un-quantized tensor is dead after the hook.
+        self.inplace = False
 
     # ------------------------------------------------------------------------------------------
     # dispatch (int_quantizer.py:92-122)
     # ------------------------------------------------------------------------------------------
-    def __call__(self, tensor, id, tag="", stat_id=None, override_att=None, weight_correction=None):
-        """``weight_correction=(bias_corr, var_corr)`` is an extension used by this package's manager: the
-        per-output-channel mean / variance correction of inference_quantization_manager.py:374-391 is applied
-        inside the same kernel launch that quantizes the weight."""
+    def __call__(self, tensor, id, tag="", stat_id=None, override_att=None, weight_correction=None, bias=None):
+        """Extensions used by this package's manager (both default to the reference behaviour):
+        ``weight_correction=(bias_corr, var_corr)``: the per-output-channel mean / variance correction of
+        inference_quantization_manager.py:374-391 is applied inside the same launch that quantizes the weight;
+        ``bias``: a per-channel vector added to the tensor before anything else inside the kernel (the folded-BN
+        convolution bias, so the convolution itself can run bias-free and a whole pass over the activation is saved)."""
         if override_att is not None:
             orig_att = getattr(self, override_att[0])
             setattr(self, override_att[0], override_att[1])
         try:
             self._unsupported(stat_id)
+            if bias is not None and not self._bias_fusable(tensor):
+                # what the convolution would have added (in place when the caller gave the tensor up)
+                b = bias.view((1, -1) + (1,) * (tensor.dim() - 2))
+                tensor = tensor.add_(b) if self.inplace else tensor + b
+                bias = None
             if self.clipping != "no":
                 if self.mtd_quant:
-                    res = self.mid_tread_quantize_activation(tensor, id)
+                    res = self.mid_tread_quantize_activation(tensor, id, bias=bias)
                 else:
-                    res = self.gemmlowpClippingQuantize(tensor, id, tag, stat_id=stat_id, clip_type=self.clipping)
+                    res = self.gemmlowpClippingQuantize(tensor, id, tag, stat_id=stat_id, clip_type=self.clipping, bias=bias)
             elif self.pcq_w:
                 if self.mtd_quant:
                     res = self.mid_tread_quantize_weights_per_channel(tensor, id, weight_correction)
@@ -115,9 +125,9 @@ class IntQuantizer(object):
                     res = self.gemmlowpQuantizeWeightsPerChannel(tensor, id, weight_correction=weight_correction)
             elif self._pc_act(tensor):
                 if self.mtd_quant:
-                    res = self.mid_tread_quantize_activation_per_channel(tensor, id)
+                    res = self.mid_tread_quantize_activation_per_channel(tensor, id, bias=bias)
                 else:
-                    res = self.gemmlowpQuantizeActivationPerChannel(tensor, id, tag, stat_id=stat_id)
+                    res = self.gemmlowpQuantizeActivationPerChannel(tensor, id, tag, stat_id=stat_id, bias=bias)
             else:
                 res = self.gemmlowpMinMaxQuantize(tensor, tag, stat_id=stat_id, weight_correction=weight_correction)
         finally:
@@ -148,6 +158,14 @@ class IntQuantizer(object):
     def _positive(self):
         return bool(self.force_positive or self.half_range)
 
+    def _bias_fusable(self, tensor):
+        """The kernel takes a per-GROUP addend: only the per-channel activation layouts have channel = group."""
+        return bool((self.clipping != "no" or not self.pcq_w) and self._pc_act(tensor) and tensor.shape[1] > 1
+                    and not self.kld)
+
+    def _out(self, tensor):
+        return tensor if (self.inplace and tensor.is_contiguous()) else None
+
     @staticmethod
     def _nchw_layout(tensor):
         n, c = tensor.shape[0], tensor.shape[1]
@@ -168,7 +186,7 @@ class IntQuantizer(object):
     # ------------------------------------------------------------------------------------------
     # dispatch targets
     # ------------------------------------------------------------------------------------------
-    def gemmlowpClippingQuantize(self, tensor, id, tag="", stat_id=None, clip_type="laplace"):
+    def gemmlowpClippingQuantize(self, tensor, id, tag="", stat_id=None, clip_type="laplace", bias=None):
         """ACIQ clipping, int_quantizer.py:327-359: per channel (pcq_a, 4-D, HW>1, C>1; fp32 parameter math,
         optional bit allocation) or per tensor (float64 parameter math)."""
         self._unsupported(stat_id)
@@ -177,9 +195,11 @@ class IntQuantizer(object):
             return ops.fused(tensor, self._nchw_layout(tensor), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
                              leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(),
                              bit_alloc=self.bit_alloc_act, bit_alloc_prior=self._prior(),
-                             bit_alloc_round=self.bit_alloc_round, bit_alloc_target=self.bit_alloc_target_act)
+                             bit_alloc_round=self.bit_alloc_round, bit_alloc_target=self.bit_alloc_target_act,
+                             bias=bias, out=self._out(tensor))
         return ops.fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
-                         leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(), solve_f64=True)
+                         leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(), solve_f64=True,
+                         out=self._out(tensor))
 
     def gemmlowpMinMaxQuantize(self, tensor, tag="", stat_id=None, weight_correction=None):
         """Per-tensor min/max range through the compiled-leaf arithmetic, int_quantizer.py:361-379 + :605-614.
@@ -193,10 +213,10 @@ class IntQuantizer(object):
                              bias_corr=weight_correction[0], var_corr=weight_correction[1], **kw)
         if avg:
             n = tensor.shape[0]
-            return ops.fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_GROUP_MEAN, **kw)
-        return ops.fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, **kw)
+            return ops.fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_GROUP_MEAN, out=self._out(tensor), **kw)
+        return ops.fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, out=self._out(tensor), **kw)
 
-    def gemmlowpQuantizeActivationPerChannel(self, tensor, id, tag="", stat_id=None, min_=None, max_=None):
+    def gemmlowpQuantizeActivationPerChannel(self, tensor, id, tag="", stat_id=None, min_=None, max_=None, bias=None):
         """Per-channel min/max (0 lower bound when positive) with optional bit allocation, int_quantizer.py:409-451."""
         self._unsupported(stat_id)
         layout = self._nchw_layout(tensor)
@@ -204,7 +224,9 @@ class IntQuantizer(object):
             return ops.fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
                              num_bits=self.num_bits, positive=self._positive(), bit_alloc=self.bit_alloc_act,
                              bit_alloc_prior=self._prior(), bit_alloc_round=self.bit_alloc_round,
-                             bit_alloc_target=self.bit_alloc_target_act)
+                             bit_alloc_target=self.bit_alloc_target_act, bias=bias, out=self._out(tensor))
+        if bias is not None:
+            tensor = tensor + bias.view(1, -1, 1, 1)
         # explicit bounds (API compatibility): statistics pass for what is missing, then the given-parameter leaf
         st = ops.fused(tensor, layout, num_bits=min(self.num_bits, 8), bit_alloc=self.bit_alloc_act,
                        bit_alloc_prior=self._prior(), bit_alloc_round=self.bit_alloc_round,
@@ -249,15 +271,17 @@ class IntQuantizer(object):
         return ops.fused(tensor, (1, rows, tensor.numel() // rows), leaf=L.LEAF_MIDTREAD, positive=False,
                          mt_target=self.bit_alloc_target_weight, mt_clip=False, bias_corr=bc, var_corr=vc)
 
-    def mid_tread_quantize_activation(self, tensor, id):
+    def mid_tread_quantize_activation(self, tensor, id, bias=None):
         if self._pc_act(tensor):
-            return self.mid_tread_quantize_activation_per_channel(tensor, id)
+            return self.mid_tread_quantize_activation_per_channel(tensor, id, bias=bias)
+        if bias is not None:
+            tensor = tensor + bias.view((1, -1) + (1,) * (tensor.dim() - 2))
         return ops.fused(tensor, (1, 1, tensor.numel()), leaf=L.LEAF_MIDTREAD, positive=self._positive(),
-                         mt_target=self.bit_alloc_target_act, mt_clip=True)
+                         mt_target=self.bit_alloc_target_act, mt_clip=True, out=self._out(tensor))
 
-    def mid_tread_quantize_activation_per_channel(self, tensor, id):
+    def mid_tread_quantize_activation_per_channel(self, tensor, id, bias=None):
         return ops.fused(tensor, self._nchw_layout(tensor), leaf=L.LEAF_MIDTREAD, positive=self._positive(),
-                         mt_target=self.bit_alloc_target_act, mt_clip=True)
+                         mt_target=self.bit_alloc_target_act, mt_clip=True, bias=bias, out=self._out(tensor))
 
     def mid_tread_quantization(self, tensor, id, target, clip=False, sym=True):
         """[R, K] view, int_quantizer.py:185-225.  Returns (quantized, None) like the reference without entropy."""

@@ -160,7 +160,11 @@ class QuantizationManagerInference(object):
         if args.stats_mode != "no":
             raise NotImplementedError("stats_mode %r: offline statistics are the next scope row (SURVEY.md 8f)" % args.stats_mode)
         self._factory = quantizer_factory or _default_factory
-        self._fuse_weight_correction = quantizer_factory is None
+        # extensions of this package's CUDA quantizer (a foreign factory - the CPU oracle - gets plain reference calls)
+        self._native = quantizer_factory is None
+        self._fuse_weight_correction = self._native
+        self.fuse_conv_bias = self._native   # run hooked convolutions bias-free, add the bias inside the fused kernel
+        self.inplace_activations = self._native
         self.fused_relu = args.arch is not None and (args.arch in FUSED_RELU_ARCHS or "squeezenet" in args.arch)
         self.ignore_ids = []
         self.quantizers = {}
@@ -169,11 +173,16 @@ class QuantizationManagerInference(object):
         self.record = False
         self._hooks = []
         self._patched = []
+        self._debiased = []
         self._orig_init = {}
         self._counters = {}
         if self.quantize:
             self.__fill_quantizers__(args.qtype, qparams, args.arch, args.qweight)
             self.quantizer_default = self._load("int8", qparams)
+            if self.inplace_activations:
+                for tag, q in list(self.quantizers.items()) + [("", self.quantizer_default)]:
+                    if tag.startswith("activation") or tag in ("", "ignored"):
+                        q.inplace = True
             if args.qtype == "int4":
                 self.set_8bit_list(["conv%d_activation" % i for i in [0]])  # createTruncationManager, :334-340
 
@@ -279,6 +288,12 @@ class QuantizationManagerInference(object):
                 m.forward = _identity_forward
                 self._patched.append(m)
                 continue
+            if cls is nn.Conv2d and self.fuse_conv_bias and self.enabled and m.bias is not None:
+                # the convolution runs bias-free; the (folded-BN) bias is added inside the fused quantization kernel
+                m._fq_bias = m.bias.data
+                m._fq_bias_param = m.bias
+                m.bias = None
+                self._debiased.append(m)
             hook = {nn.Conv2d: self._conv_hook, nn.Linear: self._linear_hook, nn.MaxPool2d: self._maxpool_hook,
                     nn.AvgPool2d: self._avgpool_hook, nn.BatchNorm2d: self._bn_hook}[cls]
             self._hooks.append(m.register_forward_hook(hook))
@@ -291,13 +306,19 @@ class QuantizationManagerInference(object):
         for m in self._patched:
             m.__dict__.pop("forward", None)
         self._patched = []
+        for m in self._debiased:
+            m.bias = m._fq_bias_param
+            del m._fq_bias, m._fq_bias_param
+        self._debiased = []
 
     def _conv_hook(self, m, inputs, out):
+        bias = getattr(m, "_fq_bias", None)
         if not self.enabled:
-            return None
+            return None if bias is None else out + bias.view(1, -1, 1, 1)
         tag = "activation_classifier" if out.shape[1] == 1000 else "activation"
+        extra = {} if bias is None else {"bias": bias}
         return self.quantize_instant(out, "conv%d_activation" % m._fq_id, tag, half_range=hasattr(m, "before_relu"),
-                                     verbose=self.verbose)
+                                     verbose=self.verbose, **extra)
 
     def _linear_hook(self, m, inputs, out):
         if not self.enabled:

@@ -23,19 +23,22 @@ def profile_collect():
     traffic: 'D' two statistics passes + apply (16 B/elem), 'B' one statistics pass + apply (12), 'A' apply only (8),
     'S' statistics only."""
     torch.cuda.synchronize()
-    modes = {}
-    for mode, elems, nbytes, e0, e1 in _prof["records"]:
-        m = modes.setdefault(mode, {"launches": 0, "elems": 0, "bytes": 0, "ms": 0.0})
-        m["launches"] += 1
-        m["elems"] += elems
-        m["bytes"] += nbytes
-        m["ms"] += e0.elapsed_time(e1)
-    return {"launches": _prof["launches"], "modes": modes}
+    modes, shapes = {}, {}
+    for mode, elems, nbytes, e0, e1, tag in _prof["records"]:
+        ms = e0.elapsed_time(e1)
+        for table, key in ((modes, mode), (shapes, "%s %s" % (mode, tag))):
+            m = table.setdefault(key, {"launches": 0, "elems": 0, "bytes": 0, "ms": 0.0})
+            m["launches"] += 1
+            m["elems"] += elems
+            m["bytes"] += nbytes
+            m["ms"] += ms
+    return {"launches": _prof["launches"], "modes": modes, "shapes": shapes}
 
 
 class _Timed(object):
-    def __init__(self, mode, elems, bytes_per_elem):
+    def __init__(self, mode, elems, bytes_per_elem, tag=""):
         self.args = (mode, elems, elems * bytes_per_elem)
+        self.tag = tag
 
     def __enter__(self):
         _prof["launches"] += 1
@@ -48,7 +51,7 @@ class _Timed(object):
     def __exit__(self, *exc):
         if _prof["on"]:
             self.e1.record()
-            _prof["records"].append(self.args + (self.e0, self.e1))
+            _prof["records"].append(self.args + (self.e0, self.e1, self.tag))
 
 
 def _stream_handle(device):
@@ -182,7 +185,7 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
                     (bit_alloc and num_bits <= 4 and scope == L.SCOPE_GROUP))
         mode = "S" if stats_only else ("D" if two_pass else "B")
         bpe = (8 if two_pass else 4) + (0 if stats_only else 8)
-        with _Timed(mode, x.numel(), bpe):
+        with _Timed(mode, x.numel(), bpe, "%dx%dx%d" % (outer, groups, inner)):
             L.check(lib.fqb200_fused(ctypes.byref(d), x.data_ptr(), out.data_ptr() if out is not None else None,
                                      ws.data_ptr(), ws.numel(), stream))
     if stats_only:

@@ -378,6 +378,33 @@ def test_fused_noncontiguous_and_inplace_and_determinism(fq):
     assert torch.equal(out, q(base, "c", "activation"))
 
 
+def test_fused_bias_operand_and_inplace_flag(fq):
+    """x + bias[c] inside the kernel == quantizing the tensor the convolution would have produced with its bias,
+    bit for bit, for every per-channel path; the in-place flag returns the same values in the caller's buffer."""
+    torch.manual_seed(3)
+    for shape in ((6, 20, 14, 14), (5, 12, 7, 7), (3, 8, 5, 6)):
+        x = torch.randn(*shape, device="cuda") * 1.5
+        b = torch.randn(shape[1], device="cuda")
+        for kw in (dict(clipping="laplace", pcq_act=True, bit_alloc_act=True), dict(pcq_act=True),
+                   dict(clipping="gaus", pcq_act=True), dict(clipping="laplace", pcq_act=True, mtd_quant=True)):
+            for hr in (False, True):
+                q = fq.int_quantizer("int4", params(**kw))
+                q.pcq_w = False
+                q.half_range = hr
+                want = q(x + b.view(1, -1, 1, 1), "c", "activation")
+                got = q(x, "c", "activation", bias=b)
+                assert torch.equal(got, want), (shape, kw, hr)
+                q.inplace = True
+                buf = x.clone()
+                got2 = q(buf, "c", "activation", bias=b)
+                assert got2.data_ptr() == buf.data_ptr() and torch.equal(got2, want)
+    # paths whose groups are not channels fall back to adding the bias first
+    q = fq.int_quantizer("int8", params())
+    x = torch.randn(4, 6, 5, 5, device="cuda")
+    b = torch.randn(6, device="cuda")
+    assert torch.equal(q(x, "c", "activation", bias=b), q(x + b.view(1, -1, 1, 1), "c", "activation"))
+
+
 def test_full_size_properties(fq):
     """ResNet-50 sized activation (config 3, batch 64 slice): per-channel level count, range, idempotence of the grid."""
     torch.manual_seed(1)
