@@ -211,12 +211,20 @@ __device__ __forceinline__ void grid_exit(GridSync* gs) {
 // a fraction of the HBM bandwidth; pulling small units instead ends every phase within one unit time.
 // Consecutive ids are neighbouring channels of the same batch slab, so what the CTAs touch concurrently is a
 // nearly contiguous window of memory.  Every unit leaves one partial at slot u.
+//
+// Rows whose length is not a multiple of 4 floats (7x7 feature maps: 49) are walked with 128-bit accesses as well:
+// `bundle` (2 or 4) consecutive channels form one streaming group whose row IS 16-byte aligned (4 x 49 floats =
+// 49 vectors), and the CTA stride is cut down to the largest multiple of that row length, so that every thread
+// always sits on the same column of the row: the channel(s) its four floats belong to never change.
 struct Geometry {
-  unsigned groups;          // G
+  unsigned groups;          // streaming groups: channels / bundle
+  unsigned channels;        // G of the descriptor (what the statistics / parameters are indexed by)
+  unsigned bundle;          // channels per streaming group: 1, or 2 / 4 when inner % 4 != 0
+  unsigned stride;          // threads that walk a unit: kThreads, or the largest multiple of inner_v below it (bundled)
   unsigned parts;           // P
-  unsigned units;           // P * G
-  unsigned inner_v;         // inner / VEC
-  unsigned step_q, step_r;  // kThreads / inner_v, kThreads % inner_v
+  unsigned units;           // P * groups
+  unsigned inner_v;         // vectors per row of a streaming group
+  unsigned step_q, step_r;  // stride / inner_v, stride % inner_v
   unsigned red_lanes;       // lanes per group in the leader's partial reductions (power of two <= 32)
   unsigned part_v;          // vectors per part: ceil(group_v / P) (the last part of a group may be shorter)
   unsigned long long group_v;    // outer * inner_v: vectors per group (< 2^32, checked by the host)
@@ -289,7 +297,8 @@ __device__ __forceinline__ void cursor_step(const Geometry& geo, Cursor& c) {
 }
 
 struct UnitInfo {
-  unsigned g;      // group
+  unsigned g;      // streaming group
+  unsigned p;      // part
   unsigned mine;   // vectors this thread visits
   unsigned trips;  // ring steps of this thread's WARP (= `mine` of its first lane): warp-uniform loop count
   Cursor start;    // this thread's first vector
@@ -297,15 +306,15 @@ struct UnitInfo {
 template <bool REV>
 __device__ __forceinline__ UnitInfo unit_info(const Geometry& geo, unsigned u) {
   UnitInfo ui;
-  const unsigned p = u / geo.groups;
-  ui.g = u - p * geo.groups;
+  ui.p = u / geo.groups;
+  ui.g = u - ui.p * geo.groups;
   const unsigned gv = static_cast<unsigned>(geo.group_v);
-  const unsigned vb = p * geo.part_v;  // 32-bit: group_v < 2^32
+  const unsigned vb = ui.p * geo.part_v;  // 32-bit: group_v < 2^32
   const unsigned len = min(geo.part_v, gv - vb);
-  constexpr unsigned S = kThreads;
+  const unsigned S = geo.stride;
   const unsigned t = threadIdx.x, t0 = threadIdx.x & ~31u;
-  ui.mine = (t < len) ? (len - t + S - 1u) / S : 0u;
-  ui.trips = (t0 < len) ? (len - t0 + S - 1u) / S : 0u;
+  ui.mine = (t < len && t < S) ? (len - t + S - 1u) / S : 0u;
+  ui.trips = (t0 < len && t0 < S) ? (len - t0 + S - 1u) / S : 0u;
   const unsigned v0 = (ui.mine == 0) ? vb : (REV ? vb + (len - 1u - t) : vb + t);
   const unsigned a0 = v0 / geo.inner_v;
   ui.start.j = v0 - a0 * geo.inner_v;
@@ -314,9 +323,9 @@ __device__ __forceinline__ UnitInfo unit_info(const Geometry& geo, unsigned u) {
 }
 
 // Stream every unit this CTA manages to pull through `acc`:
-//   acc.begin(g)            unit starts (load per-group constants, reset accumulators)
+//   acc.begin(ui)           unit starts (load per-group constants, reset accumulators); ui.start.j is the thread's column
 //   acc.consume(x, off)     one vector (off = its index from the tensor base, in vectors)
-//   acc.end(u, g)           unit done: CTA-wide combine + partial store; MUST contain at least one __syncthreads()
+//   acc.end(ui)             unit done: CTA-wide combine + partial store; MUST contain at least one __syncthreads()
 // `counter` is this phase's unit counter in the workspace (zero at launch), or nullptr for a static round-robin
 // assignment (ticket k of CTA b = b + k * gridDim.x; used by the workspace-free given-parameter kernel).
 // REV walks ids and vectors backwards.
@@ -358,7 +367,7 @@ __device__ __forceinline__ void stream_units(const Geometry& geo, const float* b
   UnitInfo cu = unit_info<REV>(geo, unit_of(ticket));
   Cursor cc = cu.start;
   unsigned cdone = 0;  // ring steps done in the consumed unit
-  acc.begin(cu.g);
+  acc.begin(cu);
   // issue side (at most one unit ahead: that is as far as ss.ids is guaranteed visible)
   unsigned iseq = 0;
   UnitInfo iu = cu;
@@ -408,7 +417,7 @@ __device__ __forceinline__ void stream_units(const Geometry& geo, const float* b
     if (cdone == cu.trips) {
       // ---- unit boundary
       if (threadIdx.x == 0) ss.ids[(seq + 2u) & 3u] = pending;  // visible after the barrier inside end()
-      acc.end(unit_of(ticket), cu.g);
+      acc.end(cu);
       ++seq;
       ticket = ss.ids[seq & 3u];
       if (ticket >= total) break;
@@ -416,7 +425,7 @@ __device__ __forceinline__ void stream_units(const Geometry& geo, const float* b
       cu = (iseq == seq) ? ahead : unit_info<REV>(geo, unit_of(ticket));  // usually the issue side is already there
       cc = cu.start;
       cdone = 0;
-      acc.begin(cu.g);
+      acc.begin(cu);
       continue;
     }
     cp_async_wait<D - 1>();  // the oldest group (slot `head`) has landed

@@ -64,6 +64,7 @@ struct FusedArgs {
   int need_dev;      // phase S2 required (b and/or std)
   const float *g_delta, *g_offset, *g_bits;
   int given_per_group;
+  unsigned inner;      // floats per channel row (bundled layouts locate channel boundaries with it)
   double n_per_group;  // outer * inner
   float* out_stats;
   unsigned long long* dbg;  // development: globaltimer stamps of the phase boundaries (NULL in production)
@@ -105,15 +106,15 @@ __device__ __forceinline__ void reduce_partials3(const Geometry& geo, const T0* 
   const unsigned L = geo.red_lanes;
   const unsigned sub = threadIdx.x % L;
   const unsigned per_sweep = kThreads / L;
-  for (unsigned g0 = 0; g0 < geo.groups; g0 += per_sweep) {
+  for (unsigned g0 = 0; g0 < geo.channels; g0 += per_sweep) {
     const unsigned g = g0 + threadIdx.x / L;
     T0 a0 = id0;
     T1 a1 = id1;
     T2 a2 = id2;
-    if (g < geo.groups) {
+    if (g < geo.channels) {
 #pragma unroll 4
       for (unsigned p = sub; p < geo.parts; p += L) {
-        const size_t slot = static_cast<size_t>(p) * geo.groups + g;
+        const size_t slot = static_cast<size_t>(p) * geo.channels + g;
         if (p0) a0 = op0(a0, ld_ws(p0 + slot));
         if (p1) a1 = op1(a1, ld_ws(p1 + slot));
         if (p2) a2 = op2(a2, ld_ws(p2 + slot));
@@ -124,7 +125,7 @@ __device__ __forceinline__ void reduce_partials3(const Geometry& geo, const T0* 
       a1 = op1(a1, __shfl_xor_sync(0xffffffffu, a1, o));
       a2 = op2(a2, __shfl_xor_sync(0xffffffffu, a2, o));
     }
-    if (g < geo.groups && sub == 0) {
+    if (g < geo.channels && sub == 0) {
       if (p0) o0[g] = a0;
       if (p1) o1[g] = a1;
       if (p2) o2[g] = a2;
@@ -134,7 +135,7 @@ __device__ __forceinline__ void reduce_partials3(const Geometry& geo, const T0* 
 
 // per-group bit allocation, int_quantizer.py:381-407 (get_bits_alloc_fixed_target).  All threads of the CTA.
 __device__ __noinline__ void solve_bit_alloc(const FusedArgs& A, LeaderSmem& sm) {
-  const unsigned G = A.geo.groups;
+  const unsigned G = A.geo.channels;
   const float* prior = (A.prior == FQB200_PRIOR_STD) ? A.gstd : A.gb;
   // p = alpha^(2/3)  (torch.pow with a python-float exponent -> fp32 powf)
   double local = 0.0;
@@ -263,7 +264,7 @@ __device__ __forceinline__ void export_stats(const FusedArgs& A, unsigned g, flo
 
 // mid-tread parameters, int_quantizer.py:185-214 (+ :128-145)
 __device__ __noinline__ void solve_mid_tread(const FusedArgs& A, LeaderSmem& sm) {
-  const unsigned G = A.geo.groups;
+  const unsigned G = A.geo.channels;
   double local = 0.0;
   for (unsigned g = threadIdx.x; g < G; g += kThreads) {
     float p = powf(A.gstd[g], 0.6666666666666666f);
@@ -313,7 +314,7 @@ __device__ __noinline__ void solve_mid_tread(const FusedArgs& A, LeaderSmem& sm)
 
 // The parameter solve: runs once per launch, after the last statistics phase.
 __device__ __noinline__ void solve_params(const FusedArgs& A, LeaderSmem& sm) {
-  const unsigned G = A.geo.groups;
+  const unsigned G = A.geo.channels;
   if (A.leaf == FQB200_LEAF_MIDTREAD) {
     solve_mid_tread(A, sm);
     return;
@@ -375,6 +376,9 @@ __device__ __noinline__ void solve_params(const FusedArgs& A, LeaderSmem& sm) {
 struct PhaseSmem {
   float f0[kWarps], f1[kWarps];
   double d0[kWarps], d1[kWarps];
+  // bundled layouts: one row per channel of the bundle
+  float bf0[4][kWarps], bf1[4][kWarps];
+  double bd0[4][kWarps], bd1[4][kWarps];
 };
 
 #ifndef FQB_USTATS
@@ -425,11 +429,11 @@ struct AccStats1 {
   PhaseSmem& sm;
   float mn, mx, bias;
   double s;
-  __device__ __forceinline__ void begin(unsigned g) {
+  __device__ __forceinline__ void begin(const UnitInfo& ui) {
     mn = INFINITY;
     mx = -INFINITY;
     s = 0.0;
-    bias = A.bias ? __ldg(A.bias + g) : 0.f;  // x + 0 when there is none
+    bias = A.bias ? __ldg(A.bias + ui.g) : 0.f;  // x + 0 when there is none
   }
   __device__ __forceinline__ void consume(const float4& v, unsigned) {
     const float x0 = __fadd_rn(v.x, bias), x1 = __fadd_rn(v.y, bias), x2 = __fadd_rn(v.z, bias), x3 = __fadd_rn(v.w, bias);
@@ -443,10 +447,11 @@ struct AccStats1 {
     mx = fmaxf(mx, x);
     s += static_cast<double>(x);
   }
-  __device__ __forceinline__ void end(unsigned u, unsigned) {
+  __device__ __forceinline__ void end(const UnitInfo& ui) {
     double unused = 0.0;
     block_combine(sm, mn, mx, s, unused, true, false);
     if (threadIdx.x == 0) {
+      const size_t u = static_cast<size_t>(ui.p) * A.geo.channels + ui.g;
       st_ws(A.pmin + u, mn);
       st_ws(A.pmax + u, mx);
       st_ws(A.psum + u, s);
@@ -466,9 +471,9 @@ struct AccStats2 {
   double* out_sq;
   float mu, bias;
   double sa, sq;
-  __device__ __forceinline__ void begin(unsigned g) {
-    mu = ld_ws(mean + g);
-    bias = (with_bias && A.bias) ? __ldg(A.bias + g) : 0.f;
+  __device__ __forceinline__ void begin(const UnitInfo& ui) {
+    mu = ld_ws(mean + ui.g);
+    bias = (with_bias && A.bias) ? __ldg(A.bias + ui.g) : 0.f;
     sa = 0.0;
     sq = 0.0;
   }
@@ -483,10 +488,11 @@ struct AccStats2 {
     sa += static_cast<double>(fabsf(d));
     sq += static_cast<double>(__fmul_rn(d, d));
   }
-  __device__ __forceinline__ void end(unsigned u, unsigned) {
+  __device__ __forceinline__ void end(const UnitInfo& ui) {
     float f0 = 0.f, f1 = 0.f;
     block_combine(sm, f0, f1, sa, sq, false, true);
     if (threadIdx.x == 0) {
+      const size_t u = static_cast<size_t>(ui.p) * A.geo.channels + ui.g;
       if (out_abs) st_ws(out_abs + u, sa);
       st_ws(out_sq + u, sq);
     }
@@ -529,6 +535,166 @@ __device__ __forceinline__ float leaf_apply(float x, const LeafParam& q, const D
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// bundled layouts (inner % 4 != 0): every thread sits on a fixed column of the bundle row, so its four floats always
+// belong to channel cA (the first `split` of them) and, when the vector straddles a row end, channel cA + 1.
+// ------------------------------------------------------------------------------------------------
+struct Column {
+  unsigned chA;    // global channel of the first element
+  unsigned split;  // 1..4 elements belong to chA, the rest to chA + 1
+};
+__device__ __forceinline__ Column column_of(const FusedArgs& A, const UnitInfo& ui) {
+  const unsigned inner = A.inner;  // floats per channel row
+  const unsigned e0 = 4u * ui.start.j;
+  const unsigned cA = e0 / inner;
+  Column c;
+  c.chA = ui.g * A.geo.bundle + cA;
+  c.split = min(4u, inner - (e0 - cA * inner));
+  return c;
+}
+
+// CTA-wide per-channel combine for one bundle: thread values (A-part for channel cA, B-part for cA+1) -> one result
+// per channel of the bundle, valid in thread 0 (arrays indexed by channel within the bundle).  Two barriers.
+template <bool USE_F, bool USE_D1>
+__device__ __forceinline__ void bundle_combine(PhaseSmem& sm, unsigned bundle, unsigned cA, bool hasB, float fA0, float fA1,
+                                               double dA0, double dA1, float fB0, float fB1, double dB0, double dB1,
+                                               float (&rf0)[4], float (&rf1)[4], double (&rd0)[4], double (&rd1)[4]) {
+  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();  // previous unit's readers are done with sm
+  for (unsigned ch = 0; ch < bundle; ++ch) {
+    const bool a = (cA == ch), b = hasB && (cA + 1u == ch);
+    float v0 = a ? fA0 : INFINITY, v1 = a ? fA1 : -INFINITY;
+    double s0 = a ? dA0 : 0.0, s1 = a ? dA1 : 0.0;
+    if (b) {
+      v0 = fminf(v0, fB0);
+      v1 = fmaxf(v1, fB1);
+      s0 += dB0;
+      s1 += dB1;
+    }
+    if (USE_F) {
+      v0 = warp_reduce(v0, OpMin());
+      v1 = warp_reduce(v1, OpMax());
+    }
+    s0 = warp_reduce(s0, OpAdd());
+    if (USE_D1) s1 = warp_reduce(s1, OpAdd());
+    if (l == 0) {
+      sm.bf0[ch][w] = v0;
+      sm.bf1[ch][w] = v1;
+      sm.bd0[ch][w] = s0;
+      sm.bd1[ch][w] = s1;
+    }
+  }
+  __syncthreads();
+  if (w == 0) {
+    for (unsigned ch = 0; ch < bundle; ++ch) {
+      float a = (l < kWarps) ? sm.bf0[ch][l] : INFINITY, b = (l < kWarps) ? sm.bf1[ch][l] : -INFINITY;
+      double c = (l < kWarps) ? sm.bd0[ch][l] : 0.0, d = (l < kWarps) ? sm.bd1[ch][l] : 0.0;
+#pragma unroll
+      for (int o = kWarps / 2; o > 0; o >>= 1) {
+        a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+      }
+      rf0[ch] = a;
+      rf1[ch] = b;
+      rd0[ch] = c;
+      rd1[ch] = d;
+    }
+  }
+}
+
+struct AccStats1B {
+  const FusedArgs& A;
+  PhaseSmem& sm;
+  Column col;
+  float mnA, mxA, mnB, mxB, biasA, biasB;
+  double sA, sB;
+  __device__ __forceinline__ void begin(const UnitInfo& ui) {
+    col = column_of(A, ui);
+    mnA = mnB = INFINITY;
+    mxA = mxB = -INFINITY;
+    sA = sB = 0.0;
+    biasA = A.bias ? __ldg(A.bias + col.chA) : 0.f;
+    biasB = (A.bias && col.split < 4u) ? __ldg(A.bias + col.chA + 1u) : 0.f;
+  }
+  __device__ __forceinline__ void consume(const float4& v, unsigned) {
+    const unsigned sp = col.split;
+    const float x0 = __fadd_rn(v.x, biasA);
+    const float x1 = __fadd_rn(v.y, sp > 1u ? biasA : biasB);
+    const float x2 = __fadd_rn(v.z, sp > 2u ? biasA : biasB);
+    const float x3 = __fadd_rn(v.w, sp > 3u ? biasA : biasB);
+    // A part
+    mnA = fminf(mnA, fminf(fminf(x0, sp > 1u ? x1 : INFINITY), fminf(sp > 2u ? x2 : INFINITY, sp > 3u ? x3 : INFINITY)));
+    mxA = fmaxf(mxA, fmaxf(fmaxf(x0, sp > 1u ? x1 : -INFINITY), fmaxf(sp > 2u ? x2 : -INFINITY, sp > 3u ? x3 : -INFINITY)));
+    sA += static_cast<double>(__fadd_rn(__fadd_rn(x0, sp > 1u ? x1 : 0.f), __fadd_rn(sp > 2u ? x2 : 0.f, sp > 3u ? x3 : 0.f)));
+    if (sp < 4u) {  // per-thread constant: only the few columns that straddle a row end come here
+      mnB = fminf(mnB, fminf(fminf(sp > 1u ? INFINITY : x1, sp > 2u ? INFINITY : x2), x3));
+      mxB = fmaxf(mxB, fmaxf(fmaxf(sp > 1u ? -INFINITY : x1, sp > 2u ? -INFINITY : x2), x3));
+      sB += static_cast<double>(__fadd_rn(__fadd_rn(sp > 1u ? 0.f : x1, sp > 2u ? 0.f : x2), x3));
+    }
+  }
+  __device__ __forceinline__ void end(const UnitInfo& ui) {
+    float r0[4], r1[4];
+    double d0[4], d1[4];
+    const unsigned base = ui.g * A.geo.bundle;
+    bundle_combine<true, false>(sm, A.geo.bundle, col.chA - base, col.split < 4u, mnA, mxA, sA, 0.0, mnB, mxB, sB, 0.0, r0, r1, d0, d1);
+    if (threadIdx.x == 0) {
+      for (unsigned ch = 0; ch < A.geo.bundle; ++ch) {
+        const size_t u = static_cast<size_t>(ui.p) * A.geo.channels + base + ch;
+        st_ws(A.pmin + u, r0[ch]);
+        st_ws(A.pmax + u, r1[ch]);
+        st_ws(A.psum + u, d0[ch]);
+      }
+    }
+  }
+};
+
+struct AccStats2B {
+  const FusedArgs& A;
+  PhaseSmem& sm;
+  Column col;
+  float muA, muB, biasA, biasB;
+  double saA, sqA, saB, sqB;
+  __device__ __forceinline__ void begin(const UnitInfo& ui) {
+    col = column_of(A, ui);
+    const bool hasB = col.split < 4u;
+    muA = ld_ws(A.gmean + col.chA);
+    muB = hasB ? ld_ws(A.gmean + col.chA + 1u) : 0.f;
+    biasA = A.bias ? __ldg(A.bias + col.chA) : 0.f;
+    biasB = (A.bias && hasB) ? __ldg(A.bias + col.chA + 1u) : 0.f;
+    saA = sqA = saB = sqB = 0.0;
+  }
+  __device__ __forceinline__ void consume(const float4& v, unsigned) {
+    const unsigned sp = col.split;
+    const float d0 = __fsub_rn(__fadd_rn(v.x, biasA), muA);
+    const float d1 = __fsub_rn(__fadd_rn(v.y, sp > 1u ? biasA : biasB), sp > 1u ? muA : muB);
+    const float d2 = __fsub_rn(__fadd_rn(v.z, sp > 2u ? biasA : biasB), sp > 2u ? muA : muB);
+    const float d3 = __fsub_rn(__fadd_rn(v.w, sp > 3u ? biasA : biasB), sp > 3u ? muA : muB);
+    const float a1 = sp > 1u ? d1 : 0.f, a2 = sp > 2u ? d2 : 0.f, a3 = sp > 3u ? d3 : 0.f;
+    saA += static_cast<double>(__fadd_rn(__fadd_rn(fabsf(d0), fabsf(a1)), __fadd_rn(fabsf(a2), fabsf(a3))));
+    sqA += static_cast<double>(__fmaf_rn(a3, a3, __fmaf_rn(a2, a2, __fmaf_rn(a1, a1, __fmul_rn(d0, d0)))));
+    if (sp < 4u) {
+      const float b1 = sp > 1u ? 0.f : d1, b2 = sp > 2u ? 0.f : d2;
+      saB += static_cast<double>(__fadd_rn(__fadd_rn(fabsf(b1), fabsf(b2)), fabsf(d3)));
+      sqB += static_cast<double>(__fmaf_rn(d3, d3, __fmaf_rn(b2, b2, __fmul_rn(b1, b1))));
+    }
+  }
+  __device__ __forceinline__ void end(const UnitInfo& ui) {
+    float r0[4], r1[4];
+    double d0[4], d1[4];
+    const unsigned base = ui.g * A.geo.bundle;
+    bundle_combine<false, true>(sm, A.geo.bundle, col.chA - base, col.split < 4u, 0.f, 0.f, saA, sqA, 0.f, 0.f, saB, sqB, r0, r1, d0, d1);
+    if (threadIdx.x == 0) {
+      for (unsigned ch = 0; ch < A.geo.bundle; ++ch) {
+        const size_t u = static_cast<size_t>(ui.p) * A.geo.channels + base + ch;
+        st_ws(A.pabs + u, d0[ch]);
+        st_ws(A.psq + u, d1[ch]);
+      }
+    }
+  }
+};
+
 __device__ __forceinline__ LeafParam load_leaf_param(const LeafParam* lp, unsigned idx) {
   const float4 raw = ld_ws(reinterpret_cast<const float4*>(lp) + idx);
   LeafParam q;
@@ -550,7 +716,8 @@ struct AccApply {
   Divisor dv;
   float bias;
   double sy;
-  __device__ __forceinline__ void begin(unsigned g) {
+  __device__ __forceinline__ void begin(const UnitInfo& ui) {
+    const unsigned g = ui.g;
     if (GIVEN) {
       const unsigned pi = A.given_per_group ? g : 0u;
       const float bits = A.g_bits ? __ldg(A.g_bits + g) : static_cast<float>(A.num_bits);
@@ -588,12 +755,12 @@ struct AccApply {
     else
       one<false>(x, off);
   }
-  __device__ __forceinline__ void end(unsigned u, unsigned) {
+  __device__ __forceinline__ void end(const UnitInfo& ui) {
     if (ACC) {
       float f0 = 0.f, f1 = 0.f;
       double unused = 0.0;
       block_combine(sm, f0, f1, sy, unused, false, false);
-      if (threadIdx.x == 0) st_ws(A.psum + u, sy);
+      if (threadIdx.x == 0) st_ws(A.psum + static_cast<size_t>(ui.p) * A.geo.channels + ui.g, sy);
     } else {
       __syncthreads();  // the engine publishes the next unit ids at this barrier
     }
@@ -606,7 +773,8 @@ struct AccCorr {
   const FusedArgs& A;
   float mq, mo, kv;
   bool vc, bc;
-  __device__ __forceinline__ void begin(unsigned g) {
+  __device__ __forceinline__ void begin(const UnitInfo& ui) {
+    const unsigned g = ui.g;
     mq = ld_ws(A.cq + g);
     mo = ld_ws(A.co + g);
     kv = A.var_corr ? ld_ws(A.ck + g) : 1.f;
@@ -622,7 +790,58 @@ struct AccCorr {
     st_tensor(reinterpret_cast<float4*>(A.out) + off, make_float4(fix(y.x), fix(y.y), fix(y.z), fix(y.w)));
   }
   __device__ __forceinline__ void consume(const float& y, unsigned off) { st_tensor(A.out + off, fix(y)); }
-  __device__ __forceinline__ void end(unsigned, unsigned) { __syncthreads(); }
+  __device__ __forceinline__ void end(const UnitInfo&) { __syncthreads(); }
+};
+
+template <int LEAF>
+struct AccApplyB {
+  const FusedArgs& A;
+  Column col;
+  LeafParam qA, qB;
+  Divisor dvA, dvB;
+  float biasA, biasB;
+  __device__ __forceinline__ void begin(const UnitInfo& ui) {
+    col = column_of(A, ui);
+    const bool hasB = col.split < 4u;
+    const bool per_group = (A.scope == FQB200_SCOPE_GROUP);
+    qA = load_leaf_param(A.lp, per_group ? col.chA : 0u);
+    qB = hasB ? load_leaf_param(A.lp, per_group ? col.chA + 1u : 0u) : qA;
+    dvA = make_divisor(qA.a);
+    dvB = make_divisor(qB.a);
+    biasA = A.bias ? __ldg(A.bias + col.chA) : 0.f;
+    biasB = (A.bias && hasB) ? __ldg(A.bias + col.chA + 1u) : biasA;
+  }
+  template <bool FAST>
+  __device__ __forceinline__ float elem(float x, bool inA) const {
+    LeafParam q;
+    Divisor dv;
+    q.a = inA ? qA.a : qB.a;
+    q.b = inA ? qA.b : qB.b;
+    q.c = inA ? qA.c : qB.c;
+    q.flags = inA ? qA.flags : qB.flags;
+    dv.s = q.a;
+    dv.r = inA ? dvA.r : dvB.r;
+    dv.fast = FAST;
+    float gq;
+    return leaf_apply<LEAF, FAST>(__fadd_rn(x, inA ? biasA : biasB), q, dv, 0.f, gq);
+  }
+  template <bool FAST>
+  __device__ __forceinline__ void one(const float4& x, unsigned off) {
+    const unsigned sp = col.split;
+    float4 y;
+    y.x = elem<FAST>(x.x, true);
+    y.y = elem<FAST>(x.y, sp > 1u);
+    y.z = elem<FAST>(x.z, sp > 2u);
+    y.w = elem<FAST>(x.w, sp > 3u);
+    st_tensor(reinterpret_cast<float4*>(A.out) + off, y);
+  }
+  __device__ __forceinline__ void consume(const float4& x, unsigned off) {
+    if (dvA.fast && dvB.fast)
+      one<true>(x, off);
+    else
+      one<false>(x, off);
+  }
+  __device__ __forceinline__ void end(const UnitInfo&) { __syncthreads(); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -631,8 +850,12 @@ struct AccCorr {
 // One instantiation per (vector width, leaf, second statistics pass?, weight correction?) so that each kernel holds
 // only the loops it runs.  Phase directions: S1 forward, S2 backward, A forward again (backward when there is no S2):
 // each phase starts on the bytes the previous one touched last, which are still in L2.
-template <int VEC, int LEAF, bool DEV, bool CORR>
+// MODE: 4 = 128-bit path, 1 = scalar path, 8 = bundled 128-bit path (inner % 4 != 0, see Geometry)
+template <int MODE, int LEAF, bool DEV, bool CORR>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __grid_constant__ FusedArgs A) {
+  constexpr int VEC = (MODE == 1) ? 1 : 4;
+  constexpr bool BUNDLED = (MODE == 8);
+  static_assert(!(BUNDLED && CORR), "weight correction runs on the plain layouts");
   __shared__ PhaseSmem psm;
   __shared__ LeaderSmem lsm;
   __shared__ StreamSmem ssm;
@@ -642,7 +865,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
 
   // ---- S1
   if (blockIdx.x == 0) stamp(A, 0);
-  {
+  if constexpr (BUNDLED) {
+    AccStats1B acc{A, psm};
+    stream_units<4, false>(geo, A.in, &A.sync->unit_counter[0], ssm, acc);
+  } else {
     AccStats1<VEC> acc{A, psm};
     stream_units<VEC, false>(geo, A.in, &A.sync->unit_counter[0], ssm, acc);
   }
@@ -651,7 +877,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
     stamp(A, 2);
     reduce_partials3(geo, A.pmin, A.gmin, INFINITY, OpMin(), A.pmax, A.gmax, -INFINITY, OpMax(), A.psum, A.gmean_d, 0.0, OpAdd());
     __syncthreads();
-    for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) {
+    for (unsigned g = threadIdx.x; g < geo.channels; g += kThreads) {
       const double m = A.gmean_d[g] / n;
       A.gmean_d[g] = m;
       A.gmean[g] = static_cast<float>(m);
@@ -665,7 +891,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
 
   // ---- S2
   if constexpr (DEV) {
-    {
+    if constexpr (BUNDLED) {
+      AccStats2B acc{A, psm};
+      stream_units<4, true>(geo, A.in, &A.sync->unit_counter[1], ssm, acc);
+    } else {
       AccStats2<VEC> acc{A, psm, A.gmean, true, A.pabs, A.psq};
       stream_units<VEC, true>(geo, A.in, &A.sync->unit_counter[1], ssm, acc);
     }
@@ -673,12 +902,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
     if (grid_arrive(A.sync, epoch, &lsm.flag)) {
       stamp(A, 6);
       double* tabs = A.psum;              // [>= G] free now
-      double* tsq = A.psum + geo.groups;  // psum holds units + 2G doubles
+      double* tsq = A.psum + geo.channels;  // psum holds slots + 2G doubles
       reduce_partials3(geo, A.pabs, tabs, 0.0, OpAdd(), A.psq, tsq, 0.0, OpAdd(), static_cast<const double*>(nullptr),
                        static_cast<double*>(nullptr), 0.0, OpAdd());
       __syncthreads();
       stamp(A, 10);
-      for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) {
+      for (unsigned g = threadIdx.x; g < geo.channels; g += kThreads) {
         A.gb[g] = static_cast<float>(tabs[g] / n);
         // sum (x - mu32)^2 -> sum (x - mu)^2 with the exact mean; unbiased (torch.std default)
         const double dm = A.gmean_d[g] - static_cast<double>(A.gmean[g]);
@@ -697,7 +926,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
 
   // ---- A (+ C)
   if (!A.stats_only) {
-    {
+    if constexpr (BUNDLED) {
+      AccApplyB<LEAF> acc{A};
+      stream_units<4, !DEV>(geo, A.in, &A.sync->unit_counter[2], ssm, acc);
+    } else {
       AccApply<VEC, LEAF, CORR, false, false> acc{A, psm};
       stream_units<VEC, !DEV>(geo, A.in, &A.sync->unit_counter[2], ssm, acc);
     }
@@ -708,7 +940,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
         reduce_partials3(geo, A.psum, tmp, 0.0, OpAdd(), static_cast<const double*>(nullptr), static_cast<double*>(nullptr), 0.0,
                          OpAdd(), static_cast<const double*>(nullptr), static_cast<double*>(nullptr), 0.0, OpAdd());
         __syncthreads();
-        for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) {
+        for (unsigned g = threadIdx.x; g < geo.channels; g += kThreads) {
           A.cq[g] = static_cast<float>(tmp[g] / n);
           A.co[g] = A.gmean[g];
         }
@@ -724,7 +956,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
           reduce_partials3(geo, A.psq, tmp, 0.0, OpAdd(), static_cast<const double*>(nullptr), static_cast<double*>(nullptr), 0.0,
                            OpAdd(), static_cast<const double*>(nullptr), static_cast<double*>(nullptr), 0.0, OpAdd());
           __syncthreads();
-          for (unsigned g = threadIdx.x; g < geo.groups; g += kThreads) {
+          for (unsigned g = threadIdx.x; g < geo.channels; g += kThreads) {
             // tmp = sum (y - fl32(mean_q))^2 ; fl32(mean_q) stands in for the mean (error O(ulp^2))
             const float sdq = static_cast<float>(sqrt(tmp[g] / (n - 1.0)));
             A.ck[g] = __fdiv_rn(A.gstd[g], __fadd_rn(sdq, 1e-8f));
@@ -827,23 +1059,30 @@ DeviceInfo g_dev[64];
 // dynamic shared memory of a launch: the cp.async ring of the 128-bit path
 size_t dyn_smem(int vec) { return static_cast<size_t>(vec == 4 ? fqb::ring_bytes<4>() : fqb::ring_bytes<1>()); }
 
-// the 24 instantiations of the fused kernel: (VEC 4|1) x (leaf 0..2) x (second statistics pass) x (weight correction)
-template <int VEC, int LEAF>
+// the instantiations of the fused kernel: (mode 4 | 1 | 8) x (leaf 0..2) x (second statistics pass) x (weight correction;
+// not for the bundled mode)
+template <int MODE, int LEAF>
 const void* fused_ptr2(bool dev, bool corr) {
-  if (dev) return corr ? reinterpret_cast<const void*>(fqb::fq_fused_kernel<VEC, LEAF, true, true>)
-                       : reinterpret_cast<const void*>(fqb::fq_fused_kernel<VEC, LEAF, true, false>);
-  return corr ? reinterpret_cast<const void*>(fqb::fq_fused_kernel<VEC, LEAF, false, true>)
-              : reinterpret_cast<const void*>(fqb::fq_fused_kernel<VEC, LEAF, false, false>);
-}
-const void* fused_kernel_ptr(int vec, int leaf, bool dev, bool corr) {
-  if (vec == 4) {
-    if (leaf == FQB200_LEAF_TORCH) return fused_ptr2<4, FQB200_LEAF_TORCH>(dev, corr);
-    if (leaf == FQB200_LEAF_COMPILED) return fused_ptr2<4, FQB200_LEAF_COMPILED>(dev, corr);
-    return fused_ptr2<4, FQB200_LEAF_MIDTREAD>(dev, corr);
+  if constexpr (MODE == 8) {
+    return dev ? reinterpret_cast<const void*>(fqb::fq_fused_kernel<8, LEAF, true, false>)
+               : reinterpret_cast<const void*>(fqb::fq_fused_kernel<8, LEAF, false, false>);
+  } else {
+    if (dev) return corr ? reinterpret_cast<const void*>(fqb::fq_fused_kernel<MODE, LEAF, true, true>)
+                         : reinterpret_cast<const void*>(fqb::fq_fused_kernel<MODE, LEAF, true, false>);
+    return corr ? reinterpret_cast<const void*>(fqb::fq_fused_kernel<MODE, LEAF, false, true>)
+                : reinterpret_cast<const void*>(fqb::fq_fused_kernel<MODE, LEAF, false, false>);
   }
-  if (leaf == FQB200_LEAF_TORCH) return fused_ptr2<1, FQB200_LEAF_TORCH>(dev, corr);
-  if (leaf == FQB200_LEAF_COMPILED) return fused_ptr2<1, FQB200_LEAF_COMPILED>(dev, corr);
-  return fused_ptr2<1, FQB200_LEAF_MIDTREAD>(dev, corr);
+}
+template <int MODE>
+const void* fused_ptr1(int leaf, bool dev, bool corr) {
+  if (leaf == FQB200_LEAF_TORCH) return fused_ptr2<MODE, FQB200_LEAF_TORCH>(dev, corr);
+  if (leaf == FQB200_LEAF_COMPILED) return fused_ptr2<MODE, FQB200_LEAF_COMPILED>(dev, corr);
+  return fused_ptr2<MODE, FQB200_LEAF_MIDTREAD>(dev, corr);
+}
+const void* fused_kernel_ptr(int mode, int leaf, bool dev, bool corr) {
+  if (mode == 4) return fused_ptr1<4>(leaf, dev, corr);
+  if (mode == 8) return fused_ptr1<8>(leaf, dev, corr);
+  return fused_ptr1<1>(leaf, dev, corr);
 }
 
 // optimum of 2*exp(-a) + a^2/(3 w^2): a*exp(a) = 3 w^2 (Lambert W), Newton in float64.  The reference gets the
@@ -875,16 +1114,21 @@ int get_device(DeviceInfo** out) {
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
     per_sm = 1 << 20;
-    for (int v = 0; v < 24; ++v) {
-      int n = 0;
-      const int vw = (v & 1) ? 1 : 4;
-      const void* fn = fused_kernel_ptr(vw, (v >> 1) % 3, (v / 6) & 1, v / 12);
-      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem(vw)));
-      if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kThreads, dyn_smem(vw));
-      if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
-      if (n < per_sm) per_sm = n;
-    }
+    const int modes[3] = {4, 1, 8};
+    for (int mi = 0; mi < 3; ++mi)
+      for (int leaf = 0; leaf < 3; ++leaf)
+        for (int dv = 0; dv < 2; ++dv)
+          for (int cr = 0; cr < 2; ++cr) {
+            if (modes[mi] == 8 && cr) continue;
+            int n = 0;
+            const void* fn = fused_kernel_ptr(modes[mi], leaf, dv != 0, cr != 0);
+            const int smem = static_cast<int>(dyn_smem(modes[mi] == 1 ? 1 : 4));
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kThreads, smem);
+            if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+            if (n < per_sm) per_sm = n;
+          }
     if (per_sm < 1) return fail(FQB200_ERR_CUDA, "fused kernel does not fit on an SM%s");
     e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, false>),
                              cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem(4)));
@@ -916,21 +1160,35 @@ int get_device(DeviceInfo** out) {
 
 struct Plan {
   fqb::Geometry geo;
-  int vec;
+  int vec;   // 4 or 1: floats per access
+  int mode;  // 4, 1, or 8 (bundled 128-bit path)
   int grid;
 };
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// Choose vector width, the number of parts per group (unit size) and the grid size; fill the geometry.
-int make_plan(int64_t outer, int64_t groups, int64_t inner, bool can_vec, int max_ctas, Plan* pl) {
+// Choose the access mode (128-bit, bundled 128-bit, scalar), the number of parts per group (unit size) and the grid
+// size; fill the geometry.
+int make_plan(int64_t outer, int64_t groups, int64_t inner, bool can_vec, bool allow_bundle, int max_ctas, Plan* pl) {
   if (outer <= 0 || groups <= 0 || inner <= 0) return fail(FQB200_ERR_INVALID, "non-positive tensor extent%s");
   if (groups > 0x3fffffffLL || outer > 0x7fffffffLL || inner > 0x7fffffffLL * 4LL)
     return fail(FQB200_ERR_UNSUPPORTED, "tensor extent exceeds 2^31%s");
-  const int vec = (can_vec && inner % 4 == 0) ? 4 : 1;
-  const uint64_t inner_v = static_cast<uint64_t>(inner / vec);
+  int vec = (can_vec && inner % 4 == 0) ? 4 : 1;
+  int mode = vec;
+  uint64_t bundle = 1;
+  if (vec == 1 && can_vec && allow_bundle && inner >= 4) {
+    const uint64_t b = (inner % 2 == 0) ? 2 : 4;
+    const uint64_t row_v = b * static_cast<uint64_t>(inner) / 4;
+    if (groups % b == 0 && row_v <= static_cast<uint64_t>(fqb::kThreads)) {
+      bundle = b;
+      vec = 4;
+      mode = 8;
+    }
+  }
+  const uint64_t G = static_cast<uint64_t>(groups) / bundle;                // streaming groups
+  const uint64_t inner_v = bundle * static_cast<uint64_t>(inner) / vec;       // vectors per streaming-group row
   if (inner_v > 0xffffffffULL) return fail(FQB200_ERR_UNSUPPORTED, "row too long%s");
-  const uint64_t G = static_cast<uint64_t>(groups);
+  const uint64_t stride = (mode == 8) ? (fqb::kThreads / inner_v) * inner_v : fqb::kThreads;
   const uint64_t group_v = static_cast<uint64_t>(outer) * inner_v;
   const uint64_t total_v = group_v * G;
   if (total_v >= (1ULL << 32)) return fail(FQB200_ERR_UNSUPPORTED, "tensors of 2^32 vectors (64 GB) and more are not supported%s");
@@ -938,30 +1196,36 @@ int make_plan(int64_t outer, int64_t groups, int64_t inner, bool can_vec, int ma
   // Units: about `per_cta` per CTA so that dynamic assignment can even out the CTAs' unequal speeds, but no
   // smaller than one full ring (kRingDepth sweeps of the CTA) when the group allows it.
   static const uint64_t per_cta = getenv("FQB_UNITS_PER_CTA") ? strtoull(getenv("FQB_UNITS_PER_CTA"), nullptr, 10) : 8;  // development knob
-  const uint64_t min_unit_v = static_cast<uint64_t>(fqb::kRingDepth) * fqb::kThreads;
+  const uint64_t min_unit_v = static_cast<uint64_t>(fqb::kRingDepth) * stride;
   uint64_t parts = (per_cta * ctas + G - 1) / G;
   const uint64_t max_parts = group_v / min_unit_v > 0 ? group_v / min_unit_v : 1;
   if (parts > max_parts) parts = max_parts;
   if (parts < 1) parts = 1;
   while ((group_v + parts - 1) / parts >= 0x7fffffffULL) ++parts;  // unit lengths are 32-bit
-  parts = (group_v + ((group_v + parts - 1) / parts) - 1) / ((group_v + parts - 1) / parts);  // no empty trailing part
+  uint64_t part_v = (group_v + parts - 1) / parts;
+  if (mode == 8) part_v = (part_v + inner_v - 1) / inner_v * inner_v;  // whole rows: every thread keeps its column
+  parts = (group_v + part_v - 1) / part_v;  // no empty trailing part
   if (parts * G >= 0xfffffff0ULL) return fail(FQB200_ERR_UNSUPPORTED, "too many work units%s");
   const uint64_t units = parts * G;
-  // leader reductions: cover all groups in one sweep when possible (kThreads / lanes >= G), never more lanes than parts
+  // leader reductions: cover all channels in one sweep when possible (kThreads / lanes >= channels), never more lanes than parts
   unsigned lanes = 32;
-  while (lanes > 1 && (static_cast<uint64_t>(fqb::kThreads / lanes) < G || (lanes >> 1) >= parts)) lanes >>= 1;
+  while (lanes > 1 && (static_cast<uint64_t>(fqb::kThreads / lanes) < static_cast<uint64_t>(groups) || (lanes >> 1) >= parts)) lanes >>= 1;
   fqb::Geometry& g = pl->geo;
-  g.groups = static_cast<unsigned>(groups);
+  g.groups = static_cast<unsigned>(G);
+  g.channels = static_cast<unsigned>(groups);
+  g.bundle = static_cast<unsigned>(bundle);
+  g.stride = static_cast<unsigned>(stride);
   g.parts = static_cast<unsigned>(parts);
   g.units = static_cast<unsigned>(units);
   g.inner_v = static_cast<unsigned>(inner_v);
-  g.step_q = static_cast<unsigned>(fqb::kThreads / inner_v);
-  g.step_r = static_cast<unsigned>(fqb::kThreads % inner_v);
+  g.step_q = static_cast<unsigned>(stride / inner_v);
+  g.step_r = static_cast<unsigned>(stride % inner_v);
   g.red_lanes = lanes;
-  g.part_v = static_cast<unsigned>((group_v + parts - 1) / parts);
+  g.part_v = static_cast<unsigned>(part_v);
   g.group_v = group_v;
   g.row_pitch = G * inner_v;
   pl->vec = vec;
+  pl->mode = mode;
   pl->grid = static_cast<int>(units < ctas ? units : ctas);
   return FQB200_OK;
 }
@@ -969,14 +1233,13 @@ int make_plan(int64_t outer, int64_t groups, int64_t inner, bool can_vec, int ma
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // workspace layout; returns total bytes, fills pointers when base != nullptr.  Partials: one slot per unit.
-size_t carve(char* base, uint64_t units, uint64_t groups, fqb::FusedArgs* A) {
+size_t carve(char* base, uint64_t slots, uint64_t groups, fqb::FusedArgs* A) {
   size_t off = 0;
   auto take = [&](size_t bytes) {
     char* p = base ? base + off : nullptr;
     off = align_up(off + bytes, 256);
     return p;
   };
-  const uint64_t slots = units;
   char* sync = take(sizeof(fqb::GridSync));
   char* pmin = take(slots * sizeof(float));
   char* pmax = take(slots * sizeof(float));
@@ -1047,11 +1310,14 @@ size_t fqb200_workspace_bytes(const fqb200_desc* d) {
   int resident = 148 * fqb::kCtasPerSm;  // without a device (build container) assume a B200
   DeviceInfo* di = nullptr;
   if (get_device(&di) == FQB200_OK) resident = di->resident;
-  Plan a, b;
-  if (make_plan(d->outer, d->groups, d->inner, true, resident, &a) != FQB200_OK) return 0;
-  if (make_plan(d->outer, d->groups, d->inner, false, resident, &b) != FQB200_OK) return 0;
-  const uint64_t units = a.geo.units > b.geo.units ? a.geo.units : b.geo.units;
-  return carve(nullptr, units, static_cast<uint64_t>(d->groups), nullptr);
+  Plan a, b, c;
+  if (make_plan(d->outer, d->groups, d->inner, true, true, resident, &a) != FQB200_OK) return 0;
+  if (make_plan(d->outer, d->groups, d->inner, true, false, resident, &b) != FQB200_OK) return 0;
+  if (make_plan(d->outer, d->groups, d->inner, false, false, resident, &c) != FQB200_OK) return 0;
+  uint64_t parts = a.geo.parts;
+  if (b.geo.parts > parts) parts = b.geo.parts;
+  if (c.geo.parts > parts) parts = c.geo.parts;
+  return carve(nullptr, parts * static_cast<uint64_t>(d->groups), static_cast<uint64_t>(d->groups), nullptr);
 }
 
 int fqb200_workspace_init(void* workspace, size_t bytes, void* stream) {
@@ -1125,7 +1391,7 @@ int fqb200_quantize1(const float* in, float* out, float* grid, int64_t outer, in
   if (rc != FQB200_OK) return rc;
   Plan pl;
   const bool can_vec = aligned16(in) && aligned16(out) && (!grid || aligned16(grid));
-  rc = make_plan(outer, groups, inner, can_vec, di->resident * 2, &pl);
+  rc = make_plan(outer, groups, inner, can_vec, false, di->resident * 2, &pl);
   if (rc != FQB200_OK) return rc;
   fqb::FusedArgs A;
   memset(&A, 0, sizeof(A));
@@ -1168,14 +1434,14 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   if (d->bias && d->scope == FQB200_SCOPE_GROUP_MEAN)
     return fail(FQB200_ERR_UNSUPPORTED, "a per-group bias needs groups = channels (scope GROUP or TENSOR)%s");
   const bool can_vec = aligned16(in) && (d->stats_only || aligned16(out));
-  rc = make_plan(d->outer, d->groups, d->inner, can_vec, di->resident, &pl);
+  rc = make_plan(d->outer, d->groups, d->inner, can_vec, !(d->bias_corr || d->var_corr), di->resident, &pl);
   if (rc != FQB200_OK) return rc;
   fqb::FusedArgs A;
   memset(&A, 0, sizeof(A));
-  const size_t need = carve(nullptr, pl.geo.units, pl.geo.groups, nullptr);
+  const size_t need = carve(nullptr, static_cast<uint64_t>(pl.geo.parts) * pl.geo.channels, pl.geo.channels, nullptr);
   if (!workspace || workspace_bytes < need) return fail(FQB200_ERR_WORKSPACE, "workspace smaller than fqb200_workspace_bytes()%s");
   if (!aligned16(workspace)) return fail(FQB200_ERR_WORKSPACE, "workspace must be 16-byte aligned%s");
-  carve(static_cast<char*>(workspace), pl.geo.units, pl.geo.groups, &A);
+  carve(static_cast<char*>(workspace), static_cast<uint64_t>(pl.geo.parts) * pl.geo.channels, pl.geo.channels, &A);
   A.geo = pl.geo;
   A.in = in;
   A.out = out;
@@ -1198,6 +1464,7 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   A.out_stats = d->out_stats;
   A.bias = d->bias;
   A.dbg = g_dbg_timing;
+  A.inner = static_cast<unsigned>(d->inner);
   A.n_per_group = static_cast<double>(d->outer) * static_cast<double>(d->inner);
   const bool alloc = d->bit_alloc && d->num_bits <= 4 && d->scope == FQB200_SCOPE_GROUP && d->leaf != FQB200_LEAF_MIDTREAD;
   A.need_dev = (d->range_mode != FQB200_RANGE_MINMAX) || alloc || d->var_corr || d->leaf == FQB200_LEAF_MIDTREAD ||
@@ -1205,7 +1472,7 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   void* args[] = {&A};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-  e = cudaLaunchCooperativeKernel(fused_kernel_ptr(pl.vec, d->leaf, A.need_dev != 0, d->bias_corr || d->var_corr), dim3(pl.grid),
+  e = cudaLaunchCooperativeKernel(fused_kernel_ptr(pl.mode, d->leaf, A.need_dev != 0, d->bias_corr || d->var_corr), dim3(pl.grid),
                                   dim3(fqb::kThreads), args, dyn_smem(pl.vec), st);
   if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cooperative launch fq_fused_kernel: %s", cudaGetErrorString(e));
   return FQB200_OK;
@@ -1220,9 +1487,9 @@ int fqb200_debug_timing(unsigned long long* dev_buf) {
 // development hook (not part of the drop-in surface): the item shape make_plan picks for a layout
 int fqb200_debug_plan(int64_t outer, int64_t groups, int64_t inner, int max_ctas, int64_t* out6) {
   Plan pl;
-  int rc = make_plan(outer, groups, inner, true, max_ctas, &pl);
+  int rc = make_plan(outer, groups, inner, true, true, max_ctas, &pl);
   if (rc != FQB200_OK) return rc;
-  out6[0] = pl.vec; out6[1] = pl.grid; out6[2] = pl.geo.parts; out6[3] = pl.geo.red_lanes; out6[4] = pl.geo.units;
+  out6[0] = pl.mode; out6[1] = pl.grid; out6[2] = pl.geo.parts; out6[3] = pl.geo.red_lanes; out6[4] = pl.geo.units;
   out6[5] = static_cast<int64_t>((pl.geo.group_v + pl.geo.parts - 1) / pl.geo.parts);
   return FQB200_OK;
 }

@@ -378,6 +378,39 @@ def test_fused_noncontiguous_and_inplace_and_determinism(fq):
     assert torch.equal(out, q(base, "c", "activation"))
 
 
+@pytest.mark.parametrize("shape", [(16, 64, 7, 7), (5, 12, 7, 7), (9, 8, 3, 3), (4, 6, 5, 5), (7, 16, 9, 5), (3, 4, 11, 2), (64, 256, 7, 7)])
+def test_bundled_layout_matches_scalar_path_and_oracle(fq, O, shape):
+    """H*W not a multiple of 4: channels are walked in bundles of 2/4 with 128-bit accesses.  Same results as the
+    scalar walk of the same data (forced by a 4-byte-misaligned view) and as the oracle."""
+    from cnn_quantization_b200 import _lib as L
+    x = regen(dict(seed=sum(shape) + 5, shape=shape, dist="laplace"))
+    xt = torch.from_numpy(x)
+    n, c = shape[0], shape[1]
+    hw = x.size // (n * c)
+    lay = (n, c, hw)
+    xa = cuda(x)
+    pad = torch.empty(x.size + 1, device="cuda")
+    xm = pad[1:].view(shape)  # same values, base pointer off by 4 bytes -> scalar mode
+    xm.copy_(xa)
+    bias = torch.randn(c, device="cuda")
+    for kw in (dict(range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True), dict(range_mode=L.RANGE_LAPLACE, num_bits=4, positive=True),
+               dict(range_mode=L.RANGE_MINMAX, num_bits=4), dict(range_mode=L.RANGE_GAUS, num_bits=3),
+               dict(leaf=L.LEAF_MIDTREAD, mt_target=4.0, mt_clip=True)):
+        for b in (None, bias):
+            y4, s4 = fq.ops.fused(xa, lay, want_stats=True, bias=b, **kw)
+            y1, s1 = fq.ops.fused(xm, lay, want_stats=True, bias=b, **kw)
+            assert torch.allclose(s4[:, :7], s1[:, :7], rtol=2e-6, atol=1e-6), (shape, kw)
+            assert torch.equal(s4[:, 7], s1[:, 7])  # bit widths
+            step = float(s4[:, 8].max()) + 1e-9
+            frac, worst = fq_mismatch(y4.cpu().numpy(), y1.cpu().numpy(), step)
+            assert frac <= max(FLIP_FRAC, 2.0 / x.size) and worst <= 1.01, (shape, kw, frac, worst)
+    want, parts = O.clipping_quantize(xt, 4, "laplace", True, False, True, "gaus", None, True, return_parts=True)
+    got = fq.ops.fused(xa, lay, range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True)
+    step = float(torch.as_tensor(parts["delta"]).max()) + 1e-6
+    frac, worst = fq_mismatch(got.cpu().numpy(), want.numpy(), step)
+    assert frac <= max(FLIP_FRAC, 2.0 / x.size) and worst <= 1.01, (shape, frac, worst)
+
+
 def test_fused_bias_operand_and_inplace_flag(fq):
     """x + bias[c] inside the kernel == quantizing the tensor the convolution would have produced with its bias,
     bit for bit, for every per-channel path; the in-place flag returns the same values in the caller's buffer."""
