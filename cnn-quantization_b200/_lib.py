@@ -67,7 +67,7 @@ def load():
     lib.fqb200_float2gemmlowp.restype = i32
     lib.fqb200_float2gemmlowp.argtypes = [vp, vp, i64, f32, f32, i32, i32, i32, vp, vp]
     lib.fqb200_quantize1.restype = i32
-    lib.fqb200_quantize1.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, i32, i32, vp]
+    lib.fqb200_quantize1.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, i32, i32, vp, vp]
     lib.fqb200_fused.restype = i32
     lib.fqb200_fused.argtypes = [ctypes.POINTER(Desc), vp, vp, vp, ctypes.c_size_t, vp]
     lib.fqb200_test_division.restype = i32

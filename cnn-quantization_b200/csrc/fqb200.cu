@@ -1378,7 +1378,7 @@ int fqb200_float2gemmlowp(const float* in, float* out, int64_t n, float range, f
 
 int fqb200_quantize1(const float* in, float* out, float* grid, int64_t outer, int64_t groups, int64_t inner,
                      const float* delta, const float* offset, const float* bits, int per_group, int num_bits,
-                     void* stream) {
+                     const float* bias, void* stream) {
   g_err[0] = 0;
   if (outer == 0 || groups == 0 || inner == 0) return FQB200_OK;
   if (!in || !out || !delta || !offset) return fail(FQB200_ERR_INVALID, "null pointer%s");
@@ -1405,6 +1405,7 @@ int fqb200_quantize1(const float* in, float* out, float* grid, int64_t outer, in
   A.g_offset = offset;
   A.g_bits = bits;
   A.given_per_group = per_group;
+  A.bias = bias;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pl.vec == 4) {
     if (grid) fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, true><<<pl.grid, fqb::kThreads, dyn_smem(4), st>>>(A);

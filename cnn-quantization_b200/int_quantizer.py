@@ -87,7 +87,11 @@ class IntQuantizer(object):
         self.alpha_gaus_positive = {1: 1.71, 2: 2.15, 3: 2.55, 4: 2.93, 5: 3.28, 6: 3.61, 7: 3.92, 8: 4.2}
         self.alpha_laplace = {0: 1.05, 1: 1.86, 2: 2.83, 3: 3.89, 4: 5.03, 5: 6.2, 6: 7.41, 7: 8.64, 8: 9.89}
         self.alpha_laplace_positive = {0: 1.86, 1: 2.83, 2: 3.89, 3: 5.02, 4: 6.2, 5: 7.41, 6: 8.64, 7: 9.89, 8: 11.16}
-        self.sm = None  # statistics manager class (offline statistics: not built yet)
+        # statistics manager for `-sm use`: a zero-argument callable returning the manager (the reference stores the
+        # singleton CLASS here, inference_quantization_manager.py:413,450,464,471; any object with
+        # get_tensor_stat(id, stat, kind) works)
+        self.sm = None
+        self._stat_cache = {}  # offline-statistics parameters are constants of a layer: solved once, kept on the device
         self.force_positive = False
         self.half_range = False
         # extension (default off = reference behaviour): overwrite the input tensor instead of allocating the result.
@@ -146,9 +150,9 @@ class IntQuantizer(object):
     # ------------------------------------------------------------------------------------------
     def _unsupported(self, stat_id):
         if self.kld:
-            raise NotImplementedError("KLD thresholds need offline statistics (SURVEY.md 8f: next)")
-        if stat_id is not None:
-            raise NotImplementedError("offline statistics (-sm use) are the next scope row (SURVEY.md 8f)")
+            raise NotImplementedError("KLD thresholds are outside the hot-path scope (SURVEY.md section 2, #9)")
+        if stat_id is not None and self.sm is None:
+            raise RuntimeError("stat_id given but no statistics manager is attached to this quantizer (q.sm)")
         if self.measure_entropy:
             raise NotImplementedError("entropy measurement (-me) is the next scope row (SURVEY.md 8f)")
 
@@ -184,12 +188,86 @@ class IntQuantizer(object):
         return L.PRIOR_STD if self.bit_alloc_prior == "gaus" else L.PRIOR_B
 
     # ------------------------------------------------------------------------------------------
+    # offline statistics (`-sm use`): every tensor becomes "mode A" - parameters known up front, one read + one write
+    # ------------------------------------------------------------------------------------------
+    def _stat(self, stat_id, name, kind="mean"):
+        return self.sm().get_tensor_stat(stat_id, name, kind)
+
+    def _cached(self, key, build):
+        v = self._stat_cache.get(key)
+        if v is None:
+            v = self._stat_cache[key] = build()
+        return v
+
+    def _stat_bits(self, stat_id, device, target):
+        """Per-channel bit widths from the collected prior statistic (int_quantizer.py:236-247, :430-438)."""
+        prior = "std" if self.bit_alloc_prior == "gaus" else "b"
+        pr = _to_dev(np.asarray(self._stat(stat_id, prior, "mean"), dtype=np.float32), device)
+        return self.get_bits_alloc_fixed_target(pr, target, self.bit_alloc_round)
+
+    def _clipping_params_from_stats(self, tensor, stat_id, clip_type):
+        """(delta, offset, bits, per_channel) of gemmlowpClippingQuantize in use mode (int_quantizer.py:327-359 with
+        :227-300), computed once per (layer, configuration)."""
+        positive = self._positive()
+        pc_shape = self._pc_act(tensor)
+        key = ("clip", stat_id, clip_type, self.num_bits, positive, pc_shape, self.bit_alloc_act, self.bit_alloc_prior,
+               self.bit_alloc_round, self.bit_alloc_target_act, str(tensor.device))
+
+        def build():
+            dev = tensor.device
+            mn, mx, mean = (self._stat(stat_id, k, "mean") for k in ("min", "max", "mean"))
+            per_channel = pc_shape and np.size(mn) > 1 and np.size(mx) > 1
+            table_l = self.alpha_laplace_positive if positive else self.alpha_laplace
+            table_g = self.alpha_gaus_positive if positive else self.alpha_gaus
+            bits = None
+            if clip_type == "laplace":
+                b = self._stat(stat_id, "b", "mean")
+                if self.bit_alloc_act and per_channel and self.num_bits <= 4:
+                    bits = self._stat_bits(stat_id, dev, self.bit_alloc_target_act)
+                    factor = torch.tensor(np.array([table_l[int(v)] for v in bits.tolist()]), dtype=torch.float32, device=dev)
+                else:
+                    factor = table_l[self.num_bits]
+                alpha = _to_dev(np.asarray(b, dtype=np.float32) if per_channel else b, dev) * factor
+            elif clip_type == "gaus":
+                alpha = self._stat(stat_id, "std", "mean") * table_g[self.num_bits]
+            elif "std" in clip_type:
+                alpha = float(clip_type.replace("std", "")) * self._stat(stat_id, "std", "mean")
+            else:
+                raise NotImplementedError("clipping %r is not supported with offline statistics" % clip_type)
+            if per_channel:
+                rng, off = self.alpha2DeltaOffset(alpha if isinstance(alpha, torch.Tensor) else np.asarray(alpha, dtype=np.float32),
+                                                  np.asarray(mx, dtype=np.float32), np.asarray(mn, dtype=np.float32),
+                                                  np.asarray(mean, dtype=np.float32))
+                off_t = _to_dev(off, dev)
+                rng_t = _to_dev(rng, dev)
+                max_t = off_t + rng_t                      # :351
+                c = tensor.shape[1]
+                off_t = off_t.reshape(-1).expand(c) if off_t.numel() == 1 else off_t.reshape(-1)
+                if self.bit_alloc_act and self.num_bits <= 4 and bits is None:
+                    bits = self._stat_bits(stat_id, dev, self.bit_alloc_target_act)
+                return (max_t.reshape(-1) - off_t).contiguous(), off_t.contiguous(), bits, True
+            alpha_f = float(alpha)
+            rng, off = self.alpha2DeltaOffset(alpha_f, float(mx), float(mn), float(mean))
+            return (torch.tensor(rng, dtype=torch.float32, device=dev), torch.tensor(off, dtype=torch.float32, device=dev),
+                    None, False)
+
+        return self._cached(key, build)
+
+    # ------------------------------------------------------------------------------------------
     # dispatch targets
     # ------------------------------------------------------------------------------------------
     def gemmlowpClippingQuantize(self, tensor, id, tag="", stat_id=None, clip_type="laplace", bias=None):
         """ACIQ clipping, int_quantizer.py:327-359: per channel (pcq_a, 4-D, HW>1, C>1; fp32 parameter math,
         optional bit allocation) or per tensor (float64 parameter math)."""
         self._unsupported(stat_id)
+        if stat_id is not None:
+            delta, offset, bits, per_channel = self._clipping_params_from_stats(tensor, stat_id, clip_type)
+            if per_channel:
+                return ops.quantize1(tensor, delta, offset, self.num_bits, bits=bits, layout=self._nchw_layout(tensor),
+                                     bias=bias, out=self._out(tensor))
+            if bias is not None:
+                tensor = tensor.add_(bias.view(1, -1, 1, 1)) if self.inplace else tensor + bias.view(1, -1, 1, 1)
+            return ops.quantize1(tensor, delta, offset, self.num_bits, out=self._out(tensor))
         mode, k = self._range_mode(clip_type)
         if self._pc_act(tensor) and tensor.shape[1] > 1:
             return ops.fused(tensor, self._nchw_layout(tensor), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
@@ -205,6 +283,17 @@ class IntQuantizer(object):
         """Per-tensor min/max range through the compiled-leaf arithmetic, int_quantizer.py:361-379 + :605-614.
         Activations (tag contains 'activation', not 'classifier') use the batch average of per-sample min/max."""
         self._unsupported(stat_id)
+        if stat_id is not None:
+            # int_quantizer.py:362-369: collected min/max ('mean' kind, or min-of-min / max-of-max), compiled leaf
+            kmin, kmax = ("mean", "mean") if self.stats_kind == "mean" else ("min", "max")
+            min_ = float(self._stat(stat_id, "min", kmin))
+            max_ = float(self._stat(stat_id, "max", kmax))
+            if self._positive():
+                min_ = 0.0
+            delta = np.float32(max_) - np.float32(min_)
+            preserve_zero = bool((np.float32(min_) + delta) > 0 and min_ < 0)
+            return ops.float2gemmlowp(tensor, float(delta), min_, self.num_bits, self.int_exp, preserve_zero, None,
+                                      out=self._out(tensor)) if delta > 0 else tensor
         avg = ("activation" in tag and "classifier" not in tag)
         kw = dict(range_mode=L.RANGE_MINMAX, leaf=L.LEAF_COMPILED, num_bits=self.num_bits, positive=self._positive())
         if weight_correction is not None and any(weight_correction):
@@ -220,6 +309,21 @@ class IntQuantizer(object):
         """Per-channel min/max (0 lower bound when positive) with optional bit allocation, int_quantizer.py:409-451."""
         self._unsupported(stat_id)
         layout = self._nchw_layout(tensor)
+        if stat_id is not None and min_ is None and max_ is None:
+            key = ("pc", stat_id, self.num_bits, self._positive(), self.stats_kind, self.bit_alloc_act, self.bit_alloc_prior,
+                   self.bit_alloc_round, self.bit_alloc_target_act, str(tensor.device))
+
+            def build():
+                dev, c = tensor.device, layout[1]
+                mn = torch.zeros(c, device=dev) if self._positive() else _to_dev(
+                    np.asarray(self._stat(stat_id, "min", self.stats_kind), dtype=np.float32), dev).reshape(-1)
+                mx = _to_dev(np.asarray(self._stat(stat_id, "max", self.stats_kind), dtype=np.float32), dev).reshape(-1)
+                bits = self._stat_bits(stat_id, dev, self.bit_alloc_target_act) if (self.bit_alloc_act and self.num_bits <= 4) else None
+                return (mx - mn).contiguous(), mn.contiguous(), bits
+
+            delta, offset, bits = self._cached(key, build)
+            return ops.quantize1(tensor, delta, offset, self.num_bits, bits=bits, layout=layout, bias=bias,
+                                 out=self._out(tensor))
         if min_ is None and max_ is None:
             return ops.fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
                              num_bits=self.num_bits, positive=self._positive(), bit_alloc=self.bit_alloc_act,

@@ -10,7 +10,8 @@ call sites, same ``quantize_instant`` / ``quantize_model`` semantics, but
   weight bias / variance correction of ``quantize_model`` (:374-391) happens inside the weight's launch;
 * nothing is a process-wide singleton: several managers can exist (one per rank / model).
 
-Scope: ``-sm no`` (on-the-fly statistics), the mode every BASELINE config runs.  ``collect`` / ``use`` raise.
+``-sm no`` (on-the-fly statistics) is the mode every BASELINE config runs; ``collect`` / ``use`` (offline statistics,
+SURVEY.md 8f rank 1) and ``-bca`` (rank 2, use mode only) are implemented on top of the same kernels.
 """
 import argparse
 from itertools import count
@@ -35,7 +36,7 @@ def make_args(**over):
              per_channel_quant_weights=False, per_channel_quant_act=False, bit_alloc_act=False, bit_alloc_weight=False,
              bit_alloc_rmode="round", bit_alloc_prior="gaus", bit_alloc_target_act=None, bit_alloc_target_weight=None,
              bias_corr_act=False, bias_corr_weight=False, var_corr_weight=False, measure_entropy=False,
-             mid_thread_quant=False, rho_act=None, rho_weight=None, preserve_zero=False)
+             mid_thread_quant=False, rho_act=None, rho_weight=None, preserve_zero=False, stats_base_dir=None)
     d.update(over)
     return argparse.Namespace(**d)
 
@@ -157,14 +158,37 @@ class QuantizationManagerInference(object):
         self.bcorr_act = args.bias_corr_act
         self.bcorr_weight = args.bias_corr_weight
         self.vcorr_weight = args.var_corr_weight
-        if args.stats_mode != "no":
-            raise NotImplementedError("stats_mode %r: offline statistics are the next scope row (SURVEY.md 8f)" % args.stats_mode)
+        if args.stats_mode not in ("no", "collect", "use"):
+            raise ValueError("stats_mode must be one of no / collect / use, got %r" % (args.stats_mode,))
+        self.stats_mode = args.stats_mode
         self._factory = quantizer_factory or _default_factory
         # extensions of this package's CUDA quantizer (a foreign factory - the CPU oracle - gets plain reference calls)
         self._native = quantizer_factory is None
+        if not self._native and self.stats_mode != "no":
+            raise NotImplementedError("offline statistics run through this package's CUDA quantizers only")
         self._fuse_weight_correction = self._native
-        self.fuse_conv_bias = self._native   # run hooked convolutions bias-free, add the bias inside the fused kernel
-        self.inplace_activations = self._native
+        # run hooked convolutions bias-free and add the bias inside the fused kernel (statistics collection wants the
+        # tensor the network actually produces, so not in collect mode)
+        self.fuse_conv_bias = self._native and self.stats_mode != "collect"
+        # activation bias correction needs the un-quantized tensor after the quantizer ran
+        self.inplace_activations = self._native and not (self.stats_mode == "use" and args.bias_corr_act)
+        # offline statistics (inference_quantization_manager.py:299-318)
+        self.stats_manager = None
+        self._sm_tensor = self._sm_channel = None
+        if self.stats_mode != "no":
+            from .statistics import StatisticManager, StatisticManagerPerChannel
+            sf = args.stats_folder if args.stats_folder is not None else args.arch
+            base = getattr(args, "stats_base_dir", None)
+            if self.stats_mode == "collect":
+                print("Collecting statistics...")
+                if args.per_channel_quant_act:
+                    self.stats_manager = StatisticManagerPerChannel(sf, load_stats=False, batch_avg=args.stats_batch_avg, base_dir=base)
+                else:
+                    self.stats_manager = StatisticManager(sf, load_stats=False, batch_avg=args.stats_batch_avg, base_dir=base)
+            else:
+                if args.per_channel_quant_act:
+                    self._sm_channel = StatisticManagerPerChannel(sf, load_stats=True, base_dir=base)
+                self._sm_tensor = StatisticManager(sf, load_stats=True, base_dir=base)
         self.fused_relu = args.arch is not None and (args.arch in FUSED_RELU_ARCHS or "squeezenet" in args.arch)
         self.ignore_ids = []
         self.quantizers = {}
@@ -179,6 +203,14 @@ class QuantizationManagerInference(object):
         if self.quantize:
             self.__fill_quantizers__(args.qtype, qparams, args.arch, args.qweight)
             self.quantizer_default = self._load("int8", qparams)
+            if self.stats_mode == "use":
+                # which statistics each tag reads (IntQuantizer.__init__ :88 + the overrides of __fill_quantizers__)
+                per_tensor = lambda: self._sm_tensor
+                per_channel = (lambda: self._sm_channel) if self._sm_channel is not None else per_tensor
+                for tag, q in list(self.quantizers.items()) + [("", self.quantizer_default)]:
+                    if isinstance(q, DummyQuantizer):
+                        continue
+                    q.sm = per_channel if tag in ("activation", "weight", "weight_classifier", "") else per_tensor
             if self.inplace_activations:
                 for tag, q in list(self.quantizers.items()) + [("", self.quantizer_default)]:
                     if tag.startswith("activation") or tag in ("", "ignored"):
@@ -272,6 +304,8 @@ class QuantizationManagerInference(object):
     def __exit__(self, *exc):
         self.disable()
         self.detach()
+        if self.stats_manager is not None:
+            self.stats_manager.__exit__()  # collect mode: write the CSV / pickle files
 
     # -- call sites: forward hooks reproducing the *WithId.forward bodies (:58-74, :84-101, :162-217, :227-250, :262-283)
     def attach(self, model):
@@ -311,42 +345,87 @@ class QuantizationManagerInference(object):
             del m._fq_bias, m._fq_bias_param
         self._debiased = []
 
+    def _stat_id(self, activation_id):
+        return activation_id if self.stats_mode == "use" else None
+
     def _conv_hook(self, m, inputs, out):
         bias = getattr(m, "_fq_bias", None)
         if not self.enabled:
             return None if bias is None else out + bias.view(1, -1, 1, 1)
+        activation_id = "conv%d_activation" % m._fq_id
         tag = "activation_classifier" if out.shape[1] == 1000 else "activation"
+        if self.stats_mode == "collect":
+            self.stats_manager.save_tensor_stats(out, getattr(m, "internal_name", activation_id), activation_id)
+            return None
         extra = {} if bias is None else {"bias": bias}
-        return self.quantize_instant(out, "conv%d_activation" % m._fq_id, tag, half_range=hasattr(m, "before_relu"),
+        half_range = hasattr(m, "before_relu")
+        if self.stats_mode == "use" and self.bcorr_act:
+            ref = out if bias is None else out + bias.view(1, -1, 1, 1)  # the un-quantized activation
+            out_q = self.quantize_instant(ref, activation_id, tag, stat_id=activation_id, half_range=half_range,
+                                          verbose=self.verbose)
+            return self._activation_bias_correction(ref, out_q, half_range or self.fused_relu)
+        return self.quantize_instant(out, activation_id, tag, stat_id=self._stat_id(activation_id), half_range=half_range,
                                      verbose=self.verbose, **extra)
+
+    @staticmethod
+    def _activation_bias_correction(out, out_q, relu_first):
+        """``-bca`` (inference_quantization_manager.py:180-196): per channel, the difference of the sums of the
+        (rectified) activation and its quantized version, divided by the number of positive entries, is added back
+        where the quantized activation is positive.  Reductions over (N, H, W) directly on NCHW (no transposes)."""
+        if relu_first:
+            out = torch.nn.functional.relu(out)
+        dims = (0, 2, 3)
+        q_bias = out.sum(dims) - out_q.sum(dims)
+        count = (out > 0).sum(dims).to(q_bias.dtype)
+        q_bias = q_bias / (count + 1e-8)
+        out_q += (out_q > 0).to(out_q.dtype) * q_bias.view(1, -1, 1, 1)
+        return out_q
 
     def _linear_hook(self, m, inputs, out):
         if not self.enabled:
             return None
         classifier = m.weight.shape[0] == 1000
+        activation_id = "linear%d_activation" % m._fq_id
         tag = "activation_classifier" if classifier else "activation_linear"
+        if self.stats_mode == "collect":
+            self.stats_manager.save_tensor_stats(out, tag, activation_id, force_global_min_max=("classifier" in tag))
+            return None
         half_range = hasattr(m, "before_relu") if not classifier else False
-        return self.quantize_instant(out, "linear%d_activation" % m._fq_id, tag, half_range=half_range, verbose=self.verbose)
+        return self.quantize_instant(out, activation_id, tag, stat_id=self._stat_id(activation_id), half_range=half_range,
+                                     verbose=self.verbose)
 
     def _maxpool_hook(self, m, inputs, out):
         if not self.enabled:
             return None
-        return self.quantize_instant(out, "maxpool%d_out" % m._fq_id, "activation_pooling", verbose=self.verbose)
+        out_id = "maxpool%d_out" % m._fq_id
+        if self.stats_mode == "collect":
+            self.stats_manager.save_tensor_stats(out, "activation_pooling", out_id)
+            return None
+        return self.quantize_instant(out, out_id, "activation_pooling", stat_id=self._stat_id(out_id), verbose=self.verbose)
 
     def _avgpool_hook(self, m, inputs, out):
         if not self.enabled:
             return None
-        # the reference passes the tag in the id slot here (:99): the tensor goes through the DEFAULT quantizer
+        out_id = "avgpool%d_out" % m._fq_id
         tag_act = "activation_classifier" if out.shape[1] == 1000 else "activation_pooling"
-        return self.quantize_instant(out, tag_act, verbose=self.verbose)
+        if self.stats_mode == "collect":
+            self.stats_manager.save_tensor_stats(out, tag_act, out_id)
+            return None
+        # the reference passes the tag in the id slot here (:96,:99): the tensor goes through the DEFAULT quantizer
+        return self.quantize_instant(out, tag_act, stat_id=self._stat_id(out_id), verbose=self.verbose)
 
     def _bn_hook(self, m, inputs, out):
         if self.bn_folding and hasattr(m, "absorbed"):
             return inputs[0]  # :264-265: an absorbed BN is the identity
         if not self.enabled:
             return None
-        # same argument-order slip as the reference (:278): id="activation", tag="" -> default quantizer
-        return self.quantize_instant(out, "activation", half_range=hasattr(m, "before_relu"), verbose=self.verbose)
+        activation_id = "bn%d_activation" % m._fq_id
+        if self.stats_mode == "collect":
+            self.stats_manager.save_tensor_stats(out, "activation", activation_id)
+            return None
+        # same argument-order slip as the reference (:275,:278): id="activation", tag="" -> default quantizer
+        return self.quantize_instant(out, "activation", stat_id=self._stat_id(activation_id),
+                                     half_range=hasattr(m, "before_relu"), verbose=self.verbose)
 
     # -- quantize_instant (:549-562) ------------------------------------------------------------------------
     def quantize_instant(self, tensor, id, tag="", stat_id=None, half_range=False, override_att=None, verbose=False,
@@ -365,6 +444,8 @@ class QuantizationManagerInference(object):
 
     # -- quantize_model (:352-393) ---------------------------------------------------------------------------
     def quantize_model(self, model):
+        if self.stats_mode == "collect":
+            return  # :353-354: weights stay fp32 while statistics are collected
         import torchvision
         inception = isinstance(model, torchvision.models.Inception3)
         corr = (bool(self.bcorr_weight), bool(self.vcorr_weight))

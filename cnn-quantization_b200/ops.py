@@ -99,7 +99,7 @@ def float2gemmlowp(x, range_, offset, num_bits, int_exp, enforce_true_zero, nois
     return out
 
 
-def quantize1(x, delta, offset, num_bits, bits=None, layout=None, want_grid=False):
+def quantize1(x, delta, offset, num_bits, bits=None, layout=None, want_grid=False, out=None, bias=None):
     """C ABI fqb200_quantize1.  ``layout`` = (outer, groups, inner); default: [R, K] rows with per-row
     parameters when ``delta`` has R elements, else one parameter set for the whole tensor."""
     _require_cuda_f32(x, "tensor")
@@ -123,13 +123,19 @@ def quantize1(x, delta, offset, num_bits, bits=None, layout=None, want_grid=Fals
         bits = torch.as_tensor(bits, dtype=torch.float32, device=dev).contiguous()
         if bits.numel() != groups:
             raise ValueError("bit_alloc must have %d elements" % groups)
-    out = torch.empty_like(x)
+    if bias is not None:
+        _require_cuda_f32(bias, "bias")
+        bias = bias.contiguous()
+        if bias.numel() != groups:
+            raise ValueError("bias must have one element per group (%d)" % groups)
+    if out is None:
+        out = torch.empty_like(x)
     grid = torch.empty_like(x) if want_grid else None
-    with torch.cuda.device(dev), _Timed("A", x.numel(), 8):
+    with torch.cuda.device(dev), _Timed("A", x.numel(), 8, "%dx%dx%d" % (outer, groups, inner)):
         L.check(lib.fqb200_quantize1(x.data_ptr(), out.data_ptr(), grid.data_ptr() if want_grid else None,
                                      outer, groups, inner, delta.data_ptr(), offset.data_ptr(),
                                      bits.data_ptr() if bits is not None else None, int(per_group), int(num_bits),
-                                     _stream_handle(dev)))
+                                     bias.data_ptr() if bias is not None else None, _stream_handle(dev)))
     return (out, grid) if want_grid else out
 
 

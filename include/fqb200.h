@@ -127,11 +127,12 @@ int fqb200_float2gemmlowp(const float* in, float* out, int64_t n, float range, f
  * a3 - `IntQuantizer.__gemmlowpQuantize1__(tensor, delta, offset, bit_alloc)`, parameters on the device:
  * `delta`/`offset` hold `groups` floats (per_group=1) or one float (per_group=0); `bits` is NULL or
  * `groups` floats (per-row bit widths).  Tensor viewed [outer][groups][inner] (a [R,K] matrix is
- * outer=1, groups=R, inner=K).  Optional `grid` receives the integer grid q (fp32 integers).
+ * outer=1, groups=R, inner=K).  Optional `grid` receives the integer grid q (fp32 integers).  Optional `bias`
+ * (`groups` floats) is added to every element of its group first, like fqb200_desc.bias.  `out` may alias `in`.
  */
 int fqb200_quantize1(const float* in, float* out, float* grid, int64_t outer, int64_t groups, int64_t inner,
                      const float* delta, const float* offset, const float* bits, int per_group, int num_bits,
-                     void* stream);
+                     const float* bias, void* stream);
 
 /*
  * a4/a5/a6/a11/a12(+a7-a10, a13) - statistics -> parameters -> quantize-dequantize (-> weight

@@ -63,7 +63,7 @@ def test_argument_validation_without_gpu(lib):
     assert b"scope" in lib.fqb200_last_error()
     assert lib.fqb200_float2gemmlowp(None, None, -1, 1.0, 0.0, 8, 0, 1, None, None) == _lib.ERR_INVALID
     assert lib.fqb200_float2gemmlowp(None, None, 0, 1.0, 0.0, 8, 0, 1, None, None) == _lib.OK  # empty tensor: no-op
-    assert lib.fqb200_quantize1(None, None, None, 1, 4, 4, None, None, None, 1, 4, None) == _lib.ERR_INVALID
+    assert lib.fqb200_quantize1(None, None, None, 1, 4, 4, None, None, None, 1, 4, None, None) == _lib.ERR_INVALID
 
 
 def test_no_cpu_fallback():

@@ -91,8 +91,11 @@ def test_tag_table_overrides():
     assert q["weight_classifier"].num_bits == 8 and q["weight_classifier"].pcq_w
     assert qm.get_quantizer("no-such-tag") is qm.quantizer_default
     assert qm.ignore_ids == ["conv0_activation"]
-    with pytest.raises(NotImplementedError):
-        M.QuantizationManagerInference(M.make_args(qtype="int8", stats_mode="use"), {})
+    with pytest.raises(NotImplementedError):  # offline statistics need this package's CUDA quantizers
+        M.QuantizationManagerInference(M.make_args(qtype="int8", stats_mode="use"), {}, quantizer_factory=O.oracle_int_quantizer)
+    with pytest.raises(FileNotFoundError):    # use mode without collected files
+        a = M.make_args(qtype="int8", stats_mode="use", stats_base_dir="/nonexistent/fqb200")
+        M.QuantizationManagerInference(a, M.get_params(a))
 
 
 def test_bn_folding_is_exact_for_eval_bn():
