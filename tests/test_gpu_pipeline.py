@@ -70,3 +70,24 @@ def test_validate_accumulates_like_average_meters():
     loss, top1, top5, n = pipeline.reduce_metrics(total)
     qm.detach()
     assert n == 12 and 0 <= top1 <= top5 <= 100 and np.isfinite(loss)
+
+
+@pytest.mark.parametrize("config", ["resnet50_w8a8", "resnet50_w4a4", "resnet101_w4a4", "vgg16_w4a4", "vgg16_w4a4_mtq", "resnet18_w4a4"])
+def test_every_baseline_config_runs_and_quantizes(config):
+    """Every BASELINE.json configuration (small batch / image): finite logits, activations really on a coarse grid."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from cnn_quantization_b200 import ops, pipeline
+    model, qm = pipeline.build_quantized_model(config, "cuda")
+    qm.record = True
+    x, t = pipeline.synthetic_batch(4, seed=3, hw=64)
+    ops.profile_reset(enable=True)
+    with torch.no_grad():
+        y = model(x.cuda())
+    prof = ops.profile_collect()
+    ops.profile_reset(enable=False)
+    qm.detach()
+    assert torch.isfinite(y).all()
+    expected = {"resnet50": 55, "resnet101": 106, "vgg16": 21, "resnet18": 22}[pipeline.CONFIGS[config]["arch"]]
+    assert len(qm.calls) == expected
+    assert prof["launches"] == expected  # exactly one kernel launch per hooked tensor
