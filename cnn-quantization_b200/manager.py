@@ -142,6 +142,18 @@ def _identity_forward(x):
     return x
 
 
+def _relu_forward_skipping(relu):
+    """forward of an nn.ReLU that returns tensors tagged non-negative by the quantization hook untouched."""
+    orig = type(relu).forward
+
+    def forward(x):
+        if getattr(x, "_fq_nonneg", False):
+            return x
+        return orig(relu, x)
+
+    return forward
+
+
 class QuantizationManagerInference(object):
     """``with QuantizationManagerInference(args, qparams) as qm: model = build(); qm.attach(model); qm.quantize_model(model)``.
 
@@ -170,6 +182,9 @@ class QuantizationManagerInference(object):
         # run hooked convolutions bias-free and add the bias inside the fused kernel (statistics collection wants the
         # tensor the network actually produces, so not in collect mode)
         self.fuse_conv_bias = self._native and self.stats_mode != "collect"
+        # a half-range / force-positive quantization returns values >= 0 (offset 0 -> zero point 0): the ReLU that
+        # follows it is the identity, so the hooked ReLU modules skip the pass over tensors tagged by the conv hook
+        self.skip_redundant_relu = self._native
         # activation bias correction needs the un-quantized tensor after the quantizer ran
         self.inplace_activations = self._native and not (self.stats_mode == "use" and args.bias_corr_act)
         # offline statistics (inference_quantization_manager.py:299-318)
@@ -312,6 +327,10 @@ class QuantizationManagerInference(object):
         """Register the forward hooks.  Modules built outside ``enable()`` get ids in ``model.modules()`` order."""
         fallback = {cls: count(0) for cls in _STAMPED}
         for m in model.modules():
+            if self.skip_redundant_relu and self.enabled and type(m) is nn.ReLU and self.stats_mode != "collect":
+                m.forward = _relu_forward_skipping(m)
+                self._patched.append(m)
+                continue
             cls = next((c for c in _STAMPED if type(m) is c), None)
             if cls is None:
                 continue
@@ -364,8 +383,11 @@ class QuantizationManagerInference(object):
             out_q = self.quantize_instant(ref, activation_id, tag, stat_id=activation_id, half_range=half_range,
                                           verbose=self.verbose)
             return self._activation_bias_correction(ref, out_q, half_range or self.fused_relu)
-        return self.quantize_instant(out, activation_id, tag, stat_id=self._stat_id(activation_id), half_range=half_range,
-                                     verbose=self.verbose, **extra)
+        res = self.quantize_instant(out, activation_id, tag, stat_id=self._stat_id(activation_id), half_range=half_range,
+                                    verbose=self.verbose, **extra)
+        if self.skip_redundant_relu and (half_range or self.fused_relu) and tag == "activation" and not self.bcorr_act:
+            res._fq_nonneg = True  # range starts at 0 with zero point 0: every value is q * scale >= 0
+        return res
 
     @staticmethod
     def _activation_bias_correction(out, out_q, relu_first):

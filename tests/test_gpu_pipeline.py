@@ -91,3 +91,45 @@ def test_every_baseline_config_runs_and_quantizes(config):
     expected = {"resnet50": 55, "resnet101": 106, "vgg16": 21, "resnet18": 22}[pipeline.CONFIGS[config]["arch"]]
     assert len(qm.calls) == expected
     assert prof["launches"] == expected  # exactly one kernel launch per hooked tensor
+
+
+@pytest.mark.parametrize("config", ["resnet50_w4a4", "vgg16_w4a4", "resnet50_w8a8"])
+def test_pipeline_extensions_do_not_change_results(config):
+    """Conv-bias fusion, in-place activations and skipping the ReLU after a half-range quantization are exact
+    rewrites: switching them all off gives bit-identical logits."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from cnn_quantization_b200 import manager as M, pipeline
+    import torchvision.models as models
+    x, _ = pipeline.synthetic_batch(4, seed=11, hw=64)
+
+    def run(native_extensions):
+        flags = dict(pipeline.CONFIGS[config])
+        args = M.make_args(**flags)
+        qm = M.QuantizationManagerInference(args, M.get_params(args))
+        if not native_extensions:
+            qm.fuse_conv_bias = qm.skip_redundant_relu = False
+            for q in list(qm.quantizers.values()) + [qm.quantizer_default]:
+                if hasattr(q, "inplace"):
+                    q.inplace = False
+        qm.enable()
+        try:
+            torch.manual_seed(12345)
+            model = models.__dict__[args.arch](weights=None)
+        finally:
+            qm.stop_stamping()
+        M.set_node_names(model)
+        if "resnet" in args.arch:
+            M.resnet_mark_before_relu(model)
+            M.search_absorbe_bn(model)
+            qm.bn_folding = True
+        model.eval().cuda()
+        qm.quantize_model(model)
+        qm.attach(model)
+        with torch.no_grad():
+            y = model(x.cuda().clone())
+        qm.detach()
+        return y
+
+    a, b = run(True), run(False)
+    assert torch.equal(a, b)
