@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=2, help="images per step of the CPU reference arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short BASELINE configs[1] (W8A8) run")
     return ap.parse_args()
 
 
@@ -263,6 +264,8 @@ def run_fqb200(args):
             "clocks": clocks,
             "check": {"loss": loss, "top1": top1, "top5": top5, "images": n_img},
         }
+        if world == 1 and not args.no_secondary and args.config == "resnet50_w4a4":
+            line["config1_w8a8"] = secondary_w8a8(args, dev, peak)
         if world == 1 and not args.no_cpu_baseline:
             ips, sec, cores = cpu_pipeline_images_per_s(args.config, args.cpu_batch, 1, 0)
             line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
@@ -270,6 +273,38 @@ def run_fqb200(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary_w8a8(args, dev, peak):
+    """BASELINE configs[1] (ResNet-50 W8A8 per tensor, --qtype int8, batch 512): 3 timed steps, inputs resident.
+    All 55 activation tensors take mode B (per-sample min/max statistics + apply, 12 B/element)."""
+    import torch
+    from cnn_quantization_b200 import ops, pipeline
+    model, qm = pipeline.build_quantized_model("resnet50_w8a8", dev)
+    x, t = pipeline.synthetic_batch(args.batch, seed=7)
+    x, t = x.to(dev), t.to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            pipeline.accuracy_counts(model(x), t)
+        torch.cuda.synchronize()
+        ops.profile_reset(enable=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            pipeline.accuracy_counts(model(x), t)
+        e1.record()
+        torch.cuda.synchronize()
+    prof = ops.profile_collect()
+    ops.profile_reset(enable=False)
+    qm.detach()
+    ms = e0.elapsed_time(e1) / 3
+    b = prof["modes"].get("B", {"bytes": 0, "ms": 0.0, "launches": 0})
+    gbs = (b["bytes"] / 1e9) / (b["ms"] / 1e3) if b["ms"] else None
+    return {"workload": "BASELINE configs[1]: resnet50_w8a8 (--qtype int8), batch %d" % args.batch, "value": args.batch / (ms / 1e3),
+            "unit": UNIT, "ms_per_step": ms, "steps": 3,
+            "roofline": {"kernel": "fq_fused_kernel mode B (min/max statistics + apply)", "algorithmic_bytes_per_elem": 12,
+                         "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak if gbs else None,
+                         "launches": b["launches"]}}
 
 
 def main():

@@ -34,6 +34,7 @@ class Desc(ctypes.Structure):
         ("bias_corr", ctypes.c_int32), ("var_corr", ctypes.c_int32), ("stats_only", ctypes.c_int32),
         ("out_stats", ctypes.c_void_p),
         ("bias", ctypes.c_void_p),
+        ("bias_period", ctypes.c_int64),
     ]
 
 

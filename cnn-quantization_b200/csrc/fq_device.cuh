@@ -324,7 +324,7 @@ __device__ __forceinline__ UnitInfo unit_info(const Geometry& geo, unsigned u) {
 
 // Stream every unit this CTA manages to pull through `acc`:
 //   acc.begin(ui)           unit starts (load per-group constants, reset accumulators); ui.start.j is the thread's column
-//   acc.consume(x, off)     one vector (off = its index from the tensor base, in vectors)
+//   acc.consume(x, off, j)  one vector (off = its index from the tensor base, j = its column in the row, in vectors)
 //   acc.end(ui)             unit done: CTA-wide combine + partial store; MUST contain at least one __syncthreads()
 // `counter` is this phase's unit counter in the workspace (zero at launch), or nullptr for a static round-robin
 // assignment (ticket k of CTA b = b + k * gridDim.x; used by the workspace-free given-parameter kernel).
@@ -439,7 +439,7 @@ __device__ __forceinline__ void stream_units(const Geometry& geo, const float* b
       bubbles |= 1u << head;
     head = (head + 1u) & (D - 1u);
     if (active) {
-      acc.consume(x, cc.off);
+      acc.consume(x, cc.off, cc.j);
       cursor_step<REV>(geo, cc);
     }
     if (!bubble) ++cdone;

@@ -52,6 +52,8 @@ struct FusedArgs {
   const float* in;
   float* out;
   const float* bias;   // optional per-group addend applied to x before everything else (folded-BN conv bias)
+  unsigned long long bias_magic;  // 0: bias[g];  else ceil(2^40 / period_v): bias[(j * magic) >> 40], j = column in vectors
+                                  // (per-tensor / per-sample layouts, where a row holds C channels of period_v vectors each)
   float* grid_out;     // optional integer grid (quantize1)
   // configuration (mirrors fqb200_desc)
   int scope, range_mode, leaf, num_bits, positive, solve_f64;
@@ -422,8 +424,17 @@ __device__ __forceinline__ void block_combine(PhaseSmem& sm, float& mn, float& m
   }
 }
 
+// the bias addend of a vector: per group, or per channel inside the row (bias_magic != 0)
+// BIASJ is a compile-time switch: the column j is dead code (and with it the consume-side cursor of the statistics
+// phases) in every kernel that does not need it.
+template <bool BIASJ>
+__device__ __forceinline__ float bias_at(const FusedArgs& A, float group_bias, unsigned j) {
+  if (!BIASJ) return group_bias;
+  return __ldg(A.bias + static_cast<unsigned>((static_cast<unsigned long long>(j) * A.bias_magic) >> 40));
+}
+
 // S1: min / max / sum per unit  (int_quantizer.py:541-546)
-template <int VEC>
+template <int VEC, bool BIASJ = false>
 struct AccStats1 {
   const FusedArgs& A;
   PhaseSmem& sm;
@@ -433,16 +444,17 @@ struct AccStats1 {
     mn = INFINITY;
     mx = -INFINITY;
     s = 0.0;
-    bias = A.bias ? __ldg(A.bias + ui.g) : 0.f;  // x + 0 when there is none
+    bias = (A.bias && !BIASJ) ? __ldg(A.bias + ui.g) : 0.f;  // x + 0 when there is none
   }
-  __device__ __forceinline__ void consume(const float4& v, unsigned) {
-    const float x0 = __fadd_rn(v.x, bias), x1 = __fadd_rn(v.y, bias), x2 = __fadd_rn(v.z, bias), x3 = __fadd_rn(v.w, bias);
+  __device__ __forceinline__ void consume(const float4& v, unsigned, unsigned j) {
+    const float bj = bias_at<BIASJ>(A, bias, j);
+    const float x0 = __fadd_rn(v.x, bj), x1 = __fadd_rn(v.y, bj), x2 = __fadd_rn(v.z, bj), x3 = __fadd_rn(v.w, bj);
     mn = fminf(mn, fminf(fminf(x0, x1), fminf(x2, x3)));
     mx = fmaxf(mx, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
     s += static_cast<double>(__fadd_rn(__fadd_rn(x0, x1), __fadd_rn(x2, x3)));
   }
-  __device__ __forceinline__ void consume(const float& v, unsigned) {
-    const float x = __fadd_rn(v, bias);
+  __device__ __forceinline__ void consume(const float& v, unsigned, unsigned j) {
+    const float x = __fadd_rn(v, bias_at<BIASJ>(A, bias, j));
     mn = fminf(mn, x);
     mx = fmaxf(mx, x);
     s += static_cast<double>(x);
@@ -477,13 +489,13 @@ struct AccStats2 {
     sa = 0.0;
     sq = 0.0;
   }
-  __device__ __forceinline__ void consume(const float4& v, unsigned) {
+  __device__ __forceinline__ void consume(const float4& v, unsigned, unsigned j) {
     const float d0 = __fsub_rn(__fadd_rn(v.x, bias), mu), d1 = __fsub_rn(__fadd_rn(v.y, bias), mu);
     const float d2 = __fsub_rn(__fadd_rn(v.z, bias), mu), d3 = __fsub_rn(__fadd_rn(v.w, bias), mu);
     sa += static_cast<double>(__fadd_rn(__fadd_rn(fabsf(d0), fabsf(d1)), __fadd_rn(fabsf(d2), fabsf(d3))));
     sq += static_cast<double>(__fmaf_rn(d3, d3, __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)))));
   }
-  __device__ __forceinline__ void consume(const float& v, unsigned) {
+  __device__ __forceinline__ void consume(const float& v, unsigned, unsigned j) {
     const float d = __fsub_rn(__fadd_rn(v, bias), mu);
     sa += static_cast<double>(fabsf(d));
     sq += static_cast<double>(__fmul_rn(d, d));
@@ -618,7 +630,7 @@ struct AccStats1B {
     biasA = A.bias ? __ldg(A.bias + col.chA) : 0.f;
     biasB = (A.bias && col.split < 4u) ? __ldg(A.bias + col.chA + 1u) : 0.f;
   }
-  __device__ __forceinline__ void consume(const float4& v, unsigned) {
+  __device__ __forceinline__ void consume(const float4& v, unsigned, unsigned j) {
     const unsigned sp = col.split;
     const float x0 = __fadd_rn(v.x, biasA);
     const float x1 = __fadd_rn(v.y, sp > 1u ? biasA : biasB);
@@ -665,7 +677,7 @@ struct AccStats2B {
     biasB = (A.bias && hasB) ? __ldg(A.bias + col.chA + 1u) : 0.f;
     saA = sqA = saB = sqB = 0.0;
   }
-  __device__ __forceinline__ void consume(const float4& v, unsigned) {
+  __device__ __forceinline__ void consume(const float4& v, unsigned, unsigned j) {
     const unsigned sp = col.split;
     const float d0 = __fsub_rn(__fadd_rn(v.x, biasA), muA);
     const float d1 = __fsub_rn(__fadd_rn(v.y, sp > 1u ? biasA : biasB), sp > 1u ? muA : muB);
@@ -708,7 +720,7 @@ __device__ __forceinline__ LeafParam load_leaf_param(const LeafParam* lp, unsign
 // A: quantize - clip - dequantize one unit with its group's (or the tensor's) parameters held in registers.
 // ACC: also accumulate sum(y) (weight bias correction); GRID: also store the integer grid; GIVEN: derive the leaf
 // parameters from caller-provided delta / offset / bits instead of the solved table.
-template <int VEC, int LEAF, bool ACC, bool GRID, bool GIVEN>
+template <int VEC, int LEAF, bool ACC, bool GRID, bool GIVEN, bool BIASJ = false>
 struct AccApply {
   const FusedArgs& A;
   PhaseSmem& sm;
@@ -726,11 +738,11 @@ struct AccApply {
       q = load_leaf_param(A.lp, (A.scope == FQB200_SCOPE_GROUP) ? g : 0u);
     }
     dv = make_divisor(q.a);
-    bias = A.bias ? __ldg(A.bias + g) : 0.f;
+    bias = (A.bias && !BIASJ) ? __ldg(A.bias + g) : 0.f;
     sy = 0.0;
   }
   template <bool FAST>
-  __device__ __forceinline__ void one(const float4& x, unsigned off) {
+  __device__ __forceinline__ void one(const float4& x, unsigned off, float bias) {
     float4 y, gq;
     y.x = leaf_apply<LEAF, FAST>(__fadd_rn(x.x, bias), q, dv, 0.f, gq.x);
     y.y = leaf_apply<LEAF, FAST>(__fadd_rn(x.y, bias), q, dv, 0.f, gq.y);
@@ -741,7 +753,7 @@ struct AccApply {
     if (ACC) sy += static_cast<double>(__fadd_rn(__fadd_rn(y.x, y.y), __fadd_rn(y.z, y.w)));
   }
   template <bool FAST>
-  __device__ __forceinline__ void one(const float& x, unsigned off) {
+  __device__ __forceinline__ void one(const float& x, unsigned off, float bias) {
     float gq;
     const float y = leaf_apply<LEAF, FAST>(__fadd_rn(x, bias), q, dv, 0.f, gq);
     st_tensor(A.out + off, y);
@@ -749,11 +761,12 @@ struct AccApply {
     if (ACC) sy += static_cast<double>(y);
   }
   template <typename V>
-  __device__ __forceinline__ void consume(const V& x, unsigned off) {
+  __device__ __forceinline__ void consume(const V& x, unsigned off, unsigned j) {
+    const float bj = bias_at<BIASJ>(A, bias, j);
     if (dv.fast)  // CTA-uniform
-      one<true>(x, off);
+      one<true>(x, off, bj);
     else
-      one<false>(x, off);
+      one<false>(x, off, bj);
   }
   __device__ __forceinline__ void end(const UnitInfo& ui) {
     if (ACC) {
@@ -786,10 +799,10 @@ struct AccCorr {
     if (bc) y = __fadd_rn(__fsub_rn(y, mq), mo);
     return y;
   }
-  __device__ __forceinline__ void consume(const float4& y, unsigned off) {
+  __device__ __forceinline__ void consume(const float4& y, unsigned off, unsigned) {
     st_tensor(reinterpret_cast<float4*>(A.out) + off, make_float4(fix(y.x), fix(y.y), fix(y.z), fix(y.w)));
   }
-  __device__ __forceinline__ void consume(const float& y, unsigned off) { st_tensor(A.out + off, fix(y)); }
+  __device__ __forceinline__ void consume(const float& y, unsigned off, unsigned) { st_tensor(A.out + off, fix(y)); }
   __device__ __forceinline__ void end(const UnitInfo&) { __syncthreads(); }
 };
 
@@ -835,7 +848,7 @@ struct AccApplyB {
     y.w = elem<FAST>(x.w, sp > 3u);
     st_tensor(reinterpret_cast<float4*>(A.out) + off, y);
   }
-  __device__ __forceinline__ void consume(const float4& x, unsigned off) {
+  __device__ __forceinline__ void consume(const float4& x, unsigned off, unsigned) {
     if (dvA.fast && dvB.fast)
       one<true>(x, off);
     else
@@ -851,11 +864,14 @@ struct AccApplyB {
 // only the loops it runs.  Phase directions: S1 forward, S2 backward, A forward again (backward when there is no S2):
 // each phase starts on the bytes the previous one touched last, which are still in L2.
 // MODE: 4 = 128-bit path, 1 = scalar path, 8 = bundled 128-bit path (inner % 4 != 0, see Geometry)
-template <int MODE, int LEAF, bool DEV, bool CORR>
+// BIASJ: the bias is indexed by the channel inside the row (fqb200_desc.bias_period); instantiated for the one
+// configuration that uses it (128-bit path, min/max range, compiled leaf: the per-tensor / per-sample activations).
+template <int MODE, int LEAF, bool DEV, bool CORR, bool BIASJ = false>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __grid_constant__ FusedArgs A) {
   constexpr int VEC = (MODE == 1) ? 1 : 4;
   constexpr bool BUNDLED = (MODE == 8);
   static_assert(!(BUNDLED && CORR), "weight correction runs on the plain layouts");
+  static_assert(!BIASJ || (MODE == 4 && !DEV && !CORR), "bias_period: 128-bit path, one statistics pass, no correction");
   __shared__ PhaseSmem psm;
   __shared__ LeaderSmem lsm;
   __shared__ StreamSmem ssm;
@@ -869,7 +885,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
     AccStats1B acc{A, psm};
     stream_units<4, false>(geo, A.in, &A.sync->unit_counter[0], ssm, acc);
   } else {
-    AccStats1<VEC> acc{A, psm};
+    AccStats1<VEC, BIASJ> acc{A, psm};
     stream_units<VEC, false>(geo, A.in, &A.sync->unit_counter[0], ssm, acc);
   }
   if (blockIdx.x == 0) stamp(A, 1);
@@ -930,7 +946,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
       AccApplyB<LEAF> acc{A};
       stream_units<4, !DEV>(geo, A.in, &A.sync->unit_counter[2], ssm, acc);
     } else {
-      AccApply<VEC, LEAF, CORR, false, false> acc{A, psm};
+      AccApply<VEC, LEAF, CORR, false, false, BIASJ> acc{A, psm};
       stream_units<VEC, !DEV>(geo, A.in, &A.sync->unit_counter[2], ssm, acc);
     }
     if (blockIdx.x == 0) stamp(A, 9);
@@ -1129,6 +1145,14 @@ int get_device(DeviceInfo** out) {
             if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
             if (n < per_sm) per_sm = n;
           }
+    {
+      int n = 0;
+      const void* fn = reinterpret_cast<const void*>(fqb::fq_fused_kernel<4, FQB200_LEAF_COMPILED, false, false, true>);
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem(4)));
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kThreads, dyn_smem(4));
+      if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "bias-period kernel setup: %s", cudaGetErrorString(e));
+      if (n < per_sm) per_sm = n;
+    }
     if (per_sm < 1) return fail(FQB200_ERR_CUDA, "fused kernel does not fit on an SM%s");
     e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, false>),
                              cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem(4)));
@@ -1432,8 +1456,8 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   rc = get_device(&di);
   if (rc != FQB200_OK) return rc;
   Plan pl;
-  if (d->bias && d->scope == FQB200_SCOPE_GROUP_MEAN)
-    return fail(FQB200_ERR_UNSUPPORTED, "a per-group bias needs groups = channels (scope GROUP or TENSOR)%s");
+  if (d->bias && d->bias_period <= 0 && d->scope == FQB200_SCOPE_GROUP_MEAN)
+    return fail(FQB200_ERR_UNSUPPORTED, "a per-group bias needs groups = channels (scope GROUP or TENSOR); use bias_period%s");
   const bool can_vec = aligned16(in) && (d->stats_only || aligned16(out));
   rc = make_plan(d->outer, d->groups, d->inner, can_vec, !(d->bias_corr || d->var_corr), di->resident, &pl);
   if (rc != FQB200_OK) return rc;
@@ -1464,6 +1488,16 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   A.stats_only = d->stats_only;
   A.out_stats = d->out_stats;
   A.bias = d->bias;
+  A.bias_magic = 0;
+  if (d->bias && d->bias_period > 0) {
+    // bias indexed by the channel inside the row: needs whole vectors per channel and an exact magic division
+    const uint64_t pv = static_cast<uint64_t>(d->bias_period) / pl.vec;
+    if (pl.mode != 4 || d->leaf != FQB200_LEAF_COMPILED || d->range_mode != FQB200_RANGE_MINMAX || d->bias_corr || d->var_corr ||
+        d->stats_only || d->bias_period % pl.vec != 0 || d->inner % d->bias_period != 0 || pv == 0 ||
+        static_cast<uint64_t>(pl.geo.inner_v) * pv >= (1ull << 40) || pl.geo.inner_v >= (1u << 24))
+      return fail(FQB200_ERR_UNSUPPORTED, "bias_period does not fit this layout%s");
+    A.bias_magic = ((1ull << 40) + pv - 1) / pv;
+  }
   A.dbg = g_dbg_timing;
   A.inner = static_cast<unsigned>(d->inner);
   A.n_per_group = static_cast<double>(d->outer) * static_cast<double>(d->inner);
@@ -1473,7 +1507,9 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   void* args[] = {&A};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-  e = cudaLaunchCooperativeKernel(fused_kernel_ptr(pl.mode, d->leaf, A.need_dev != 0, d->bias_corr || d->var_corr), dim3(pl.grid),
+  const void* kernel = A.bias_magic ? reinterpret_cast<const void*>(fqb::fq_fused_kernel<4, FQB200_LEAF_COMPILED, false, false, true>)
+                                    : fused_kernel_ptr(pl.mode, d->leaf, A.need_dev != 0, d->bias_corr || d->var_corr);
+  e = cudaLaunchCooperativeKernel(kernel, dim3(pl.grid),
                                   dim3(fqb::kThreads), args, dyn_smem(pl.vec), st);
   if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cooperative launch fq_fused_kernel: %s", cudaGetErrorString(e));
   return FQB200_OK;

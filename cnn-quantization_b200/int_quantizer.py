@@ -133,7 +133,7 @@ class IntQuantizer(object):
                 else:
                     res = self.gemmlowpQuantizeActivationPerChannel(tensor, id, tag, stat_id=stat_id, bias=bias)
             else:
-                res = self.gemmlowpMinMaxQuantize(tensor, tag, stat_id=stat_id, weight_correction=weight_correction)
+                res = self.gemmlowpMinMaxQuantize(tensor, tag, stat_id=stat_id, weight_correction=weight_correction, bias=bias)
         finally:
             if override_att is not None:
                 setattr(self, override_att[0], orig_att)
@@ -163,9 +163,14 @@ class IntQuantizer(object):
         return bool(self.force_positive or self.half_range)
 
     def _bias_fusable(self, tensor):
-        """The kernel takes a per-GROUP addend: only the per-channel activation layouts have channel = group."""
-        return bool((self.clipping != "no" or not self.pcq_w) and self._pc_act(tensor) and tensor.shape[1] > 1
-                    and not self.kld)
+        """Where the kernel can add the convolution bias itself: the per-channel activation layouts (channel = group)
+        and the per-tensor / per-sample min-max layouts of 4-D tensors with H*W % 4 == 0 (bias_period = H*W)."""
+        if self.kld or self.mtd_quant and not self._pc_act(tensor):
+            return False
+        if (self.clipping != "no" or not self.pcq_w) and self._pc_act(tensor) and tensor.shape[1] > 1:
+            return True
+        minmax = self.clipping == "no" and not self.pcq_w and not self._pc_act(tensor)
+        return bool(minmax and tensor.dim() == 4 and (tensor.shape[2] * tensor.shape[3]) % 4 == 0)
 
     def _out(self, tensor):
         return tensor if (self.inplace and tensor.is_contiguous()) else None
@@ -279,10 +284,13 @@ class IntQuantizer(object):
                          leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(), solve_f64=True,
                          out=self._out(tensor))
 
-    def gemmlowpMinMaxQuantize(self, tensor, tag="", stat_id=None, weight_correction=None):
+    def gemmlowpMinMaxQuantize(self, tensor, tag="", stat_id=None, weight_correction=None, bias=None):
         """Per-tensor min/max range through the compiled-leaf arithmetic, int_quantizer.py:361-379 + :605-614.
         Activations (tag contains 'activation', not 'classifier') use the batch average of per-sample min/max."""
         self._unsupported(stat_id)
+        if bias is not None and stat_id is not None:
+            tensor = tensor.add_(bias.view(1, -1, 1, 1)) if self.inplace else tensor + bias.view(1, -1, 1, 1)
+            bias = None
         if stat_id is not None:
             # int_quantizer.py:362-369: collected min/max ('mean' kind, or min-of-min / max-of-max), compiled leaf
             kmin, kmax = ("mean", "mean") if self.stats_kind == "mean" else ("min", "max")
@@ -296,13 +304,19 @@ class IntQuantizer(object):
                                       out=self._out(tensor)) if delta > 0 else tensor
         avg = ("activation" in tag and "classifier" not in tag)
         kw = dict(range_mode=L.RANGE_MINMAX, leaf=L.LEAF_COMPILED, num_bits=self.num_bits, positive=self._positive())
+        if bias is not None:
+            kw.update(bias=bias, bias_period=tensor.shape[2] * tensor.shape[3])
         if weight_correction is not None and any(weight_correction):
             rows = tensor.shape[0]
             return ops.fused(tensor, (1, rows, tensor.numel() // rows), scope=L.SCOPE_TENSOR,
                              bias_corr=weight_correction[0], var_corr=weight_correction[1], **kw)
+        n = tensor.shape[0]
         if avg:
-            n = tensor.shape[0]
             return ops.fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_GROUP_MEAN, out=self._out(tensor), **kw)
+        if bias is not None:
+            # rows = samples so that the channel of an element is its column / (H*W); the global min / max is the
+            # min / max of the per-row ones (scope TENSOR): identical to the flat per-tensor reduction
+            return ops.fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_TENSOR, out=self._out(tensor), **kw)
         return ops.fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, out=self._out(tensor), **kw)
 
     def gemmlowpQuantizeActivationPerChannel(self, tensor, id, tag="", stat_id=None, min_=None, max_=None, bias=None):

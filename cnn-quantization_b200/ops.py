@@ -142,7 +142,7 @@ def quantize1(x, delta, offset, num_bits, bits=None, layout=None, want_grid=Fals
 def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH, num_bits=8,
           positive=False, solve_f64=False, clip_k=0.0, bit_alloc=False, bit_alloc_prior=L.PRIOR_STD,
           bit_alloc_round=True, bit_alloc_target=None, mt_target=0.0, mt_clip=False, bias_corr=False,
-          var_corr=False, stats_only=False, want_stats=False, out=None, bias=None):
+          var_corr=False, stats_only=False, want_stats=False, out=None, bias=None, bias_period=0):
     """C ABI fqb200_fused: statistics -> parameters -> quantize/dequantize in one launch.
 
     Returns ``out`` (or ``(out, stats)`` with ``want_stats``; ``stats`` alone with ``stats_only``), where
@@ -166,11 +166,14 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
     if bias is not None:
         _require_cuda_f32(bias, "bias")
         bias = bias.contiguous()
-        if bias.numel() != groups:
-            raise ValueError("bias must have one element per group (%d)" % groups)
+        want = inner // bias_period if bias_period else groups
+        if bias.numel() != want:
+            raise ValueError("bias must have %d elements" % want)
         d.bias = bias.data_ptr()
+        d.bias_period = int(bias_period)
     else:
         d.bias = None
+        d.bias_period = 0
     stats = None
     if want_stats or stats_only:
         stats = torch.zeros((groups, L.STATS_STRIDE), dtype=torch.float32, device=dev)

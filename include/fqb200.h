@@ -100,7 +100,11 @@ typedef struct fqb200_desc {
   const float* bias;  /* optional device vector of `groups` floats added to every element of its group before
                          anything else (x + bias[g], one fp32 rounding): the folded-BN convolution bias, so the
                          caller can run its convolution bias-free and skip a full read+write pass over the
-                         activation.  NULL = none.  Not available with scope GROUP_MEAN. */
+                         activation.  NULL = none. */
+  int64_t bias_period; /* 0: bias[g] (groups are channels).  > 0: the row of a group holds inner / bias_period channels
+                          of bias_period floats each and element i of the row gets bias[i / bias_period] - the
+                          per-tensor and per-sample layouts of an NCHW activation (bias_period = H*W).  Needs
+                          bias_period % 4 == 0 on the 128-bit path. */
 } fqb200_desc;
 
 /* ---- library ---------------------------------------------------------------------------------- */

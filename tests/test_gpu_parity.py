@@ -431,8 +431,16 @@ def test_fused_bias_operand_and_inplace_flag(fq):
                 buf = x.clone()
                 got2 = q(buf, "c", "activation", bias=b)
                 assert got2.data_ptr() == buf.data_ptr() and torch.equal(got2, want)
-    # paths whose groups are not channels fall back to adding the bias first
+    # per-tensor / per-sample min-max layouts: the bias is indexed by the channel inside the row (bias_period = H*W) ...
     q = fq.int_quantizer("int8", params())
+    for shape in ((4, 6, 4, 4), (3, 64, 14, 14), (2, 5, 6, 2)):
+        x = torch.randn(*shape, device="cuda")
+        b = torch.randn(shape[1], device="cuda")
+        for tag, hr in (("activation", False), ("activation", True), ("activation_classifier", False)):
+            q.half_range = hr
+            assert torch.equal(q(x, "c", tag, bias=b), q(x + b.view(1, -1, 1, 1), "c", tag)), (shape, tag, hr)
+    q.half_range = False
+    # ... and where H*W is not a multiple of 4 the bias is added first
     x = torch.randn(4, 6, 5, 5, device="cuda")
     b = torch.randn(6, device="cuda")
     assert torch.equal(q(x, "c", "activation", bias=b), q(x + b.view(1, -1, 1, 1), "c", "activation"))
