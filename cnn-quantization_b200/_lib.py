@@ -35,6 +35,7 @@ class Desc(ctypes.Structure):
         ("out_stats", ctypes.c_void_p),
         ("bias", ctypes.c_void_p),
         ("bias_period", ctypes.c_int64),
+        ("out_hist", ctypes.c_void_p),
     ]
 
 

@@ -69,7 +69,8 @@ struct FusedArgs {
   unsigned inner;      // floats per channel row (bundled layouts locate channel boundaries with it)
   double n_per_group;  // outer * inner
   float* out_stats;
-  unsigned long long* dbg;  // development: globaltimer stamps of the phase boundaries (NULL in production)
+  unsigned long long* hist;  // optional 256-bin histogram of the integer grid (entropy measurement, `-me`), accumulated
+  unsigned long long* dbg;   // development: globaltimer stamps of the phase boundaries (NULL in production)
   // workspace
   GridSync* sync;
   float *pmin, *pmax;                   // [items]
@@ -381,7 +382,26 @@ struct PhaseSmem {
   // bundled layouts: one row per channel of the bundle
   float bf0[4][kWarps], bf1[4][kWarps];
   double bd0[4][kWarps], bd1[4][kWarps];
+  // `-me`: per-warp histograms of the integer grid (the grid of the torch leaf lives in [0, 255])
+  unsigned hist[kWarps][256];
 };
+
+__device__ __forceinline__ void hist_clear(PhaseSmem& sm) {
+  for (unsigned i = threadIdx.x; i < kWarps * 256u; i += kThreads) (&sm.hist[0][0])[i] = 0u;
+  __syncthreads();
+}
+__device__ __forceinline__ void hist_add(PhaseSmem& sm, float q) {
+  if (q >= 0.f && q <= 255.f) atomicAdd(&sm.hist[threadIdx.x >> 5][static_cast<unsigned>(q)], 1u);  // NaN falls through
+}
+__device__ __forceinline__ void hist_flush(PhaseSmem& sm, unsigned long long* out) {
+  __syncthreads();
+  for (unsigned b = threadIdx.x; b < 256u; b += kThreads) {
+    unsigned long long c = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) c += sm.hist[w][b];
+    if (c) atomicAdd(out + b, c);
+  }
+}
 
 #ifndef FQB_USTATS
 #define FQB_USTATS 4
@@ -751,6 +771,12 @@ struct AccApply {
     st_tensor(reinterpret_cast<float4*>(A.out) + off, y);
     if (GRID) st_tensor(reinterpret_cast<float4*>(A.grid_out) + off, gq);
     if (ACC) sy += static_cast<double>(__fadd_rn(__fadd_rn(y.x, y.y), __fadd_rn(y.z, y.w)));
+    if (LEAF == FQB200_LEAF_TORCH && A.hist) {  // launch-uniform
+      hist_add(sm, gq.x);
+      hist_add(sm, gq.y);
+      hist_add(sm, gq.z);
+      hist_add(sm, gq.w);
+    }
   }
   template <bool FAST>
   __device__ __forceinline__ void one(const float& x, unsigned off, float bias) {
@@ -759,6 +785,7 @@ struct AccApply {
     st_tensor(A.out + off, y);
     if (GRID) st_tensor(A.grid_out + off, gq);
     if (ACC) sy += static_cast<double>(y);
+    if (LEAF == FQB200_LEAF_TORCH && A.hist) hist_add(sm, gq);
   }
   template <typename V>
   __device__ __forceinline__ void consume(const V& x, unsigned off, unsigned j) {
@@ -809,6 +836,7 @@ struct AccCorr {
 template <int LEAF>
 struct AccApplyB {
   const FusedArgs& A;
+  PhaseSmem& sm;
   Column col;
   LeafParam qA, qB;
   Divisor dvA, dvB;
@@ -825,7 +853,7 @@ struct AccApplyB {
     biasB = (A.bias && hasB) ? __ldg(A.bias + col.chA + 1u) : biasA;
   }
   template <bool FAST>
-  __device__ __forceinline__ float elem(float x, bool inA) const {
+  __device__ __forceinline__ float elem(float x, bool inA) {
     LeafParam q;
     Divisor dv;
     q.a = inA ? qA.a : qB.a;
@@ -836,7 +864,9 @@ struct AccApplyB {
     dv.r = inA ? dvA.r : dvB.r;
     dv.fast = FAST;
     float gq;
-    return leaf_apply<LEAF, FAST>(__fadd_rn(x, inA ? biasA : biasB), q, dv, 0.f, gq);
+    const float y = leaf_apply<LEAF, FAST>(__fadd_rn(x, inA ? biasA : biasB), q, dv, 0.f, gq);
+    if (LEAF == FQB200_LEAF_TORCH && A.hist) hist_add(sm, gq);
+    return y;
   }
   template <bool FAST>
   __device__ __forceinline__ void one(const float4& x, unsigned off) {
@@ -942,13 +972,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
 
   // ---- A (+ C)
   if (!A.stats_only) {
+    if (LEAF == FQB200_LEAF_TORCH && A.hist) hist_clear(psm);
     if constexpr (BUNDLED) {
-      AccApplyB<LEAF> acc{A};
+      AccApplyB<LEAF> acc{A, psm};
       stream_units<4, !DEV>(geo, A.in, &A.sync->unit_counter[2], ssm, acc);
     } else {
       AccApply<VEC, LEAF, CORR, false, false, BIASJ> acc{A, psm};
       stream_units<VEC, !DEV>(geo, A.in, &A.sync->unit_counter[2], ssm, acc);
     }
+    if (LEAF == FQB200_LEAF_TORCH && A.hist) hist_flush(psm, A.hist);
     if (blockIdx.x == 0) stamp(A, 9);
     if constexpr (CORR) {
       if (grid_arrive(A.sync, epoch, &lsm.flag)) {
@@ -1488,6 +1520,8 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   A.stats_only = d->stats_only;
   A.out_stats = d->out_stats;
   A.bias = d->bias;
+  A.hist = d->out_hist;
+  if (d->out_hist && d->leaf != FQB200_LEAF_TORCH) return fail(FQB200_ERR_UNSUPPORTED, "out_hist: torch leaf only%s");
   A.bias_magic = 0;
   if (d->bias && d->bias_period > 0) {
     // bias indexed by the channel inside the row: needs whole vectors per channel and an exact magic division

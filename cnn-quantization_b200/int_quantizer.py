@@ -97,6 +97,7 @@ class IntQuantizer(object):
         # extension (default off = reference behaviour): overwrite the input tensor instead of allocating the result.
         # The manager switches it on for activation tags, where the un-quantized tensor is dead after the hook.
         self.inplace = False
+        self.last_entropy = None  # 0-d device tensor of the most recent `-me` measurement
 
     # ------------------------------------------------------------------------------------------
     # dispatch (int_quantizer.py:92-122)
@@ -153,8 +154,8 @@ class IntQuantizer(object):
             raise NotImplementedError("KLD thresholds are outside the hot-path scope (SURVEY.md section 2, #9)")
         if stat_id is not None and self.sm is None:
             raise RuntimeError("stat_id given but no statistics manager is attached to this quantizer (q.sm)")
-        if self.measure_entropy:
-            raise NotImplementedError("entropy measurement (-me) is the next scope row (SURVEY.md 8f)")
+        if self.measure_entropy and self.mtd_quant:
+            raise NotImplementedError("entropy measurement of the mid-tread grid is not implemented")
 
     def _pc_act(self, tensor):
         return bool(self.pcq_a and len(tensor.shape) > 3 and (tensor.shape[2] > 1 or tensor.shape[3] > 1))
@@ -174,6 +175,24 @@ class IntQuantizer(object):
 
     def _out(self, tensor):
         return tensor if (self.inplace and tensor.is_contiguous()) else None
+
+    # `-me`: the apply phase histograms the integer grid into 256 counters; the Shannon entropy of
+    # utils/entropy.py:6-17 (which runs torch.unique over the whole tensor) is a 256-element computation afterwards
+    def _hist(self, tensor):
+        return torch.zeros(256, dtype=torch.int64, device=tensor.device) if self.measure_entropy else None
+
+    @staticmethod
+    def entropy_from_hist(hist):
+        p = hist[hist > 0].to(torch.float32)
+        p = p / p.sum()
+        return -(p * torch.log2(p)).sum()
+
+    def _log_entropy(self, hist, id, meter, numel):
+        if hist is None:
+            return
+        self.last_entropy = self.entropy_from_hist(hist)
+        if self.logger is not None:
+            self.logger.log_metric(id + ".entropy", self.last_entropy.item(), step="auto", meterId=meter, weight=numel)
 
     @staticmethod
     def _nchw_layout(tensor):
@@ -275,11 +294,14 @@ class IntQuantizer(object):
             return ops.quantize1(tensor, delta, offset, self.num_bits, out=self._out(tensor))
         mode, k = self._range_mode(clip_type)
         if self._pc_act(tensor) and tensor.shape[1] > 1:
-            return ops.fused(tensor, self._nchw_layout(tensor), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
-                             leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(),
-                             bit_alloc=self.bit_alloc_act, bit_alloc_prior=self._prior(),
-                             bit_alloc_round=self.bit_alloc_round, bit_alloc_target=self.bit_alloc_target_act,
-                             bias=bias, out=self._out(tensor))
+            hist = self._hist(tensor)  # the reference measures entropy in gemmlowpQuantizeActivationPerChannel (:442-445)
+            res = ops.fused(tensor, self._nchw_layout(tensor), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
+                            leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(),
+                            bit_alloc=self.bit_alloc_act, bit_alloc_prior=self._prior(),
+                            bit_alloc_round=self.bit_alloc_round, bit_alloc_target=self.bit_alloc_target_act,
+                            bias=bias, out=self._out(tensor), hist=hist)
+            self._log_entropy(hist, id, "avg.entropy.act", tensor.numel())
+            return res
         return ops.fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
                          leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(), solve_f64=True,
                          out=self._out(tensor))
@@ -339,10 +361,13 @@ class IntQuantizer(object):
             return ops.quantize1(tensor, delta, offset, self.num_bits, bits=bits, layout=layout, bias=bias,
                                  out=self._out(tensor))
         if min_ is None and max_ is None:
-            return ops.fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
-                             num_bits=self.num_bits, positive=self._positive(), bit_alloc=self.bit_alloc_act,
-                             bit_alloc_prior=self._prior(), bit_alloc_round=self.bit_alloc_round,
-                             bit_alloc_target=self.bit_alloc_target_act, bias=bias, out=self._out(tensor))
+            hist = self._hist(tensor)
+            res = ops.fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
+                            num_bits=self.num_bits, positive=self._positive(), bit_alloc=self.bit_alloc_act,
+                            bit_alloc_prior=self._prior(), bit_alloc_round=self.bit_alloc_round,
+                            bit_alloc_target=self.bit_alloc_target_act, bias=bias, out=self._out(tensor), hist=hist)
+            self._log_entropy(hist, id, "avg.entropy.act", tensor.numel())
+            return res
         if bias is not None:
             tensor = tensor + bias.view(1, -1, 1, 1)
         # explicit bounds (API compatibility): statistics pass for what is missing, then the given-parameter leaf
@@ -377,10 +402,13 @@ class IntQuantizer(object):
                 bits = self.get_bits_alloc_fixed_target(t.std(-1), self.bit_alloc_target_weight, self.bit_alloc_round)
             return ops.quantize1(tensor, mx - mn, mn, self.num_bits, bits=bits, layout=layout)
         bc, vc = weight_correction if weight_correction is not None else (False, False)
-        return ops.fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
-                         num_bits=self.num_bits, positive=False, bit_alloc=self.bit_alloc_weight,
-                         bit_alloc_prior=L.PRIOR_STD, bit_alloc_round=self.bit_alloc_round,
-                         bit_alloc_target=self.bit_alloc_target_weight, bias_corr=bc, var_corr=vc)
+        hist = self._hist(tensor)
+        res = ops.fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
+                        num_bits=self.num_bits, positive=False, bit_alloc=self.bit_alloc_weight,
+                        bit_alloc_prior=L.PRIOR_STD, bit_alloc_round=self.bit_alloc_round,
+                        bit_alloc_target=self.bit_alloc_target_weight, bias_corr=bc, var_corr=vc, hist=hist)
+        self._log_entropy(hist, id, "avg.entropy.weight", tensor.numel())
+        return res
 
     # mid-tread "bin allocation" quantizer, int_quantizer.py:147-225
     def mid_tread_quantize_weights_per_channel(self, tensor, id, weight_correction=None):
@@ -413,7 +441,9 @@ class IntQuantizer(object):
     def __gemmlowpQuantize1__(self, tensor, delta, offset, bit_alloc=None, measure_entropy=False):
         """int_quantizer.py:557-603: [R, K] tensor with [R] parameters, or any shape with 0-d parameters."""
         if measure_entropy:
-            raise NotImplementedError("entropy measurement is the next scope row (SURVEY.md 8f)")
+            out, grid = ops.quantize1(tensor, delta, offset, self.num_bits, bits=bit_alloc, want_grid=True)
+            hist = torch.bincount(grid.flatten().to(torch.int64).clamp_(0, 255), minlength=256)
+            return out, self.entropy_from_hist(hist)
         return ops.quantize1(tensor, delta, offset, self.num_bits, bits=bit_alloc)
 
     def __gemmlowpQuantize__(self, tensor, delta, offset):

@@ -142,7 +142,7 @@ def quantize1(x, delta, offset, num_bits, bits=None, layout=None, want_grid=Fals
 def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH, num_bits=8,
           positive=False, solve_f64=False, clip_k=0.0, bit_alloc=False, bit_alloc_prior=L.PRIOR_STD,
           bit_alloc_round=True, bit_alloc_target=None, mt_target=0.0, mt_clip=False, bias_corr=False,
-          var_corr=False, stats_only=False, want_stats=False, out=None, bias=None, bias_period=0):
+          var_corr=False, stats_only=False, want_stats=False, out=None, bias=None, bias_period=0, hist=None):
     """C ABI fqb200_fused: statistics -> parameters -> quantize/dequantize in one launch.
 
     Returns ``out`` (or ``(out, stats)`` with ``want_stats``; ``stats`` alone with ``stats_only``), where
@@ -174,6 +174,12 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
     else:
         d.bias = None
         d.bias_period = 0
+    if hist is not None:
+        if hist.dtype != torch.int64 or hist.numel() != 256 or not hist.is_cuda or not hist.is_contiguous():
+            raise ValueError("hist must be a contiguous CUDA int64 tensor of 256 counters")
+        d.out_hist = hist.data_ptr()
+    else:
+        d.out_hist = None
     stats = None
     if want_stats or stats_only:
         stats = torch.zeros((groups, L.STATS_STRIDE), dtype=torch.float32, device=dev)

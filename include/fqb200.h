@@ -105,6 +105,9 @@ typedef struct fqb200_desc {
                           of bias_period floats each and element i of the row gets bias[i / bias_period] - the
                           per-tensor and per-sample layouts of an NCHW activation (bias_period = H*W).  Needs
                           bias_period % 4 == 0 on the 128-bit path. */
+  unsigned long long* out_hist; /* optional device array of 256 counters: the launch ADDS the histogram of the integer
+                          grid q (torch leaf: q in [0, 255]) to it - what the reference's `-me` entropy measurement
+                          needs (utils/entropy.py:6-17 on output.int(), int_quantizer.py:586-587) without torch.unique. */
 } fqb200_desc;
 
 /* ---- library ---------------------------------------------------------------------------------- */

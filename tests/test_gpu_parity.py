@@ -446,6 +446,51 @@ def test_fused_bias_operand_and_inplace_flag(fq):
     assert torch.equal(q(x, "c", "activation", bias=b), q(x + b.view(1, -1, 1, 1), "c", "activation"))
 
 
+def test_entropy_measurement_matches_reference_definition(fq, O):
+    """`-me`: Shannon entropy of the integer grid (utils/entropy.py:6-17 on output.int()), here from the fused 256-bin
+    histogram instead of torch.unique over the tensor."""
+    class Log(object):
+        def __init__(self):
+            self.rows = []
+
+        def log_metric(self, name, value, step=None, meterId=None, weight=None):
+            self.rows.append((name, value, meterId, weight))
+
+    def shannon(grid):
+        pk = torch.unique(grid.flatten().int(), return_counts=True)[1].float()
+        p = pk / pk.sum()
+        return float(-(p * torch.log2(p)).sum())
+
+    for shape in ((6, 16, 14, 14), (5, 8, 7, 7)):
+        x = regen(dict(seed=sum(shape), shape=shape, dist="laplace"))
+        xt = torch.from_numpy(x)
+        log = Log()
+        q = fq.int_quantizer("int4", params(clipping="laplace", pcq_act=True, bit_alloc_act=True, measure_entropy=True, logger=log))
+        q.pcq_w = False
+        y = q(cuda(x), "conv3_activation", "activation")
+        _, parts = O.clipping_quantize(xt, 4, "laplace", True, False, True, "gaus", None, True, return_parts=True)
+        n, c = shape[0], shape[1]
+        t = xt.transpose(0, 1).contiguous().view(c, -1)
+        _, grid = O.gemmlowp_quantize1(t, parts["delta"], parts["offset"], 4, bit_alloc=parts["bits"], return_grid=True)
+        want = shannon(grid)
+        assert len(log.rows) == 1 and log.rows[0][0] == "conv3_activation.entropy" and log.rows[0][2] == "avg.entropy.act"
+        assert log.rows[0][3] == x.size and abs(log.rows[0][1] - want) < 2e-3, (log.rows, want)
+        assert 0 < want < 4.5
+    # weights, and the compatibility path of the leaf itself
+    w = (regen(dict(seed=9, shape=(16, 8, 3, 3))) * 0.05).astype(np.float32)
+    log = Log()
+    q = fq.int_quantizer("int4", params(pcq_weights=True, bit_alloc_weight=True, measure_entropy=True, logger=log))
+    q.pcq_a = False
+    q(cuda(w), "layer1.0.conv1.weight", "weight")
+    wt = torch.from_numpy(w).view(16, -1)
+    _, parts = O.quantize_weights_per_channel(torch.from_numpy(w), 4, True, return_parts=True)
+    _, grid = O.gemmlowp_quantize1(wt, parts["delta"], parts["offset"], 4, bit_alloc=parts["bits"], return_grid=True)
+    assert abs(log.rows[0][1] - shannon(grid)) < 2e-3 and log.rows[0][2] == "avg.entropy.weight"
+    out, ent = q.__gemmlowpQuantize1__(cuda(w).view(16, -1), cuda(parts["delta"]), cuda(parts["offset"]), bit_alloc=cuda(parts["bits"]),
+                                       measure_entropy=True)
+    assert abs(float(ent) - shannon(grid)) < 1e-5
+
+
 def test_full_size_properties(fq):
     """ResNet-50 sized activation (config 3, batch 64 slice): per-channel level count, range, idempotence of the grid."""
     torch.manual_seed(1)
