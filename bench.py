@@ -34,6 +34,8 @@ def parse():
     ap.add_argument("--config", default="resnet50_w4a4")
     ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=2, help="images per step of the CPU reference arm / cpu_baseline")
+    ap.add_argument("--channels-last", action="store_true",
+                    help="run the model and the fused kernels on NHWC tensors (no cuDNN layout conversions)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short BASELINE configs[1] (W8A8) run")
     return ap.parse_args()
@@ -162,8 +164,8 @@ def run_fqb200(args):
     fq._lib.load()
     torch.backends.cudnn.benchmark = True  # inference_sim.py:205
 
-    model, qm = pipeline.build_quantized_model(args.config, dev)
-    x_host, t_host = pipeline.synthetic_batch(args.batch, seed=1000 + rank, pin=True)
+    model, qm = pipeline.build_quantized_model(args.config, dev, channels_last=args.channels_last)
+    x_host, t_host = pipeline.synthetic_batch(args.batch, seed=1000 + rank, pin=True, channels_last=args.channels_last)
     x_dev, t_dev = x_host.to(dev), t_host.to(dev)
     total = torch.zeros(4, device=dev)
 
@@ -246,7 +248,7 @@ def run_fqb200(args):
                                    "3x224x224, random-init torchvision weights" % (args.config, args.batch),
                        "parallelism": "dp%d (batch sharded per rank, one all-reduce of 4 metrics)" % world,
                        "l2": "inputs larger than L2 (308 MB input, every hooked tensor 51 MB - 1.6 GB)",
-                       "conv": "cuDNN fp32 NCHW via torch (third party in the reference too)"},
+                       "conv": "cuDNN fp32 %s via torch (third party in the reference too)" % ("NHWC" if args.channels_last else "NCHW")},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": x_host.numel() * 4 + t_host.numel() * 8, "d2h_bytes_per_step": 16},
             "gpu_launches": prof["launches"],

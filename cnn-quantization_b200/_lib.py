@@ -35,6 +35,7 @@ class Desc(ctypes.Structure):
         ("out_stats", ctypes.c_void_p),
         ("bias", ctypes.c_void_p),
         ("bias_period", ctypes.c_int64),
+        ("channels_last", ctypes.c_int32),
         ("out_hist", ctypes.c_void_p),
     ]
 

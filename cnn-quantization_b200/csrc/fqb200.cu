@@ -80,7 +80,13 @@ struct FusedArgs {
   float *gdelta, *goffset;              // [G]
   LeafParam* lp;                        // [G] (entry 0 when the parameters are per tensor)
   float *cq, *co, *ck;                  // [G] weight correction: mean(w_q), mean(w), variance factor
+  // channels-last kernels: per-channel accumulators combined with atomics, zero between launches (fixed place in
+  // the workspace, right after the barrier words)
+  unsigned *amin_inv, *amax;            // max of ~enc(x) (= min) and of enc(x), enc = order-preserving uint encoding
+  double *asum, *aabs, *asq;
 };
+
+constexpr unsigned kMaxNhwcChannels = 4096;
 
 __device__ __forceinline__ void stamp(const FusedArgs& A, int slot) {
   if (A.dbg && threadIdx.x == 0) {
@@ -1021,6 +1027,273 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
   grid_exit(A.sync);
 }
 
+// ------------------------------------------------------------------------------------------------
+// channels-last (NHWC) activations: [N][H*W][C] in memory, the channel is the fastest dimension
+// ------------------------------------------------------------------------------------------------
+// With C/4 dividing the CTA width every thread always holds the same four channels, so the whole tensor is ONE flat
+// stream (no cursor arithmetic, no per-unit combine): accumulators and leaf parameters of those four channels stay in
+// registers for the whole phase, the threads of a CTA that share a column are combined through shared memory once
+// per phase, and CTAs meet in per-channel accumulators with atomics (float min/max through an order-preserving
+// integer encoding, sums as float64 atomicAdd).  Sums are therefore combined in a run-dependent order - in float64,
+// i.e. identical after rounding to fp32 except on exact ties; min / max / the integer grid given equal parameters
+// are exact.
+__device__ __forceinline__ unsigned enc_ordered(float x) {
+  const unsigned b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(unsigned e) {
+  return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
+}
+
+// shared-memory staging of the per-phase combine lives in the (idle) ring memory
+struct NhwcStage {
+  float f0[4][kThreads];
+  float f1[4][kThreads];
+  double d0[4][kThreads];
+  double d1[4][kThreads];
+};
+static_assert(sizeof(NhwcStage) <= static_cast<size_t>(ring_bytes<4>()), "combine staging must fit in the ring memory");
+
+// Reduce, for every channel of this CTA's columns, the values of the threads sharing the column; `emit(channel, f0, f1,
+// d0, d1)` is called once per channel by one thread.  cv = C / 4 columns, kThreads / cv threads per column.
+template <typename Emit>
+__device__ __forceinline__ void nhwc_combine(unsigned cv, const float (&f0)[4], const float (&f1)[4], const double (&d0)[4],
+                                             const double (&d1)[4], Emit&& emit) {
+  extern __shared__ __align__(16) unsigned char fq_ring[];
+  NhwcStage& st = *reinterpret_cast<NhwcStage*>(fq_ring);
+  __syncthreads();  // every thread is done with its ring slots
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    st.f0[k][threadIdx.x] = f0[k];
+    st.f1[k][threadIdx.x] = f1[k];
+    st.d0[k][threadIdx.x] = d0[k];
+    st.d1[k][threadIdx.x] = d1[k];
+  }
+  __syncthreads();
+  for (unsigned i = threadIdx.x; i < 4u * cv; i += kThreads) {
+    const unsigned col = i % cv, k = i / cv;
+    float a = INFINITY, b = -INFINITY;
+    double c = 0.0, d = 0.0;
+    for (unsigned t = col; t < kThreads; t += cv) {
+      a = fminf(a, st.f0[k][t]);
+      b = fmaxf(b, st.f1[k][t]);
+      c += st.d0[k][t];
+      d += st.d1[k][t];
+    }
+    emit(4u * col + k, a, b, c, d);
+  }
+  __syncthreads();
+}
+
+// Sums run in fp32 over kNhwcChunk consecutive vectors of a thread (same accuracy class as the 4-element fp32 tree of
+// the NCHW path) and are then folded into float64: 4x fewer F2F + DADD in an issue-bound loop.
+constexpr unsigned kNhwcChunk = 8;
+
+struct AccStats1N {
+  const FusedArgs& A;
+  float mn[4], mx[4], bias[4], fs[4];
+  double s[4];
+  unsigned cnt;
+  __device__ __forceinline__ void init(unsigned cv) {
+    const unsigned c0 = 4u * (threadIdx.x % cv);
+    cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mn[k] = INFINITY;
+      mx[k] = -INFINITY;
+      s[k] = 0.0;
+      fs[k] = 0.f;
+      bias[k] = A.bias ? __ldg(A.bias + c0 + k) : 0.f;
+    }
+  }
+  __device__ __forceinline__ void flush() {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s[k] += static_cast<double>(fs[k]);
+      fs[k] = 0.f;
+    }
+    cnt = 0;
+  }
+  __device__ __forceinline__ void begin(const UnitInfo&) {}
+  __device__ __forceinline__ void consume(const float4& v, unsigned, unsigned) {
+    const float x[4] = {__fadd_rn(v.x, bias[0]), __fadd_rn(v.y, bias[1]), __fadd_rn(v.z, bias[2]), __fadd_rn(v.w, bias[3])};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mn[k] = fminf(mn[k], x[k]);
+      mx[k] = fmaxf(mx[k], x[k]);
+      fs[k] = __fadd_rn(fs[k], x[k]);
+    }
+    if (++cnt == kNhwcChunk) flush();
+  }
+  __device__ __forceinline__ void end(const UnitInfo&) { __syncthreads(); }
+};
+
+struct AccStats2N {
+  const FusedArgs& A;
+  float mu[4], bias[4], fa[4], fq[4];
+  double sa[4], sq[4];
+  unsigned cnt;
+  __device__ __forceinline__ void init(unsigned cv) {
+    const unsigned c0 = 4u * (threadIdx.x % cv);
+    cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mu[k] = ld_ws(A.gmean + c0 + k);
+      bias[k] = A.bias ? __ldg(A.bias + c0 + k) : 0.f;
+      sa[k] = 0.0;
+      sq[k] = 0.0;
+      fa[k] = 0.f;
+      fq[k] = 0.f;
+    }
+  }
+  __device__ __forceinline__ void flush() {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sa[k] += static_cast<double>(fa[k]);
+      sq[k] += static_cast<double>(fq[k]);
+      fa[k] = 0.f;
+      fq[k] = 0.f;
+    }
+    cnt = 0;
+  }
+  __device__ __forceinline__ void begin(const UnitInfo&) {}
+  __device__ __forceinline__ void consume(const float4& v, unsigned, unsigned) {
+    const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = __fsub_rn(__fadd_rn(x[k], bias[k]), mu[k]);
+      fa[k] = __fadd_rn(fa[k], fabsf(d));
+      fq[k] = __fmaf_rn(d, d, fq[k]);
+    }
+    if (++cnt == kNhwcChunk) flush();
+  }
+  __device__ __forceinline__ void end(const UnitInfo&) { __syncthreads(); }
+};
+
+template <int LEAF>
+struct AccApplyN {
+  const FusedArgs& A;
+  PhaseSmem& sm;
+  LeafParam q[4];
+  float r[4], bias[4];
+  bool fast;
+  __device__ __forceinline__ void init(unsigned cv) {
+    const unsigned c0 = 4u * (threadIdx.x % cv);
+    fast = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      q[k] = load_leaf_param(A.lp, c0 + k);
+      const Divisor dv = make_divisor(q[k].a);
+      r[k] = dv.r;
+      fast = fast && dv.fast;
+      bias[k] = A.bias ? __ldg(A.bias + c0 + k) : 0.f;
+    }
+  }
+  __device__ __forceinline__ void begin(const UnitInfo&) {}
+  template <bool FAST>
+  __device__ __forceinline__ void one(const float4& v, unsigned off) {
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    float y[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      Divisor dv;
+      dv.s = q[k].a;
+      dv.r = r[k];
+      dv.fast = FAST;
+      float gq;
+      y[k] = leaf_apply<LEAF, FAST>(__fadd_rn(x[k], bias[k]), q[k], dv, 0.f, gq);
+      if (LEAF == FQB200_LEAF_TORCH && A.hist) hist_add(sm, gq);
+    }
+    st_tensor(reinterpret_cast<float4*>(A.out) + off, make_float4(y[0], y[1], y[2], y[3]));
+  }
+  __device__ __forceinline__ void consume(const float4& v, unsigned off, unsigned) {
+    if (fast)
+      one<true>(v, off);
+    else
+      one<false>(v, off);
+  }
+  __device__ __forceinline__ void end(const UnitInfo&) { __syncthreads(); }
+};
+
+template <int LEAF, bool DEV>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_nhwc_kernel(const __grid_constant__ FusedArgs A) {
+  __shared__ PhaseSmem psm;
+  __shared__ LeaderSmem lsm;
+  __shared__ StreamSmem ssm;
+  unsigned epoch = 0;
+  const Geometry& geo = A.geo;
+  const unsigned C = geo.channels, cv = C / 4u;
+  const double n = A.n_per_group;
+
+  // ---- S1
+  {
+    AccStats1N acc{A};
+    acc.init(cv);
+    stream_units<4, false>(geo, A.in, &A.sync->unit_counter[0], ssm, acc);
+    acc.flush();
+    const double zero[4] = {0.0, 0.0, 0.0, 0.0};
+    nhwc_combine(cv, acc.mn, acc.mx, acc.s, zero, [&](unsigned c, float mn, float mx, double s, double) {
+      atomicMax(A.amin_inv + c, ~enc_ordered(mn));
+      atomicMax(A.amax + c, enc_ordered(mx));
+      atomicAdd(A.asum + c, s);
+    });
+  }
+  if (grid_arrive(A.sync, epoch, &lsm.flag)) {
+    for (unsigned c = threadIdx.x; c < C; c += kThreads) {
+      A.gmin[c] = dec_ordered(~ld_ws(A.amin_inv + c));
+      A.gmax[c] = dec_ordered(ld_ws(A.amax + c));
+      const double m = ld_ws(A.asum + c) / n;
+      A.gmean_d[c] = m;
+      A.gmean[c] = static_cast<float>(m);
+      A.amin_inv[c] = 0u;  // re-arm for the next launch
+      A.amax[c] = 0u;
+      A.asum[c] = 0.0;
+    }
+    __syncthreads();
+    if (!DEV) solve_params(A, lsm);
+    grid_release(A.sync, epoch);
+  }
+
+  // ---- S2
+  if constexpr (DEV) {
+    {
+      AccStats2N acc{A};
+      acc.init(cv);
+      stream_units<4, false>(geo, A.in, &A.sync->unit_counter[1], ssm, acc);
+      acc.flush();
+      const float fz[4] = {0.f, 0.f, 0.f, 0.f};
+      nhwc_combine(cv, fz, fz, acc.sa, acc.sq, [&](unsigned c, float, float, double sa, double sq) {
+        atomicAdd(A.aabs + c, sa);
+        atomicAdd(A.asq + c, sq);
+      });
+    }
+    if (grid_arrive(A.sync, epoch, &lsm.flag)) {
+      for (unsigned c = threadIdx.x; c < C; c += kThreads) {
+        A.gb[c] = static_cast<float>(ld_ws(A.aabs + c) / n);
+        const double dm = A.gmean_d[c] - static_cast<double>(A.gmean[c]);
+        double ss = ld_ws(A.asq + c) - n * dm * dm;
+        if (ss < 0.0) ss = 0.0;
+        A.gstd[c] = static_cast<float>(sqrt(ss / (n - 1.0)));
+        A.aabs[c] = 0.0;
+        A.asq[c] = 0.0;
+      }
+      __syncthreads();
+      solve_params(A, lsm);
+      grid_release(A.sync, epoch);
+    }
+  }
+
+  // ---- A
+  if (!A.stats_only) {
+    if (LEAF == FQB200_LEAF_TORCH && A.hist) hist_clear(psm);
+    AccApplyN<LEAF> acc{A, psm};
+    acc.init(cv);
+    stream_units<4, false>(geo, A.in, &A.sync->unit_counter[2], ssm, acc);
+    if (LEAF == FQB200_LEAF_TORCH && A.hist) hist_flush(psm, A.hist);
+  }
+  grid_exit(A.sync);
+}
+
 // Standalone a1 with host-side scalars (gemmlowp.cu:30-45): flat grid-stride, parameters by value.
 template <int VEC, bool NOISE, bool FAST>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
@@ -1127,6 +1400,13 @@ const void* fused_ptr1(int leaf, bool dev, bool corr) {
   if (leaf == FQB200_LEAF_COMPILED) return fused_ptr2<MODE, FQB200_LEAF_COMPILED>(dev, corr);
   return fused_ptr2<MODE, FQB200_LEAF_MIDTREAD>(dev, corr);
 }
+const void* nhwc_kernel_ptr(int leaf, bool dev) {
+  if (leaf == FQB200_LEAF_MIDTREAD)
+    return dev ? reinterpret_cast<const void*>(fqb::fq_fused_nhwc_kernel<FQB200_LEAF_MIDTREAD, true>)
+               : reinterpret_cast<const void*>(fqb::fq_fused_nhwc_kernel<FQB200_LEAF_MIDTREAD, false>);
+  return dev ? reinterpret_cast<const void*>(fqb::fq_fused_nhwc_kernel<FQB200_LEAF_TORCH, true>)
+             : reinterpret_cast<const void*>(fqb::fq_fused_nhwc_kernel<FQB200_LEAF_TORCH, false>);
+}
 const void* fused_kernel_ptr(int mode, int leaf, bool dev, bool corr) {
   if (mode == 4) return fused_ptr1<4>(leaf, dev, corr);
   if (mode == 8) return fused_ptr1<8>(leaf, dev, corr);
@@ -1185,6 +1465,15 @@ int get_device(DeviceInfo** out) {
       if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "bias-period kernel setup: %s", cudaGetErrorString(e));
       if (n < per_sm) per_sm = n;
     }
+    for (int leaf = 0; leaf < 3; leaf += 2)
+      for (int dv = 0; dv < 2; ++dv) {
+        int n = 0;
+        const void* fn = nhwc_kernel_ptr(leaf, dv != 0);
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem(4)));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kThreads, dyn_smem(4));
+        if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "channels-last kernel setup: %s", cudaGetErrorString(e));
+        if (n < per_sm) per_sm = n;
+      }
     if (per_sm < 1) return fail(FQB200_ERR_CUDA, "fused kernel does not fit on an SM%s");
     e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, false>),
                              cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem(4)));
@@ -1286,6 +1575,46 @@ int make_plan(int64_t outer, int64_t groups, int64_t inner, bool can_vec, bool a
   return FQB200_OK;
 }
 
+// channels-last plan: the tensor [outer][inner][groups] (groups fastest) as ONE flat stream of outer*inner*groups/4
+// vectors; every thread keeps its column (= its four channels) as long as groups/4 divides the CTA width and every
+// unit starts on a multiple of the CTA width.
+int make_plan_nhwc(int64_t outer, int64_t groups, int64_t inner, int max_ctas, Plan* pl) {
+  if (outer <= 0 || groups <= 0 || inner <= 0) return fail(FQB200_ERR_INVALID, "non-positive tensor extent%s");
+  const uint64_t cv = static_cast<uint64_t>(groups) / 4;
+  if (groups % 4 != 0 || cv == 0 || fqb::kThreads % cv != 0 || static_cast<uint64_t>(groups) > fqb::kMaxNhwcChannels)
+    return fail(FQB200_ERR_UNSUPPORTED, "channels-last needs C %% 4 == 0, C/4 dividing 512 and C <= 4096%s");
+  const uint64_t total_v = static_cast<uint64_t>(outer) * static_cast<uint64_t>(inner) * cv;
+  if (total_v >= (1ULL << 32)) return fail(FQB200_ERR_UNSUPPORTED, "tensors of 2^32 vectors (64 GB) and more are not supported%s");
+  const uint64_t ctas = static_cast<uint64_t>(max_ctas);
+  static const uint64_t per_cta = getenv("FQB_UNITS_PER_CTA") ? strtoull(getenv("FQB_UNITS_PER_CTA"), nullptr, 10) : 8;
+  const uint64_t quantum = static_cast<uint64_t>(fqb::kThreads);
+  const uint64_t min_unit_v = static_cast<uint64_t>(fqb::kRingDepth) * quantum;
+  uint64_t parts = per_cta * ctas;
+  const uint64_t max_parts = total_v / min_unit_v > 0 ? total_v / min_unit_v : 1;
+  if (parts > max_parts) parts = max_parts;
+  uint64_t part_v = (total_v + parts - 1) / parts;
+  part_v = (part_v + quantum - 1) / quantum * quantum;
+  parts = (total_v + part_v - 1) / part_v;
+  fqb::Geometry& g = pl->geo;
+  g.groups = 1;
+  g.channels = static_cast<unsigned>(groups);
+  g.bundle = 1;
+  g.stride = fqb::kThreads;
+  g.parts = static_cast<unsigned>(parts);
+  g.units = static_cast<unsigned>(parts);
+  g.inner_v = static_cast<unsigned>(total_v);
+  g.step_q = 0;
+  g.step_r = static_cast<unsigned>(fqb::kThreads % total_v);
+  g.red_lanes = 1;
+  g.part_v = static_cast<unsigned>(part_v);
+  g.group_v = total_v;
+  g.row_pitch = total_v;
+  pl->vec = 4;
+  pl->mode = 2;
+  pl->grid = static_cast<int>(parts < ctas ? parts : ctas);
+  return FQB200_OK;
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // workspace layout; returns total bytes, fills pointers when base != nullptr.  Partials: one slot per unit.
@@ -1297,6 +1626,9 @@ size_t carve(char* base, uint64_t slots, uint64_t groups, fqb::FusedArgs* A) {
     return p;
   };
   char* sync = take(sizeof(fqb::GridSync));
+  // channels-last accumulators: fixed place and size so that no other launch ever writes there (they must stay zero)
+  char* acc_u = take(2 * fqb::kMaxNhwcChannels * sizeof(unsigned));
+  char* acc_d = take(3 * fqb::kMaxNhwcChannels * sizeof(double));
   char* pmin = take(slots * sizeof(float));
   char* pmax = take(slots * sizeof(float));
   char* psum = take((slots + 2 * groups) * sizeof(double));
@@ -1327,6 +1659,11 @@ size_t carve(char* base, uint64_t slots, uint64_t groups, fqb::FusedArgs* A) {
     A->ck = f + 11 * groups;
     A->gmean_d = reinterpret_cast<double*>(gd);
     A->lp = reinterpret_cast<fqb::LeafParam*>(lp);
+    A->amin_inv = reinterpret_cast<unsigned*>(acc_u);
+    A->amax = A->amin_inv + fqb::kMaxNhwcChannels;
+    A->asum = reinterpret_cast<double*>(acc_d);
+    A->aabs = A->asum + fqb::kMaxNhwcChannels;
+    A->asq = A->aabs + fqb::kMaxNhwcChannels;
   }
   return off;
 }
@@ -1366,6 +1703,7 @@ size_t fqb200_workspace_bytes(const fqb200_desc* d) {
   int resident = 148 * fqb::kCtasPerSm;  // without a device (build container) assume a B200
   DeviceInfo* di = nullptr;
   if (get_device(&di) == FQB200_OK) resident = di->resident;
+  if (d->channels_last) return carve(nullptr, 0, static_cast<uint64_t>(d->groups), nullptr);
   Plan a, b, c;
   if (make_plan(d->outer, d->groups, d->inner, true, true, resident, &a) != FQB200_OK) return 0;
   if (make_plan(d->outer, d->groups, d->inner, true, false, resident, &b) != FQB200_OK) return 0;
@@ -1377,8 +1715,9 @@ size_t fqb200_workspace_bytes(const fqb200_desc* d) {
 }
 
 int fqb200_workspace_init(void* workspace, size_t bytes, void* stream) {
-  if (!workspace || bytes < sizeof(fqb::GridSync)) return fail(FQB200_ERR_WORKSPACE, "workspace too small%s");
-  cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(fqb::GridSync), static_cast<cudaStream_t>(stream));
+  const size_t head = carve(nullptr, 0, 0, nullptr);  // barrier words + channels-last accumulators
+  if (!workspace || bytes < head) return fail(FQB200_ERR_WORKSPACE, "workspace too small%s");
+  cudaError_t e = cudaMemsetAsync(workspace, 0, head, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
   return FQB200_OK;
 }
@@ -1491,14 +1830,23 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   if (d->bias && d->bias_period <= 0 && d->scope == FQB200_SCOPE_GROUP_MEAN)
     return fail(FQB200_ERR_UNSUPPORTED, "a per-group bias needs groups = channels (scope GROUP or TENSOR); use bias_period%s");
   const bool can_vec = aligned16(in) && (d->stats_only || aligned16(out));
-  rc = make_plan(d->outer, d->groups, d->inner, can_vec, !(d->bias_corr || d->var_corr), di->resident, &pl);
+  if (d->channels_last) {
+    if (!can_vec || d->scope != FQB200_SCOPE_GROUP || d->leaf == FQB200_LEAF_COMPILED || d->bias_corr || d->var_corr ||
+        d->bias_period > 0)
+      return fail(FQB200_ERR_UNSUPPORTED, "channels_last: per-channel torch / mid-tread leaves on aligned tensors only%s");
+    rc = make_plan_nhwc(d->outer, d->groups, d->inner, di->resident, &pl);
+  } else {
+    rc = make_plan(d->outer, d->groups, d->inner, can_vec, !(d->bias_corr || d->var_corr), di->resident, &pl);
+  }
   if (rc != FQB200_OK) return rc;
   fqb::FusedArgs A;
   memset(&A, 0, sizeof(A));
-  const size_t need = carve(nullptr, static_cast<uint64_t>(pl.geo.parts) * pl.geo.channels, pl.geo.channels, nullptr);
+  // per-unit partial slots; the channels-last kernels combine through the fixed accumulators instead
+  const uint64_t slots = (pl.mode == 2) ? 0 : static_cast<uint64_t>(pl.geo.parts) * pl.geo.channels;
+  const size_t need = carve(nullptr, slots, pl.geo.channels, nullptr);
   if (!workspace || workspace_bytes < need) return fail(FQB200_ERR_WORKSPACE, "workspace smaller than fqb200_workspace_bytes()%s");
   if (!aligned16(workspace)) return fail(FQB200_ERR_WORKSPACE, "workspace must be 16-byte aligned%s");
-  carve(static_cast<char*>(workspace), static_cast<uint64_t>(pl.geo.parts) * pl.geo.channels, pl.geo.channels, &A);
+  carve(static_cast<char*>(workspace), slots, pl.geo.channels, &A);
   A.geo = pl.geo;
   A.in = in;
   A.out = out;
@@ -1542,7 +1890,8 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   const void* kernel = A.bias_magic ? reinterpret_cast<const void*>(fqb::fq_fused_kernel<4, FQB200_LEAF_COMPILED, false, false, true>)
-                                    : fused_kernel_ptr(pl.mode, d->leaf, A.need_dev != 0, d->bias_corr || d->var_corr);
+                       : pl.mode == 2 ? nhwc_kernel_ptr(d->leaf, A.need_dev != 0)
+                                      : fused_kernel_ptr(pl.mode, d->leaf, A.need_dev != 0, d->bias_corr || d->var_corr);
   e = cudaLaunchCooperativeKernel(kernel, dim3(pl.grid),
                                   dim3(fqb::kThreads), args, dyn_smem(pl.vec), st);
   if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cooperative launch fq_fused_kernel: %s", cudaGetErrorString(e));

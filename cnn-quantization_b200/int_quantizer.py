@@ -171,10 +171,23 @@ class IntQuantizer(object):
         if (self.clipping != "no" or not self.pcq_w) and self._pc_act(tensor) and tensor.shape[1] > 1:
             return True
         minmax = self.clipping == "no" and not self.pcq_w and not self._pc_act(tensor)
-        return bool(minmax and tensor.dim() == 4 and (tensor.shape[2] * tensor.shape[3]) % 4 == 0)
+        return bool(minmax and tensor.dim() == 4 and tensor.is_contiguous() and (tensor.shape[2] * tensor.shape[3]) % 4 == 0)
+
+    @staticmethod
+    def _dense(tensor):
+        return tensor.is_contiguous() or (tensor.dim() == 4 and tensor.is_contiguous(memory_format=torch.channels_last))
 
     def _out(self, tensor):
-        return tensor if (self.inplace and tensor.is_contiguous()) else None
+        return tensor if (self.inplace and self._dense(tensor)) else None
+
+    @staticmethod
+    def _channels_last(tensor):
+        """An NCHW-shaped activation stored NHWC that the channels-last kernels take as is (else it is made
+        NCHW-contiguous first, like every other strided input)."""
+        if tensor.dim() != 4 or tensor.is_contiguous() or not tensor.is_contiguous(memory_format=torch.channels_last):
+            return False
+        c = tensor.shape[1]
+        return c % 4 == 0 and c <= 4096 and 512 % (c // 4) == 0
 
     # `-me` (SURVEY.md 8f rank 3): the apply phase histograms the integer grid into 256 counters; the Shannon entropy of
     # utils/entropy.py:6-17 (which runs torch.unique over the whole tensor) is a 256-element computation afterwards
@@ -299,12 +312,12 @@ class IntQuantizer(object):
                             leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(),
                             bit_alloc=self.bit_alloc_act, bit_alloc_prior=self._prior(),
                             bit_alloc_round=self.bit_alloc_round, bit_alloc_target=self.bit_alloc_target_act,
-                            bias=bias, out=self._out(tensor), hist=hist)
+                            bias=bias, out=self._out(tensor), hist=hist, channels_last=self._channels_last(tensor))
             self._log_entropy(hist, id, "avg.entropy.act", tensor.numel())
             return res
         return ops.fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
                          leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(), solve_f64=True,
-                         out=self._out(tensor))
+                         out=self._out(tensor), any_dense_format=True)
 
     def gemmlowpMinMaxQuantize(self, tensor, tag="", stat_id=None, weight_correction=None, bias=None):
         """Per-tensor min/max range through the compiled-leaf arithmetic, int_quantizer.py:361-379 + :605-614.
@@ -333,6 +346,7 @@ class IntQuantizer(object):
             return ops.fused(tensor, (1, rows, tensor.numel() // rows), scope=L.SCOPE_TENSOR,
                              bias_corr=weight_correction[0], var_corr=weight_correction[1], **kw)
         n = tensor.shape[0]
+        kw["any_dense_format"] = bias is None  # min / max and a scalar apply do not care about the order inside a sample
         if avg:
             return ops.fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_GROUP_MEAN, out=self._out(tensor), **kw)
         if bias is not None:
@@ -365,7 +379,8 @@ class IntQuantizer(object):
             res = ops.fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
                             num_bits=self.num_bits, positive=self._positive(), bit_alloc=self.bit_alloc_act,
                             bit_alloc_prior=self._prior(), bit_alloc_round=self.bit_alloc_round,
-                            bit_alloc_target=self.bit_alloc_target_act, bias=bias, out=self._out(tensor), hist=hist)
+                            bit_alloc_target=self.bit_alloc_target_act, bias=bias, out=self._out(tensor), hist=hist,
+                            channels_last=self._channels_last(tensor))
             self._log_entropy(hist, id, "avg.entropy.act", tensor.numel())
             return res
         if bias is not None:
@@ -427,7 +442,8 @@ class IntQuantizer(object):
 
     def mid_tread_quantize_activation_per_channel(self, tensor, id, bias=None):
         return ops.fused(tensor, self._nchw_layout(tensor), leaf=L.LEAF_MIDTREAD, positive=self._positive(),
-                         mt_target=self.bit_alloc_target_act, mt_clip=True, bias=bias, out=self._out(tensor))
+                         mt_target=self.bit_alloc_target_act, mt_clip=True, bias=bias, out=self._out(tensor),
+                         channels_last=self._channels_last(tensor))
 
     def mid_tread_quantization(self, tensor, id, target, clip=False, sym=True):
         """[R, K] view, int_quantizer.py:185-225.  Returns (quantized, None) like the reference without entropy."""

@@ -142,14 +142,22 @@ def quantize1(x, delta, offset, num_bits, bits=None, layout=None, want_grid=Fals
 def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH, num_bits=8,
           positive=False, solve_f64=False, clip_k=0.0, bit_alloc=False, bit_alloc_prior=L.PRIOR_STD,
           bit_alloc_round=True, bit_alloc_target=None, mt_target=0.0, mt_clip=False, bias_corr=False,
-          var_corr=False, stats_only=False, want_stats=False, out=None, bias=None, bias_period=0, hist=None):
+          var_corr=False, stats_only=False, want_stats=False, out=None, bias=None, bias_period=0, hist=None,
+          channels_last=False, any_dense_format=False):
     """C ABI fqb200_fused: statistics -> parameters -> quantize/dequantize in one launch.
 
     Returns ``out`` (or ``(out, stats)`` with ``want_stats``; ``stats`` alone with ``stats_only``), where
     ``stats`` is a [groups, 12] tensor with columns ``_lib.STAT_COLUMNS``."""
     _require_cuda_f32(x, "tensor")
     lib = L.load()
-    x = x.contiguous()
+    is_cl = x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+    if channels_last:
+        # layout = (N, C, H*W) of a tensor stored [N][H*W][C]
+        if not is_cl:
+            raise ValueError("channels_last=True needs a channels-last contiguous 4-D tensor")
+    elif not (any_dense_format and is_cl):
+        # any_dense_format: the layout does not care about the order inside a sample (per-tensor / per-sample min-max)
+        x = x.contiguous()
     dev = x.device
     outer, groups, inner = (int(v) for v in layout)
     if outer * groups * inner != x.numel():
@@ -163,6 +171,7 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
     d.bit_alloc_target = float(bit_alloc_target if bit_alloc_target is not None else num_bits)
     d.mt_target, d.mt_clip = float(mt_target), int(bool(mt_clip))
     d.bias_corr, d.var_corr, d.stats_only = int(bool(bias_corr)), int(bool(var_corr)), int(bool(stats_only))
+    d.channels_last = int(bool(channels_last))
     if bias is not None:
         _require_cuda_f32(bias, "bias")
         bias = bias.contiguous()

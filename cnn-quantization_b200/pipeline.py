@@ -56,10 +56,12 @@ def build_quantized_model(config, device, seed=12345, quantizer_factory=None, ch
     return model, qm
 
 
-def synthetic_batch(batch, seed, device="cpu", hw=224, pin=False):
+def synthetic_batch(batch, seed, device="cpu", hw=224, pin=False, channels_last=False):
     """ImageNet-shaped input batch + labels; N(0,1) per pixel is what a normalised image roughly looks like."""
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(batch, 3, hw, hw, generator=g)
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
     t = torch.randint(0, 1000, (batch,), generator=g)
     if pin and torch.cuda.is_available():
         x, t = x.pin_memory(), t.pin_memory()

@@ -72,6 +72,7 @@ extern "C" {
  *   per-output-channel weight [O,I,k,k]   outer=1  groups=O    inner=I*k*k
  *   per-tensor                            outer=1  groups=1    inner=numel
  *   per-sample averaged min/max           outer=1  groups=N    inner=C*H*W, scope=GROUP_MEAN
+ *   per-channel activation stored NHWC    outer=N  groups=C    inner=H*W, channels_last=1 (memory [N][H*W][C])
  */
 typedef struct fqb200_desc {
   int64_t outer, groups, inner;
@@ -105,6 +106,10 @@ typedef struct fqb200_desc {
                           of bias_period floats each and element i of the row gets bias[i / bias_period] - the
                           per-tensor and per-sample layouts of an NCHW activation (bias_period = H*W).  Needs
                           bias_period % 4 == 0 on the 128-bit path. */
+  int32_t channels_last; /* 1: the tensor is [outer][inner][groups] in memory (groups fastest), i.e. an NCHW-shaped
+                          activation stored channels-last (NHWC).  Per-channel scope with the torch / mid-tread leaves;
+                          needs groups % 4 == 0, groups/4 dividing 512, groups <= 4096.  Sums of different CTAs meet in
+                          float64 atomics: statistics are reproducible to fp32 rounding, not bit for bit. */
   unsigned long long* out_hist; /* optional device array of 256 counters: the launch ADDS the histogram of the integer
                           grid q (torch leaf: q in [0, 255]) to it - what the reference's `-me` entropy measurement
                           needs (utils/entropy.py:6-17 on output.int(), int_quantizer.py:586-587) without torch.unique. */

@@ -411,6 +411,47 @@ def test_bundled_layout_matches_scalar_path_and_oracle(fq, O, shape):
     assert frac <= max(FLIP_FRAC, 2.0 / x.size) and worst <= 1.01, (shape, frac, worst)
 
 
+@pytest.mark.parametrize("shape", [(6, 64, 14, 14), (3, 16, 7, 7), (5, 8, 3, 5), (2, 256, 6, 6), (4, 2048, 2, 2), (9, 4, 5, 5), (16, 128, 28, 28)])
+def test_channels_last_matches_nchw(fq, shape):
+    """The same activation stored NHWC goes through the channels-last kernels: same statistics, same grid."""
+    from cnn_quantization_b200 import _lib as L
+    x = cuda(regen(dict(seed=sum(shape) + 9, shape=shape, dist="laplace")))
+    xcl = x.contiguous(memory_format=torch.channels_last)
+    n, c = shape[0], shape[1]
+    lay = (n, c, shape[2] * shape[3])
+    bias = torch.randn(c, device="cuda")
+    for kw in (dict(range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True), dict(range_mode=L.RANGE_LAPLACE, num_bits=4, positive=True, bit_alloc=True),
+               dict(range_mode=L.RANGE_MINMAX, num_bits=4), dict(range_mode=L.RANGE_GAUS, num_bits=3),
+               dict(leaf=L.LEAF_MIDTREAD, mt_target=4.0, mt_clip=True)):
+        for b in (None, bias):
+            y0, s0 = fq.ops.fused(x, lay, want_stats=True, bias=b, **kw)
+            y1, s1 = fq.ops.fused(xcl, lay, want_stats=True, bias=b, channels_last=True, **kw)
+            assert y1.is_contiguous(memory_format=torch.channels_last) and y1.shape == x.shape
+            assert torch.allclose(s0[:, :7], s1[:, :7], rtol=2e-6, atol=1e-6), (shape, kw)
+            assert torch.equal(s0[:, 7], s1[:, 7])
+            step = float(s0[:, 8].max()) + 1e-9
+            frac, worst = fq_mismatch(y1.cpu().numpy(), y0.cpu().numpy(), step)
+            assert frac <= max(FLIP_FRAC, 2.0 / x.numel()) and worst <= 1.01, (shape, kw, frac, worst)
+    # through the quantizer: dispatch on the memory format, in place, entropy histogram, back-to-back launches (the
+    # per-channel atomic accumulators must be left zeroed)
+    q = fq.int_quantizer("int4", params(clipping="laplace", pcq_act=True, bit_alloc_act=True, measure_entropy=True))
+    q.pcq_w = False
+    a = q(x, "c", "activation")
+    e0 = float(q.last_entropy)
+    for _ in range(3):
+        b_ = q(xcl.clone(), "c", "activation")
+    assert b_.is_contiguous(memory_format=torch.channels_last)
+    frac, worst = fq_mismatch(b_.cpu().numpy(), a.cpu().numpy(), float(a.abs().max()))
+    assert frac <= max(FLIP_FRAC, 2.0 / x.numel())
+    assert abs(float(q.last_entropy) - e0) < 2e-3
+    q8 = fq.int_quantizer("int8", params())  # per-sample min/max: any dense format, no copy
+    q8.inplace = True
+    buf = xcl.clone()
+    r = q8(buf, "p", "activation_pooling")
+    assert r.data_ptr() == buf.data_ptr()
+    assert torch.allclose(r, fq.int_quantizer("int8", params())(x, "p", "activation_pooling"), atol=1e-6)
+
+
 def test_fused_bias_operand_and_inplace_flag(fq):
     """x + bias[c] inside the kernel == quantizing the tensor the convolution would have produced with its bias,
     bit for bit, for every per-channel path; the in-place flag returns the same values in the caller's buffer."""

@@ -133,3 +133,25 @@ def test_pipeline_extensions_do_not_change_results(config):
 
     a, b = run(True), run(False)
     assert torch.equal(a, b)
+
+
+def test_channels_last_pipeline_matches_nchw():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from cnn_quantization_b200 import ops, pipeline
+    torch.backends.cudnn.allow_tf32 = False
+    x, _ = pipeline.synthetic_batch(4, seed=5, hw=64)
+    outs = []
+    for cl in (False, True):
+        model, qm = pipeline.build_quantized_model("resnet50_w4a4", "cuda", channels_last=cl)
+        xin = x.cuda().contiguous(memory_format=torch.channels_last) if cl else x.cuda()
+        ops.profile_reset(enable=True)
+        with torch.no_grad():
+            outs.append(model(xin).float().cpu().numpy())
+        prof = ops.profile_collect()
+        ops.profile_reset(enable=False)
+        qm.detach()
+        assert prof["launches"] == 55
+    a, b = outs
+    cos = float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b)))
+    assert cos > 0.97, cos
