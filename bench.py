@@ -267,7 +267,12 @@ def run_fqb200(args):
             "check": {"loss": loss, "top1": top1, "top5": top5, "images": n_img},
         }
         if world == 1 and not args.no_secondary and args.config == "resnet50_w4a4":
-            line["config1_w8a8"] = secondary_w8a8(args, dev, peak)
+            line["config1_w8a8"] = secondary(args, dev, peak, "resnet50_w8a8", False, "B",
+                                             "BASELINE configs[1]: resnet50_w8a8 (--qtype int8), per-sample min/max + apply")
+            if not args.channels_last:
+                line["channels_last_variant"] = secondary(args, dev, peak, args.config, True, "D",
+                                                          "headline config with the model in torch.channels_last "
+                                                          "(fq_fused_nhwc_kernel, cuDNN NHWC convs); opt-in: --channels-last")
         if world == 1 and not args.no_cpu_baseline:
             ips, sec, cores = cpu_pipeline_images_per_s(args.config, args.cpu_batch, 1, 0)
             line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
@@ -277,14 +282,16 @@ def run_fqb200(args):
         dist.destroy_process_group()
 
 
-def secondary_w8a8(args, dev, peak):
-    """BASELINE configs[1] (ResNet-50 W8A8 per tensor, --qtype int8, batch 512): 3 timed steps, inputs resident.
-    All 55 activation tensors take mode B (per-sample min/max statistics + apply, 12 B/element)."""
+def secondary(args, dev, peak, config, channels_last, mode, note):
+    """A short (3 timed steps, inputs resident) run of another configuration next to the headline one; reports the
+    pipeline rate and the roofline of the dominant kernel mode (D: 16 B/element, B: 12 B/element)."""
     import torch
     from cnn_quantization_b200 import ops, pipeline
-    model, qm = pipeline.build_quantized_model("resnet50_w8a8", dev)
-    x, t = pipeline.synthetic_batch(args.batch, seed=7)
+    model, qm = pipeline.build_quantized_model(config, dev, channels_last=channels_last)
+    x, t = pipeline.synthetic_batch(args.batch, seed=7, channels_last=channels_last)
     x, t = x.to(dev), t.to(dev)
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
     with torch.no_grad():
         for _ in range(3):
             pipeline.accuracy_counts(model(x), t)
@@ -299,12 +306,15 @@ def secondary_w8a8(args, dev, peak):
     prof = ops.profile_collect()
     ops.profile_reset(enable=False)
     qm.detach()
+    del model, qm, x
+    torch.cuda.empty_cache()
     ms = e0.elapsed_time(e1) / 3
-    b = prof["modes"].get("B", {"bytes": 0, "ms": 0.0, "launches": 0})
+    b = prof["modes"].get(mode, {"bytes": 0, "ms": 0.0, "launches": 0})
     gbs = (b["bytes"] / 1e9) / (b["ms"] / 1e3) if b["ms"] else None
-    return {"workload": "BASELINE configs[1]: resnet50_w8a8 (--qtype int8), batch %d" % args.batch, "value": args.batch / (ms / 1e3),
-            "unit": UNIT, "ms_per_step": ms, "steps": 3,
-            "roofline": {"kernel": "fq_fused_kernel mode B (min/max statistics + apply)", "algorithmic_bytes_per_elem": 12,
+    quant_ms = sum(m["ms"] for m in prof["modes"].values()) / 3
+    return {"workload": "%s, batch %d" % (note, args.batch), "value": args.batch / (ms / 1e3),
+            "unit": UNIT, "ms_per_step": ms, "steps": 3, "quant_ms_per_step": quant_ms,
+            "roofline": {"kernel": "fused kernel mode %s" % mode, "algorithmic_bytes_per_elem": {"D": 16, "B": 12}[mode],
                          "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak if gbs else None,
                          "launches": b["launches"]}}
 

@@ -428,6 +428,30 @@ __device__ __forceinline__ void stream_units(const Geometry& geo, const float* b
       acc.begin(cu);
       continue;
     }
+    // ---- steady state: for the next n ring steps every lane of this warp both consumes and issues a real vector
+    // and no slot is a bubble, so none of the bookkeeping below is needed (the loop is issue-bound: DESIGN.md).
+    // All the quantities involved are warp-uniform except `mine`, hence the warp-wide minimum.
+    if (bubbles == 0u && !iexhausted) {
+      const unsigned nc = cu.mine > cdone ? cu.mine - cdone : 0u;
+      const unsigned ni = iu.mine > idone ? iu.mine - idone : 0u;
+      const unsigned n = __reduce_min_sync(0xffffffffu, min(nc, ni));
+      if (n >= 2u) {
+        for (unsigned k = 0; k < n; ++k) {
+          cp_async_wait<D - 1>();
+          V x;
+          lds_vec(ring + head * kSlot, x);
+          cp_async_vec(ring + head * kSlot, src + ic.off);
+          cp_async_commit();
+          cursor_step<REV>(geo, ic);
+          head = (head + 1u) & (D - 1u);
+          acc.consume(x, cc.off, cc.j);
+          cursor_step<REV>(geo, cc);
+        }
+        cdone += n;
+        idone += n;
+        continue;
+      }
+    }
     cp_async_wait<D - 1>();  // the oldest group (slot `head`) has landed
     const bool bubble = (bubbles >> head) & 1u;
     const bool active = !bubble && cdone < cu.mine;

@@ -1054,10 +1054,15 @@ struct NhwcStage {
 };
 static_assert(sizeof(NhwcStage) <= static_cast<size_t>(ring_bytes<4>()), "combine staging must fit in the ring memory");
 
+// Column (group of 4 channels) a thread works on.  A unit starts at a multiple of kThreads vectors and cv divides
+// kThreads, so a forward walk puts thread t on column t % cv; a backward (REV) walk starts from the unit's last vector
+// (whose column is cv - 1) and mirrors the assignment.
+__device__ __forceinline__ unsigned nhwc_column(unsigned t, unsigned cv, bool rev) { return rev ? cv - 1u - t % cv : t % cv; }
+
 // Reduce, for every channel of this CTA's columns, the values of the threads sharing the column; `emit(channel, f0, f1,
 // d0, d1)` is called once per channel by one thread.  cv = C / 4 columns, kThreads / cv threads per column.
 template <typename Emit>
-__device__ __forceinline__ void nhwc_combine(unsigned cv, const float (&f0)[4], const float (&f1)[4], const double (&d0)[4],
+__device__ __forceinline__ void nhwc_combine(unsigned cv, bool rev, const float (&f0)[4], const float (&f1)[4], const double (&d0)[4],
                                              const double (&d1)[4], Emit&& emit) {
   extern __shared__ __align__(16) unsigned char fq_ring[];
   NhwcStage& st = *reinterpret_cast<NhwcStage*>(fq_ring);
@@ -1074,7 +1079,7 @@ __device__ __forceinline__ void nhwc_combine(unsigned cv, const float (&f0)[4], 
     const unsigned col = i % cv, k = i / cv;
     float a = INFINITY, b = -INFINITY;
     double c = 0.0, d = 0.0;
-    for (unsigned t = col; t < kThreads; t += cv) {
+    for (unsigned t = nhwc_column(col, cv, rev); t < kThreads; t += cv) {
       a = fminf(a, st.f0[k][t]);
       b = fmaxf(b, st.f1[k][t]);
       c += st.d0[k][t];
@@ -1094,8 +1099,8 @@ struct AccStats1N {
   float mn[4], mx[4], bias[4], fs[4];
   double s[4];
   unsigned cnt;
-  __device__ __forceinline__ void init(unsigned cv) {
-    const unsigned c0 = 4u * (threadIdx.x % cv);
+  __device__ __forceinline__ void init(unsigned cv, bool rev) {
+    const unsigned c0 = 4u * nhwc_column(threadIdx.x, cv, rev);
     cnt = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -1133,8 +1138,8 @@ struct AccStats2N {
   float mu[4], bias[4], fa[4], fq[4];
   double sa[4], sq[4];
   unsigned cnt;
-  __device__ __forceinline__ void init(unsigned cv) {
-    const unsigned c0 = 4u * (threadIdx.x % cv);
+  __device__ __forceinline__ void init(unsigned cv, bool rev) {
+    const unsigned c0 = 4u * nhwc_column(threadIdx.x, cv, rev);
     cnt = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -1177,8 +1182,8 @@ struct AccApplyN {
   LeafParam q[4];
   float r[4], bias[4];
   bool fast;
-  __device__ __forceinline__ void init(unsigned cv) {
-    const unsigned c0 = 4u * (threadIdx.x % cv);
+  __device__ __forceinline__ void init(unsigned cv, bool rev) {
+    const unsigned c0 = 4u * nhwc_column(threadIdx.x, cv, rev);
     fast = true;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -1193,18 +1198,20 @@ struct AccApplyN {
   template <bool FAST>
   __device__ __forceinline__ void one(const float4& v, unsigned off) {
     const float x[4] = {v.x, v.y, v.z, v.w};
-    float y[4];
+    float y[4], gq[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       Divisor dv;
       dv.s = q[k].a;
       dv.r = r[k];
       dv.fast = FAST;
-      float gq;
-      y[k] = leaf_apply<LEAF, FAST>(__fadd_rn(x[k], bias[k]), q[k], dv, 0.f, gq);
-      if (LEAF == FQB200_LEAF_TORCH && A.hist) hist_add(sm, gq);
+      y[k] = leaf_apply<LEAF, FAST>(__fadd_rn(x[k], bias[k]), q[k], dv, 0.f, gq[k]);
     }
     st_tensor(reinterpret_cast<float4*>(A.out) + off, make_float4(y[0], y[1], y[2], y[3]));
+    if (LEAF == FQB200_LEAF_TORCH && A.hist) {  // one uniform branch per vector, after the store
+#pragma unroll
+      for (int k = 0; k < 4; ++k) hist_add(sm, gq[k]);
+    }
   }
   __device__ __forceinline__ void consume(const float4& v, unsigned off, unsigned) {
     if (fast)
@@ -1226,19 +1233,23 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_nhwc_kernel(con
   const double n = A.n_per_group;
 
   // ---- S1
+  if (blockIdx.x == 0) stamp(A, 0);
   {
     AccStats1N acc{A};
-    acc.init(cv);
+    acc.init(cv, false);
     stream_units<4, false>(geo, A.in, &A.sync->unit_counter[0], ssm, acc);
     acc.flush();
+    if (blockIdx.x == 0) stamp(A, 13);
     const double zero[4] = {0.0, 0.0, 0.0, 0.0};
-    nhwc_combine(cv, acc.mn, acc.mx, acc.s, zero, [&](unsigned c, float mn, float mx, double s, double) {
+    nhwc_combine(cv, false, acc.mn, acc.mx, acc.s, zero, [&](unsigned c, float mn, float mx, double s, double) {
       atomicMax(A.amin_inv + c, ~enc_ordered(mn));
       atomicMax(A.amax + c, enc_ordered(mx));
       atomicAdd(A.asum + c, s);
     });
   }
+  if (blockIdx.x == 0) stamp(A, 1);
   if (grid_arrive(A.sync, epoch, &lsm.flag)) {
+    stamp(A, 2);
     for (unsigned c = threadIdx.x; c < C; c += kThreads) {
       A.gmin[c] = dec_ordered(~ld_ws(A.amin_inv + c));
       A.gmax[c] = dec_ordered(ld_ws(A.amax + c));
@@ -1251,23 +1262,28 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_nhwc_kernel(con
     }
     __syncthreads();
     if (!DEV) solve_params(A, lsm);
+    stamp(A, 3);
     grid_release(A.sync, epoch);
   }
+  if (blockIdx.x == 0) stamp(A, 4);
 
   // ---- S2
   if constexpr (DEV) {
     {
       AccStats2N acc{A};
-      acc.init(cv);
-      stream_units<4, false>(geo, A.in, &A.sync->unit_counter[1], ssm, acc);
+      acc.init(cv, true);  // phases alternate direction: the tail of the previous pass is still in L2
+      stream_units<4, true>(geo, A.in, &A.sync->unit_counter[1], ssm, acc);
       acc.flush();
+      if (blockIdx.x == 0) stamp(A, 14);
       const float fz[4] = {0.f, 0.f, 0.f, 0.f};
-      nhwc_combine(cv, fz, fz, acc.sa, acc.sq, [&](unsigned c, float, float, double sa, double sq) {
+      nhwc_combine(cv, true, fz, fz, acc.sa, acc.sq, [&](unsigned c, float, float, double sa, double sq) {
         atomicAdd(A.aabs + c, sa);
         atomicAdd(A.asq + c, sq);
       });
     }
+    if (blockIdx.x == 0) stamp(A, 5);
     if (grid_arrive(A.sync, epoch, &lsm.flag)) {
+      stamp(A, 6);
       for (unsigned c = threadIdx.x; c < C; c += kThreads) {
         A.gb[c] = static_cast<float>(ld_ws(A.aabs + c) / n);
         const double dm = A.gmean_d[c] - static_cast<double>(A.gmean[c]);
@@ -1279,17 +1295,20 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_nhwc_kernel(con
       }
       __syncthreads();
       solve_params(A, lsm);
+      stamp(A, 7);
       grid_release(A.sync, epoch);
     }
+    if (blockIdx.x == 0) stamp(A, 8);
   }
 
   // ---- A
   if (!A.stats_only) {
     if (LEAF == FQB200_LEAF_TORCH && A.hist) hist_clear(psm);
     AccApplyN<LEAF> acc{A, psm};
-    acc.init(cv);
-    stream_units<4, false>(geo, A.in, &A.sync->unit_counter[2], ssm, acc);
+    acc.init(cv, !DEV);
+    stream_units<4, !DEV>(geo, A.in, &A.sync->unit_counter[2], ssm, acc);
     if (LEAF == FQB200_LEAF_TORCH && A.hist) hist_flush(psm, A.hist);
+    if (blockIdx.x == 0) stamp(A, 9);
   }
   grid_exit(A.sync);
 }
