@@ -33,12 +33,16 @@ def parse():
     ap.add_argument("--impl", default="fqb200", choices=["fqb200", "reference"])
     ap.add_argument("--config", default="resnet50_w4a4")
     ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
-    ap.add_argument("--cpu-batch", type=int, default=2, help="images per step of the CPU reference arm / cpu_baseline")
-    ap.add_argument("--channels-last", action="store_true",
-                    help="run the model and the fused kernels on NHWC tensors (no cuDNN layout conversions)")
+    ap.add_argument("--cpu-batch", type=int, default=32, help="images per step of the CPU reference arm / cpu_baseline")
+    ap.add_argument("--nchw", action="store_true",
+                    help="keep the model's tensors in contiguous NCHW memory (fq_fused_kernel) instead of the default "
+                         "torch.channels_last memory format (fq_fused_nhwc_kernel, no cuDNN layout conversions)")
+    ap.add_argument("--channels-last", action="store_true", help="accepted for compatibility: this is the default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short BASELINE configs[1] (W8A8) run")
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.channels_last = not args.nchw
+    return args
 
 
 def peaks():
@@ -107,7 +111,8 @@ def cpu_pipeline_images_per_s(config, batch, steps, warmup):
     import torch
     from cnn_quantization_b200 import pipeline
     from oracle import fq_oracle
-    cores = os.cpu_count() or 1
+    from oracle.host import host_threads
+    cores = host_threads()
     torch.set_num_threads(cores)
     model, qm = pipeline.build_quantized_model(config, "cpu", quantizer_factory=fq_oracle.oracle_int_quantizer)
     x, t = pipeline.synthetic_batch(batch, seed=1)
@@ -126,8 +131,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 2))
-    warm = 1 if args.warmup > 0 else 0
+    steps = max(1, min(args.steps, 10))  # ~3 s per 32-image step on 16 host threads
+    warm = max(0, min(args.warmup, 2))
     ips, sec, cores = cpu_pipeline_images_per_s(args.config, args.cpu_batch, steps, warm)
     sample = "%d steps of %d images (of the %d-image batch) through the oracle port of int_quantizer.py, %d host threads" % (
         steps, args.cpu_batch, args.batch, cores)
@@ -248,11 +253,14 @@ def run_fqb200(args):
                                    "3x224x224, random-init torchvision weights" % (args.config, args.batch),
                        "parallelism": "dp%d (batch sharded per rank, one all-reduce of 4 metrics)" % world,
                        "l2": "inputs larger than L2 (308 MB input, every hooked tensor 51 MB - 1.6 GB)",
+                       "memory_format": "torch.channels_last (same logical NCHW tensors and results; --nchw selects contiguous NCHW)"
+                                        if args.channels_last else "contiguous NCHW",
                        "conv": "cuDNN fp32 %s via torch (third party in the reference too)" % ("NHWC" if args.channels_last else "NCHW")},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": x_host.numel() * 4 + t_host.numel() * 8, "d2h_bytes_per_step": 16},
             "gpu_launches": prof["launches"],
-            "roofline": {"bound": "hbm", "kernel": "fq_fused_kernel<4> mode D (stats, deviations, apply)",
+            "roofline": {"bound": "hbm", "kernel": "%s mode D (stats, deviations, apply)" % (
+                             "fq_fused_nhwc_kernel" if args.channels_last else "fq_fused_kernel<4>"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "peak_source": peak_src, "traffic": None, "launches": dom["launches"],
                          "algorithmic_bytes_per_elem": 16, "avg_launch_ms": dom["ms"] / max(dom["launches"], 1)},
@@ -269,14 +277,17 @@ def run_fqb200(args):
         if world == 1 and not args.no_secondary and args.config == "resnet50_w4a4":
             line["config1_w8a8"] = secondary(args, dev, peak, "resnet50_w8a8", False, "B",
                                              "BASELINE configs[1]: resnet50_w8a8 (--qtype int8), per-sample min/max + apply")
-            if not args.channels_last:
-                line["channels_last_variant"] = secondary(args, dev, peak, args.config, True, "D",
-                                                          "headline config with the model in torch.channels_last "
-                                                          "(fq_fused_nhwc_kernel, cuDNN NHWC convs); opt-in: --channels-last")
+            other = not args.channels_last
+            line["channels_last_variant" if other else "nchw_variant"] = secondary(
+                args, dev, peak, args.config, other, "D",
+                "headline config with the model's tensors in %s" % (
+                    "torch.channels_last memory (fq_fused_nhwc_kernel, cuDNN NHWC convs)" if other else
+                    "contiguous NCHW memory (fq_fused_kernel, cuDNN converts layouts internally); select with --nchw"))
         if world == 1 and not args.no_cpu_baseline:
-            ips, sec, cores = cpu_pipeline_images_per_s(args.config, args.cpu_batch, 1, 0)
+            ips, sec, cores = cpu_pipeline_images_per_s(args.config, args.cpu_batch, 3, 1)
             line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "1 step of %d images through the oracle port of int_quantizer.py + torch CPU convs" % args.cpu_batch}
+                                    "sample": "3 steps (after 1 warm-up) of %d images through the oracle port of int_quantizer.py "
+                                              "+ torch CPU convs, %d host threads (cgroup quota)" % (args.cpu_batch, cores)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -146,12 +146,32 @@ __device__ __forceinline__ void reduce_partials3(const Geometry& geo, const T0* 
 __device__ __noinline__ void solve_bit_alloc(const FusedArgs& A, LeaderSmem& sm) {
   const unsigned G = A.geo.channels;
   const float* prior = (A.prior == FQB200_PRIOR_STD) ? A.gstd : A.gb;
-  // p = alpha^(2/3)  (torch.pow with a python-float exponent -> fp32 powf)
+  // p = alpha^(2/3)  (torch.pow with a python-float exponent -> fp32 powf).  Up to kRegGroups groups per thread stay
+  // in registers across the iterations (G <= 2048: every CNN layer); larger G falls back to the workspace arrays.
+  constexpr unsigned kRegGroups = 4;
+  const bool in_regs = G <= kRegGroups * kThreads;
+  float pr[kRegGroups], bt[kRegGroups];
   double local = 0.0;
-  for (unsigned g = threadIdx.x; g < G; g += kThreads) {
-    float p = powf(prior[g], 0.6666666666666666f);
-    A.gprior[g] = p;
-    local += static_cast<double>(p);
+#pragma unroll
+  for (unsigned k = 0; k < kRegGroups; ++k) {
+    pr[k] = 0.f;
+    bt[k] = 0.f;
+  }
+  if (in_regs) {
+#pragma unroll
+    for (unsigned k = 0; k < kRegGroups; ++k) {
+      const unsigned g = threadIdx.x + k * kThreads;
+      if (g < G) {
+        pr[k] = powf(prior[g], 0.6666666666666666f);
+        local += static_cast<double>(pr[k]);
+      }
+    }
+  } else {
+    for (unsigned g = threadIdx.x; g < G; g += kThreads) {
+      float p = powf(prior[g], 0.6666666666666666f);
+      A.gprior[g] = p;
+      local += static_cast<double>(p);
+    }
   }
   const float psum = static_cast<float>(block_reduce(local, OpAdd(), sm.d));
   const float goal = A.ba_target;
@@ -160,17 +180,31 @@ __device__ __noinline__ void solve_bit_alloc(const FusedArgs& A, LeaderSmem& sm)
   const float inv_g = 1.0f / static_cast<float>(G);  // torch's CUDA mean multiplies by fl(1/N)
   int it = 0;
   __shared__ int warp_bits[2][kWarps];
+  auto bits_of = [&](float p, float budget) {
+    const float bins = __fdiv_rn(__fmul_rn(budget, p), psum);
+    const float lg = log2f(bins);
+    float bits = A.ba_round ? rintf(lg) : ceilf(lg);
+    if (!(bits >= 0.f)) bits = 0.f;
+    if (bits > 8.f) bits = 8.f;
+    return bits;
+  };
   while (fabsf(2.0f * half_gap) > 0.01f && it < 10) {
     const float budget = static_cast<float>(static_cast<double>(G) * exp2(m));
     int sum_bits = 0;
-    for (unsigned g = threadIdx.x; g < G; g += kThreads) {
-      const float bins = __fdiv_rn(__fmul_rn(budget, A.gprior[g]), psum);
-      const float lg = log2f(bins);
-      float bits = A.ba_round ? rintf(lg) : ceilf(lg);
-      if (!(bits >= 0.f)) bits = 0.f;
-      if (bits > 8.f) bits = 8.f;
-      A.gbits[g] = bits;
-      sum_bits += static_cast<int>(bits);
+    if (in_regs) {
+#pragma unroll
+      for (unsigned k = 0; k < kRegGroups; ++k) {
+        if (threadIdx.x + k * kThreads < G) {
+          bt[k] = bits_of(pr[k], budget);
+          sum_bits += static_cast<int>(bt[k]);
+        }
+      }
+    } else {
+      for (unsigned g = threadIdx.x; g < G; g += kThreads) {
+        const float bits = bits_of(A.gprior[g], budget);
+        A.gbits[g] = bits;
+        sum_bits += static_cast<int>(bits);
+      }
     }
     // exact integer sum: one REDUX per warp, one barrier per iteration (buffers alternate)
     sum_bits = __reduce_add_sync(0xffffffffu, sum_bits);
@@ -183,6 +217,13 @@ __device__ __noinline__ void solve_bit_alloc(const FusedArgs& A, LeaderSmem& sm)
     const float mean = __fmul_rn(static_cast<float>(total), inv_g);
     half_gap = __fmul_rn(__fsub_rn(goal, mean), 0.5f);
     m += static_cast<double>(half_gap);
+  }
+  if (in_regs) {
+#pragma unroll
+    for (unsigned k = 0; k < kRegGroups; ++k) {
+      const unsigned g = threadIdx.x + k * kThreads;
+      if (g < G) A.gbits[g] = bt[k];
+    }
   }
   __syncthreads();
 }

@@ -14,6 +14,13 @@ for p in (ROOT, GOLD):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)")
+    # the CPU checkers (torch ops, the OpenMP C leaf) must not start more threads than the container's CPU quota:
+    # 128 threads under a 16-CPU quota spend their time throttled at barriers
+    from oracle.host import host_threads
+    n = host_threads()
+    os.environ.setdefault("OMP_NUM_THREADS", str(n))
+    import torch
+    torch.set_num_threads(n)
 
 
 @pytest.fixture(scope="session")
