@@ -25,6 +25,13 @@ METRIC = "resnet50_w4a4_images_per_s"
 UNIT = "images/s"
 
 
+# DRAM traffic of the dominant kernel, from profiles/ (bench.py cannot run under ncu itself): ncu dram__bytes_read.sum +
+# dram__bytes_write.sum averaged over the 53 mode-D launches of one step of the named workload.
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {
+    ("resnet50_w4a4", 512, True): (1527.45e6, "profiles/r01e_dram_bytes_fused_launches_step1.csv"),
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -243,6 +250,7 @@ def run_fqb200(args):
         # dominant kernel: fq_fused_kernel in mode D (3 reads + 1 write = 16 B/element), per-launch CUDA events
         dom = prof["modes"].get("D", {"launches": 0, "elems": 0, "ms": 0.0, "bytes": 0})
         achieved = (dom["bytes"] / 1e9) / (dom["ms"] / 1e3) if dom["ms"] > 0 else 0.0
+        traffic, traffic_src = NCU_TRAFFIC_BYTES_PER_LAUNCH.get((args.config, args.batch, args.channels_last), (None, None))
         quant_ms = sum(m["ms"] for m in prof["modes"].values())
         quant_elems = sum(m["elems"] for m in prof["modes"].values())
         line = {
@@ -262,7 +270,9 @@ def run_fqb200(args):
             "roofline": {"bound": "hbm", "kernel": "%s mode D (stats, deviations, apply)" % (
                              "fq_fused_nhwc_kernel" if args.channels_last else "fq_fused_kernel<4>"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "peak_source": peak_src, "traffic": None, "launches": dom["launches"],
+                         "peak_source": peak_src, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, DRAM read + write)",
+                         "traffic_source": traffic_src, "launches": dom["launches"],
+                         "algorithmic_bytes_per_launch": dom["bytes"] / max(dom["launches"], 1),
                          "algorithmic_bytes_per_elem": 16, "avg_launch_ms": dom["ms"] / max(dom["launches"], 1)},
             "quant": {"gelem_per_s": quant_elems / (quant_ms / 1e3) / 1e9 if quant_ms else None,
                       "ms_per_step": quant_ms / args.steps, "share_of_step": quant_ms / ms,
