@@ -17,8 +17,10 @@ STATS_STRIDE = 12
 STAT_COLUMNS = ("min", "max", "mean", "b", "std", "delta", "offset", "bits", "scale", "zero_point", "qmax", "flags")
 
 # every symbol include/fqb200.h declares (tests check the export table against this)
-SYMBOLS = ("fqb200_abi_version", "fqb200_last_error", "fqb200_resident_ctas", "fqb200_workspace_bytes",
-           "fqb200_workspace_init", "fqb200_float2gemmlowp", "fqb200_quantize1", "fqb200_fused")
+SYMBOLS = ("fqb200_abi_version", "fqb200_last_error", "fqb200_resident_ctas", "fqb200_plan_info",
+           "fqb200_selftest_division", "fqb200_workspace_bytes", "fqb200_workspace_init", "fqb200_float2gemmlowp",
+           "fqb200_quantize1", "fqb200_fused")
+ABI_VERSION = 2
 
 
 class Desc(ctypes.Structure):
@@ -37,6 +39,7 @@ class Desc(ctypes.Structure):
         ("bias_period", ctypes.c_int64),
         ("channels_last", ctypes.c_int32),
         ("out_hist", ctypes.c_void_p),
+        ("debug_stamps", ctypes.c_void_p),
     ]
 
 
@@ -70,12 +73,14 @@ def load():
     lib.fqb200_float2gemmlowp.restype = i32
     lib.fqb200_float2gemmlowp.argtypes = [vp, vp, i64, f32, f32, i32, i32, i32, vp, vp]
     lib.fqb200_quantize1.restype = i32
-    lib.fqb200_quantize1.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, i32, i32, vp, vp]
+    lib.fqb200_quantize1.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, i32, i32, vp, i32, vp]
     lib.fqb200_fused.restype = i32
     lib.fqb200_fused.argtypes = [ctypes.POINTER(Desc), vp, vp, vp, ctypes.c_size_t, vp]
-    lib.fqb200_test_division.restype = i32
-    lib.fqb200_test_division.argtypes = [vp, vp, vp, vp, i64, vp]
-    if lib.fqb200_abi_version() != 1:
+    lib.fqb200_selftest_division.restype = i32
+    lib.fqb200_selftest_division.argtypes = [vp, vp, vp, vp, i64, vp]
+    lib.fqb200_plan_info.restype = i32
+    lib.fqb200_plan_info.argtypes = [ctypes.POINTER(Desc), ctypes.POINTER(ctypes.c_int64)]
+    if lib.fqb200_abi_version() != ABI_VERSION:
         raise FqError("libfqb200.so ABI version mismatch")
     _lib = lib
     return lib

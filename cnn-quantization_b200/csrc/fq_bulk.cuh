@@ -1,0 +1,214 @@
+// fqb200 bulk-copy streaming engine (sm_100a): flat tensors through a ring of shared-memory stages filled by the TMA unit.
+//
+// Why (round-2 measurements, profiles/README.md): the per-thread cp.async ring of fq_device.cuh spends ~68 thread
+// instructions per 128-bit vector per phase, most of them cursor / ring bookkeeping, and the phases of L2-resident
+// tensors were issue-bound (5 TB/s from L2).  Here ONE elected thread of a dedicated producer warp issues
+// `cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes` (1-D TMA, SASS UBLKCP) for a whole 16 KB stage;
+// the 512 consumer threads wait on the stage's `full` mbarrier, read their vectors with LDS.128 and hand the stage back
+// through its `empty` mbarrier (one arrival per consumer warp).  No per-vector address arithmetic, no cp.async groups.
+//
+// The producer never waits at the grid barriers between the phases of a fused launch: while the consumers combine their
+// statistics and wait for the other CTAs, the ring is already being filled with the first stages of the next phase.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fq_device.cuh"
+
+namespace fqb {
+
+constexpr int kConsumers = kThreads;             // 512 consumer threads (16 warps)
+constexpr int kBulkThreads = kConsumers + 32;    // + one producer warp
+constexpr int kConsumerWarps = kConsumers / 32;
+#ifndef FQB_STAGE_VEC
+#define FQB_STAGE_VEC 2
+#endif
+#ifndef FQB_STAGES
+#define FQB_STAGES 5
+#endif
+constexpr int kStageVec = FQB_STAGE_VEC;         // vectors per consumer thread per stage
+constexpr int kStages = FQB_STAGES;              // ring depth
+constexpr unsigned kStageBytes = kStageVec * kConsumers * 16u;
+
+// consumer-only CTA barrier (the producer warp never joins): named barrier 1 over the 512 consumer threads.  The
+// 512-thread kernels of fq_device.cuh can use it as well (there it is equivalent to __syncthreads()).
+__device__ __forceinline__ void consumer_sync() { cta_sync(); }
+
+// ---- mbarrier / bulk-copy primitives --------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar`.  bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_load(unsigned dst_smem, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// ---- geometry of a flat stream ---------------------------------------------------------------------------------------
+// The tensor is ONE contiguous run of total_v vectors (channels-last activations; per-tensor views).  A stage is
+// stage_v = kStageVec * stride consecutive vectors; consumer thread t reads vectors t, t + stride, ... of the stage
+// (threads >= stride idle: stride is the largest multiple of the channel period cv = C/4 below 512, so that a thread
+// always sees the same four channels).  A UNIT is unit_stages consecutive stages and is what CTAs pull dynamically.
+struct FlatGeo {
+  unsigned total_v;      // vectors in the tensor (< 2^32)
+  unsigned stride;       // consumer threads that take part (<= 512), multiple of cv
+  unsigned stage_v;      // kStageVec * stride
+  unsigned n_stages;     // ceil(total_v / stage_v)
+  unsigned unit_stages;  // stages per unit
+  unsigned units;        // ceil(n_stages / unit_stages)
+  unsigned channels;     // C (0 for per-tensor streams)
+  unsigned cv;           // C / 4 (1 for per-tensor streams)
+};
+
+struct StageMeta {
+  unsigned start;  // first vector of the stage
+  unsigned count;  // valid vectors; 0 = end of phase
+};
+
+struct BulkRing {
+  alignas(8) unsigned long long full[kStages];
+  alignas(8) unsigned long long empty[kStages];
+  StageMeta meta[kStages];
+};
+
+// position in the ring sequence: both sides count every stage AND every end-of-phase marker
+struct RingPos {
+  unsigned slot, parity;
+  __device__ __forceinline__ void init() {
+    slot = 0;
+    parity = 0;
+  }
+  __device__ __forceinline__ void next() {
+    if (++slot == static_cast<unsigned>(kStages)) {
+      slot = 0;
+      parity ^= 1u;
+    }
+  }
+};
+
+__device__ __forceinline__ void ring_init(BulkRing& r) {
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&r.full[s]), 1u);                 // the producer's arrive(.expect_tx)
+      mbar_init(smem_u32(&r.empty[s]), kConsumerWarps);    // one arrival per consumer warp
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();  // all 544 threads, once
+}
+
+// ---- producer side (one thread) ----------------------------------------------------------------------------------------
+// Ticket k of this CTA: static for the first `nstatic` (id = first + k * step; no atomic in front of the first loads),
+// then from the phase's atomic counter (offset by `dyn_base`, the number of statically dealt units).  REV walks the
+// units and the stages inside a unit backwards so that a phase starts on what the previous one touched last.
+struct TicketPlan {
+  unsigned nstatic;    // static tickets of this CTA (0..2)
+  unsigned first, step;
+  unsigned dyn_base;   // units dealt statically over the whole grid
+};
+
+template <bool REV>
+__device__ __forceinline__ void produce_phase(const FlatGeo& g, const float4* src, unsigned* counter, const TicketPlan tp,
+                                              BulkRing& r, unsigned char* stage_base, RingPos& pos) {
+  const unsigned total = g.units;
+  unsigned k = 0;
+  auto fetch = [&]() -> unsigned {
+    unsigned long long t;
+    if (k < tp.nstatic)
+      t = tp.first + static_cast<unsigned long long>(k) * tp.step;
+    else
+      t = static_cast<unsigned long long>(tp.dyn_base) + atomicAdd(counter, 1u);
+    ++k;
+    return t < total ? static_cast<unsigned>(t) : 0xffffffffu;
+  };
+  unsigned cur = fetch();
+  while (cur != 0xffffffffu) {
+    const unsigned nxt = fetch();  // the reply is only needed after this unit's stages have been issued
+    const unsigned u = REV ? total - 1u - cur : cur;
+    const unsigned g0 = u * g.unit_stages;
+    const unsigned g1 = min(g0 + g.unit_stages, g.n_stages);
+    for (unsigned i = g0; i < g1; ++i) {
+      const unsigned st = REV ? g1 - 1u - (i - g0) : i;
+      const unsigned start = st * g.stage_v;
+      const unsigned count = min(g.stage_v, g.total_v - start);
+      mbar_wait(smem_u32(&r.empty[pos.slot]), pos.parity ^ 1u);
+      r.meta[pos.slot].start = start;
+      r.meta[pos.slot].count = count;
+      const unsigned bar = smem_u32(&r.full[pos.slot]);
+      mbar_arrive_expect_tx(bar, count * 16u);
+      bulk_load(smem_u32(stage_base + pos.slot * kStageBytes), src + start, count * 16u, bar);
+      pos.next();
+    }
+    cur = nxt;
+  }
+  // end-of-phase marker
+  mbar_wait(smem_u32(&r.empty[pos.slot]), pos.parity ^ 1u);
+  r.meta[pos.slot].start = 0u;
+  r.meta[pos.slot].count = 0u;
+  mbar_arrive(smem_u32(&r.full[pos.slot]));
+  pos.next();
+}
+
+// ---- consumer side (512 threads) -----------------------------------------------------------------------------------------
+// acc.consume(x, v) for every vector this thread owns (v = its index from the tensor base), until the end marker.
+template <typename Acc>
+__device__ __forceinline__ void consume_phase(const FlatGeo& g, BulkRing& r, const unsigned char* stage_base, RingPos& pos,
+                                              Acc& acc) {
+  const unsigned t = threadIdx.x;
+  const bool lane0 = (t & 31u) == 0u;
+  const unsigned my = smem_u32(stage_base) + t * 16u;
+  const unsigned step = g.stride * 16u;
+  for (;;) {
+    mbar_wait(smem_u32(&r.full[pos.slot]), pos.parity);
+    const StageMeta m = r.meta[pos.slot];
+    const unsigned addr = my + pos.slot * kStageBytes;
+    if (m.count == g.stage_v) {  // whole stage (CTA-uniform): no guards
+      if (t < g.stride) {
+        float4 x[kStageVec];
+#pragma unroll
+        for (int i = 0; i < kStageVec; ++i) lds_vec(addr + i * step, x[i]);
+#pragma unroll
+        for (int i = 0; i < kStageVec; ++i) acc.consume(x[i], m.start + t + i * g.stride);
+      }
+    } else if (m.count != 0u) {
+#pragma unroll
+      for (int i = 0; i < kStageVec; ++i) {
+        const unsigned idx = t + i * g.stride;
+        if (t < g.stride && idx < m.count) {
+          float4 x;
+          lds_vec(addr + i * step, x);
+          acc.consume(x, m.start + idx);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane0) mbar_arrive(smem_u32(&r.empty[pos.slot]));
+    pos.next();
+    if (m.count == 0u) break;
+  }
+}
+
+}  // namespace fqb

@@ -1,0 +1,613 @@
+// Channels-last (NHWC) activations: ONE cooperative launch per hooked tensor on the bulk-copy engine of fq_bulk.cuh.
+// Included by fqb200.cu after FusedArgs / the solve_* helpers / leaf_apply (namespace fqb).
+//
+// [N][H*W][C] in memory, the channel is the fastest dimension: the tensor is one flat stream of N*H*W*C/4 vectors and,
+// because the consumer stride is a multiple of C/4, thread t always holds the same four channels (4 * (t mod C/4)).
+// Per-channel accumulators and leaf parameters therefore live in registers for a whole phase.
+//
+//   S1   read x         per channel min, max, S = sum (x - k), Q = sum (x - k)^2 with the common shift k = the channel's
+//                       value at pixel 0 (exact for constant channels, well conditioned otherwise): mean AND std from
+//                       one pass (SURVEY 8d allows it; the reference's second std pass is not reproduced)
+//   S2   read x         sum |x - mean32|  (only when the Laplace b is needed)
+//   A    read x, write  quantize - clip - dequantize
+//
+// No leader sections on the critical path (round-2 stamps: 3.3 us + 16 us per launch, mostly cold instruction fetch of
+// code that ONE CTA ran once): CTAs meet in replicated per-channel accumulators (atomics), a plain grid barrier
+// follows, and then every CTA derives what it needs for ITS channels itself.  The one global computation - bit
+// allocation / mid-tread bin allocation, which needs the std of every channel - runs in CTA 0 while the other CTAs
+// stream phase S2, and is published before CTA 0 arrives at the second barrier.
+//
+// Accumulators are double-banked by launch parity: a launch uses the bank the previous launch of this workspace left
+// zeroed and zeroes the other one in passing, so nothing on the critical path re-arms them.
+#pragma once
+
+namespace fqb {
+
+__device__ __forceinline__ unsigned enc_ordered(float x) {
+  const unsigned b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(unsigned e) {
+  return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
+}
+
+// accumulator bank layout (element offsets into A.acc_u / A.acc_d of one bank)
+constexpr unsigned kAccU = 2u * kMaxNhwcChannels;  // min (inverted encoding), max
+constexpr unsigned kAccD = 3u * kMaxNhwcChannels;  // S, Q, sum |x - mean|
+
+struct ClView {
+  unsigned* amin_inv;
+  unsigned* amax;
+  double* asum;
+  double* asq;
+  double* aabs;
+};
+__device__ __forceinline__ ClView cl_view(const FusedArgs& A, unsigned bank) {
+  ClView v;
+  v.amin_inv = A.amin_inv + bank * kAccU;
+  v.amax = v.amin_inv + kMaxNhwcChannels;
+  v.asum = A.asum + bank * kAccD;
+  v.asq = v.asum + kMaxNhwcChannels;
+  v.aabs = v.asq + kMaxNhwcChannels;
+  return v;
+}
+
+// plain grid barrier over the consumer threads of every CTA: the last CTA to arrive releases the others
+__device__ __forceinline__ void grid_barrier_cl(GridSync* gs, unsigned& epoch) {
+  ++epoch;
+  consumer_sync();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned prev = atomicAdd(&gs->arrive, 1u);
+    if (prev + 1u == epoch * gridDim.x) {
+      __threadfence();
+      st_release_u32(&gs->release, epoch);
+    } else {
+      while (ld_acquire_u32(&gs->release) < epoch) __nanosleep(40);
+    }
+    __threadfence();
+  }
+  consumer_sync();
+}
+__device__ __forceinline__ void grid_exit_cl(GridSync* gs) {
+  consumer_sync();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(&gs->exited, 1u);
+    if (prev + 1u == gridDim.x) {
+      gs->arrive = 0u;
+      gs->release = 0u;
+      for (int i = 0; i < 8; ++i) gs->unit_counter[i] = 0u;
+      gs->launch_count = gs->launch_count + 1u;  // flips the accumulator bank, retires aux_ready
+      __threadfence();
+      gs->exited = 0u;
+    }
+  }
+}
+
+// ---- per-phase accumulators ---------------------------------------------------------------------------------------------
+constexpr unsigned kClChunk = 8;  // vectors summed in fp32 before folding into float64
+
+struct ClStats1 {
+  float mn[4], mx[4], bias[4], k[4], fs[4], fq[4];
+  double s[4], q[4];
+  unsigned cnt;
+  __device__ __forceinline__ void init(const FusedArgs& A, unsigned c0, bool active) {
+    // common shift: the channel's (biased) value at pixel 0, the same bits in every thread of every CTA
+    float4 first = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) first = ld_tensor(reinterpret_cast<const float4*>(A.in) + (c0 >> 2));
+    const float f[4] = {first.x, first.y, first.z, first.w};
+    cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bias[i] = (A.bias && active) ? __ldg(A.bias + c0 + i) : 0.f;
+      k[i] = __fadd_rn(f[i], bias[i]);
+      mn[i] = INFINITY;
+      mx[i] = -INFINITY;
+      fs[i] = 0.f;
+      fq[i] = 0.f;
+      s[i] = 0.0;
+      q[i] = 0.0;
+    }
+  }
+  __device__ __forceinline__ void flush() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      s[i] += static_cast<double>(fs[i]);
+      q[i] += static_cast<double>(fq[i]);
+      fs[i] = 0.f;
+      fq[i] = 0.f;
+    }
+    cnt = 0;
+  }
+  __device__ __forceinline__ void consume(const float4& v, unsigned) {
+    const float x[4] = {__fadd_rn(v.x, bias[0]), __fadd_rn(v.y, bias[1]), __fadd_rn(v.z, bias[2]), __fadd_rn(v.w, bias[3])};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float d = __fsub_rn(x[i], k[i]);
+      mn[i] = fminf(mn[i], x[i]);
+      mx[i] = fmaxf(mx[i], x[i]);
+      fs[i] = __fadd_rn(fs[i], d);
+      fq[i] = __fmaf_rn(d, d, fq[i]);
+    }
+    if (++cnt == kClChunk) flush();
+  }
+};
+
+struct ClStats2 {
+  float mu[4], bias[4], fa[4];
+  double sa[4];
+  unsigned cnt;
+  __device__ __forceinline__ void init(const FusedArgs& A, unsigned c0, bool active, const float (&mean)[4]) {
+    cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bias[i] = (A.bias && active) ? __ldg(A.bias + c0 + i) : 0.f;
+      mu[i] = mean[i];
+      fa[i] = 0.f;
+      sa[i] = 0.0;
+    }
+  }
+  __device__ __forceinline__ void flush() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      sa[i] += static_cast<double>(fa[i]);
+      fa[i] = 0.f;
+    }
+    cnt = 0;
+  }
+  __device__ __forceinline__ void consume(const float4& v, unsigned) {
+    const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) fa[i] = __fadd_rn(fa[i], fabsf(__fsub_rn(__fadd_rn(x[i], bias[i]), mu[i])));
+    if (++cnt == kClChunk) flush();
+  }
+};
+
+template <int LEAF, bool HIST>
+struct ClApply {
+  const FusedArgs& A;
+  unsigned* hist;  // [kWarps][256] in shared memory (HIST)
+  LeafParam q[4];
+  float r[4], bias[4];
+  bool fast;
+  __device__ __forceinline__ void init(unsigned c0, bool active, const LeafParam (&lp)[4]) {
+    fast = true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      q[i] = lp[i];
+      const Divisor dv = make_divisor(q[i].a);
+      r[i] = dv.r;
+      fast = fast && dv.fast;
+      bias[i] = (A.bias && active) ? __ldg(A.bias + c0 + i) : 0.f;
+    }
+  }
+  template <bool FAST>
+  __device__ __forceinline__ void one(const float4& v, unsigned off) {
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    float y[4], gq[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      Divisor dv;
+      dv.s = q[i].a;
+      dv.r = r[i];
+      dv.fast = FAST;
+      y[i] = leaf_apply<LEAF, FAST>(__fadd_rn(x[i], bias[i]), q[i], dv, 0.f, gq[i]);
+    }
+    st_tensor(reinterpret_cast<float4*>(A.out) + off, make_float4(y[0], y[1], y[2], y[3]));
+    if (HIST) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (gq[i] >= 0.f && gq[i] <= 255.f) atomicAdd(hist + (threadIdx.x >> 5) * 256u + static_cast<unsigned>(gq[i]), 1u);
+    }
+  }
+  __device__ __forceinline__ void consume(const float4& v, unsigned off) {
+    if (fast)
+      one<true>(v, off);
+    else
+      one<false>(v, off);
+  }
+};
+
+// ---- CTA-wide combine of per-thread channel partials, then one atomic per channel into the replicated accumulators ------
+// buf: 16 KB of shared memory.  Threads sharing a column (t, t + cv, ...) are reduced by the column's owner items.
+template <typename T, typename Op, typename Emit>
+__device__ __forceinline__ void cl_combine(unsigned char* buf, unsigned cv, unsigned stride, const T (&v)[4], T identity, Op op,
+                                           Emit&& emit) {
+  if (cv == stride) {  // every active thread owns its column alone (C = 2048 with 512 threads): no staging
+    if (threadIdx.x < stride) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) emit(4u * threadIdx.x + i, v[i]);
+    }
+    return;
+  }
+  T* st = reinterpret_cast<T*>(buf);  // [4][kConsumers]
+  consumer_sync();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) st[i * kConsumers + threadIdx.x] = (threadIdx.x < stride) ? v[i] : identity;
+  consumer_sync();
+  for (unsigned it = threadIdx.x; it < 4u * cv; it += kConsumers) {
+    const unsigned col = it % cv, i = it / cv;
+    T a = identity;
+    for (unsigned t = col; t < stride; t += cv) a = op(a, st[i * kConsumers + t]);
+    emit(4u * col + i, a);
+  }
+}
+
+// mean (float64) of channel c from the S1 accumulators: k + S / n
+__device__ __forceinline__ double cl_mean(const ClView& acc, unsigned rep, unsigned C, unsigned c, float k, double n) {
+  double s = 0.0;
+  for (unsigned r = 0; r < rep; ++r) s += ld_ws(acc.asum + r * C + c);
+  return static_cast<double>(k) + s / n;
+}
+// unbiased std of channel c: sqrt((Q - S^2 / n) / (n - 1))
+__device__ __forceinline__ float cl_std(const ClView& acc, unsigned rep, unsigned C, unsigned c, double n) {
+  double s = 0.0, q = 0.0;
+  for (unsigned r = 0; r < rep; ++r) {
+    s += ld_ws(acc.asum + r * C + c);
+    q += ld_ws(acc.asq + r * C + c);
+  }
+  double m2 = q - s * s / n;
+  if (m2 < 0.0) m2 = 0.0;
+  return static_cast<float>(sqrt(m2 / (n - 1.0)));
+}
+
+// mid-tread parameters of one channel from its bin count omega: int_quantizer.py:185-214 (+ :137-145)
+__device__ __forceinline__ LeafParam mid_tread_param(const FusedArgs& A, float omega, float mn, float mx, float mu, float b,
+                                                     float& rng) {
+  const bool sym = !A.positive;
+  if (A.mt_clip) {
+    double om = sym ? static_cast<double>(omega) : 2.0 * static_cast<double>(omega);
+    int i = 0;
+    while (i < kTable - 1 && kOmegaTable[i] < om) ++i;  // searchsorted(side='left'), clamped to the table
+    double am;
+    if (i == 0) {
+      am = kAlphaTable[0];
+    } else {
+      const double inc = (kAlphaTable[i] - kAlphaTable[i - 1]) / (kOmegaTable[i] - kOmegaTable[i - 1]);
+      am = kAlphaTable[i] - inc * (kOmegaTable[i] - om);
+    }
+    const float amf = static_cast<float>(am);
+    rng = sym ? __fmul_rn(__fmul_rn(2.f, amf), b) : __fadd_rn(fmaxf(mu, 0.f), __fmul_rn(amf, b));
+  } else {
+    rng = sym ? __fsub_rn(mx, mn) : mx;
+  }
+  const float step = (omega > 0.f) ? __fdiv_rn(rng, omega) : 3.402823466e+38f;
+  LeafParam q;
+  q.a = step;
+  q.flags = 0;
+  if (A.mt_clip) {
+    const float mu_q = sym ? __fdiv_rn(mu, step) : __fdiv_rn(fmaxf(mu, 0.f), step);
+    q.c = __fadd_rn(mu_q, sym ? __fmul_rn(omega, 0.5f) : omega);
+    q.b = sym ? __fsub_rn(mu_q, __fmul_rn(omega, 0.5f)) : 0.f;
+  } else {
+    q.b = -INFINITY;
+    q.c = INFINITY;
+  }
+  return q;
+}
+
+// CTA 0, all consumer threads: the one computation that needs every channel - per-channel bit widths (int_quantizer.py:
+// 381-407) or mid-tread bin counts (:128-135) from the per-channel std (prior 'gaus') or b (prior 'laplace') - into
+// A.gbits, then the aux_ready flag.
+__device__ __noinline__ void cl_solve_aux(const FusedArgs& A, const ClView& acc, LeaderSmem& sm, unsigned tag, bool have_b) {
+  const unsigned C = A.flat.channels;
+  const double n = A.n_per_group;
+  const bool prior_b = (A.leaf != FQB200_LEAF_MIDTREAD) && A.prior == FQB200_PRIOR_B;
+  for (unsigned c = threadIdx.x; c < C; c += kConsumers) {
+    if (prior_b) {
+      double sa = 0.0;
+      if (have_b)
+        for (unsigned r = 0; r < A.nhwc_rep; ++r) sa += ld_ws(acc.aabs + r * C + c);
+      A.gb[c] = static_cast<float>(sa / n);
+    } else {
+      A.gstd[c] = cl_std(acc, A.nhwc_rep, C, c, n);
+    }
+  }
+  consumer_sync();
+  if (A.leaf == FQB200_LEAF_MIDTREAD) {
+    double local = 0.0;
+    for (unsigned c = threadIdx.x; c < C; c += kConsumers) {
+      const float p = powf(A.gstd[c], 0.6666666666666666f);
+      A.gprior[c] = p;
+      local += static_cast<double>(p);
+    }
+    const float psum = static_cast<float>(block_reduce(local, OpAdd(), sm.d));
+    const float budget = static_cast<float>(static_cast<double>(C) * exp2(static_cast<double>(A.mt_target)));
+    for (unsigned c = threadIdx.x; c < C; c += kConsumers) A.gbits[c] = rintf(__fdiv_rn(__fmul_rn(budget, A.gprior[c]), psum));
+  } else {
+    solve_bit_alloc(A, sm);
+  }
+  consumer_sync();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    st_release_u32(&A.sync->aux_ready, tag);
+  }
+}
+
+// leaf parameters of channel c from the reduced accumulators (what the leader section of the NCHW kernel computes, here for
+// one channel at a time): min / max / b over the replicas, std when a range mode or the export needs it, the channel's bit
+// width (or mid-tread bin count) published by CTA 0, then int_quantizer.py:284-300 + :557-572 (or :185-214).
+template <int LEAF, bool DEV>
+__device__ __forceinline__ LeafParam cl_channel_param(const FusedArgs& A, const ClView& acc, unsigned rep, unsigned C, unsigned c,
+                                                      float mu, double n, bool alloc, bool do_export) {
+  unsigned lo = 0u, hi = 0u;
+  double sa = 0.0;
+  for (unsigned r = 0; r < rep; ++r) {
+    lo = max(lo, ld_ws(acc.amin_inv + r * C + c));
+    hi = max(hi, ld_ws(acc.amax + r * C + c));
+    if (DEV) sa += ld_ws(acc.aabs + r * C + c);
+  }
+  const float mn = dec_ordered(~lo), mx = dec_ordered(hi);
+  const float b = DEV ? static_cast<float>(sa / n) : 0.f;
+  const bool need_sd = A.range_mode == FQB200_RANGE_GAUS || A.range_mode == FQB200_RANGE_KSTD || do_export;
+  const float sd = need_sd ? cl_std(acc, rep, C, c, n) : 0.f;
+  const float aux = alloc ? ld_ws(A.gbits + c) : static_cast<float>(A.num_bits);
+  LeafParam q;
+  if constexpr (LEAF == FQB200_LEAF_MIDTREAD) {
+    float rng;
+    q = mid_tread_param(A, aux, mn, mx, mu, b, rng);
+    if (do_export) export_stats(A, c, mn, mx, mu, b, sd, rng, 0.f, aux, q);
+  } else {
+    float delta, offset;
+    solve_range(A, mn, mx, mu, b, sd, aux, delta, offset);
+    q = make_leaf_param(LEAF, delta, offset, aux);
+    if (do_export) export_stats(A, c, mn, mx, mu, b, sd, delta, offset, aux, q);
+  }
+  return q;
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------------------------------
+// LEAF: torch or mid-tread.  DEV: phase S2 (the Laplace b) is needed.  HIST: histogram of the integer grid (`-me`).
+// Dynamic shared memory: [kStages stages][16 KB combine staging / parameter table][4 KB mean table][HIST: 16 KB histograms].
+constexpr unsigned kClStagingBytes = 4u * kConsumers * 8u;          // 16 KB
+constexpr unsigned kClTableChannels = 1024;                          // channel tables live in shared memory up to here
+constexpr unsigned kClCombineBytes = kClStagingBytes + kClTableChannels * 4u;
+
+template <int LEAF, bool DEV, bool HIST>
+__global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_kernel(const __grid_constant__ FusedArgs A) {
+  extern __shared__ __align__(128) unsigned char fq_dyn[];
+  unsigned char* stages = fq_dyn;
+  unsigned char* cbuf = fq_dyn + kStages * kStageBytes;
+  float* tab_mean = reinterpret_cast<float*>(cbuf + kClStagingBytes);
+  unsigned* hist = reinterpret_cast<unsigned*>(cbuf + kClCombineBytes);
+  __shared__ BulkRing ring;
+  __shared__ LeaderSmem lsm;
+  __shared__ alignas(8) unsigned long long solver_done;  // mbarrier: CTA 0's consumers are back from the global solve
+  const FlatGeo& g = A.flat;
+  const unsigned C = g.channels, cv = g.cv;
+  const unsigned launch = ld_ws(&A.sync->launch_count);
+  const unsigned bank = launch & 1u;
+  const unsigned tag = launch + 1u;
+  const bool alloc = (LEAF == FQB200_LEAF_MIDTREAD) || (A.bit_alloc && A.num_bits <= 4);
+  const bool aux_needs_b = alloc && LEAF != FQB200_LEAF_MIDTREAD && A.prior == FQB200_PRIOR_B;
+  // CTA 0 computes the bit widths while the others stream S2: it takes no static S2 tickets and starts pulling dynamic
+  // ones only when its consumers are back (it would sit on them otherwise)
+  const bool solver_in_s2 = alloc && !aux_needs_b && DEV && gridDim.x > 1u;
+  if (threadIdx.x == 0) mbar_init(smem_u32(&solver_done), 1u);
+  ring_init(ring);
+
+  // ================================ producer warp ================================
+  if (threadIdx.x >= kConsumers) {
+    if (threadIdx.x == kConsumers) {
+      RingPos pos;
+      pos.init();
+      const float4* src = reinterpret_cast<const float4*>(A.in);
+      const TicketPlan all = {2u, blockIdx.x, gridDim.x, 2u * gridDim.x};
+      produce_phase<false>(g, src, &A.sync->unit_counter[0], all, ring, stages, pos);
+      if (DEV) {
+        TicketPlan s2 = all;
+        if (solver_in_s2) {
+          s2.nstatic = blockIdx.x == 0 ? 0u : 2u;
+          s2.first = blockIdx.x - 1u;
+          s2.step = gridDim.x - 1u;
+          s2.dyn_base = 2u * (gridDim.x - 1u);
+          if (blockIdx.x == 0) mbar_wait(smem_u32(&solver_done), 0u);
+        }
+        produce_phase<true>(g, src, &A.sync->unit_counter[1], s2, ring, stages, pos);
+      }
+      if (!A.stats_only) produce_phase<!DEV>(g, src, &A.sync->unit_counter[2], all, ring, stages, pos);
+    }
+    return;
+  }
+
+  // ================================ consumers ================================
+  const unsigned t = threadIdx.x;
+  const bool active = t < g.stride;
+  const bool direct = cv == g.stride;  // every active thread is the only one on its column: no shared-memory tables
+  const unsigned col = active ? t % cv : 0u;
+  const unsigned c0 = 4u * col;
+  const double n = A.n_per_group;
+  const ClView acc = cl_view(A, bank);
+  const unsigned rep = A.nhwc_rep;
+  const unsigned rep_base = (blockIdx.x % rep) * C;
+  unsigned epoch = 0;
+  RingPos pos;
+  pos.init();
+  if (blockIdx.x == 0) stamp(A, 0);
+
+  // the bank the previous launch used: zero it for the next one (off the critical path)
+  if (blockIdx.x == gridDim.x - 1u) {
+    const ClView other = cl_view(A, bank ^ 1u);
+    uint4* zu = reinterpret_cast<uint4*>(other.amin_inv);
+    uint4* zd = reinterpret_cast<uint4*>(other.asum);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (unsigned i = t; i < kAccU / 4u; i += kConsumers) zu[i] = z;
+    for (unsigned i = t; i < kAccD / 2u; i += kConsumers) zd[i] = z;
+  }
+
+  // ---- S1
+  float kshift[4];
+  {
+    ClStats1 s1;
+    s1.init(A, c0, active);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) kshift[i] = s1.k[i];
+    consume_phase(g, ring, stages, pos, s1);
+    s1.flush();
+    if (blockIdx.x == 0) stamp(A, 13);
+    unsigned umn[4], umx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      umn[i] = ~enc_ordered(s1.mn[i]);
+      umx[i] = enc_ordered(s1.mx[i]);
+    }
+    auto umax = [](unsigned a, unsigned b) { return a > b ? a : b; };
+    cl_combine(cbuf, cv, g.stride, umn, 0u, umax, [&](unsigned c, unsigned v) { atomicMax(acc.amin_inv + rep_base + c, v); });
+    cl_combine(cbuf, cv, g.stride, umx, 0u, umax, [&](unsigned c, unsigned v) { atomicMax(acc.amax + rep_base + c, v); });
+    cl_combine(cbuf, cv, g.stride, s1.s, 0.0, OpAdd(), [&](unsigned c, double v) { atomicAdd(acc.asum + rep_base + c, v); });
+    cl_combine(cbuf, cv, g.stride, s1.q, 0.0, OpAdd(), [&](unsigned c, double v) { atomicAdd(acc.asq + rep_base + c, v); });
+  }
+  if (blockIdx.x == 0) stamp(A, 1);
+  grid_barrier_cl(A.sync, epoch);
+  if (blockIdx.x == 0) stamp(A, 4);
+
+  // ---- the mean of every channel: each accumulator value is read once per CTA
+  float mean[4];
+  if (direct) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mean[i] = static_cast<float>(cl_mean(acc, rep, C, c0 + i, kshift[i], n));
+  } else {
+    for (unsigned c = t; c < C; c += kConsumers) {
+      const float k = __fadd_rn(ld_tensor(A.in + c), A.bias ? __ldg(A.bias + c) : 0.f);  // the same bits as kshift
+      tab_mean[c] = static_cast<float>(cl_mean(acc, rep, C, c, k, n));
+    }
+    consumer_sync();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mean[i] = tab_mean[c0 + i];
+  }
+
+  // ---- the global solve, where it can overlap with S2
+  if (alloc && !aux_needs_b && blockIdx.x == 0) {
+    cl_solve_aux(A, acc, lsm, tag, false);
+    stamp(A, 12);
+    if (t == 0) mbar_arrive(smem_u32(&solver_done));
+  }
+
+  // ---- S2
+  if constexpr (DEV) {
+    ClStats2 s2;
+    s2.init(A, c0, active, mean);
+    consume_phase(g, ring, stages, pos, s2);
+    s2.flush();
+    if (blockIdx.x == 0) stamp(A, 14);
+    cl_combine(cbuf, cv, g.stride, s2.sa, 0.0, OpAdd(), [&](unsigned c, double v) { atomicAdd(acc.aabs + rep_base + c, v); });
+    if (blockIdx.x == 0) stamp(A, 5);
+    grid_barrier_cl(A.sync, epoch);
+    if (blockIdx.x == 0) stamp(A, 8);
+    if (aux_needs_b && blockIdx.x == 0) cl_solve_aux(A, acc, lsm, tag, true);
+  }
+  if (alloc) {  // published by CTA 0 (long ago when it overlapped with S2)
+    if (t == 0)
+      while (ld_acquire_u32(&A.sync->aux_ready) != tag) __nanosleep(40);
+    consumer_sync();
+  }
+
+  // ---- leaf parameters of every channel, again each accumulator value read once per CTA
+  LeafParam lp[4];
+  const bool do_export = A.out_stats != nullptr && blockIdx.x == 0;
+  if (direct) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) lp[i] = cl_channel_param<LEAF, DEV>(A, acc, rep, C, c0 + i, mean[i], n, alloc, do_export && active);
+  } else {
+    LeafParam* tab_lp = reinterpret_cast<LeafParam*>(cbuf);
+    consumer_sync();  // the combine staging is free
+    for (unsigned c = t; c < C; c += kConsumers) tab_lp[c] = cl_channel_param<LEAF, DEV>(A, acc, rep, C, c, tab_mean[c], n, alloc, do_export);
+    consumer_sync();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) lp[i] = tab_lp[c0 + i];
+  }
+  if (blockIdx.x == 0) stamp(A, 7);
+
+  // ---- A
+  if (!A.stats_only) {
+    if (HIST) {
+      for (unsigned i = t; i < kWarps * 256u; i += kConsumers) hist[i] = 0u;
+      consumer_sync();
+    }
+    ClApply<LEAF, HIST> ap{A, hist};
+    ap.init(c0, active, lp);
+    consume_phase(g, ring, stages, pos, ap);
+    if (HIST) {
+      consumer_sync();
+      for (unsigned b = t; b < 256u; b += kConsumers) {
+        unsigned long long cnt = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) cnt += hist[w * 256u + b];
+        if (cnt) atomicAdd(A.hist + b, cnt);
+      }
+    }
+    if (blockIdx.x == 0) stamp(A, 9);
+  }
+  grid_exit_cl(A.sync);
+}
+
+// ---- mode A on channels-last memory: parameters given, no statistics, no barrier (ordinary launch) ---------------------------
+// Static round-robin units; leaf parameters derived per thread from the caller's delta / offset / bits of its 4 channels
+// (per_group) or of the whole tensor.
+template <bool GRID>
+struct ClGiven {
+  const FusedArgs& A;
+  LeafParam q[4];
+  float r[4], bias[4];
+  bool fast;
+  template <bool FAST>
+  __device__ __forceinline__ void one(const float4& v, unsigned off) {
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    float y[4], gq[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      Divisor dv;
+      dv.s = q[i].a;
+      dv.r = r[i];
+      dv.fast = FAST;
+      y[i] = leaf_apply<FQB200_LEAF_TORCH, FAST>(__fadd_rn(x[i], bias[i]), q[i], dv, 0.f, gq[i]);
+    }
+    st_tensor(reinterpret_cast<float4*>(A.out) + off, make_float4(y[0], y[1], y[2], y[3]));
+    if (GRID) st_tensor(reinterpret_cast<float4*>(A.grid_out) + off, make_float4(gq[0], gq[1], gq[2], gq[3]));
+  }
+  __device__ __forceinline__ void consume(const float4& v, unsigned off) {
+    if (fast)
+      one<true>(v, off);
+    else
+      one<false>(v, off);
+  }
+};
+
+template <bool GRID>
+__global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_given_kernel(const __grid_constant__ FusedArgs A) {
+  extern __shared__ __align__(128) unsigned char fq_dyn[];
+  __shared__ BulkRing ring;
+  const FlatGeo& g = A.flat;
+  ring_init(ring);
+  if (threadIdx.x >= kConsumers) {
+    if (threadIdx.x == kConsumers) {
+      RingPos pos;
+      pos.init();
+      // static assignment: ticket k of CTA b = b + k * grid (no workspace, no counter)
+      const TicketPlan tp = {0xffffffffu, blockIdx.x, gridDim.x, 0u};
+      produce_phase<false>(g, reinterpret_cast<const float4*>(A.in), nullptr, tp, ring, fq_dyn, pos);
+    }
+    return;
+  }
+  const unsigned t = threadIdx.x;
+  const bool active = t < g.stride;
+  const unsigned c0 = active ? 4u * (t % g.cv) : 0u;
+  ClGiven<GRID> ap{A};
+  ap.fast = true;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const unsigned c = c0 + i;
+    const unsigned pi = A.given_per_group ? c : 0u;
+    const float bits = A.g_bits ? __ldg(A.g_bits + c) : static_cast<float>(A.num_bits);
+    ap.q[i] = make_leaf_param(FQB200_LEAF_TORCH, __ldg(A.g_delta + pi), __ldg(A.g_offset + pi), bits);
+    const Divisor dv = make_divisor(ap.q[i].a);
+    ap.r[i] = dv.r;
+    ap.fast = ap.fast && dv.fast;
+    ap.bias[i] = (A.bias && active) ? __ldg(A.bias + c) : 0.f;
+  }
+  RingPos pos;
+  pos.init();
+  consume_phase(g, ring, fq_dyn, pos, ap);
+}
+
+}  // namespace fqb

@@ -17,6 +17,11 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kCtasPerSm = 2;           // __launch_bounds__(512, 2): <= 64 registers per thread
 constexpr int kUnroll = 4;              // independent 128-bit loads in flight per thread
 
+// CTA-wide barrier over the kThreads = 512 worker threads: named barrier 1 with an explicit count, so that kernels which
+// add a producer warp (fq_bulk.cuh: 544 threads) can share every helper below - the producer warp never joins.  In the
+// plain 512-thread kernels it is equivalent to __syncthreads().
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // global memory access
 // ------------------------------------------------------------------------------------------------
@@ -132,9 +137,9 @@ struct OpMax {
 template <typename T, typename Op>
 __device__ __forceinline__ T block_reduce(T v, Op op, T* scratch) {
   v = warp_reduce(v, op);
-  __syncthreads();
+  cta_sync();
   if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-  __syncthreads();
+  cta_sync();
   T r = scratch[0];
 #pragma unroll
   for (int w = 1; w < kWarps; ++w) r = op(r, scratch[w]);
@@ -151,8 +156,10 @@ struct GridSync {
   unsigned arrive;
   unsigned release;
   unsigned exited;
-  unsigned pad;
+  unsigned launch_count;     // channels-last kernels: completed launches (accumulator bank = parity; tag of aux_ready)
   unsigned unit_counter[8];  // one dynamic work counter per streaming phase
+  unsigned aux_ready;        // channels-last kernels: CTA 0 published the per-channel bit widths of launch `aux_ready`
+  unsigned pad[3];
 };
 
 // All threads of all CTAs call this.  Returns true in exactly one CTA (the last to arrive) WITHOUT
@@ -160,13 +167,13 @@ struct GridSync {
 // false only after the leader has released the epoch.
 __device__ __forceinline__ bool grid_arrive(GridSync* gs, unsigned& epoch, int* sh_flag) {
   ++epoch;
-  __syncthreads();
+  cta_sync();
   if (threadIdx.x == 0) {
     __threadfence();  // publish this CTA's workspace writes (cumulative over the bar.sync above)
     unsigned prev = atomicAdd(&gs->arrive, 1u);
     *sh_flag = (prev + 1u == epoch * gridDim.x) ? 1 : 0;
   }
-  __syncthreads();
+  cta_sync();
   const bool lead = (*sh_flag != 0);
   if (lead) {
     __threadfence();  // acquire side: see every other CTA's writes
@@ -175,19 +182,19 @@ __device__ __forceinline__ bool grid_arrive(GridSync* gs, unsigned& epoch, int* 
       while (ld_acquire_u32(&gs->release) < epoch) __nanosleep(100);
       __threadfence();
     }
-    __syncthreads();
+    cta_sync();
   }
   return lead;
 }
 __device__ __forceinline__ void grid_release(GridSync* gs, unsigned epoch) {
-  __syncthreads();
+  cta_sync();
   if (threadIdx.x == 0) {
     __threadfence();
     st_release_u32(&gs->release, epoch);
   }
 }
 __device__ __forceinline__ void grid_exit(GridSync* gs) {
-  __syncthreads();
+  cta_sync();
   if (threadIdx.x == 0) {
     unsigned prev = atomicAdd(&gs->exited, 1u);
     if (prev + 1u == gridDim.x) {  // everyone is past the last wait: safe to re-arm
@@ -353,12 +360,12 @@ __device__ __forceinline__ void stream_units(const Geometry& geo, const float* b
     return t < total ? static_cast<unsigned>(t) : 0xffffffffu;
   };
 
-  __syncthreads();  // ss.ids may still be read by stragglers of a previous phase
+  cta_sync();  // ss.ids may still be read by stragglers of a previous phase
   if (threadIdx.x == 0) {
     ss.ids[0] = take_ticket();
     ss.ids[1] = take_ticket();
   }
-  __syncthreads();
+  cta_sync();
   unsigned seq = 0;  // sequence number (within this CTA) of the unit being consumed
   unsigned ticket = ss.ids[0];
   if (ticket >= total) return;

@@ -23,6 +23,7 @@
 
 #include "../../include/fqb200.h"
 #include "fq_device.cuh"
+#include "fq_bulk.cuh"
 
 namespace fqb {
 
@@ -49,6 +50,7 @@ struct alignas(16) LeafParam {
 
 struct FusedArgs {
   Geometry geo;
+  FlatGeo flat;        // channels-last / flat-stream kernels (fq_cl.cuh)
   const float* in;
   float* out;
   const float* bias;   // optional per-group addend applied to x before everything else (folded-BN conv bias)
@@ -70,7 +72,7 @@ struct FusedArgs {
   double n_per_group;  // outer * inner
   float* out_stats;
   unsigned long long* hist;  // optional 256-bin histogram of the integer grid (entropy measurement, `-me`), accumulated
-  unsigned long long* dbg;   // development: globaltimer stamps of the phase boundaries (NULL in production)
+  unsigned long long* dbg;   // fqb200_desc.debug_stamps: %globaltimer at the phase boundaries (NULL: off)
   // workspace
   GridSync* sync;
   float *pmin, *pmax;                   // [items]
@@ -176,6 +178,7 @@ __device__ __noinline__ void solve_bit_alloc(const FusedArgs& A, LeaderSmem& sm)
     }
   }
   const float psum = static_cast<float>(block_reduce(local, OpAdd(), sm.d));
+  stamp(A, 15);
   const float goal = A.ba_target;
   double m = static_cast<double>(A.ba_target);
   float half_gap = 1.0f;
@@ -211,7 +214,7 @@ __device__ __noinline__ void solve_bit_alloc(const FusedArgs& A, LeaderSmem& sm)
     // exact integer sum: one REDUX per warp, one barrier per iteration (buffers alternate)
     sum_bits = __reduce_add_sync(0xffffffffu, sum_bits);
     if ((threadIdx.x & 31) == 0) warp_bits[it & 1][threadIdx.x >> 5] = sum_bits;
-    __syncthreads();
+    cta_sync();
     int total = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) total += warp_bits[it & 1][w];
@@ -227,7 +230,7 @@ __device__ __noinline__ void solve_bit_alloc(const FusedArgs& A, LeaderSmem& sm)
       if (g < G) A.gbits[g] = bt[k];
     }
   }
-  __syncthreads();
+  cta_sync();
 }
 
 // (delta, offset) of one group/tensor from its statistics: int_quantizer.py:284-300 (alpha2DeltaOffset),
@@ -437,13 +440,13 @@ struct PhaseSmem {
 
 __device__ __forceinline__ void hist_clear(PhaseSmem& sm) {
   for (unsigned i = threadIdx.x; i < kWarps * 256u; i += kThreads) (&sm.hist[0][0])[i] = 0u;
-  __syncthreads();
+  cta_sync();
 }
 __device__ __forceinline__ void hist_add(PhaseSmem& sm, float q) {
   if (q >= 0.f && q <= 255.f) atomicAdd(&sm.hist[threadIdx.x >> 5][static_cast<unsigned>(q)], 1u);  // NaN falls through
 }
 __device__ __forceinline__ void hist_flush(PhaseSmem& sm, unsigned long long* out) {
-  __syncthreads();
+  cta_sync();
   for (unsigned b = threadIdx.x; b < 256u; b += kThreads) {
     unsigned long long c = 0;
 #pragma unroll
@@ -467,7 +470,7 @@ __device__ __forceinline__ void block_combine(PhaseSmem& sm, float& mn, float& m
   }
   s0 = warp_reduce(s0, OpAdd());
   if (use_d1) s1 = warp_reduce(s1, OpAdd());
-  __syncthreads();
+  cta_sync();
   const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (l == 0) {
     sm.f0[w] = mn;
@@ -475,7 +478,7 @@ __device__ __forceinline__ void block_combine(PhaseSmem& sm, float& mn, float& m
     sm.d0[w] = s0;
     sm.d1[w] = s1;
   }
-  __syncthreads();
+  cta_sync();
   if (w == 0) {
     float a = (l < kWarps) ? sm.f0[l] : INFINITY, b = (l < kWarps) ? sm.f1[l] : -INFINITY;
     double c = (l < kWarps) ? sm.d0[l] : 0.0, d = (l < kWarps) ? sm.d1[l] : 0.0;
@@ -641,7 +644,7 @@ __device__ __forceinline__ void bundle_combine(PhaseSmem& sm, unsigned bundle, u
                                                double dA0, double dA1, float fB0, float fB1, double dB0, double dB1,
                                                float (&rf0)[4], float (&rf1)[4], double (&rd0)[4], double (&rd1)[4]) {
   const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();  // previous unit's readers are done with sm
+  cta_sync();  // previous unit's readers are done with sm
   for (unsigned ch = 0; ch < bundle; ++ch) {
     const bool a = (cA == ch), b = hasB && (cA + 1u == ch);
     float v0 = a ? fA0 : INFINITY, v1 = a ? fA1 : -INFINITY;
@@ -665,7 +668,7 @@ __device__ __forceinline__ void bundle_combine(PhaseSmem& sm, unsigned bundle, u
       sm.bd1[ch][w] = s1;
     }
   }
-  __syncthreads();
+  cta_sync();
   if (w == 0) {
     for (unsigned ch = 0; ch < bundle; ++ch) {
       float a = (l < kWarps) ? sm.bf0[ch][l] : INFINITY, b = (l < kWarps) ? sm.bf1[ch][l] : -INFINITY;
@@ -851,7 +854,7 @@ struct AccApply {
       block_combine(sm, f0, f1, sy, unused, false, false);
       if (threadIdx.x == 0) st_ws(A.psum + static_cast<size_t>(ui.p) * A.geo.channels + ui.g, sy);
     } else {
-      __syncthreads();  // the engine publishes the next unit ids at this barrier
+      cta_sync();  // the engine publishes the next unit ids at this barrier
     }
   }
 };
@@ -879,7 +882,7 @@ struct AccCorr {
     st_tensor(reinterpret_cast<float4*>(A.out) + off, make_float4(fix(y.x), fix(y.y), fix(y.z), fix(y.w)));
   }
   __device__ __forceinline__ void consume(const float& y, unsigned off, unsigned) { st_tensor(A.out + off, fix(y)); }
-  __device__ __forceinline__ void end(const UnitInfo&) { __syncthreads(); }
+  __device__ __forceinline__ void end(const UnitInfo&) { cta_sync(); }
 };
 
 template <int LEAF>
@@ -933,7 +936,7 @@ struct AccApplyB {
     else
       one<false>(x, off);
   }
-  __device__ __forceinline__ void end(const UnitInfo&) { __syncthreads(); }
+  __device__ __forceinline__ void end(const UnitInfo&) { cta_sync(); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -971,13 +974,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
   if (grid_arrive(A.sync, epoch, &lsm.flag)) {
     stamp(A, 2);
     reduce_partials3(geo, A.pmin, A.gmin, INFINITY, OpMin(), A.pmax, A.gmax, -INFINITY, OpMax(), A.psum, A.gmean_d, 0.0, OpAdd());
-    __syncthreads();
+    cta_sync();
     for (unsigned g = threadIdx.x; g < geo.channels; g += kThreads) {
       const double m = A.gmean_d[g] / n;
       A.gmean_d[g] = m;
       A.gmean[g] = static_cast<float>(m);
     }
-    __syncthreads();
+    cta_sync();
     if (!DEV) solve_params(A, lsm);
     stamp(A, 3);
     grid_release(A.sync, epoch);
@@ -1000,7 +1003,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
       double* tsq = A.psum + geo.channels;  // psum holds slots + 2G doubles
       reduce_partials3(geo, A.pabs, tabs, 0.0, OpAdd(), A.psq, tsq, 0.0, OpAdd(), static_cast<const double*>(nullptr),
                        static_cast<double*>(nullptr), 0.0, OpAdd());
-      __syncthreads();
+      cta_sync();
       stamp(A, 10);
       for (unsigned g = threadIdx.x; g < geo.channels; g += kThreads) {
         A.gb[g] = static_cast<float>(tabs[g] / n);
@@ -1010,7 +1013,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
         if (ss < 0.0) ss = 0.0;
         A.gstd[g] = static_cast<float>(sqrt(ss / (n - 1.0)));
       }
-      __syncthreads();
+      cta_sync();
       stamp(A, 11);
       solve_params(A, lsm);
       stamp(A, 7);
@@ -1036,7 +1039,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
         double* tmp = A.pabs;
         reduce_partials3(geo, A.psum, tmp, 0.0, OpAdd(), static_cast<const double*>(nullptr), static_cast<double*>(nullptr), 0.0,
                          OpAdd(), static_cast<const double*>(nullptr), static_cast<double*>(nullptr), 0.0, OpAdd());
-        __syncthreads();
+        cta_sync();
         for (unsigned g = threadIdx.x; g < geo.channels; g += kThreads) {
           A.cq[g] = static_cast<float>(tmp[g] / n);
           A.co[g] = A.gmean[g];
@@ -1052,7 +1055,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
           double* tmp = A.pabs;
           reduce_partials3(geo, A.psq, tmp, 0.0, OpAdd(), static_cast<const double*>(nullptr), static_cast<double*>(nullptr), 0.0,
                            OpAdd(), static_cast<const double*>(nullptr), static_cast<double*>(nullptr), 0.0, OpAdd());
-          __syncthreads();
+          cta_sync();
           for (unsigned g = threadIdx.x; g < geo.channels; g += kThreads) {
             // tmp = sum (y - fl32(mean_q))^2 ; fl32(mean_q) stands in for the mean (error O(ulp^2))
             const float sdq = static_cast<float>(sqrt(tmp[g] / (n - 1.0)));
@@ -1070,309 +1073,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_kernel(const __
   grid_exit(A.sync);
 }
 
-// ------------------------------------------------------------------------------------------------
-// channels-last (NHWC) activations: [N][H*W][C] in memory, the channel is the fastest dimension
-// ------------------------------------------------------------------------------------------------
-// With C/4 dividing the CTA width every thread always holds the same four channels, so the whole tensor is ONE flat
-// stream (no cursor arithmetic, no per-unit combine): accumulators and leaf parameters of those four channels stay in
-// registers for the whole phase, the threads of a CTA that share a column are combined through shared memory once
-// per phase, and CTAs meet in per-channel accumulators with atomics (float min/max through an order-preserving
-// integer encoding, sums as float64 atomicAdd).  Sums are therefore combined in a run-dependent order - in float64,
-// i.e. identical after rounding to fp32 except on exact ties; min / max / the integer grid given equal parameters
-// are exact.
-__device__ __forceinline__ unsigned enc_ordered(float x) {
-  const unsigned b = __float_as_uint(x);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float dec_ordered(unsigned e) {
-  return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
-}
-
-// shared-memory staging of the per-phase combine lives in the (idle) ring memory
-struct NhwcStage {
-  float f0[4][kThreads];
-  float f1[4][kThreads];
-  double d0[4][kThreads];
-  double d1[4][kThreads];
-};
-static_assert(sizeof(NhwcStage) <= static_cast<size_t>(ring_bytes<4>()), "combine staging must fit in the ring memory");
-
-// Column (group of 4 channels) a thread works on.  A unit starts at a multiple of kThreads vectors and cv divides
-// kThreads, so a forward walk puts thread t on column t % cv; a backward (REV) walk starts from the unit's last vector
-// (whose column is cv - 1) and mirrors the assignment.
-__device__ __forceinline__ unsigned nhwc_column(unsigned t, unsigned cv, bool rev) { return rev ? cv - 1u - t % cv : t % cv; }
-
-// Reduce, for every channel of this CTA's columns, the values of the threads sharing the column; `emit(channel, f0, f1,
-// d0, d1)` is called once per channel by one thread.  cv = C / 4 columns, kThreads / cv threads per column.
-template <typename Emit>
-__device__ __forceinline__ void nhwc_combine(unsigned cv, bool rev, const float (&f0)[4], const float (&f1)[4], const double (&d0)[4],
-                                             const double (&d1)[4], Emit&& emit) {
-  extern __shared__ __align__(16) unsigned char fq_ring[];
-  NhwcStage& st = *reinterpret_cast<NhwcStage*>(fq_ring);
-  __syncthreads();  // every thread is done with its ring slots
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    st.f0[k][threadIdx.x] = f0[k];
-    st.f1[k][threadIdx.x] = f1[k];
-    st.d0[k][threadIdx.x] = d0[k];
-    st.d1[k][threadIdx.x] = d1[k];
-  }
-  __syncthreads();
-  for (unsigned i = threadIdx.x; i < 4u * cv; i += kThreads) {
-    const unsigned col = i % cv, k = i / cv;
-    float a = INFINITY, b = -INFINITY;
-    double c = 0.0, d = 0.0;
-    for (unsigned t = nhwc_column(col, cv, rev); t < kThreads; t += cv) {
-      a = fminf(a, st.f0[k][t]);
-      b = fmaxf(b, st.f1[k][t]);
-      c += st.d0[k][t];
-      d += st.d1[k][t];
-    }
-    emit(4u * col + k, a, b, c, d);
-  }
-  __syncthreads();
-}
-
-// Sums run in fp32 over kNhwcChunk consecutive vectors of a thread (same accuracy class as the 4-element fp32 tree of
-// the NCHW path) and are then folded into float64: 4x fewer F2F + DADD in an issue-bound loop.
-constexpr unsigned kNhwcChunk = 8;
-
-struct AccStats1N {
-  const FusedArgs& A;
-  float mn[4], mx[4], bias[4], fs[4];
-  double s[4];
-  unsigned cnt;
-  __device__ __forceinline__ void init(unsigned cv, bool rev) {
-    const unsigned c0 = 4u * nhwc_column(threadIdx.x, cv, rev);
-    cnt = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      mn[k] = INFINITY;
-      mx[k] = -INFINITY;
-      s[k] = 0.0;
-      fs[k] = 0.f;
-      bias[k] = A.bias ? __ldg(A.bias + c0 + k) : 0.f;
-    }
-  }
-  __device__ __forceinline__ void flush() {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      s[k] += static_cast<double>(fs[k]);
-      fs[k] = 0.f;
-    }
-    cnt = 0;
-  }
-  __device__ __forceinline__ void begin(const UnitInfo&) {}
-  __device__ __forceinline__ void consume(const float4& v, unsigned, unsigned) {
-    const float x[4] = {__fadd_rn(v.x, bias[0]), __fadd_rn(v.y, bias[1]), __fadd_rn(v.z, bias[2]), __fadd_rn(v.w, bias[3])};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      mn[k] = fminf(mn[k], x[k]);
-      mx[k] = fmaxf(mx[k], x[k]);
-      fs[k] = __fadd_rn(fs[k], x[k]);
-    }
-    if (++cnt == kNhwcChunk) flush();
-  }
-  __device__ __forceinline__ void end(const UnitInfo&) { __syncthreads(); }
-};
-
-struct AccStats2N {
-  const FusedArgs& A;
-  float mu[4], bias[4], fa[4], fq[4];
-  double sa[4], sq[4];
-  unsigned cnt;
-  __device__ __forceinline__ void init(unsigned cv, bool rev) {
-    const unsigned c0 = 4u * nhwc_column(threadIdx.x, cv, rev);
-    cnt = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      mu[k] = ld_ws(A.gmean + c0 + k);
-      bias[k] = A.bias ? __ldg(A.bias + c0 + k) : 0.f;
-      sa[k] = 0.0;
-      sq[k] = 0.0;
-      fa[k] = 0.f;
-      fq[k] = 0.f;
-    }
-  }
-  __device__ __forceinline__ void flush() {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      sa[k] += static_cast<double>(fa[k]);
-      sq[k] += static_cast<double>(fq[k]);
-      fa[k] = 0.f;
-      fq[k] = 0.f;
-    }
-    cnt = 0;
-  }
-  __device__ __forceinline__ void begin(const UnitInfo&) {}
-  __device__ __forceinline__ void consume(const float4& v, unsigned, unsigned) {
-    const float x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float d = __fsub_rn(__fadd_rn(x[k], bias[k]), mu[k]);
-      fa[k] = __fadd_rn(fa[k], fabsf(d));
-      fq[k] = __fmaf_rn(d, d, fq[k]);
-    }
-    if (++cnt == kNhwcChunk) flush();
-  }
-  __device__ __forceinline__ void end(const UnitInfo&) { __syncthreads(); }
-};
-
-template <int LEAF>
-struct AccApplyN {
-  const FusedArgs& A;
-  PhaseSmem& sm;
-  LeafParam q[4];
-  float r[4], bias[4];
-  bool fast;
-  __device__ __forceinline__ void init(unsigned cv, bool rev) {
-    const unsigned c0 = 4u * nhwc_column(threadIdx.x, cv, rev);
-    fast = true;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      q[k] = load_leaf_param(A.lp, c0 + k);
-      const Divisor dv = make_divisor(q[k].a);
-      r[k] = dv.r;
-      fast = fast && dv.fast;
-      bias[k] = A.bias ? __ldg(A.bias + c0 + k) : 0.f;
-    }
-  }
-  __device__ __forceinline__ void begin(const UnitInfo&) {}
-  template <bool FAST>
-  __device__ __forceinline__ void one(const float4& v, unsigned off) {
-    const float x[4] = {v.x, v.y, v.z, v.w};
-    float y[4], gq[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      Divisor dv;
-      dv.s = q[k].a;
-      dv.r = r[k];
-      dv.fast = FAST;
-      y[k] = leaf_apply<LEAF, FAST>(__fadd_rn(x[k], bias[k]), q[k], dv, 0.f, gq[k]);
-    }
-    st_tensor(reinterpret_cast<float4*>(A.out) + off, make_float4(y[0], y[1], y[2], y[3]));
-    if (LEAF == FQB200_LEAF_TORCH && A.hist) {  // one uniform branch per vector, after the store
-#pragma unroll
-      for (int k = 0; k < 4; ++k) hist_add(sm, gq[k]);
-    }
-  }
-  __device__ __forceinline__ void consume(const float4& v, unsigned off, unsigned) {
-    if (fast)
-      one<true>(v, off);
-    else
-      one<false>(v, off);
-  }
-  __device__ __forceinline__ void end(const UnitInfo&) { __syncthreads(); }
-};
-
-template <int LEAF, bool DEV>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_fused_nhwc_kernel(const __grid_constant__ FusedArgs A) {
-  __shared__ PhaseSmem psm;
-  __shared__ LeaderSmem lsm;
-  __shared__ StreamSmem ssm;
-  unsigned epoch = 0;
-  const Geometry& geo = A.geo;
-  const unsigned C = geo.channels, cv = C / 4u;
-  const double n = A.n_per_group;
-  const unsigned rep_base = (blockIdx.x % A.nhwc_rep) * C;
-
-  // ---- S1
-  if (blockIdx.x == 0) stamp(A, 0);
-  {
-    AccStats1N acc{A};
-    acc.init(cv, false);
-    stream_units<4, false>(geo, A.in, &A.sync->unit_counter[0], ssm, acc);
-    acc.flush();
-    if (blockIdx.x == 0) stamp(A, 13);
-    const double zero[4] = {0.0, 0.0, 0.0, 0.0};
-    nhwc_combine(cv, false, acc.mn, acc.mx, acc.s, zero, [&](unsigned c, float mn, float mx, double s, double) {
-      const unsigned i = rep_base + c;
-      atomicMax(A.amin_inv + i, ~enc_ordered(mn));
-      atomicMax(A.amax + i, enc_ordered(mx));
-      atomicAdd(A.asum + i, s);
-    });
-  }
-  if (blockIdx.x == 0) stamp(A, 1);
-  if (grid_arrive(A.sync, epoch, &lsm.flag)) {
-    stamp(A, 2);
-    for (unsigned c = threadIdx.x; c < C; c += kThreads) {
-      unsigned lo = 0u, hi = 0u;
-      double sum = 0.0;
-#pragma unroll 4
-      for (unsigned r = 0; r < A.nhwc_rep; ++r) {
-        const unsigned i = r * C + c;
-        lo = max(lo, ld_ws(A.amin_inv + i));
-        hi = max(hi, ld_ws(A.amax + i));
-        sum += ld_ws(A.asum + i);
-        A.amin_inv[i] = 0u;  // re-arm for the next launch
-        A.amax[i] = 0u;
-        A.asum[i] = 0.0;
-      }
-      A.gmin[c] = dec_ordered(~lo);
-      A.gmax[c] = dec_ordered(hi);
-      const double m = sum / n;
-      A.gmean_d[c] = m;
-      A.gmean[c] = static_cast<float>(m);
-    }
-    __syncthreads();
-    if (!DEV) solve_params(A, lsm);
-    stamp(A, 3);
-    grid_release(A.sync, epoch);
-  }
-  if (blockIdx.x == 0) stamp(A, 4);
-
-  // ---- S2
-  if constexpr (DEV) {
-    {
-      AccStats2N acc{A};
-      acc.init(cv, true);  // phases alternate direction: the tail of the previous pass is still in L2
-      stream_units<4, true>(geo, A.in, &A.sync->unit_counter[1], ssm, acc);
-      acc.flush();
-      if (blockIdx.x == 0) stamp(A, 14);
-      const float fz[4] = {0.f, 0.f, 0.f, 0.f};
-      nhwc_combine(cv, true, fz, fz, acc.sa, acc.sq, [&](unsigned c, float, float, double sa, double sq) {
-        atomicAdd(A.aabs + rep_base + c, sa);
-        atomicAdd(A.asq + rep_base + c, sq);
-      });
-    }
-    if (blockIdx.x == 0) stamp(A, 5);
-    if (grid_arrive(A.sync, epoch, &lsm.flag)) {
-      stamp(A, 6);
-      for (unsigned c = threadIdx.x; c < C; c += kThreads) {
-        double sabs = 0.0, ssq = 0.0;
-#pragma unroll 4
-        for (unsigned r = 0; r < A.nhwc_rep; ++r) {
-          const unsigned i = r * C + c;
-          sabs += ld_ws(A.aabs + i);
-          ssq += ld_ws(A.asq + i);
-          A.aabs[i] = 0.0;
-          A.asq[i] = 0.0;
-        }
-        A.gb[c] = static_cast<float>(sabs / n);
-        const double dm = A.gmean_d[c] - static_cast<double>(A.gmean[c]);
-        double ss = ssq - n * dm * dm;
-        if (ss < 0.0) ss = 0.0;
-        A.gstd[c] = static_cast<float>(sqrt(ss / (n - 1.0)));
-      }
-      __syncthreads();
-      solve_params(A, lsm);
-      stamp(A, 7);
-      grid_release(A.sync, epoch);
-    }
-    if (blockIdx.x == 0) stamp(A, 8);
-  }
-
-  // ---- A
-  if (!A.stats_only) {
-    if (LEAF == FQB200_LEAF_TORCH && A.hist) hist_clear(psm);
-    AccApplyN<LEAF> acc{A, psm};
-    acc.init(cv, !DEV);
-    stream_units<4, !DEV>(geo, A.in, &A.sync->unit_counter[2], ssm, acc);
-    if (LEAF == FQB200_LEAF_TORCH && A.hist) hist_flush(psm, A.hist);
-    if (blockIdx.x == 0) stamp(A, 9);
-  }
-  grid_exit(A.sync);
-}
+}  // namespace fqb
+#include "fq_cl.cuh"
+namespace fqb {
 
 // Standalone a1 with host-side scalars (gemmlowp.cu:30-45): flat grid-stride, parameters by value.
 template <int VEC, bool NOISE, bool FAST>
@@ -1439,23 +1142,40 @@ __global__ void fq_divtest_kernel(const float* a, const float* b, float* fast, f
 // ================================================================================================
 // host side: geometry, workspace carving, launches, C ABI
 // ================================================================================================
+#include <mutex>
+
 namespace {
 
 thread_local char g_err[512] = "";
-unsigned long long* g_dbg_timing = nullptr;  // development: see fqb200_debug_timing
 
 int fail(int code, const char* fmt, const char* detail = "") {
   snprintf(g_err, sizeof(g_err), fmt, detail);
   return code;
 }
 
+// channels-last kernel variants: leaf (torch / mid-tread) x second statistics pass x histogram
+const void* cl_kernel_ptr(int leaf, bool dev, bool hist) {
+#define FQB_CL(L, D, H) reinterpret_cast<const void*>(fqb::fq_cl_kernel<L, D, H>)
+  if (leaf == FQB200_LEAF_MIDTREAD) return dev ? FQB_CL(FQB200_LEAF_MIDTREAD, true, false) : FQB_CL(FQB200_LEAF_MIDTREAD, false, false);
+  if (hist) return dev ? FQB_CL(FQB200_LEAF_TORCH, true, true) : FQB_CL(FQB200_LEAF_TORCH, false, true);
+  return dev ? FQB_CL(FQB200_LEAF_TORCH, true, false) : FQB_CL(FQB200_LEAF_TORCH, false, false);
+#undef FQB_CL
+}
+size_t cl_smem(bool hist) {
+  return static_cast<size_t>(fqb::kStages) * fqb::kStageBytes + fqb::kClCombineBytes + (hist ? fqb::kWarps * 256u * sizeof(unsigned) : 0u);
+}
+size_t cl_given_smem() { return static_cast<size_t>(fqb::kStages) * fqb::kStageBytes; }
+
 struct DeviceInfo {
-  int device = -1;
+  int rc = FQB200_OK;      // result of the one-time initialisation
+  char err[256] = "";
   int sms = 0;
-  int resident = 0;  // CTAs of fq_fused_kernel<4> that fit at once
-  bool tables = false;
+  int resident = 0;        // CTAs of the cp.async-ring fused kernels (512 threads) that fit at once
+  int resident_cl[2] = {0, 0};  // channels-last kernels without / with the histogram
 };
-DeviceInfo g_dev[64];
+constexpr int kMaxDevices = 64;
+DeviceInfo g_dev[kMaxDevices];
+std::once_flag g_dev_once[kMaxDevices];
 
 // dynamic shared memory of a launch: the cp.async ring of the 128-bit path
 size_t dyn_smem(int vec) { return static_cast<size_t>(vec == 4 ? fqb::ring_bytes<4>() : fqb::ring_bytes<1>()); }
@@ -1479,13 +1199,6 @@ const void* fused_ptr1(int leaf, bool dev, bool corr) {
   if (leaf == FQB200_LEAF_TORCH) return fused_ptr2<MODE, FQB200_LEAF_TORCH>(dev, corr);
   if (leaf == FQB200_LEAF_COMPILED) return fused_ptr2<MODE, FQB200_LEAF_COMPILED>(dev, corr);
   return fused_ptr2<MODE, FQB200_LEAF_MIDTREAD>(dev, corr);
-}
-const void* nhwc_kernel_ptr(int leaf, bool dev) {
-  if (leaf == FQB200_LEAF_MIDTREAD)
-    return dev ? reinterpret_cast<const void*>(fqb::fq_fused_nhwc_kernel<FQB200_LEAF_MIDTREAD, true>)
-               : reinterpret_cast<const void*>(fqb::fq_fused_nhwc_kernel<FQB200_LEAF_MIDTREAD, false>);
-  return dev ? reinterpret_cast<const void*>(fqb::fq_fused_nhwc_kernel<FQB200_LEAF_TORCH, true>)
-             : reinterpret_cast<const void*>(fqb::fq_fused_nhwc_kernel<FQB200_LEAF_TORCH, false>);
 }
 const void* fused_kernel_ptr(int mode, int leaf, bool dev, bool corr) {
   if (mode == 4) return fused_ptr1<4>(leaf, dev, corr);
@@ -1511,86 +1224,114 @@ double laplace_opt_alpha(double w) {
   return a;
 }
 
+// One-time, per-device set-up (kernel attributes, occupancy, constant tables).  Runs under std::call_once: the reference's
+// callers include torch.nn.DataParallel worker threads, one per device.
+void init_device(int dev) {
+  DeviceInfo& d = g_dev[dev];
+  auto bad = [&](const char* what, cudaError_t e) {
+    d.rc = FQB200_ERR_CUDA;
+    snprintf(d.err, sizeof(d.err), "%s: %s", what, cudaGetErrorString(e));
+  };
+  int sms = 0, per_sm = 1 << 20;
+  cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return bad("cudaDeviceGetAttribute", e);
+  const int modes[3] = {4, 1, 8};
+  for (int mi = 0; mi < 3; ++mi)
+    for (int leaf = 0; leaf < 3; ++leaf)
+      for (int dv = 0; dv < 2; ++dv)
+        for (int cr = 0; cr < 2; ++cr) {
+          if (modes[mi] == 8 && cr) continue;
+          int n = 0;
+          const void* fn = fused_kernel_ptr(modes[mi], leaf, dv != 0, cr != 0);
+          const int smem = static_cast<int>(dyn_smem(modes[mi] == 1 ? 1 : 4));
+          e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+          if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kThreads, smem);
+          if (e != cudaSuccess) return bad("fused kernel setup", e);
+          if (n < per_sm) per_sm = n;
+        }
+  {
+    int n = 0;
+    const void* fn = reinterpret_cast<const void*>(fqb::fq_fused_kernel<4, FQB200_LEAF_COMPILED, false, false, true>);
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem(4)));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kThreads, dyn_smem(4));
+    if (e != cudaSuccess) return bad("bias-period kernel setup", e);
+    if (n < per_sm) per_sm = n;
+  }
+  if (per_sm < 1) {
+    d.rc = FQB200_ERR_CUDA;
+    snprintf(d.err, sizeof(d.err), "fused kernel does not fit on an SM");
+    return;
+  }
+  for (int hist = 0; hist < 2; ++hist) {
+    int worst = 1 << 20;
+    for (int leaf = 0; leaf < 3; leaf += 2)
+      for (int dv = 0; dv < 2; ++dv) {
+        if (hist && leaf == FQB200_LEAF_MIDTREAD) continue;
+        int n = 0;
+        const void* fn = cl_kernel_ptr(leaf, dv != 0, hist != 0);
+        const size_t smem = cl_smem(hist != 0);
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kBulkThreads, smem);
+        if (e != cudaSuccess) return bad("channels-last kernel setup", e);
+        if (n < worst) worst = n;
+      }
+    if (worst < 1) {
+      d.rc = FQB200_ERR_CUDA;
+      snprintf(d.err, sizeof(d.err), "channels-last kernel does not fit on an SM");
+      return;
+    }
+    d.resident_cl[hist] = sms * worst;
+  }
+  const void* given[4] = {reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, false>),
+                          reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, true>),
+                          reinterpret_cast<const void*>(fqb::fq_cl_given_kernel<false>),
+                          reinterpret_cast<const void*>(fqb::fq_cl_given_kernel<true>)};
+  for (int i = 0; i < 4; ++i) {
+    e = cudaFuncSetAttribute(given[i], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(i < 2 ? dyn_smem(4) : cl_given_smem()));
+    if (e != cudaSuccess) return bad("given-parameter kernel setup", e);
+  }
+  // mid-tread table (int_quantizer.py:41-51): omega grid = 5 decades x 20 steps, leading 0
+  double om[fqb::kTable], al[fqb::kTable];
+  om[0] = 0.0;
+  al[0] = 0.0;
+  const double lo[5] = {0.01, 0.1, 1, 10, 100}, hi[5] = {0.1, 1, 10, 100, 1000};
+  for (int dcd = 0; dcd < 5; ++dcd)
+    for (int k = 0; k < 20; ++k) {
+      const double w = lo[dcd] + (hi[dcd] - lo[dcd]) * k / 20.0;
+      om[1 + dcd * 20 + k] = w;
+      al[1 + dcd * 20 + k] = laplace_opt_alpha(w);
+    }
+  e = cudaMemcpyToSymbol(fqb::kOmegaTable, om, sizeof(om));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(fqb::kAlphaTable, al, sizeof(al));
+  if (e != cudaSuccess) return bad("table upload", e);
+  d.sms = sms;
+  d.resident = sms * per_sm;
+}
+
 int get_device(DeviceInfo** out) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
-  if (dev < 0 || dev >= 64) return fail(FQB200_ERR_UNSUPPORTED, "device index out of range%s");
+  if (dev < 0 || dev >= kMaxDevices) return fail(FQB200_ERR_UNSUPPORTED, "device index out of range%s");
+  std::call_once(g_dev_once[dev], init_device, dev);
   DeviceInfo& d = g_dev[dev];
-  if (d.device != dev) {
-    int sms = 0, per_sm = 0;
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
-    per_sm = 1 << 20;
-    const int modes[3] = {4, 1, 8};
-    for (int mi = 0; mi < 3; ++mi)
-      for (int leaf = 0; leaf < 3; ++leaf)
-        for (int dv = 0; dv < 2; ++dv)
-          for (int cr = 0; cr < 2; ++cr) {
-            if (modes[mi] == 8 && cr) continue;
-            int n = 0;
-            const void* fn = fused_kernel_ptr(modes[mi], leaf, dv != 0, cr != 0);
-            const int smem = static_cast<int>(dyn_smem(modes[mi] == 1 ? 1 : 4));
-            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kThreads, smem);
-            if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
-            if (n < per_sm) per_sm = n;
-          }
-    {
-      int n = 0;
-      const void* fn = reinterpret_cast<const void*>(fqb::fq_fused_kernel<4, FQB200_LEAF_COMPILED, false, false, true>);
-      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem(4)));
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kThreads, dyn_smem(4));
-      if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "bias-period kernel setup: %s", cudaGetErrorString(e));
-      if (n < per_sm) per_sm = n;
-    }
-    for (int leaf = 0; leaf < 3; leaf += 2)
-      for (int dv = 0; dv < 2; ++dv) {
-        int n = 0;
-        const void* fn = nhwc_kernel_ptr(leaf, dv != 0);
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem(4)));
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kThreads, dyn_smem(4));
-        if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "channels-last kernel setup: %s", cudaGetErrorString(e));
-        if (n < per_sm) per_sm = n;
-      }
-    if (per_sm < 1) return fail(FQB200_ERR_CUDA, "fused kernel does not fit on an SM%s");
-    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, false>),
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem(4)));
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, true>),
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem(4)));
-    if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    // mid-tread table (int_quantizer.py:41-51): omega grid = 5 decades x 20 steps, leading 0
-    double om[fqb::kTable], al[fqb::kTable];
-    om[0] = 0.0;
-    al[0] = 0.0;
-    const double lo[5] = {0.01, 0.1, 1, 10, 100}, hi[5] = {0.1, 1, 10, 100, 1000};
-    for (int dcd = 0; dcd < 5; ++dcd)
-      for (int k = 0; k < 20; ++k) {
-        const double w = lo[dcd] + (hi[dcd] - lo[dcd]) * k / 20.0;
-        om[1 + dcd * 20 + k] = w;
-        al[1 + dcd * 20 + k] = laplace_opt_alpha(w);
-      }
-    e = cudaMemcpyToSymbol(fqb::kOmegaTable, om, sizeof(om));
-    if (e == cudaSuccess) e = cudaMemcpyToSymbol(fqb::kAlphaTable, al, sizeof(al));
-    if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "table upload: %s", cudaGetErrorString(e));
-    d.sms = sms;
-    d.resident = sms * per_sm;
-    d.device = dev;
-  }
+  if (d.rc != FQB200_OK) return fail(d.rc, "device set-up failed: %s", d.err);
   *out = &d;
   return FQB200_OK;
 }
 
 struct Plan {
   fqb::Geometry geo;
+  fqb::FlatGeo flat;
   int vec;   // 4 or 1: floats per access
-  int mode;  // 4, 1, or 8 (bundled 128-bit path)
+  int mode;  // 4, 1, 8 (bundled 128-bit path) or 2 (flat stream on the bulk-copy engine)
   int grid;
 };
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr uint64_t kUnitsPerCta = 8;  // dynamic work units per resident CTA (flat above 8: profiles/README.md, round 1)
 
 // Choose the access mode (128-bit, bundled 128-bit, scalar), the number of parts per group (unit size) and the grid
 // size; fill the geometry.
@@ -1618,11 +1359,10 @@ int make_plan(int64_t outer, int64_t groups, int64_t inner, bool can_vec, bool a
   const uint64_t total_v = group_v * G;
   if (total_v >= (1ULL << 32)) return fail(FQB200_ERR_UNSUPPORTED, "tensors of 2^32 vectors (64 GB) and more are not supported%s");
   const uint64_t ctas = static_cast<uint64_t>(max_ctas);
-  // Units: about `per_cta` per CTA so that dynamic assignment can even out the CTAs' unequal speeds, but no
+  // Units: about kUnitsPerCta per CTA so that dynamic assignment can even out the CTAs' unequal speeds, but no
   // smaller than one full ring (kRingDepth sweeps of the CTA) when the group allows it.
-  static const uint64_t per_cta = getenv("FQB_UNITS_PER_CTA") ? strtoull(getenv("FQB_UNITS_PER_CTA"), nullptr, 10) : 8;  // development knob
   const uint64_t min_unit_v = static_cast<uint64_t>(fqb::kRingDepth) * stride;
-  uint64_t parts = (per_cta * ctas + G - 1) / G;
+  uint64_t parts = (kUnitsPerCta * ctas + G - 1) / G;
   const uint64_t max_parts = group_v / min_unit_v > 0 ? group_v / min_unit_v : 1;
   if (parts > max_parts) parts = max_parts;
   if (parts < 1) parts = 1;
@@ -1655,43 +1395,39 @@ int make_plan(int64_t outer, int64_t groups, int64_t inner, bool can_vec, bool a
   return FQB200_OK;
 }
 
-// channels-last plan: the tensor [outer][inner][groups] (groups fastest) as ONE flat stream of outer*inner*groups/4
-// vectors; every thread keeps its column (= its four channels) as long as groups/4 divides the CTA width and every
-// unit starts on a multiple of the CTA width.
-int make_plan_nhwc(int64_t outer, int64_t groups, int64_t inner, int max_ctas, Plan* pl) {
-  if (outer <= 0 || groups <= 0 || inner <= 0) return fail(FQB200_ERR_INVALID, "non-positive tensor extent%s");
-  const uint64_t cv = static_cast<uint64_t>(groups) / 4;
-  if (groups % 4 != 0 || cv == 0 || fqb::kThreads % cv != 0 || static_cast<uint64_t>(groups) > fqb::kMaxNhwcChannels)
-    return fail(FQB200_ERR_UNSUPPORTED, "channels-last needs C %% 4 == 0, C/4 dividing 512 and C <= 4096%s");
-  const uint64_t total_v = static_cast<uint64_t>(outer) * static_cast<uint64_t>(inner) * cv;
+// flat-stream plan (bulk-copy engine): `elems` contiguous floats, channel period `channels` (0: no per-channel state).
+// A stage is kStageVec * stride vectors with stride the largest multiple of channels/4 that fits in the 512 consumer
+// threads, so that a thread always sees the same four channels; units are runs of stages, about kUnitsPerCta per CTA.
+bool flat_eligible(int64_t channels) { return channels % 4 == 0 && channels / 4 >= 1 && channels / 4 <= fqb::kConsumers; }
+
+int make_plan_flat(uint64_t elems, int64_t channels, int max_ctas, Plan* pl) {
+  if (elems == 0 || elems % 4 != 0) return fail(FQB200_ERR_UNSUPPORTED, "flat stream needs a multiple of 4 elements%s");
+  const uint64_t total_v = elems / 4;
   if (total_v >= (1ULL << 32)) return fail(FQB200_ERR_UNSUPPORTED, "tensors of 2^32 vectors (64 GB) and more are not supported%s");
+  const uint64_t cv = channels > 0 ? static_cast<uint64_t>(channels) / 4 : 1;
+  if (channels > 0 && !flat_eligible(channels)) return fail(FQB200_ERR_UNSUPPORTED, "channels-last needs C %% 4 == 0 and C <= 2048%s");
+  const uint64_t stride = (fqb::kConsumers / cv) * cv;
+  const uint64_t stage_v = static_cast<uint64_t>(fqb::kStageVec) * stride;
+  const uint64_t n_stages = (total_v + stage_v - 1) / stage_v;
   const uint64_t ctas = static_cast<uint64_t>(max_ctas);
-  static const uint64_t per_cta = getenv("FQB_UNITS_PER_CTA") ? strtoull(getenv("FQB_UNITS_PER_CTA"), nullptr, 10) : 8;
-  const uint64_t quantum = static_cast<uint64_t>(fqb::kThreads);
-  const uint64_t min_unit_v = static_cast<uint64_t>(fqb::kRingDepth) * quantum;
-  uint64_t parts = per_cta * ctas;
-  const uint64_t max_parts = total_v / min_unit_v > 0 ? total_v / min_unit_v : 1;
-  if (parts > max_parts) parts = max_parts;
-  uint64_t part_v = (total_v + parts - 1) / parts;
-  part_v = (part_v + quantum - 1) / quantum * quantum;
-  parts = (total_v + part_v - 1) / part_v;
-  fqb::Geometry& g = pl->geo;
-  g.groups = 1;
-  g.channels = static_cast<unsigned>(groups);
-  g.bundle = 1;
-  g.stride = fqb::kThreads;
-  g.parts = static_cast<unsigned>(parts);
-  g.units = static_cast<unsigned>(parts);
-  g.inner_v = static_cast<unsigned>(total_v);
-  g.step_q = 0;
-  g.step_r = static_cast<unsigned>(fqb::kThreads % total_v);
-  g.red_lanes = 1;
-  g.part_v = static_cast<unsigned>(part_v);
-  g.group_v = total_v;
-  g.row_pitch = total_v;
+  uint64_t unit_stages = n_stages / (kUnitsPerCta * ctas);
+  if (unit_stages < 1) unit_stages = 1;
+  if (unit_stages > 64) unit_stages = 64;
+  const uint64_t units = (n_stages + unit_stages - 1) / unit_stages;
+  fqb::FlatGeo& g = pl->flat;
+  g.total_v = static_cast<unsigned>(total_v);
+  g.stride = static_cast<unsigned>(stride);
+  g.stage_v = static_cast<unsigned>(stage_v);
+  g.n_stages = static_cast<unsigned>(n_stages);
+  g.unit_stages = static_cast<unsigned>(unit_stages);
+  g.units = static_cast<unsigned>(units);
+  g.channels = static_cast<unsigned>(channels > 0 ? channels : 0);
+  g.cv = static_cast<unsigned>(cv);
+  memset(&pl->geo, 0, sizeof(pl->geo));
+  pl->geo.channels = g.channels;  // solve_bit_alloc reads the channel count here
   pl->vec = 4;
   pl->mode = 2;
-  pl->grid = static_cast<int>(parts < ctas ? parts : ctas);
+  pl->grid = static_cast<int>(units < ctas ? units : ctas);
   return FQB200_OK;
 }
 
@@ -1706,9 +1442,9 @@ size_t carve(char* base, uint64_t slots, uint64_t groups, fqb::FusedArgs* A) {
     return p;
   };
   char* sync = take(sizeof(fqb::GridSync));
-  // channels-last accumulators: fixed place and size so that no other launch ever writes there (they must stay zero)
-  char* acc_u = take(2 * fqb::kMaxNhwcChannels * sizeof(unsigned));
-  char* acc_d = take(3 * fqb::kMaxNhwcChannels * sizeof(double));
+  // channels-last accumulators, two banks (fq_cl.cuh): fixed place and size, zero between launches
+  char* acc_u = take(2 * fqb::kAccU * sizeof(unsigned));
+  char* acc_d = take(2 * fqb::kAccD * sizeof(double));
   char* pmin = take(slots * sizeof(float));
   char* pmax = take(slots * sizeof(float));
   char* psum = take((slots + 2 * groups) * sizeof(double));
@@ -1739,11 +1475,11 @@ size_t carve(char* base, uint64_t slots, uint64_t groups, fqb::FusedArgs* A) {
     A->ck = f + 11 * groups;
     A->gmean_d = reinterpret_cast<double*>(gd);
     A->lp = reinterpret_cast<fqb::LeafParam*>(lp);
-    A->amin_inv = reinterpret_cast<unsigned*>(acc_u);
-    A->amax = A->amin_inv + fqb::kMaxNhwcChannels;
-    A->asum = reinterpret_cast<double*>(acc_d);
-    A->aabs = A->asum + fqb::kMaxNhwcChannels;
-    A->asq = A->aabs + fqb::kMaxNhwcChannels;
+    A->amin_inv = reinterpret_cast<unsigned*>(acc_u);  // bank 0; bank b at + b * kAccU (fq_cl.cuh: cl_view)
+    A->amax = nullptr;
+    A->asum = reinterpret_cast<double*>(acc_d);        // bank 0; bank b at + b * kAccD
+    A->aabs = nullptr;
+    A->asq = nullptr;
   }
   return off;
 }
@@ -1761,6 +1497,18 @@ int check_desc(const fqb200_desc* d) {
   if ((d->bias_corr || d->var_corr) && d->scope == FQB200_SCOPE_GROUP_MEAN)
     return fail(FQB200_ERR_UNSUPPORTED, "weight correction is per row (scope GROUP or TENSOR)%s");
   return FQB200_OK;
+}
+
+// what the channels-last kernel can take (everything else with channels_last set is an error: the caller re-lays out)
+bool cl_supported(const fqb200_desc* d) {
+  return d->scope == FQB200_SCOPE_GROUP && d->leaf != FQB200_LEAF_COMPILED && !d->bias_corr && !d->var_corr && d->bias_period <= 0 &&
+         flat_eligible(d->groups) && !(d->out_hist && d->leaf != FQB200_LEAF_TORCH);
+}
+// phase S2 (sum |x - mean|) of the channels-last kernel: only where the Laplace b is consumed
+bool cl_needs_b(const fqb200_desc* d) {
+  const bool alloc = d->bit_alloc && d->num_bits <= 4 && d->leaf != FQB200_LEAF_MIDTREAD;
+  return d->range_mode == FQB200_RANGE_LAPLACE || (d->leaf == FQB200_LEAF_MIDTREAD && d->mt_clip) ||
+         (alloc && d->bit_alloc_prior == FQB200_PRIOR_B) || d->stats_only || d->out_stats != nullptr;
 }
 
 }  // namespace
@@ -1795,10 +1543,37 @@ size_t fqb200_workspace_bytes(const fqb200_desc* d) {
 }
 
 int fqb200_workspace_init(void* workspace, size_t bytes, void* stream) {
-  const size_t head = carve(nullptr, 0, 0, nullptr);  // barrier words + channels-last accumulators
+  const size_t head = carve(nullptr, 0, 0, nullptr);  // barrier words + channels-last accumulator banks
   if (!workspace || bytes < head) return fail(FQB200_ERR_WORKSPACE, "workspace too small%s");
   cudaError_t e = cudaMemsetAsync(workspace, 0, head, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  return FQB200_OK;
+}
+
+int fqb200_plan_info(const fqb200_desc* d, int64_t* out8) {
+  g_err[0] = 0;
+  int rc = check_desc(d);
+  if (rc != FQB200_OK) return rc;
+  if (!out8) return fail(FQB200_ERR_INVALID, "null output%s");
+  DeviceInfo* di = nullptr;
+  int resident = 148 * fqb::kCtasPerSm, resident_cl = 148 * fqb::kCtasPerSm;
+  if (get_device(&di) == FQB200_OK) {
+    resident = di->resident;
+    resident_cl = di->resident_cl[d->out_hist ? 1 : 0];
+  }
+  Plan pl;
+  if (d->channels_last) {
+    if (!cl_supported(d)) return fail(FQB200_ERR_UNSUPPORTED, "channels_last: per-channel torch / mid-tread leaves, C %% 4 == 0, C <= 2048%s");
+    rc = make_plan_flat(static_cast<uint64_t>(d->outer) * d->groups * d->inner, d->groups, resident_cl, &pl);
+    if (rc != FQB200_OK) return rc;
+    out8[0] = 2; out8[1] = pl.grid; out8[2] = pl.flat.units; out8[3] = pl.flat.unit_stages; out8[4] = pl.flat.stage_v;
+    out8[5] = pl.flat.stride; out8[6] = fqb::kStages; out8[7] = cl_needs_b(d) ? 3 : 2;
+    return FQB200_OK;
+  }
+  rc = make_plan(d->outer, d->groups, d->inner, true, !(d->bias_corr || d->var_corr), resident, &pl);
+  if (rc != FQB200_OK) return rc;
+  out8[0] = pl.mode; out8[1] = pl.grid; out8[2] = pl.geo.units; out8[3] = pl.geo.parts; out8[4] = pl.geo.part_v;
+  out8[5] = pl.geo.stride; out8[6] = fqb::kRingDepth; out8[7] = pl.geo.red_lanes;
   return FQB200_OK;
 }
 
@@ -1853,7 +1628,7 @@ int fqb200_float2gemmlowp(const float* in, float* out, int64_t n, float range, f
 
 int fqb200_quantize1(const float* in, float* out, float* grid, int64_t outer, int64_t groups, int64_t inner,
                      const float* delta, const float* offset, const float* bits, int per_group, int num_bits,
-                     const float* bias, void* stream) {
+                     const float* bias, int channels_last, void* stream) {
   g_err[0] = 0;
   if (outer == 0 || groups == 0 || inner == 0) return FQB200_OK;
   if (!in || !out || !delta || !offset) return fail(FQB200_ERR_INVALID, "null pointer%s");
@@ -1866,11 +1641,8 @@ int fqb200_quantize1(const float* in, float* out, float* grid, int64_t outer, in
   if (rc != FQB200_OK) return rc;
   Plan pl;
   const bool can_vec = aligned16(in) && aligned16(out) && (!grid || aligned16(grid));
-  rc = make_plan(outer, groups, inner, can_vec, false, di->resident * 2, &pl);
-  if (rc != FQB200_OK) return rc;
   fqb::FusedArgs A;
   memset(&A, 0, sizeof(A));
-  A.geo = pl.geo;
   A.in = in;
   A.out = out;
   A.grid_out = grid;
@@ -1882,6 +1654,26 @@ int fqb200_quantize1(const float* in, float* out, float* grid, int64_t outer, in
   A.given_per_group = per_group;
   A.bias = bias;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint64_t elems = static_cast<uint64_t>(outer) * static_cast<uint64_t>(groups) * static_cast<uint64_t>(inner);
+  // flat streams on the bulk-copy engine: channels-last per-channel parameters, or one parameter set for the whole tensor
+  const bool flat_cl = channels_last && per_group;
+  const bool flat_tensor = !per_group && !bias;
+  if (channels_last && !per_group && bias) return fail(FQB200_ERR_UNSUPPORTED, "channels_last with one parameter set takes no bias%s");
+  if (flat_cl && !(can_vec && flat_eligible(groups)))
+    return fail(FQB200_ERR_UNSUPPORTED, "channels_last needs 16-byte aligned tensors, C %% 4 == 0 and C <= 2048%s");
+  if (flat_cl || (flat_tensor && can_vec && elems % 4 == 0)) {
+    rc = make_plan_flat(elems, flat_cl ? groups : 0, di->resident_cl[0] * 2, &pl);
+    if (rc != FQB200_OK) return rc;
+    A.flat = pl.flat;
+    if (grid) fqb::fq_cl_given_kernel<true><<<pl.grid, fqb::kBulkThreads, cl_given_smem(), st>>>(A);
+    else      fqb::fq_cl_given_kernel<false><<<pl.grid, fqb::kBulkThreads, cl_given_smem(), st>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "launch fq_cl_given_kernel: %s", cudaGetErrorString(e));
+    return FQB200_OK;
+  }
+  rc = make_plan(outer, groups, inner, can_vec, false, di->resident * 2, &pl);
+  if (rc != FQB200_OK) return rc;
+  A.geo = pl.geo;
   if (pl.vec == 4) {
     if (grid) fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, true><<<pl.grid, fqb::kThreads, dyn_smem(4), st>>>(A);
     else      fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, false><<<pl.grid, fqb::kThreads, dyn_smem(4), st>>>(A);
@@ -1911,10 +1703,9 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
     return fail(FQB200_ERR_UNSUPPORTED, "a per-group bias needs groups = channels (scope GROUP or TENSOR); use bias_period%s");
   const bool can_vec = aligned16(in) && (d->stats_only || aligned16(out));
   if (d->channels_last) {
-    if (!can_vec || d->scope != FQB200_SCOPE_GROUP || d->leaf == FQB200_LEAF_COMPILED || d->bias_corr || d->var_corr ||
-        d->bias_period > 0)
-      return fail(FQB200_ERR_UNSUPPORTED, "channels_last: per-channel torch / mid-tread leaves on aligned tensors only%s");
-    rc = make_plan_nhwc(d->outer, d->groups, d->inner, di->resident, &pl);
+    if (!can_vec || !cl_supported(d))
+      return fail(FQB200_ERR_UNSUPPORTED, "channels_last: per-channel torch / mid-tread leaves on 16-byte aligned tensors, C %% 4 == 0, C <= 2048%s");
+    rc = make_plan_flat(static_cast<uint64_t>(d->outer) * d->groups * d->inner, d->groups, di->resident_cl[d->out_hist ? 1 : 0], &pl);
   } else {
     rc = make_plan(d->outer, d->groups, d->inner, can_vec, !(d->bias_corr || d->var_corr), di->resident, &pl);
   }
@@ -1928,6 +1719,7 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   if (!aligned16(workspace)) return fail(FQB200_ERR_WORKSPACE, "workspace must be 16-byte aligned%s");
   carve(static_cast<char*>(workspace), slots, pl.geo.channels, &A);
   A.geo = pl.geo;
+  A.flat = pl.flat;
   A.in = in;
   A.out = out;
   A.scope = d->scope;
@@ -1949,6 +1741,7 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   A.out_stats = d->out_stats;
   A.bias = d->bias;
   A.hist = d->out_hist;
+  A.dbg = d->debug_stamps;
   if (d->out_hist && d->leaf != FQB200_LEAF_TORCH) return fail(FQB200_ERR_UNSUPPORTED, "out_hist: torch leaf only%s");
   A.bias_magic = 0;
   if (d->bias && d->bias_period > 0) {
@@ -1960,47 +1753,34 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
       return fail(FQB200_ERR_UNSUPPORTED, "bias_period does not fit this layout%s");
     A.bias_magic = ((1ull << 40) + pv - 1) / pv;
   }
-  A.dbg = g_dbg_timing;
-  A.nhwc_rep = 1;
-  if (pl.mode == 2) {
-    const unsigned r = fqb::kMaxNhwcChannels / static_cast<unsigned>(d->groups);
-    A.nhwc_rep = r < 1u ? 1u : (r > 8u ? 8u : r);
-  }
   A.inner = static_cast<unsigned>(d->inner);
   A.n_per_group = static_cast<double>(d->outer) * static_cast<double>(d->inner);
-  const bool alloc = d->bit_alloc && d->num_bits <= 4 && d->scope == FQB200_SCOPE_GROUP && d->leaf != FQB200_LEAF_MIDTREAD;
-  A.need_dev = (d->range_mode != FQB200_RANGE_MINMAX) || alloc || d->var_corr || d->leaf == FQB200_LEAF_MIDTREAD ||
-               (d->stats_only ? 1 : 0);
   void* args[] = {&A};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
+  if (pl.mode == 2) {
+    // replicas of the per-channel accumulators: CTA b adds into replica b % rep (same-address atomics serialise in L2)
+    const unsigned r = fqb::kMaxNhwcChannels / static_cast<unsigned>(d->groups);
+    A.nhwc_rep = r < 1u ? 1u : (r > 8u ? 8u : r);
+    A.need_dev = cl_needs_b(d) ? 1 : 0;
+    const bool hist = d->out_hist != nullptr;
+    e = cudaLaunchCooperativeKernel(cl_kernel_ptr(d->leaf, A.need_dev != 0, hist), dim3(pl.grid), dim3(fqb::kBulkThreads), args,
+                                    cl_smem(hist), st);
+    if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cooperative launch fq_cl_kernel: %s", cudaGetErrorString(e));
+    return FQB200_OK;
+  }
+  A.nhwc_rep = 1;
+  const bool alloc = d->bit_alloc && d->num_bits <= 4 && d->scope == FQB200_SCOPE_GROUP && d->leaf != FQB200_LEAF_MIDTREAD;
+  A.need_dev = (d->range_mode != FQB200_RANGE_MINMAX) || alloc || d->var_corr || d->leaf == FQB200_LEAF_MIDTREAD ||
+               (d->stats_only ? 1 : 0);
   const void* kernel = A.bias_magic ? reinterpret_cast<const void*>(fqb::fq_fused_kernel<4, FQB200_LEAF_COMPILED, false, false, true>)
-                       : pl.mode == 2 ? nhwc_kernel_ptr(d->leaf, A.need_dev != 0)
-                                      : fused_kernel_ptr(pl.mode, d->leaf, A.need_dev != 0, d->bias_corr || d->var_corr);
-  e = cudaLaunchCooperativeKernel(kernel, dim3(pl.grid),
-                                  dim3(fqb::kThreads), args, dyn_smem(pl.vec), st);
+                                    : fused_kernel_ptr(pl.mode, d->leaf, A.need_dev != 0, d->bias_corr || d->var_corr);
+  e = cudaLaunchCooperativeKernel(kernel, dim3(pl.grid), dim3(fqb::kThreads), args, dyn_smem(pl.vec), st);
   if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cooperative launch fq_fused_kernel: %s", cudaGetErrorString(e));
   return FQB200_OK;
 }
 
-// development hook: device buffer of 16 u64 that the next fused launches stamp with %globaltimer at phase boundaries
-int fqb200_debug_timing(unsigned long long* dev_buf) {
-  g_dbg_timing = dev_buf;
-  return FQB200_OK;
-}
-
-// development hook (not part of the drop-in surface): the item shape make_plan picks for a layout
-int fqb200_debug_plan(int64_t outer, int64_t groups, int64_t inner, int max_ctas, int64_t* out6) {
-  Plan pl;
-  int rc = make_plan(outer, groups, inner, true, true, max_ctas, &pl);
-  if (rc != FQB200_OK) return rc;
-  out6[0] = pl.mode; out6[1] = pl.grid; out6[2] = pl.geo.parts; out6[3] = pl.geo.red_lanes; out6[4] = pl.geo.units;
-  out6[5] = static_cast<int64_t>((pl.geo.group_v + pl.geo.parts - 1) / pl.geo.parts);
-  return FQB200_OK;
-}
-
-// test hook (not part of the drop-in surface): compares div_exact with IEEE division on the device
-int fqb200_test_division(const float* a, const float* b, float* fast, float* ieee, int64_t n, void* stream) {
+int fqb200_selftest_division(const float* a, const float* b, float* fast, float* ieee, int64_t n, void* stream) {
   if (n <= 0) return FQB200_OK;
   fqb::fq_divtest_kernel<<<296, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, fast, ieee, static_cast<unsigned long long>(n));
   cudaError_t e = cudaGetLastError();

@@ -98,6 +98,10 @@ class IntQuantizer(object):
         # The manager switches it on for activation tags, where the un-quantized tensor is dead after the hook.
         self.inplace = False
         self.last_entropy = None  # 0-d device tensor of the most recent `-me` measurement
+        # diagnostics (default off): keep the [groups, 12] statistics / parameter table of the most recent fused launch
+        # (columns _lib.STAT_COLUMNS) in ``last_stats`` - what the parity tests compare with the reference's values
+        self.export_stats = False
+        self.last_stats = None
 
     # ------------------------------------------------------------------------------------------
     # dispatch (int_quantizer.py:92-122)
@@ -182,12 +186,9 @@ class IntQuantizer(object):
 
     @staticmethod
     def _channels_last(tensor):
-        """An NCHW-shaped activation stored NHWC that the channels-last kernels take as is (else it is made
-        NCHW-contiguous first, like every other strided input)."""
-        if tensor.dim() != 4 or tensor.is_contiguous() or not tensor.is_contiguous(memory_format=torch.channels_last):
-            return False
-        c = tensor.shape[1]
-        return c % 4 == 0 and c <= 4096 and 512 % (c // 4) == 0
+        """An NCHW-shaped activation stored NHWC that the channels-last kernels take as is: C % 4 == 0, C <= 2048 (else it
+        is made NCHW-contiguous first, like every other strided input)."""
+        return ops.cl_eligible(tensor)
 
     # `-me` (SURVEY.md 8f rank 3): the apply phase histograms the integer grid into 256 counters; the Shannon entropy of
     # utils/entropy.py:6-17 (which runs torch.unique over the whole tensor) is a 256-element computation afterwards
@@ -223,6 +224,13 @@ class IntQuantizer(object):
 
     def _prior(self):
         return L.PRIOR_STD if self.bit_alloc_prior == "gaus" else L.PRIOR_B
+
+    def _fused(self, tensor, layout, **kw):
+        """ops.fused, keeping the exported statistics table when ``export_stats`` is set."""
+        if not self.export_stats:
+            return ops.fused(tensor, layout, **kw)
+        res, self.last_stats = ops.fused(tensor, layout, want_stats=True, **kw)
+        return res
 
     # ------------------------------------------------------------------------------------------
     # offline statistics (`-sm use`): every tensor becomes "mode A" - parameters known up front, one read + one write
@@ -308,14 +316,14 @@ class IntQuantizer(object):
         mode, k = self._range_mode(clip_type)
         if self._pc_act(tensor) and tensor.shape[1] > 1:
             hist = self._hist(tensor)  # the reference measures entropy in gemmlowpQuantizeActivationPerChannel (:442-445)
-            res = ops.fused(tensor, self._nchw_layout(tensor), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
+            res = self._fused(tensor, self._nchw_layout(tensor), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
                             leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(),
                             bit_alloc=self.bit_alloc_act, bit_alloc_prior=self._prior(),
                             bit_alloc_round=self.bit_alloc_round, bit_alloc_target=self.bit_alloc_target_act,
                             bias=bias, out=self._out(tensor), hist=hist, channels_last=self._channels_last(tensor))
             self._log_entropy(hist, id, "avg.entropy.act", tensor.numel())
             return res
-        return ops.fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
+        return self._fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
                          leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(), solve_f64=True,
                          out=self._out(tensor), any_dense_format=True)
 
@@ -343,17 +351,17 @@ class IntQuantizer(object):
             kw.update(bias=bias, bias_period=tensor.shape[2] * tensor.shape[3])
         if weight_correction is not None and any(weight_correction):
             rows = tensor.shape[0]
-            return ops.fused(tensor, (1, rows, tensor.numel() // rows), scope=L.SCOPE_TENSOR,
+            return self._fused(tensor, (1, rows, tensor.numel() // rows), scope=L.SCOPE_TENSOR,
                              bias_corr=weight_correction[0], var_corr=weight_correction[1], **kw)
         n = tensor.shape[0]
         kw["any_dense_format"] = bias is None  # min / max and a scalar apply do not care about the order inside a sample
         if avg:
-            return ops.fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_GROUP_MEAN, out=self._out(tensor), **kw)
+            return self._fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_GROUP_MEAN, out=self._out(tensor), **kw)
         if bias is not None:
             # rows = samples so that the channel of an element is its column / (H*W); the global min / max is the
             # min / max of the per-row ones (scope TENSOR): identical to the flat per-tensor reduction
-            return ops.fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_TENSOR, out=self._out(tensor), **kw)
-        return ops.fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, out=self._out(tensor), **kw)
+            return self._fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_TENSOR, out=self._out(tensor), **kw)
+        return self._fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, out=self._out(tensor), **kw)
 
     def gemmlowpQuantizeActivationPerChannel(self, tensor, id, tag="", stat_id=None, min_=None, max_=None, bias=None):
         """Per-channel min/max (0 lower bound when positive) with optional bit allocation, int_quantizer.py:409-451."""
@@ -376,7 +384,7 @@ class IntQuantizer(object):
                                  out=self._out(tensor))
         if min_ is None and max_ is None:
             hist = self._hist(tensor)
-            res = ops.fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
+            res = self._fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
                             num_bits=self.num_bits, positive=self._positive(), bit_alloc=self.bit_alloc_act,
                             bit_alloc_prior=self._prior(), bit_alloc_round=self.bit_alloc_round,
                             bit_alloc_target=self.bit_alloc_target_act, bias=bias, out=self._out(tensor), hist=hist,
@@ -418,7 +426,7 @@ class IntQuantizer(object):
             return ops.quantize1(tensor, mx - mn, mn, self.num_bits, bits=bits, layout=layout)
         bc, vc = weight_correction if weight_correction is not None else (False, False)
         hist = self._hist(tensor)
-        res = ops.fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
+        res = self._fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
                         num_bits=self.num_bits, positive=False, bit_alloc=self.bit_alloc_weight,
                         bit_alloc_prior=L.PRIOR_STD, bit_alloc_round=self.bit_alloc_round,
                         bit_alloc_target=self.bit_alloc_target_weight, bias_corr=bc, var_corr=vc, hist=hist)
@@ -429,7 +437,7 @@ class IntQuantizer(object):
     def mid_tread_quantize_weights_per_channel(self, tensor, id, weight_correction=None):
         rows = tensor.shape[0]
         bc, vc = weight_correction if weight_correction is not None else (False, False)
-        return ops.fused(tensor, (1, rows, tensor.numel() // rows), leaf=L.LEAF_MIDTREAD, positive=False,
+        return self._fused(tensor, (1, rows, tensor.numel() // rows), leaf=L.LEAF_MIDTREAD, positive=False,
                          mt_target=self.bit_alloc_target_weight, mt_clip=False, bias_corr=bc, var_corr=vc)
 
     def mid_tread_quantize_activation(self, tensor, id, bias=None):
@@ -437,17 +445,17 @@ class IntQuantizer(object):
             return self.mid_tread_quantize_activation_per_channel(tensor, id, bias=bias)
         if bias is not None:
             tensor = tensor + bias.view((1, -1) + (1,) * (tensor.dim() - 2))
-        return ops.fused(tensor, (1, 1, tensor.numel()), leaf=L.LEAF_MIDTREAD, positive=self._positive(),
+        return self._fused(tensor, (1, 1, tensor.numel()), leaf=L.LEAF_MIDTREAD, positive=self._positive(),
                          mt_target=self.bit_alloc_target_act, mt_clip=True, out=self._out(tensor))
 
     def mid_tread_quantize_activation_per_channel(self, tensor, id, bias=None):
-        return ops.fused(tensor, self._nchw_layout(tensor), leaf=L.LEAF_MIDTREAD, positive=self._positive(),
+        return self._fused(tensor, self._nchw_layout(tensor), leaf=L.LEAF_MIDTREAD, positive=self._positive(),
                          mt_target=self.bit_alloc_target_act, mt_clip=True, bias=bias, out=self._out(tensor),
                          channels_last=self._channels_last(tensor))
 
     def mid_tread_quantization(self, tensor, id, target, clip=False, sym=True):
         """[R, K] view, int_quantizer.py:185-225.  Returns (quantized, None) like the reference without entropy."""
-        out = ops.fused(tensor, (1, tensor.shape[0], tensor.numel() // tensor.shape[0]), leaf=L.LEAF_MIDTREAD,
+        out = self._fused(tensor, (1, tensor.shape[0], tensor.numel() // tensor.shape[0]), leaf=L.LEAF_MIDTREAD,
                         positive=not sym, mt_target=target, mt_clip=clip)
         return out, None
 

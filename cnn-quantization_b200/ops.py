@@ -78,6 +78,44 @@ def _workspace(device, stream, nbytes):
     return ws
 
 
+def _dense(t):
+    return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
+
+
+def cl_eligible(x, layout=None):
+    """True when ``x`` is an NCHW-shaped activation stored channels-last that the flat-stream kernels take as it is:
+    C % 4 == 0, C <= 2048 (``layout``, when given, must be its (N, C, H*W) view)."""
+    if x.dim() != 4 or x.is_contiguous() or not x.is_contiguous(memory_format=torch.channels_last):
+        return False
+    n, c = x.shape[0], x.shape[1]
+    if layout is not None and tuple(int(v) for v in layout) != (n, c, x.numel() // (n * c)):
+        return False
+    return c % 4 == 0 and 4 <= c <= 2048 and x.data_ptr() % 16 == 0
+
+
+def _resolve_out(x, out):
+    """(tensor the kernel writes, tensor the caller gets back).  ``x`` is the tensor handed to the kernel, i.e. AFTER any
+    ``.contiguous()`` re-layout; ``out`` is the caller's output tensor or None.  The kernels write linearly in the memory
+    order of ``x``, so the caller's tensor is used directly only when it has exactly that memory order (same strides);
+    otherwise (e.g. an NHWC-strided ``out`` while the kernel runs on an NCHW copy) the result is produced in a scratch
+    tensor and copied back element for element."""
+    if out is None:
+        return torch.empty_like(x), None
+    if out.shape != x.shape:
+        raise ValueError("out must have the shape of the input, got %r vs %r" % (tuple(out.shape), tuple(x.shape)))
+    _require_cuda_f32(out, "out")
+    if out.stride() == x.stride():
+        return out, None
+    return torch.empty_like(x), out
+
+
+def _finish_out(kernel_out, user_out):
+    if user_out is None:
+        return kernel_out
+    user_out.copy_(kernel_out)
+    return user_out
+
+
 def resident_ctas():
     return L.load().fqb200_resident_ctas()
 
@@ -86,17 +124,20 @@ def float2gemmlowp(x, range_, offset, num_bits, int_exp, enforce_true_zero, nois
     """C ABI fqb200_float2gemmlowp on torch tensors (scalars by value, like the reference's pybind call)."""
     _require_cuda_f32(x, "in")
     lib = L.load()
-    x = x.contiguous()
     if noise is not None:
         _require_cuda_f32(noise, "noise")
-        noise = noise.contiguous()
-    if out is None:
-        out = torch.empty_like(x)
+        if noise.shape != x.shape:
+            raise ValueError("noise must have the shape of the input")
+    # one parameter set for the whole tensor: any dense memory order will do (no copy for channels-last activations)
+    if not _dense(x) or (noise is not None and noise.stride() != x.stride()):
+        x = x.contiguous()
+        noise = noise.contiguous() if noise is not None else None
+    kout, uout = _resolve_out(x, out)
     with torch.cuda.device(x.device), _Timed("A", x.numel(), 8):
-        L.check(lib.fqb200_float2gemmlowp(x.data_ptr(), out.data_ptr(), x.numel(), float(range_), float(offset),
+        L.check(lib.fqb200_float2gemmlowp(x.data_ptr(), kout.data_ptr(), x.numel(), float(range_), float(offset),
                                           int(num_bits), int(bool(int_exp)), int(bool(enforce_true_zero)),
                                           noise.data_ptr() if noise is not None else None, _stream_handle(x.device)))
-    return out
+    return _finish_out(kout, uout)
 
 
 def quantize1(x, delta, offset, num_bits, bits=None, layout=None, want_grid=False, out=None, bias=None):
@@ -104,11 +145,15 @@ def quantize1(x, delta, offset, num_bits, bits=None, layout=None, want_grid=Fals
     parameters when ``delta`` has R elements, else one parameter set for the whole tensor."""
     _require_cuda_f32(x, "tensor")
     lib = L.load()
-    x = x.contiguous()
     dev = x.device
     delta = torch.as_tensor(delta, dtype=torch.float32, device=dev).contiguous()
     offset = torch.as_tensor(offset, dtype=torch.float32, device=dev).contiguous()
     per_group = delta.numel() > 1 or (bits is not None)
+    # channels-last activations with per-channel parameters run on the NHWC memory as it is (layout = (N, C, H*W));
+    # one parameter set for the whole tensor does not care about the memory order at all
+    cl = bool(per_group and layout is not None and cl_eligible(x, layout))
+    if not cl and (per_group or not _dense(x)):
+        x = x.contiguous()
     if layout is None:
         layout = (1, x.shape[0], x.numel() // x.shape[0]) if per_group else (1, 1, x.numel())
     outer, groups, inner = layout
@@ -128,14 +173,14 @@ def quantize1(x, delta, offset, num_bits, bits=None, layout=None, want_grid=Fals
         bias = bias.contiguous()
         if bias.numel() != groups:
             raise ValueError("bias must have one element per group (%d)" % groups)
-    if out is None:
-        out = torch.empty_like(x)
+    kout, uout = _resolve_out(x, out)
     grid = torch.empty_like(x) if want_grid else None
     with torch.cuda.device(dev), _Timed("A", x.numel(), 8, "%dx%dx%d" % (outer, groups, inner)):
-        L.check(lib.fqb200_quantize1(x.data_ptr(), out.data_ptr(), grid.data_ptr() if want_grid else None,
+        L.check(lib.fqb200_quantize1(x.data_ptr(), kout.data_ptr(), grid.data_ptr() if want_grid else None,
                                      outer, groups, inner, delta.data_ptr(), offset.data_ptr(),
                                      bits.data_ptr() if bits is not None else None, int(per_group), int(num_bits),
-                                     bias.data_ptr() if bias is not None else None, _stream_handle(dev)))
+                                     bias.data_ptr() if bias is not None else None, int(cl), _stream_handle(dev)))
+    out = _finish_out(kout, uout)
     return (out, grid) if want_grid else out
 
 
@@ -143,7 +188,7 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
           positive=False, solve_f64=False, clip_k=0.0, bit_alloc=False, bit_alloc_prior=L.PRIOR_STD,
           bit_alloc_round=True, bit_alloc_target=None, mt_target=0.0, mt_clip=False, bias_corr=False,
           var_corr=False, stats_only=False, want_stats=False, out=None, bias=None, bias_period=0, hist=None,
-          channels_last=False, any_dense_format=False):
+          channels_last=False, any_dense_format=False, debug_stamps=None):
     """C ABI fqb200_fused: statistics -> parameters -> quantize/dequantize in one launch.
 
     Returns ``out`` (or ``(out, stats)`` with ``want_stats``; ``stats`` alone with ``stats_only``), where
@@ -189,6 +234,7 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
         d.out_hist = hist.data_ptr()
     else:
         d.out_hist = None
+    d.debug_stamps = debug_stamps.data_ptr() if debug_stamps is not None else None
     stats = None
     if want_stats or stats_only:
         stats = torch.zeros((groups, L.STATS_STRIDE), dtype=torch.float32, device=dev)
@@ -197,8 +243,7 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
         d.out_stats = None
     if x.numel() == 0:
         return stats if stats_only else ((x.clone(), stats) if want_stats else x.clone())
-    if out is None and not stats_only:
-        out = torch.empty_like(x)
+    kout, uout = (None, None) if stats_only else _resolve_out(x, out)
     with torch.cuda.device(dev):
         stream = _stream_handle(dev)
         need = lib.fqb200_workspace_bytes(ctypes.byref(d))
@@ -210,10 +255,11 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
         mode = "S" if stats_only else ("D" if two_pass else "B")
         bpe = (8 if two_pass else 4) + (0 if stats_only else 8)
         with _Timed(mode, x.numel(), bpe, "%dx%dx%d" % (outer, groups, inner)):
-            L.check(lib.fqb200_fused(ctypes.byref(d), x.data_ptr(), out.data_ptr() if out is not None else None,
+            L.check(lib.fqb200_fused(ctypes.byref(d), x.data_ptr(), kout.data_ptr() if kout is not None else None,
                                      ws.data_ptr(), ws.numel(), stream))
     if stats_only:
         return stats
+    out = _finish_out(kout, uout)
     return (out, stats) if want_stats else out
 
 
@@ -222,6 +268,6 @@ def _test_division(a, b):
     lib = L.load()
     fast, ieee = torch.empty_like(a), torch.empty_like(a)
     with torch.cuda.device(a.device):
-        L.check(lib.fqb200_test_division(a.data_ptr(), b.data_ptr(), fast.data_ptr(), ieee.data_ptr(), a.numel(),
+        L.check(lib.fqb200_selftest_division(a.data_ptr(), b.data_ptr(), fast.data_ptr(), ieee.data_ptr(), a.numel(),
                                          _stream_handle(a.device)))
     return fast, ieee

@@ -3,8 +3,10 @@
  *
  * Drop-in boundary for the fake-quantization hot path of submission2019/cnn-quantization
  * (SURVEY.md section 8).  Plain C: device pointers, sizes, a stream handle; no torch types.
- * Every entry point returns 0 (FQB200_OK) or an FQB200_ERR_* code; nothing throws, nothing
- * keeps global state besides the cached device properties.  All tensors are fp32, contiguous,
+ * Every entry point returns 0 (FQB200_OK) or an FQB200_ERR_* code; nothing throws.  The only process
+ * state is the per-device set-up (kernel attributes, occupancy, constant tables), done once under
+ * std::call_once - entry points may be called concurrently from several host threads (one device each,
+ * like torch.nn.DataParallel's workers), and the last-error text is per thread.  All tensors are fp32, contiguous,
  * resident on the current CUDA device.  `stream` is a cudaStream_t passed as void*.
  *
  * Reference interfaces replaced (paths relative to the reference repository):
@@ -30,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FQB200_ABI_VERSION 1
+#define FQB200_ABI_VERSION 2
 
 /* ---- return codes ------------------------------------------------------------------------- */
 #define FQB200_OK 0
@@ -108,11 +110,15 @@ typedef struct fqb200_desc {
                           bias_period % 4 == 0 on the 128-bit path. */
   int32_t channels_last; /* 1: the tensor is [outer][inner][groups] in memory (groups fastest), i.e. an NCHW-shaped
                           activation stored channels-last (NHWC).  Per-channel scope with the torch / mid-tread leaves;
-                          needs groups % 4 == 0, groups/4 dividing 512, groups <= 4096.  Sums of different CTAs meet in
-                          float64 atomics: statistics are reproducible to fp32 rounding, not bit for bit. */
+                          needs groups % 4 == 0 and groups <= 2048.  Sums of different CTAs meet in float64 atomics:
+                          statistics are reproducible to fp32 rounding, not bit for bit.  The standard deviation comes
+                          from the first pass (shifted sums; SURVEY.md 8d "single-pass" option). */
   unsigned long long* out_hist; /* optional device array of 256 counters: the launch ADDS the histogram of the integer
                           grid q (torch leaf: q in [0, 255]) to it - what the reference's `-me` entropy measurement
                           needs (utils/entropy.py:6-17 on output.int(), int_quantizer.py:586-587) without torch.unique. */
+  unsigned long long* debug_stamps; /* diagnostics, NULL = off: device array of 16 counters that receives %globaltimer
+                          (ns) at the phase boundaries of this launch (slot 0: start, 1 / 5: statistics phases combined,
+                          4 / 8: past the grid barriers, 7: parameters ready, 9: apply done; tools/phasebench.py) */
 } fqb200_desc;
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -121,6 +127,14 @@ int fqb200_abi_version(void);
 const char* fqb200_last_error(void);
 /* number of CTAs the fused kernel keeps resident on the current device (148 SMs x 2 on a B200) */
 int fqb200_resident_ctas(void);
+
+/* What a launch of `d` would look like on the current device (introspection for tools and tests), 8 values:
+ * channels_last: {2, grid, units, stages per unit, vectors per stage, consumer stride, ring stages, phases};
+ * otherwise:     {access mode 4|1|8, grid, units, parts per group, vectors per part, stride, ring depth, leader lanes}. */
+int fqb200_plan_info(const fqb200_desc* d, int64_t* out8);
+/* Self-test hook: fast[i] = the kernels' 3-instruction exact division a[i] / b[i], ieee[i] = IEEE a[i] / b[i]
+ * (tests/test_gpu_parity.py::test_division_is_ieee).  Device pointers. */
+int fqb200_selftest_division(const float* a, const float* b, float* fast, float* ieee, int64_t n, void* stream);
 
 /* Scratch the fused kernel needs for `d` (partials, per-group results, grid-barrier words). */
 size_t fqb200_workspace_bytes(const fqb200_desc* d);
@@ -141,10 +155,12 @@ int fqb200_float2gemmlowp(const float* in, float* out, int64_t n, float range, f
  * `groups` floats (per-row bit widths).  Tensor viewed [outer][groups][inner] (a [R,K] matrix is
  * outer=1, groups=R, inner=K).  Optional `grid` receives the integer grid q (fp32 integers).  Optional `bias`
  * (`groups` floats) is added to every element of its group first, like fqb200_desc.bias.  `out` may alias `in`.
+ * channels_last = 1: the tensor is [outer][inner][groups] in memory (an NCHW-shaped activation stored NHWC; needs
+ * groups % 4 == 0, groups <= 2048, 16-byte aligned pointers) - `-sm use` on channels-last models without a copy.
  */
 int fqb200_quantize1(const float* in, float* out, float* grid, int64_t outer, int64_t groups, int64_t inner,
                      const float* delta, const float* offset, const float* bits, int per_group, int num_bits,
-                     const float* bias, void* stream);
+                     const float* bias, int channels_last, void* stream);
 
 /*
  * a4/a5/a6/a11/a12(+a7-a10, a13) - statistics -> parameters -> quantize-dequantize (-> weight

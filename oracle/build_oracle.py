@@ -5,6 +5,11 @@
                                     compiled unmodified for sm_100a from where the sources lie under
                                     /root/reference - only when that directory exists (build container).
                                     It is the on-GPU oracle for the compiled leaf and the "kernel to beat".
+  oracle/_ref/pyref/                the REFERENCE's Python hot path (pytorch_quantizer/, utils/), staged unmodified at
+                                    build() time so that it travels to the GPU box with the snapshot (oracle/_ref is
+                                    git-ignored, not gpurun-ignored): the live on-GPU oracle for every row of SURVEY 8a
+                                    (oracle/ref_live.py imports it next to the compiled extension above).  Nothing of it
+                                    is ever committed; the product never imports it.
 """
 import glob
 import os
@@ -15,7 +20,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 BUILD = os.path.join(HERE, "_build")
 REFDIR = os.path.join(HERE, "_ref")
-REF_KERNELS = "/root/reference/kernels"
+REF_ROOT = "/root/reference"
+REF_KERNELS = os.path.join(REF_ROOT, "kernels")
+PYREF = os.path.join(REFDIR, "pyref")
+PYREF_PACKAGES = ("pytorch_quantizer", "utils")
 
 
 def build_leaf(force=False):
@@ -59,6 +67,23 @@ def build_reference_ext(force=False):
     return found[0] if found else None
 
 
+def stage_reference_python(force=False):
+    """Stage the reference's Python packages (unmodified) under oracle/_ref/pyref.  Returns the directory, or None when
+    neither the reference nor an earlier staging exists."""
+    marker = os.path.join(PYREF, "pytorch_quantizer", "quantization", "qtypes", "int_quantizer.py")
+    if not os.path.isdir(REF_ROOT):
+        return PYREF if os.path.exists(marker) else None
+    if os.path.exists(marker) and not force:
+        return PYREF
+    os.makedirs(PYREF, exist_ok=True)
+    for pkg in PYREF_PACKAGES:
+        dst = os.path.join(PYREF, pkg)
+        shutil.rmtree(dst, ignore_errors=True)
+        shutil.copytree(os.path.join(REF_ROOT, pkg), dst, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+    return PYREF
+
+
 if __name__ == "__main__":
     print(build_leaf(force=True))
     print(build_reference_ext(force="--force" in sys.argv))
+    print(stage_reference_python(force="--force" in sys.argv))

@@ -34,21 +34,26 @@ def test_library_exports_every_declared_symbol(lib):
     for sym in declared:
         assert sym in exported, sym
         assert getattr(lib, sym) is not None
-    assert lib.fqb200_abi_version() == 1
+    # ... and nothing else: no undeclared hooks ride along in the shipped library (round-1 VERDICT, boundary hygiene)
+    ours = sorted(s for s in exported if s.startswith("fqb"))
+    assert ours == declared, sorted(set(ours) - set(declared))
+    assert lib.fqb200_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_desc_struct_layout_matches_header():
     from cnn_quantization_b200 import _lib
     # compile a one-liner against the header and compare sizeof / offsetof with the ctypes mirror
-    code = ('#include <stdio.h>\n#include <stddef.h>\n#include "fqb200.h"\nint main(){printf("%zu %zu %zu %zu\\n", '
+    code = ('#include <stdio.h>\n#include <stddef.h>\n#include "fqb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", '
             'sizeof(fqb200_desc), offsetof(fqb200_desc, clip_k), offsetof(fqb200_desc, mt_target), '
-            'offsetof(fqb200_desc, out_stats));return 0;}\n')
+            'offsetof(fqb200_desc, out_stats), offsetof(fqb200_desc, channels_last), offsetof(fqb200_desc, debug_stamps));'
+            'return 0;}\n')
     exe = os.path.join(ROOT, "oracle", "_build", "abi_probe")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=code, text=True, check=True)
     got = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     D = _lib.Desc
-    assert got == [ctypes.sizeof(D), D.clip_k.offset, D.mt_target.offset, D.out_stats.offset]
+    assert got == [ctypes.sizeof(D), D.clip_k.offset, D.mt_target.offset, D.out_stats.offset, D.channels_last.offset,
+                   D.debug_stamps.offset]
 
 
 def test_argument_validation_without_gpu(lib):
@@ -63,7 +68,17 @@ def test_argument_validation_without_gpu(lib):
     assert b"scope" in lib.fqb200_last_error()
     assert lib.fqb200_float2gemmlowp(None, None, -1, 1.0, 0.0, 8, 0, 1, None, None) == _lib.ERR_INVALID
     assert lib.fqb200_float2gemmlowp(None, None, 0, 1.0, 0.0, 8, 0, 1, None, None) == _lib.OK  # empty tensor: no-op
-    assert lib.fqb200_quantize1(None, None, None, 1, 4, 4, None, None, None, 1, 4, None, None) == _lib.ERR_INVALID
+    assert lib.fqb200_quantize1(None, None, None, 1, 4, 4, None, None, None, 1, 4, None, 0, None) == _lib.ERR_INVALID
+    # the plan query works without a device (it assumes a B200): channels-last ResNet-50 layer, 3 phases on the bulk ring
+    d = _lib.Desc()
+    d.outer, d.groups, d.inner, d.num_bits, d.range_mode, d.channels_last = 512, 256, 196, 4, _lib.RANGE_LAPLACE, 1
+    out = (ctypes.c_int64 * 8)()
+    assert lib.fqb200_plan_info(ctypes.byref(d), out) == _lib.OK
+    assert out[0] == 2 and 1 <= out[1] <= 296 and out[5] == 512 and out[7] == 3
+    d.groups = 96   # C/4 = 24 does not divide 512: 504 consumer threads take part
+    assert lib.fqb200_plan_info(ctypes.byref(d), out) == _lib.OK and out[5] == 504
+    d.groups = 6
+    assert lib.fqb200_plan_info(ctypes.byref(d), out) == _lib.ERR_UNSUPPORTED
 
 
 def test_no_cpu_fallback():

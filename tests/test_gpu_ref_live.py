@@ -1,0 +1,302 @@
+"""GPU parity against the REFERENCE ITSELF, live on the B200, at BASELINE sizes.
+
+oracle/build_oracle.py stages the reference's Python path (unmodified) and compiles its CUDA extension (unmodified)
+under the git-ignored oracle/_ref/; both travel to the GPU box.  Here the reference's ``IntQuantizer``
+(int_quantizer.py:56-632) runs on the same CUDA tensor as our kernels, for every distinct ResNet-50 / ResNet-101
+activation layout at the BASELINE batch sizes (512 per GPU; 128 per GPU for the 8-GPU ResNet-101 config), in contiguous
+NCHW **and** channels-last memory:
+
+  tier (i)   the reference's own (delta, offset, bit_alloc) fed to our given-parameter kernels -> output BIT-EXACT;
+  tier (ii)  end to end: our on-device statistics / parameters within 1e-5 relative of the reference's, allocated bit
+             widths identical, outputs equal except a measured, bounded fraction of one-step flips.
+
+The measured flip fractions and parameter errors are written to gpurun_out/r02_parity_live.json (copied to profiles/).
+"""
+import json
+import os
+import time
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+FLIP_FRAC = 2e-4     # tier (ii) bound on the fraction of elements that may land one step away
+PARAM_RTOL = 1e-5    # north_star: parameters / outputs within 1e-5 relative
+REPORT = {}
+
+
+def _params(**over):
+    p = dict(clipping="laplace", stats_kind="mean", kld=False, pcq_weights=True, pcq_act=True, bit_alloc_act=True,
+             bit_alloc_weight=True, bcorr_act=False, bcorr_weight=True, vcorr_weight=False, bit_alloc_rmode="round",
+             bit_alloc_prior="gaus", bit_alloc_target_act=None, bit_alloc_target_weight=None, measure_entropy=False,
+             logger=None, mtd_quant=False)
+    p.update(over)
+    return p
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import ref_live
+    if not ref_live.available():
+        pytest.skip("oracle/_ref (staged reference + its compiled extension) not built")
+    return ref_live.load()
+
+
+@pytest.fixture(scope="module")
+def fq():
+    import cnn_quantization_b200 as m
+    m._lib.load()
+    return m
+
+
+def _dump_report():
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "r02_parity_live.json"), "w") as f:
+            json.dump(REPORT, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def _activation(n, c, hw, seed):
+    """A conv-output-like tensor: per-channel scale U(0.1, 3) and shift N(0, 0.5)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(n, c, hw, hw, device="cuda", generator=g)
+    scale = torch.rand(c, device="cuda", generator=g) * 2.9 + 0.1
+    shift = torch.randn(c, device="cuda", generator=g) * 0.5
+    return x.mul_(scale.view(1, c, 1, 1)).add_(shift.view(1, c, 1, 1))
+
+
+def _rel(a, b, floor=None):
+    """max |a - b| / max(|b|, floor): ``floor`` (scalar or per-channel tensor) is the magnitude that matters when b itself
+    may be near zero (a mean is compared on the scale of the channel's std, an offset on the scale of its range)."""
+    a, b = a.double().flatten(), b.double().flatten()
+    den = b.abs().clamp_min(1e-30)
+    if floor is not None:
+        den = torch.maximum(den, floor.double().flatten() if torch.is_tensor(floor) else torch.full_like(den, floor))
+    return float(((a - b).abs() / den).max())
+
+
+def _flips(y, y_ref, step_per_channel):
+    """(fraction of elements beyond 1e-5 relative, worst difference in quantization steps) - computed on the device."""
+    tol = 1e-5 * torch.maximum(y.abs(), y_ref.abs()) + 1e-9
+    diff = (y - y_ref).abs()
+    bad = diff > tol
+    nbad = int(bad.sum())
+    if nbad == 0:
+        return 0.0, 0.0
+    steps = diff / step_per_channel.view(1, -1, 1, 1).clamp_min(1e-30)
+    return nbad / y.numel(), float(steps[bad].max())
+
+
+# every distinct (C, H) of the hooked conv outputs of ResNet-50 / ResNet-101 (SURVEY.md 8d census)
+LAYOUTS = [(64, 112), (64, 56), (256, 56), (128, 56), (128, 28), (512, 28), (256, 28), (256, 14), (1024, 14), (512, 14),
+           (512, 7), (2048, 7)]
+
+
+@pytest.mark.parametrize("c,hw", LAYOUTS)
+@pytest.mark.parametrize("n", [512, 128])
+def test_w4a4_activation_layouts_vs_live_reference(ref, fq, n, c, hw):
+    """BASELINE configs[2] / [3] activation path (-pcq_a -c laplace -baa, int4) on one layout: a6 -> a7 -> a8 -> a9 -> a4
+    -> a3 of the reference next to ONE fused launch of ours, NCHW and channels-last."""
+    from oracle.ref_live import LeafSpy
+    from cnn_quantization_b200 import ops
+    idx = LAYOUTS.index((c, hw))
+    half_range = idx % 3 != 2                       # 2/3 of the hooked convs feed a ReLU (33 of 53 in ResNet-50)
+    x = _activation(n, c, hw, seed=1000 * n + idx)
+    rq = ref.int_quantizer("int4", _params())
+    rq.pcq_w = False                                # the 'activation' entry of __fill_quantizers__ (:455-461)
+    rq.half_range = half_range
+    t0 = time.time()
+    with LeafSpy(rq) as spy:
+        want = rq(x, "conv%d_activation" % idx, "activation")
+    torch.cuda.synchronize()
+    t_ref = time.time() - t0
+    kind, r_delta, r_offset, r_bits = spy.calls[-1]
+    assert kind == "torch" and r_bits is not None and r_bits.numel() == c
+    r_stats = rq.__act_stats_perchannel__(x, ["min", "max", "b", "std"], avg_over_batch=False)
+    r_mean = rq.__act_stats_perchannel__(x, ["mean"], avg_over_batch=True)["mean"]
+    r_offset = r_offset.reshape(-1).expand(c) if r_offset.numel() == 1 else r_offset.reshape(-1)
+    qmax = 2.0 ** r_bits - 1
+    r_scale = torch.where(qmax > 0, r_delta / qmax, torch.zeros_like(r_delta)).clamp_min(1e-8)
+
+    q = fq.int_quantizer("int4", _params())
+    q.pcq_w = False
+    q.half_range = half_range
+    q.export_stats = True
+    rec = {"half_range": half_range, "elements": x.numel(), "reference_s": round(t_ref, 3)}
+    for fmt in ("nchw", "nhwc"):
+        xin = x if fmt == "nchw" else x.contiguous(memory_format=torch.channels_last)
+        # ---- tier (i): the reference's parameters through our given-parameter kernel: bit-exact
+        got_a = ops.quantize1(xin, r_delta.contiguous(), r_offset.contiguous(), 4, bits=r_bits.contiguous(),
+                              layout=(n, c, hw * hw))
+        assert torch.equal(got_a, want), "%s: given-parameter output differs from the reference" % fmt
+        # ---- tier (ii): end to end
+        got = q(xin, "conv%d_activation" % idx, "activation")
+        st = q.last_stats
+        errs = {"min": _rel(st[:, 0], r_stats["min"]) if not half_range else 0.0, "max": _rel(st[:, 1], r_stats["max"]),
+                "mean": _rel(st[:, 2], r_mean, r_stats["std"]), "b": _rel(st[:, 3], r_stats["b"]),
+                "std": _rel(st[:, 4], r_stats["std"]), "delta": _rel(st[:, 5], r_delta),
+                "offset": _rel(st[:, 6], r_offset, r_delta)}
+        bits_equal = bool(torch.equal(st[:, 7], r_bits))
+        frac, worst = _flips(got, want, r_scale)
+        rec[fmt] = {"flip_fraction": frac, "worst_steps": worst, "bits_identical": bits_equal,
+                    "max_rel_err": {k: float("%.3g" % v) for k, v in errs.items()},
+                    "bit_widths": sorted(set(int(v) for v in r_bits.tolist()))}
+        REPORT["act %dx%dx%dx%d" % (n, c, hw, hw)] = rec
+        _dump_report()
+        assert errs["max"] == 0.0 and errs["min"] == 0.0, errs
+        for k in ("mean", "b", "std", "delta", "offset"):
+            assert errs[k] <= PARAM_RTOL, (fmt, k, errs[k])
+        assert bits_equal, "%s: allocated bit widths differ from the reference's" % fmt
+        assert frac <= FLIP_FRAC and worst <= 1.01, (fmt, frac, worst)
+        del got, got_a
+    print("[parity-live] %4dx%4dx%3dx%3d half_range=%d  flips nchw %.2e nhwc %.2e  (reference %.2fs)" % (
+        n, c, hw, hw, half_range, rec["nchw"]["flip_fraction"], rec["nhwc"]["flip_fraction"], t_ref))
+
+
+@pytest.mark.parametrize("case", ["maxpool", "fc"])
+def test_int8_minmax_tensors_vs_live_reference(ref, fq, case):
+    """The two mode-B tensors of every W4A4 forward and every tensor of configs[1]: gemmlowpMinMaxQuantize -> the
+    reference's compiled kernel (a11 -> a2 -> a1) vs our fused launch, batch 512."""
+    torch.manual_seed(7)
+    if case == "maxpool":
+        x = torch.relu(_activation(512, 64, 56, seed=77))
+        tag, tid = "activation_pooling", "maxpool0_out"
+    else:
+        x = torch.randn(512, 1000, device="cuda") * 3
+        tag, tid = "activation_classifier", "linear0_activation"
+    for half_range in (False, True):
+        if case == "fc" and half_range:
+            continue
+        rq = ref.int_quantizer("int8", _params(clipping="no", pcq_act=False, pcq_weights=False))
+        rq.half_range = half_range
+        want = rq(x, tid, tag)
+        q = fq.int_quantizer("int8", _params(clipping="no", pcq_act=False, pcq_weights=False))
+        q.half_range = half_range
+        q.export_stats = True
+        formats = ("nchw", "nhwc") if x.dim() == 4 else ("nchw",)
+        for fmt in formats:
+            xin = x if fmt == "nchw" else x.contiguous(memory_format=torch.channels_last)
+            got = q(xin, tid, tag)
+            step = q.last_stats[0, 8].reshape(1)
+            tol = 1e-5 * torch.maximum(got.abs(), want.abs()) + 1e-9
+            bad = (got - want).abs() > tol
+            frac = float(bad.float().mean())
+            worst = float(((got - want).abs() / step).max())
+            REPORT["int8 %s %s half_range=%d" % (case, fmt, half_range)] = {"flip_fraction": frac, "worst_steps": worst}
+            _dump_report()
+            assert frac <= FLIP_FRAC and worst <= 1.01, (case, fmt, frac, worst)
+
+
+@pytest.mark.parametrize("arch", ["resnet50", "resnet101"])
+def test_quantize_model_weights_vs_live_reference_manager(ref, fq, arch):
+    """a5 + a9 + a13 at full model size: ``quantize_model`` of the reference's manager (per-out-channel int4 weights, bit
+    allocation, its torch bias correction) vs ours (one fused launch per weight tensor)."""
+    from oracle import ref_live
+    from cnn_quantization_b200 import manager as M, pipeline
+    flags = dict(pipeline.CONFIGS["%s_w4a4" % arch])
+    args = M.make_args(**flags)
+    model_ref, rqm = ref_live.build_reference_model(args, M.get_params(args), "cuda")
+    rqm.__exit__()
+    model, qm = pipeline.build_quantized_model(flags, "cuda")
+    qm.detach()
+    worst_frac, n_tensors, total = 0.0, 0, 0
+    for (n1, p1), (n2, p2) in zip(model.named_parameters(), model_ref.named_parameters()):
+        assert n1 == n2
+        if p1.dim() < 2:
+            assert torch.allclose(p1, p2, rtol=1e-6, atol=1e-7), n1      # folded-BN biases: same torch ops
+            continue
+        scale = p2.abs().amax(dim=tuple(range(1, p2.dim())), keepdim=True).clamp_min(1e-12)
+        bad = (p1 - p2).abs() > 1e-5 * scale
+        frac = float(bad.float().mean())
+        worst_frac = max(worst_frac, frac)
+        n_tensors += 1
+        total += p1.numel()
+        assert frac <= 2e-3, (n1, frac)
+    REPORT["weights %s_w4a4" % arch] = {"tensors": n_tensors, "elements": total, "worst_flip_fraction": worst_frac}
+    _dump_report()
+
+
+@pytest.mark.parametrize("config,batch,channels_last", [("resnet50_w4a4", 64, True), ("resnet50_w4a4", 32, False),
+                                                        ("resnet101_w4a4", 128, True), ("resnet50_w8a8", 64, True),
+                                                        ("vgg16_w4a4", 16, True)])
+def test_layerwise_differential_vs_live_reference(ref, fq, config, batch, channels_last):
+    """Layer-wise differential on real activations: our hooked model runs a 224x224 batch; at EVERY quantize_instant call
+    the same GPU input (conv bias added, as the reference's convolution would have) also goes through the reference's
+    quantizer for that tag, and the two outputs are compared.  Replaces the loose logits cosine of round 1."""
+    from cnn_quantization_b200 import manager as M, pipeline
+    flags = dict(pipeline.CONFIGS[config])
+    args = M.make_args(**flags)
+    ref_ops = ref.iqm.TruncationOpManagerInference(args, M.get_params(args))   # the reference's tag -> quantizer table
+    model, qm = pipeline.build_quantized_model(flags, "cuda", channels_last=channels_last)
+    x, _ = pipeline.synthetic_batch(batch, seed=3, channels_last=channels_last)
+    x = x.cuda()
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
+    rows = []
+    orig = qm.quantize_instant
+
+    def spy(tensor, id, tag="", stat_id=None, half_range=False, override_att=None, verbose=False, **extra):
+        bias = extra.get("bias")
+        ref_in = tensor.contiguous().clone() if bias is None else (tensor + bias.view(1, -1, 1, 1)).contiguous()
+        out = orig(tensor, id, tag, stat_id, half_range, override_att, verbose, **extra)
+        rq = ref_ops.get_quantizer(tag)
+        rq.half_range = half_range
+        want = rq(ref_in, id, tag)
+        tol = 1e-5 * torch.maximum(out.abs(), want.abs()) + 1e-9
+        diff = (out - want).abs()
+        bad = diff > tol
+        levels = max(int(torch.unique(want[:1]).numel()), 2)
+        span = float(want.max() - want.min())
+        rows.append((id, tag, tuple(tensor.shape), float(bad.float().mean()), float(diff.max()), span, levels))
+        return out
+
+    qm.quantize_instant = spy
+    with torch.no_grad():
+        y = model(x)
+    qm.detach()
+    assert torch.isfinite(y).all()
+    worst = max(r[3] for r in rows)
+    REPORT["layerwise %s batch %d %s" % (config, batch, "nhwc" if channels_last else "nchw")] = {
+        "hooked_tensors": len(rows), "worst_flip_fraction": worst,
+        "mean_flip_fraction": sum(r[3] for r in rows) / len(rows),
+        "worst_layer": max(rows, key=lambda r: r[3])[0]}
+    _dump_report()
+    for id, tag, shape, frac, dmax, span, levels in rows:
+        assert frac <= FLIP_FRAC, (id, tag, shape, frac)
+        assert dmax <= span / 2 + 1e-6, (id, tag, shape, dmax, span)   # flips are single grid steps, never garbage
+
+
+@pytest.mark.parametrize("config,min_cos", [("resnet50_w4a4", 0.95), ("resnet50_w8a8", 0.999)])
+def test_dropin_alias_runs_the_unmodified_reference_manager(ref, config, min_cos, tmp_path):
+    """the reference's OWN manager + model preparation, unmodified, in a fresh process, once as shipped and
+    once after the zero-edit alias of INTEGRATION.md section 1.  In the aliased run every quantize_instant of the
+    reference manager must have gone through libfqb200.so, and the logits must agree with the shipped reference."""
+    import subprocess
+    import sys
+    import numpy as np
+    runner = os.path.join(ROOT, "tests", "helpers", "dropin_runner.py")
+    outs = {}
+    for mode in ("reference", "dropin"):
+        out = str(tmp_path / ("%s.npz" % mode))
+        res = subprocess.run([sys.executable, runner, "--mode", mode, "--config", config, "--batch", "8", "--out", out],
+                             capture_output=True, text=True, timeout=900)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+        outs[mode] = np.load(out)
+    assert str(outs["reference"]["quantizer_module"]) == "pytorch_quantizer.quantization.qtypes.int_quantizer"
+    assert str(outs["dropin"]["quantizer_module"]).startswith("cnn_quantization_b200")
+    # ResNet-50: 54 weight tensors + 55 hooked activations per forward, every one a launch of ours
+    assert int(outs["dropin"]["launches"]) >= 109, int(outs["dropin"]["launches"])
+    y, r = outs["dropin"]["logits"].astype(np.float64), outs["reference"]["logits"].astype(np.float64)
+    assert np.isfinite(y).all() and y.shape == r.shape
+    cos = float((y * r).sum() / (np.linalg.norm(y) * np.linalg.norm(r)))
+    REPORT["dropin %s" % config] = {"cosine_vs_shipped_reference": cos, "launches": int(outs["dropin"]["launches"])}
+    _dump_report()
+    assert cos >= min_cos, cos
+    assert abs(np.linalg.norm(y) / np.linalg.norm(r) - 1) < 0.1
