@@ -19,7 +19,7 @@ STAT_COLUMNS = ("min", "max", "mean", "b", "std", "delta", "offset", "bits", "sc
 # every symbol include/fqb200.h declares (tests check the export table against this)
 SYMBOLS = ("fqb200_abi_version", "fqb200_last_error", "fqb200_resident_ctas", "fqb200_plan_info",
            "fqb200_selftest_division", "fqb200_workspace_bytes", "fqb200_workspace_init", "fqb200_float2gemmlowp",
-           "fqb200_quantize1", "fqb200_fused")
+           "fqb200_quantize1", "fqb200_quantize1_bca", "fqb200_fused", "fqb200_add_relu")
 ABI_VERSION = 2
 
 
@@ -39,6 +39,9 @@ class Desc(ctypes.Structure):
         ("bias_period", ctypes.c_int64),
         ("channels_last", ctypes.c_int32),
         ("out_hist", ctypes.c_void_p),
+        ("hist_bins", ctypes.c_int32), ("hist_offset", ctypes.c_int32),
+        ("out_hist_clamped", ctypes.c_void_p),
+        ("relu_passthrough", ctypes.c_int32),
         ("debug_stamps", ctypes.c_void_p),
     ]
 
@@ -76,6 +79,10 @@ def load():
     lib.fqb200_quantize1.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, i32, i32, vp, i32, vp]
     lib.fqb200_fused.restype = i32
     lib.fqb200_fused.argtypes = [ctypes.POINTER(Desc), vp, vp, vp, ctypes.c_size_t, vp]
+    lib.fqb200_quantize1_bca.restype = i32
+    lib.fqb200_quantize1_bca.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, i32, i32, vp, i32, vp, vp, ctypes.c_size_t, vp]
+    lib.fqb200_add_relu.restype = i32
+    lib.fqb200_add_relu.argtypes = [vp, vp, vp, i64, vp]
     lib.fqb200_selftest_division.restype = i32
     lib.fqb200_selftest_division.argtypes = [vp, vp, vp, vp, i64, vp]
     lib.fqb200_plan_info.restype = i32

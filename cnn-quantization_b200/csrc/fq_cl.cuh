@@ -52,6 +52,14 @@ __device__ __forceinline__ ClView cl_view(const FusedArgs& A, unsigned bank) {
   return v;
 }
 
+// fire-and-forget reductions on global memory (no generic-address fallback, no return value)
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_max_u32(unsigned* p, unsigned v) {
+  asm volatile("red.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // plain grid barrier over the consumer threads of every CTA: the last CTA to arrive releases the others
 __device__ __forceinline__ void grid_barrier_cl(GridSync* gs, unsigned& epoch) {
   ++epoch;
@@ -87,20 +95,25 @@ __device__ __forceinline__ void grid_exit_cl(GridSync* gs) {
 // ---- per-phase accumulators ---------------------------------------------------------------------------------------------
 constexpr unsigned kClChunk = 8;  // vectors summed in fp32 before folding into float64
 
+// S1 runs on the RAW values (the bias is a per-channel constant): min / max of x + bias are (min x) + bias and
+// (max x) + bias exactly (rounding is monotone), and mean / std of fl(x + bias) equal mean(x) + bias / std(x) up to the
+// rounding of single elements (~1e-8 relative, far inside the fp32 statistics of the reference itself).  That saves four
+// registers and one instruction per element in the phase that reads HBM.
 struct ClStats1 {
-  float mn[4], mx[4], bias[4], k[4], fs[4], fq[4];
+  float mn[4], mx[4], k[4], fs[4], fq[4];
   double s[4], q[4];
   unsigned cnt;
   __device__ __forceinline__ void init(const FusedArgs& A, unsigned c0, bool active) {
-    // common shift: the channel's (biased) value at pixel 0, the same bits in every thread of every CTA
+    // common shift: the channel's value at pixel 0, the same bits in every thread of every CTA
     float4 first = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) first = ld_tensor(reinterpret_cast<const float4*>(A.in) + (c0 >> 2));
-    const float f[4] = {first.x, first.y, first.z, first.w};
+    k[0] = first.x;
+    k[1] = first.y;
+    k[2] = first.z;
+    k[3] = first.w;
     cnt = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      bias[i] = (A.bias && active) ? __ldg(A.bias + c0 + i) : 0.f;
-      k[i] = __fadd_rn(f[i], bias[i]);
       mn[i] = INFINITY;
       mx[i] = -INFINITY;
       fs[i] = 0.f;
@@ -120,7 +133,7 @@ struct ClStats1 {
     cnt = 0;
   }
   __device__ __forceinline__ void consume(const float4& v, unsigned) {
-    const float x[4] = {__fadd_rn(v.x, bias[0]), __fadd_rn(v.y, bias[1]), __fadd_rn(v.z, bias[2]), __fadd_rn(v.w, bias[3])};
+    const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float d = __fsub_rn(x[i], k[i]);
@@ -163,15 +176,26 @@ struct ClStats2 {
   }
 };
 
+// `-me` (entropy of the integer grid, utils/entropy.py:6-17): the apply phase histograms the grid into shared memory.
+// kHistWords counters per CTA, organised as `copies` replicas of `bins` counters (warp w uses replica w % copies): 16
+// replicas of the torch leaf's 256 levels, fewer of the wider mid-tread grids.  Mid-tread grids are clamped to the
+// per-channel, generally fractional bounds c_min / c_max (int_quantizer.py:207-214); elements sitting on a bound are
+// counted per channel (they are distinct symbols for torch.unique) instead of in the integer histogram.
+constexpr unsigned kHistWords = 8192;
+
 template <int LEAF, bool HIST>
 struct ClApply {
   const FusedArgs& A;
-  unsigned* hist;  // [kWarps][256] in shared memory (HIST)
+  unsigned* hist;  // [kHistWords] in shared memory (HIST)
   LeafParam q[4];
   float r[4], bias[4];
+  unsigned nlo[4], nhi[4];  // HIST, mid-tread: elements on the lower / upper clamp bound of each channel
+  unsigned hbase;           // this warp's replica
   bool fast;
   __device__ __forceinline__ void init(unsigned c0, bool active, const LeafParam (&lp)[4]) {
     fast = true;
+    const unsigned copies = max(1u, min(static_cast<unsigned>(kWarps), kHistWords / static_cast<unsigned>(max(A.hist_bins, 1))));
+    hbase = ((threadIdx.x >> 5) % copies) * static_cast<unsigned>(A.hist_bins);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       q[i] = lp[i];
@@ -179,6 +203,24 @@ struct ClApply {
       r[i] = dv.r;
       fast = fast && dv.fast;
       bias[i] = (A.bias && active) ? __ldg(A.bias + c0 + i) : 0.f;
+      nlo[i] = 0u;
+      nhi[i] = 0u;
+    }
+  }
+  __device__ __forceinline__ void count(int i, float gq) {
+    if (LEAF == FQB200_LEAF_MIDTREAD) {
+      if (gq == q[i].c) {
+        ++nhi[i];
+        return;
+      }
+      if (gq == q[i].b) {
+        ++nlo[i];
+        return;
+      }
+    }
+    if (gq == gq) {  // NaN is not a symbol of the grid
+      const float v = fminf(fmaxf(gq + static_cast<float>(A.hist_offset), 0.f), static_cast<float>(A.hist_bins - 1));
+      atomicAdd(hist + hbase + static_cast<unsigned>(v), 1u);
     }
   }
   template <bool FAST>
@@ -196,8 +238,7 @@ struct ClApply {
     st_tensor(reinterpret_cast<float4*>(A.out) + off, make_float4(y[0], y[1], y[2], y[3]));
     if (HIST) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (gq[i] >= 0.f && gq[i] <= 255.f) atomicAdd(hist + (threadIdx.x >> 5) * 256u + static_cast<unsigned>(gq[i]), 1u);
+      for (int i = 0; i < 4; ++i) count(i, gq[i]);
     }
   }
   __device__ __forceinline__ void consume(const float4& v, unsigned off) {
@@ -233,11 +274,11 @@ __device__ __forceinline__ void cl_combine(unsigned char* buf, unsigned cv, unsi
   }
 }
 
-// mean (float64) of channel c from the S1 accumulators: k + S / n
-__device__ __forceinline__ double cl_mean(const ClView& acc, unsigned rep, unsigned C, unsigned c, float k, double n) {
+// mean (float64) of channel c (of x + bias) from the S1 accumulators: k + bias + S / n
+__device__ __forceinline__ double cl_mean(const ClView& acc, unsigned rep, unsigned C, unsigned c, float k, float bias, double n) {
   double s = 0.0;
   for (unsigned r = 0; r < rep; ++r) s += ld_ws(acc.asum + r * C + c);
-  return static_cast<double>(k) + s / n;
+  return static_cast<double>(k) + static_cast<double>(bias) + s / n;
 }
 // unbiased std of channel c: sqrt((Q - S^2 / n) / (n - 1))
 __device__ __forceinline__ float cl_std(const ClView& acc, unsigned rep, unsigned C, unsigned c, double n) {
@@ -337,7 +378,8 @@ __device__ __forceinline__ LeafParam cl_channel_param(const FusedArgs& A, const 
     hi = max(hi, ld_ws(acc.amax + r * C + c));
     if (DEV) sa += ld_ws(acc.aabs + r * C + c);
   }
-  const float mn = dec_ordered(~lo), mx = dec_ordered(hi);
+  const float cb = A.bias ? __ldg(A.bias + c) : 0.f;  // S1 ran on the raw values: min / max shift by the bias exactly
+  const float mn = __fadd_rn(dec_ordered(~lo), cb), mx = __fadd_rn(dec_ordered(hi), cb);
   const float b = DEV ? static_cast<float>(sa / n) : 0.f;
   const bool need_sd = A.range_mode == FQB200_RANGE_GAUS || A.range_mode == FQB200_RANGE_KSTD || do_export;
   const float sd = need_sd ? cl_std(acc, rep, C, c, n) : 0.f;
@@ -452,10 +494,10 @@ __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_kernel(const _
       umx[i] = enc_ordered(s1.mx[i]);
     }
     auto umax = [](unsigned a, unsigned b) { return a > b ? a : b; };
-    cl_combine(cbuf, cv, g.stride, umn, 0u, umax, [&](unsigned c, unsigned v) { atomicMax(acc.amin_inv + rep_base + c, v); });
-    cl_combine(cbuf, cv, g.stride, umx, 0u, umax, [&](unsigned c, unsigned v) { atomicMax(acc.amax + rep_base + c, v); });
-    cl_combine(cbuf, cv, g.stride, s1.s, 0.0, OpAdd(), [&](unsigned c, double v) { atomicAdd(acc.asum + rep_base + c, v); });
-    cl_combine(cbuf, cv, g.stride, s1.q, 0.0, OpAdd(), [&](unsigned c, double v) { atomicAdd(acc.asq + rep_base + c, v); });
+    cl_combine(cbuf, cv, g.stride, umn, 0u, umax, [&](unsigned c, unsigned v) { red_max_u32(acc.amin_inv + rep_base + c, v); });
+    cl_combine(cbuf, cv, g.stride, umx, 0u, umax, [&](unsigned c, unsigned v) { red_max_u32(acc.amax + rep_base + c, v); });
+    cl_combine(cbuf, cv, g.stride, s1.s, 0.0, OpAdd(), [&](unsigned c, double v) { red_add_f64(acc.asum + rep_base + c, v); });
+    cl_combine(cbuf, cv, g.stride, s1.q, 0.0, OpAdd(), [&](unsigned c, double v) { red_add_f64(acc.asq + rep_base + c, v); });
   }
   if (blockIdx.x == 0) stamp(A, 1);
   grid_barrier_cl(A.sync, epoch);
@@ -465,12 +507,11 @@ __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_kernel(const _
   float mean[4];
   if (direct) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) mean[i] = static_cast<float>(cl_mean(acc, rep, C, c0 + i, kshift[i], n));
+    for (int i = 0; i < 4; ++i)
+      mean[i] = static_cast<float>(cl_mean(acc, rep, C, c0 + i, kshift[i], (A.bias && active) ? __ldg(A.bias + c0 + i) : 0.f, n));
   } else {
-    for (unsigned c = t; c < C; c += kConsumers) {
-      const float k = __fadd_rn(ld_tensor(A.in + c), A.bias ? __ldg(A.bias + c) : 0.f);  // the same bits as kshift
-      tab_mean[c] = static_cast<float>(cl_mean(acc, rep, C, c, k, n));
-    }
+    for (unsigned c = t; c < C; c += kConsumers)
+      tab_mean[c] = static_cast<float>(cl_mean(acc, rep, C, c, ld_tensor(A.in + c), A.bias ? __ldg(A.bias + c) : 0.f, n));
     consumer_sync();
 #pragma unroll
     for (int i = 0; i < 4; ++i) mean[i] = tab_mean[c0 + i];
@@ -490,7 +531,7 @@ __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_kernel(const _
     consume_phase(g, ring, stages, pos, s2);
     s2.flush();
     if (blockIdx.x == 0) stamp(A, 14);
-    cl_combine(cbuf, cv, g.stride, s2.sa, 0.0, OpAdd(), [&](unsigned c, double v) { atomicAdd(acc.aabs + rep_base + c, v); });
+    cl_combine(cbuf, cv, g.stride, s2.sa, 0.0, OpAdd(), [&](unsigned c, double v) { red_add_f64(acc.aabs + rep_base + c, v); });
     if (blockIdx.x == 0) stamp(A, 5);
     grid_barrier_cl(A.sync, epoch);
     if (blockIdx.x == 0) stamp(A, 8);
@@ -521,7 +562,7 @@ __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_kernel(const _
   // ---- A
   if (!A.stats_only) {
     if (HIST) {
-      for (unsigned i = t; i < kWarps * 256u; i += kConsumers) hist[i] = 0u;
+      for (unsigned i = t; i < kHistWords; i += kConsumers) hist[i] = 0u;
       consumer_sync();
     }
     ClApply<LEAF, HIST> ap{A, hist};
@@ -529,11 +570,19 @@ __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_kernel(const _
     consume_phase(g, ring, stages, pos, ap);
     if (HIST) {
       consumer_sync();
-      for (unsigned b = t; b < 256u; b += kConsumers) {
+      const unsigned bins = static_cast<unsigned>(A.hist_bins);
+      const unsigned copies = max(1u, min(static_cast<unsigned>(kWarps), kHistWords / bins));
+      for (unsigned b = t; b < bins; b += kConsumers) {
         unsigned long long cnt = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) cnt += hist[w * 256u + b];
+        for (unsigned w = 0; w < copies; ++w) cnt += hist[w * bins + b];
         if (cnt) atomicAdd(A.hist + b, cnt);
+      }
+      if (LEAF == FQB200_LEAF_MIDTREAD && A.hist_clamped && active) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (ap.nlo[i]) atomicAdd(A.hist_clamped + 2u * (c0 + i), static_cast<unsigned long long>(ap.nlo[i]));
+          if (ap.nhi[i]) atomicAdd(A.hist_clamped + 2u * (c0 + i) + 1u, static_cast<unsigned long long>(ap.nhi[i]));
+        }
       }
     }
     if (blockIdx.x == 0) stamp(A, 9);
@@ -608,6 +657,181 @@ __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_given_kernel(c
   RingPos pos;
   pos.init();
   consume_phase(g, ring, fq_dyn, pos, ap);
+}
+
+// ---- `-bca`: given-parameter quantization with activation bias correction (inference_quantization_manager.py:180-196) -----
+// Per channel: q_bias = (sum r - sum y) / (#(r > 0) + 1e-8) with y the quantized activation and r the activation itself
+// (rectified first when a ReLU follows), added back where y > 0.  Two passes over x (both recompute y), one write:
+// 12 B/element where the reference makes three transposed copies, three reductions and three elementwise passes.
+struct ClBca1 {
+  const FusedArgs& A;
+  LeafParam q[4];
+  float r[4], bias[4], fr[4], fy[4];
+  double sr[4], sy[4];
+  unsigned cnt[4], n;
+  bool fast;
+  __device__ __forceinline__ void flush() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      sr[i] += static_cast<double>(fr[i]);
+      sy[i] += static_cast<double>(fy[i]);
+      fr[i] = 0.f;
+      fy[i] = 0.f;
+    }
+    n = 0;
+  }
+  template <bool FAST>
+  __device__ __forceinline__ void one(const float4& v) {
+    const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      Divisor dv;
+      dv.s = q[i].a;
+      dv.r = r[i];
+      dv.fast = FAST;
+      float gq;
+      const float xb = __fadd_rn(x[i], bias[i]);
+      const float y = leaf_apply<FQB200_LEAF_TORCH, FAST>(xb, q[i], dv, 0.f, gq);
+      const float rr = (A.relu_passthrough && xb < 0.f) ? 0.f : xb;
+      fr[i] = __fadd_rn(fr[i], rr);
+      fy[i] = __fadd_rn(fy[i], y);
+      cnt[i] += rr > 0.f ? 1u : 0u;
+    }
+    if (++n == kClChunk) flush();
+  }
+  __device__ __forceinline__ void consume(const float4& v, unsigned) {
+    if (fast)
+      one<true>(v);
+    else
+      one<false>(v);
+  }
+};
+
+struct ClBca2 {
+  const FusedArgs& A;
+  LeafParam q[4];
+  float r[4], bias[4], qb[4];
+  bool fast;
+  template <bool FAST>
+  __device__ __forceinline__ void one(const float4& v, unsigned off) {
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    float y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      Divisor dv;
+      dv.s = q[i].a;
+      dv.r = r[i];
+      dv.fast = FAST;
+      float gq;
+      y[i] = leaf_apply<FQB200_LEAF_TORCH, FAST>(__fadd_rn(x[i], bias[i]), q[i], dv, 0.f, gq);
+      if (y[i] > 0.f) y[i] = __fadd_rn(y[i], qb[i]);
+    }
+    st_tensor(reinterpret_cast<float4*>(A.out) + off, make_float4(y[0], y[1], y[2], y[3]));
+  }
+  __device__ __forceinline__ void consume(const float4& v, unsigned off) {
+    if (fast)
+      one<true>(v, off);
+    else
+      one<false>(v, off);
+  }
+};
+
+__global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_bca_kernel(const __grid_constant__ FusedArgs A) {
+  extern __shared__ __align__(128) unsigned char fq_dyn[];
+  unsigned char* stages = fq_dyn;
+  unsigned char* cbuf = fq_dyn + kStages * kStageBytes;
+  __shared__ BulkRing ring;
+  const FlatGeo& g = A.flat;
+  const unsigned C = g.channels, cv = g.cv;
+  const unsigned bank = ld_ws(&A.sync->launch_count) & 1u;
+  ring_init(ring);
+  if (threadIdx.x >= kConsumers) {
+    if (threadIdx.x == kConsumers) {
+      RingPos pos;
+      pos.init();
+      const float4* src = reinterpret_cast<const float4*>(A.in);
+      const TicketPlan all = {2u, blockIdx.x, gridDim.x, 2u * gridDim.x};
+      produce_phase<false>(g, src, &A.sync->unit_counter[0], all, ring, stages, pos);
+      produce_phase<true>(g, src, &A.sync->unit_counter[1], all, ring, stages, pos);
+    }
+    return;
+  }
+  const unsigned t = threadIdx.x;
+  const bool active = t < g.stride;
+  const unsigned c0 = active ? 4u * (t % cv) : 0u;
+  const ClView acc = cl_view(A, bank);
+  const unsigned rep = A.nhwc_rep;
+  const unsigned rep_base = (blockIdx.x % rep) * C;
+  unsigned epoch = 0;
+  RingPos pos;
+  pos.init();
+  if (blockIdx.x == gridDim.x - 1u) {  // zero the bank of the previous launch
+    const ClView other = cl_view(A, bank ^ 1u);
+    uint4* zu = reinterpret_cast<uint4*>(other.amin_inv);
+    uint4* zd = reinterpret_cast<uint4*>(other.asum);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (unsigned i = t; i < kAccU / 4u; i += kConsumers) zu[i] = z;
+    for (unsigned i = t; i < kAccD / 2u; i += kConsumers) zd[i] = z;
+  }
+  ClBca1 p1{A};
+  p1.fast = true;
+  p1.n = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const unsigned c = c0 + i;
+    const unsigned pi = A.given_per_group ? c : 0u;
+    const float bits = A.g_bits ? __ldg(A.g_bits + c) : static_cast<float>(A.num_bits);
+    p1.q[i] = make_leaf_param(FQB200_LEAF_TORCH, __ldg(A.g_delta + pi), __ldg(A.g_offset + pi), bits);
+    const Divisor dv = make_divisor(p1.q[i].a);
+    p1.r[i] = dv.r;
+    p1.fast = p1.fast && dv.fast;
+    p1.bias[i] = (A.bias && active) ? __ldg(A.bias + c) : 0.f;
+    p1.fr[i] = p1.fy[i] = 0.f;
+    p1.sr[i] = p1.sy[i] = 0.0;
+    p1.cnt[i] = 0u;
+  }
+  consume_phase(g, ring, stages, pos, p1);
+  p1.flush();
+  double dc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dc[i] = static_cast<double>(p1.cnt[i]);
+  cl_combine(cbuf, cv, g.stride, p1.sr, 0.0, OpAdd(), [&](unsigned c, double v) { red_add_f64(acc.asum + rep_base + c, v); });
+  cl_combine(cbuf, cv, g.stride, p1.sy, 0.0, OpAdd(), [&](unsigned c, double v) { red_add_f64(acc.asq + rep_base + c, v); });
+  cl_combine(cbuf, cv, g.stride, dc, 0.0, OpAdd(), [&](unsigned c, double v) { red_add_f64(acc.aabs + rep_base + c, v); });
+  grid_barrier_cl(A.sync, epoch);
+  // q_bias of every channel, each accumulator value read once per CTA (table in shared memory; direct when cv == stride)
+  auto qbias_of = [&](unsigned c) {
+    double a = 0.0, b = 0.0, n = 0.0;
+    for (unsigned r = 0; r < rep; ++r) {
+      a += ld_ws(acc.asum + r * C + c);
+      b += ld_ws(acc.asq + r * C + c);
+      n += ld_ws(acc.aabs + r * C + c);
+    }
+    // fp32 like the reference: (sum r - sum y) / (count + 1e-8)
+    return __fdiv_rn(__fsub_rn(static_cast<float>(a), static_cast<float>(b)), __fadd_rn(static_cast<float>(n), 1e-8f));
+  };
+  ClBca2 p2{A};
+  p2.fast = p1.fast;
+  if (cv == g.stride) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p2.qb[i] = qbias_of(c0 + i);
+  } else {
+    float* tab = reinterpret_cast<float*>(cbuf);
+    consumer_sync();
+    for (unsigned c = t; c < C; c += kConsumers) tab[c] = qbias_of(c);
+    consumer_sync();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p2.qb[i] = tab[c0 + i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    p2.q[i] = p1.q[i];
+    p2.r[i] = p1.r[i];
+    p2.bias[i] = p1.bias[i];
+    if (A.out_stats && blockIdx.x == 0 && t < cv) A.out_stats[c0 + i] = p2.qb[i];  // diagnostics: the correction applied
+  }
+  consume_phase(g, ring, stages, pos, p2);
+  grid_exit_cl(A.sync);
 }
 
 }  // namespace fqb

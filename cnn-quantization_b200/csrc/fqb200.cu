@@ -37,7 +37,7 @@ constexpr int kTable = 101;
 __constant__ double kOmegaTable[kTable];
 __constant__ double kAlphaTable[kTable];
 
-enum : int { FLAG_PASSTHROUGH = 1, FLAG_TRUE_ZERO = 2 };
+enum : int { FLAG_PASSTHROUGH = 1, FLAG_TRUE_ZERO = 2, FLAG_RELU = 4 };
 
 // Per-group (or per-tensor) leaf parameters as the apply phase consumes them.
 //   torch leaf:     a = scale, b = zero_point,            c = qmax
@@ -65,13 +65,16 @@ struct FusedArgs {
   float mt_target;
   int mt_clip;
   int bias_corr, var_corr, stats_only;
+  int relu_passthrough;  // fqb200_desc.relu_passthrough
   int need_dev;      // phase S2 required (b and/or std)
   const float *g_delta, *g_offset, *g_bits;
   int given_per_group;
   unsigned inner;      // floats per channel row (bundled layouts locate channel boundaries with it)
   double n_per_group;  // outer * inner
   float* out_stats;
-  unsigned long long* hist;  // optional 256-bin histogram of the integer grid (entropy measurement, `-me`), accumulated
+  unsigned long long* hist_clamped;  // mid-tread `-me`: [channels][2] elements on the lower / upper clamp bound
+  int hist_bins, hist_offset;        // integer-grid histogram: bin = clamp(q + hist_offset, 0, hist_bins - 1)
+  unsigned long long* hist;  // optional histogram of the integer grid (entropy measurement, `-me`), accumulated
   unsigned long long* dbg;   // fqb200_desc.debug_stamps: %globaltimer at the phase boundaries (NULL: off)
   // workspace
   GridSync* sync;
@@ -277,7 +280,7 @@ __device__ __forceinline__ void solve_range(const FusedArgs& A, float mn, float 
 }
 
 // leaf parameters from (delta, offset, bits)
-__device__ __forceinline__ LeafParam make_leaf_param(int leaf, float delta, float offset, float bits) {
+__device__ __forceinline__ LeafParam make_leaf_param(int leaf, float delta, float offset, float bits, bool relu = false) {
   LeafParam q;
   q.flags = 0;
   if (leaf == FQB200_LEAF_TORCH) {
@@ -295,7 +298,7 @@ __device__ __forceinline__ LeafParam make_leaf_param(int leaf, float delta, floa
       q.a = 1.f;
       q.b = 0.f;
       q.c = 0.f;
-      q.flags = FLAG_PASSTHROUGH;
+      q.flags = FLAG_PASSTHROUGH | (relu ? FLAG_RELU : 0);
       return q;
     }
     const float qmax = static_cast<float>((1 << static_cast<int>(bits)) - 1);
@@ -403,7 +406,7 @@ __device__ __noinline__ void solve_params(const FusedArgs& A, LeaderSmem& sm) {
     if (threadIdx.x == 0) {
       float delta, offset;
       solve_range(A, mn, mx, 0.f, 0.f, 0.f, static_cast<float>(A.num_bits), delta, offset);
-      const LeafParam q = make_leaf_param(A.leaf, delta, offset, static_cast<float>(A.num_bits));
+      const LeafParam q = make_leaf_param(A.leaf, delta, offset, static_cast<float>(A.num_bits), A.relu_passthrough != 0);
       A.lp[0] = q;
       A.gdelta[0] = delta;
       A.goffset[0] = offset;
@@ -417,7 +420,7 @@ __device__ __noinline__ void solve_params(const FusedArgs& A, LeaderSmem& sm) {
     const float b = A.need_dev ? A.gb[g] : 0.f, sd = A.need_dev ? A.gstd[g] : 0.f;
     float delta, offset;
     solve_range(A, mn, mx, mean, b, sd, bits, delta, offset);
-    const LeafParam q = make_leaf_param(A.leaf, delta, offset, bits);
+    const LeafParam q = make_leaf_param(A.leaf, delta, offset, bits, A.relu_passthrough != 0);
     A.lp[g] = q;
     A.gdelta[g] = delta;
     A.goffset[g] = offset;
@@ -597,7 +600,7 @@ __device__ __forceinline__ float leaf_apply(float x, const LeafParam& q, const D
     // gemmlowp.cu:10-24
     if (q.flags & FLAG_PASSTHROUGH) {
       grid = x;
-      return x;
+      return ((q.flags & FLAG_RELU) && x < 0.f) ? 0.f : x;  // the caller fused the ReLU that follows away
     }
     float t;
     if (q.flags & FLAG_TRUE_ZERO)
@@ -1127,6 +1130,44 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) fq_given_kernel(const __
   stream_units<VEC, false>(A.geo, A.in, nullptr, ssm, acc);
 }
 
+// y = max(a + b, 0): the residual add + ReLU that closes every ResNet block, one pass (2 reads + 1 write) instead of torch's
+// add_ (2R + 1W) and relu_ (1R + 1W).  fl(a + b) then the clamp: bit-identical to the two torch kernels.  NaN propagates
+// like torch.relu (x < 0 ? 0 : x).
+template <int VEC>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+    fq_add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, unsigned long long nvec) {
+  using V = typename VecT<VEC>::type;
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kThreads;
+  unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * kThreads + threadIdx.x;
+  constexpr int U = 4;
+  auto f = [](float x, float y) {
+    const float s = __fadd_rn(x, y);
+    return s < 0.f ? 0.f : s;
+  };
+  for (; i < nvec; i += U * stride) {
+    V x[U], y[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      ok[u] = i + u * stride < nvec;
+      if (ok[u]) {
+        x[u] = ld_tensor(reinterpret_cast<const V*>(a) + i + u * stride);
+        y[u] = ld_tensor(reinterpret_cast<const V*>(b) + i + u * stride);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      if constexpr (VEC == 4) {
+        st_tensor(reinterpret_cast<float4*>(out) + i + u * stride,
+                  make_float4(f(x[u].x, y[u].x), f(x[u].y, y[u].y), f(x[u].z, y[u].z), f(x[u].w, y[u].w)));
+      } else {
+        st_tensor(out + i + u * stride, f(x[u], y[u]));
+      }
+    }
+  }
+}
+
 // test hook: q[i] = div_exact(a[i], b[i]) next to IEEE a[i]/b[i]
 __global__ void fq_divtest_kernel(const float* a, const float* b, float* fast, float* ieee, unsigned long long n) {
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
@@ -1156,13 +1197,16 @@ int fail(int code, const char* fmt, const char* detail = "") {
 // channels-last kernel variants: leaf (torch / mid-tread) x second statistics pass x histogram
 const void* cl_kernel_ptr(int leaf, bool dev, bool hist) {
 #define FQB_CL(L, D, H) reinterpret_cast<const void*>(fqb::fq_cl_kernel<L, D, H>)
-  if (leaf == FQB200_LEAF_MIDTREAD) return dev ? FQB_CL(FQB200_LEAF_MIDTREAD, true, false) : FQB_CL(FQB200_LEAF_MIDTREAD, false, false);
+  if (leaf == FQB200_LEAF_MIDTREAD) {
+    if (hist) return dev ? FQB_CL(FQB200_LEAF_MIDTREAD, true, true) : FQB_CL(FQB200_LEAF_MIDTREAD, false, true);
+    return dev ? FQB_CL(FQB200_LEAF_MIDTREAD, true, false) : FQB_CL(FQB200_LEAF_MIDTREAD, false, false);
+  }
   if (hist) return dev ? FQB_CL(FQB200_LEAF_TORCH, true, true) : FQB_CL(FQB200_LEAF_TORCH, false, true);
   return dev ? FQB_CL(FQB200_LEAF_TORCH, true, false) : FQB_CL(FQB200_LEAF_TORCH, false, false);
 #undef FQB_CL
 }
 size_t cl_smem(bool hist) {
-  return static_cast<size_t>(fqb::kStages) * fqb::kStageBytes + fqb::kClCombineBytes + (hist ? fqb::kWarps * 256u * sizeof(unsigned) : 0u);
+  return static_cast<size_t>(fqb::kStages) * fqb::kStageBytes + fqb::kClCombineBytes + (hist ? fqb::kHistWords * sizeof(unsigned) : 0u);
 }
 size_t cl_given_smem() { return static_cast<size_t>(fqb::kStages) * fqb::kStageBytes; }
 
@@ -1172,6 +1216,7 @@ struct DeviceInfo {
   int sms = 0;
   int resident = 0;        // CTAs of the cp.async-ring fused kernels (512 threads) that fit at once
   int resident_cl[2] = {0, 0};  // channels-last kernels without / with the histogram
+  int resident_bca = 0;         // fq_cl_bca_kernel
 };
 constexpr int kMaxDevices = 64;
 DeviceInfo g_dev[kMaxDevices];
@@ -1266,7 +1311,6 @@ void init_device(int dev) {
     int worst = 1 << 20;
     for (int leaf = 0; leaf < 3; leaf += 2)
       for (int dv = 0; dv < 2; ++dv) {
-        if (hist && leaf == FQB200_LEAF_MIDTREAD) continue;
         int n = 0;
         const void* fn = cl_kernel_ptr(leaf, dv != 0, hist != 0);
         const size_t smem = cl_smem(hist != 0);
@@ -1281,6 +1325,14 @@ void init_device(int dev) {
       return;
     }
     d.resident_cl[hist] = sms * worst;
+  }
+  {
+    int n = 0;
+    const void* fn = reinterpret_cast<const void*>(fqb::fq_cl_bca_kernel);
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cl_smem(false)));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kBulkThreads, cl_smem(false));
+    if (e != cudaSuccess || n < 1) return bad("bias-correction kernel setup", e);
+    d.resident_bca = sms * n;
   }
   const void* given[4] = {reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, false>),
                           reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, true>),
@@ -1502,7 +1554,7 @@ int check_desc(const fqb200_desc* d) {
 // what the channels-last kernel can take (everything else with channels_last set is an error: the caller re-lays out)
 bool cl_supported(const fqb200_desc* d) {
   return d->scope == FQB200_SCOPE_GROUP && d->leaf != FQB200_LEAF_COMPILED && !d->bias_corr && !d->var_corr && d->bias_period <= 0 &&
-         flat_eligible(d->groups) && !(d->out_hist && d->leaf != FQB200_LEAF_TORCH);
+         flat_eligible(d->groups);
 }
 // phase S2 (sum |x - mean|) of the channels-last kernel: only where the Laplace b is consumed
 bool cl_needs_b(const fqb200_desc* d) {
@@ -1738,11 +1790,18 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   A.bias_corr = d->bias_corr;
   A.var_corr = d->var_corr;
   A.stats_only = d->stats_only;
+  A.relu_passthrough = d->relu_passthrough;
   A.out_stats = d->out_stats;
   A.bias = d->bias;
   A.hist = d->out_hist;
+  A.hist_bins = d->out_hist ? (d->hist_bins > 0 ? d->hist_bins : 256) : 0;
+  A.hist_offset = d->hist_offset;
+  A.hist_clamped = d->out_hist_clamped;
   A.dbg = d->debug_stamps;
-  if (d->out_hist && d->leaf != FQB200_LEAF_TORCH) return fail(FQB200_ERR_UNSUPPORTED, "out_hist: torch leaf only%s");
+  if (d->out_hist && d->leaf != FQB200_LEAF_TORCH && !d->channels_last)
+    return fail(FQB200_ERR_UNSUPPORTED, "out_hist: torch leaf, or the mid-tread leaf on channels-last tensors%s");
+  if (d->out_hist && (A.hist_bins > static_cast<int>(fqb::kHistWords) || (!d->channels_last && A.hist_bins != 256)))
+    return fail(FQB200_ERR_UNSUPPORTED, "hist_bins: 256 (default), up to 8192 on channels-last tensors%s");
   A.bias_magic = 0;
   if (d->bias && d->bias_period > 0) {
     // bias indexed by the channel inside the row: needs whole vectors per channel and an exact magic division
@@ -1777,6 +1836,70 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
                                     : fused_kernel_ptr(pl.mode, d->leaf, A.need_dev != 0, d->bias_corr || d->var_corr);
   e = cudaLaunchCooperativeKernel(kernel, dim3(pl.grid), dim3(fqb::kThreads), args, dyn_smem(pl.vec), st);
   if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cooperative launch fq_fused_kernel: %s", cudaGetErrorString(e));
+  return FQB200_OK;
+}
+
+int fqb200_quantize1_bca(const float* in, float* out, int64_t outer, int64_t groups, int64_t inner, const float* delta,
+                         const float* offset, const float* bits, int per_group, int num_bits, const float* bias, int relu_first,
+                         float* out_qbias, void* workspace, size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  if (outer == 0 || groups == 0 || inner == 0) return FQB200_OK;
+  if (!in || !out || !delta || !offset) return fail(FQB200_ERR_INVALID, "null pointer%s");
+  if ((num_bits < 1 || num_bits > 8) && !bits) return fail(FQB200_ERR_INVALID, "num_bits must be in 1..8%s");
+  if (bits && !per_group) return fail(FQB200_ERR_INVALID, "per-row bit widths need per-group parameters%s");
+  if (!(aligned16(in) && aligned16(out) && flat_eligible(groups)))
+    return fail(FQB200_ERR_UNSUPPORTED, "bias-corrected quantization runs on channels-last tensors: 16-byte aligned, C %% 4 == 0, C <= 2048%s");
+  DeviceInfo* di = nullptr;
+  int rc = get_device(&di);
+  if (rc != FQB200_OK) return rc;
+  Plan pl;
+  rc = make_plan_flat(static_cast<uint64_t>(outer) * groups * inner, groups, di->resident_bca, &pl);
+  if (rc != FQB200_OK) return rc;
+  fqb::FusedArgs A;
+  memset(&A, 0, sizeof(A));
+  const size_t need = carve(nullptr, 0, static_cast<uint64_t>(groups), nullptr);
+  if (!workspace || workspace_bytes < need) return fail(FQB200_ERR_WORKSPACE, "workspace smaller than fqb200_workspace_bytes()%s");
+  carve(static_cast<char*>(workspace), 0, static_cast<uint64_t>(groups), &A);
+  A.flat = pl.flat;
+  A.geo = pl.geo;
+  A.in = in;
+  A.out = out;
+  A.leaf = FQB200_LEAF_TORCH;
+  A.num_bits = num_bits;
+  A.g_delta = delta;
+  A.g_offset = offset;
+  A.g_bits = bits;
+  A.given_per_group = per_group;
+  A.bias = bias;
+  A.relu_passthrough = relu_first;
+  A.out_stats = out_qbias;
+  const unsigned r = fqb::kMaxNhwcChannels / static_cast<unsigned>(groups);
+  A.nhwc_rep = r < 1u ? 1u : (r > 8u ? 8u : r);
+  void* args[] = {&A};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(fqb::fq_cl_bca_kernel), dim3(pl.grid),
+                                              dim3(fqb::kBulkThreads), args, cl_smem(false), static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cooperative launch fq_cl_bca_kernel: %s", cudaGetErrorString(e));
+  return FQB200_OK;
+}
+
+int fqb200_add_relu(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  g_err[0] = 0;
+  if (n < 0) return fail(FQB200_ERR_INVALID, "negative size%s");
+  if (n == 0) return FQB200_OK;
+  if (!a || !b || !out) return fail(FQB200_ERR_INVALID, "null tensor pointer%s");
+  DeviceInfo* di = nullptr;
+  int rc = get_device(&di);
+  if (rc != FQB200_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool vec = (n % 4 == 0) && aligned16(a) && aligned16(b) && aligned16(out);
+  const unsigned long long nvec = vec ? static_cast<unsigned long long>(n / 4) : static_cast<unsigned long long>(n);
+  unsigned long long want = (nvec + fqb::kThreads * 4ull - 1) / (fqb::kThreads * 4ull);
+  const unsigned long long cap = static_cast<unsigned long long>(di->resident) * 4ull;
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  if (vec) fqb::fq_add_relu_kernel<4><<<grid, fqb::kThreads, 0, st>>>(a, b, out, nvec);
+  else     fqb::fq_add_relu_kernel<1><<<grid, fqb::kThreads, 0, st>>>(a, b, out, nvec);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "launch fq_add_relu_kernel: %s", cudaGetErrorString(e));
   return FQB200_OK;
 }
 

@@ -102,12 +102,21 @@ class IntQuantizer(object):
         # (columns _lib.STAT_COLUMNS) in ``last_stats`` - what the parity tests compare with the reference's values
         self.export_stats = False
         self.last_stats = None
+        self._relu_follows = False
+        self._bca = None
 
     # ------------------------------------------------------------------------------------------
     # dispatch (int_quantizer.py:92-122)
     # ------------------------------------------------------------------------------------------
-    def __call__(self, tensor, id, tag="", stat_id=None, override_att=None, weight_correction=None, bias=None):
-        """Extensions used by this package's manager (both default to the reference behaviour):
+    def __call__(self, tensor, id, tag="", stat_id=None, override_att=None, weight_correction=None, bias=None,
+                 relu_follows=False, bias_correct=None):
+        """Extensions used by this package's manager (all default to the reference behaviour):
+        ``bias_correct`` (None = off, else the "ReLU follows" flag of the call site): the activation bias correction of
+        Conv2dWithId.forward (`-bca`, inference_quantization_manager.py:180-196) is applied by the quantizer itself - inside
+        the given-parameter launch for channels-last tensors;
+        ``relu_follows``: the caller will skip the ReLU that follows when the result is tagged ``_fq_nonneg`` - set on
+        every result of a positive (half-range / force-positive) range, where offset 0 gives zero point 0 and every value
+        is q * scale >= 0; the compiled leaf's empty-range pass-through then returns max(x, 0) (fqb200_desc.relu_passthrough);
         ``weight_correction=(bias_corr, var_corr)``: the per-output-channel mean / variance correction of
         inference_quantization_manager.py:374-391 is applied inside the same launch that quantizes the weight;
         ``bias``: a per-channel vector added to the tensor before anything else inside the kernel (the folded-BN
@@ -115,6 +124,8 @@ class IntQuantizer(object):
         if override_att is not None:
             orig_att = getattr(self, override_att[0])
             setattr(self, override_att[0], override_att[1])
+        self._relu_follows = bool(relu_follows) and self._positive()
+        self._bca = bias_correct
         try:
             self._unsupported(stat_id)
             if bias is not None and not self._bias_fusable(tensor):
@@ -142,6 +153,10 @@ class IntQuantizer(object):
         finally:
             if override_att is not None:
                 setattr(self, override_att[0], orig_att)
+        if self._relu_follows and isinstance(res, torch.Tensor):
+            res._fq_nonneg = res._version   # void as soon as somebody modifies the tensor in place
+        self._relu_follows = False
+        self._bca = None
         return res
 
     def __repr__(self):
@@ -158,8 +173,6 @@ class IntQuantizer(object):
             raise NotImplementedError("KLD thresholds are outside the hot-path scope (SURVEY.md section 2, #9)")
         if stat_id is not None and self.sm is None:
             raise RuntimeError("stat_id given but no statistics manager is attached to this quantizer (q.sm)")
-        if self.measure_entropy and self.mtd_quant:
-            raise NotImplementedError("entropy measurement of the mid-tread grid is not implemented")
 
     def _pc_act(self, tensor):
         return bool(self.pcq_a and len(tensor.shape) > 3 and (tensor.shape[2] > 1 or tensor.shape[3] > 1))
@@ -224,6 +237,33 @@ class IntQuantizer(object):
 
     def _prior(self):
         return L.PRIOR_STD if self.bit_alloc_prior == "gaus" else L.PRIOR_B
+
+    @staticmethod
+    def bias_correction_torch(out, out_q, relu_first):
+        """`-bca` with stock torch ops (inference_quantization_manager.py:180-196; reductions over (N, H, W) directly, no
+        transposes): the fallback for tensors the fused channels-last launch does not take."""
+        if relu_first:
+            out = torch.nn.functional.relu(out)
+        dims = (0, 2, 3)
+        q_bias = out.sum(dims) - out_q.sum(dims)
+        count = (out > 0).sum(dims).to(q_bias.dtype)
+        q_bias = q_bias / (count + 1e-8)
+        out_q += (out_q > 0).to(out_q.dtype) * q_bias.view(1, -1, 1, 1)
+        return out_q
+
+    def _quantize1(self, tensor, delta, offset, bits=None, layout=None, bias=None):
+        """Mode A launch; with ``bias_correct`` set the activation bias correction rides along."""
+        if self._bca is None or tensor.dim() != 4:
+            return ops.quantize1(tensor, delta, offset, self.num_bits, bits=bits, layout=layout, bias=bias, out=self._out(tensor))
+        relu_first = bool(self._bca)
+        c = tensor.shape[1]
+        if c % 4 == 0 and 4 <= c <= 2048:
+            x = tensor if ops.cl_eligible(tensor) else tensor.contiguous(memory_format=torch.channels_last)
+            if ops.cl_eligible(x):
+                return ops.quantize1_bca(x, delta, offset, self.num_bits, bits=bits, bias=bias, relu_first=relu_first,
+                                         out=x if (self.inplace or x is not tensor) else None)
+        ref = tensor if bias is None else tensor + bias.view(1, -1, 1, 1)
+        return self.bias_correction_torch(ref, ops.quantize1(ref, delta, offset, self.num_bits, bits=bits, layout=layout), relu_first)
 
     def _fused(self, tensor, layout, **kw):
         """ops.fused, keeping the exported statistics table when ``export_stats`` is set."""
@@ -308,8 +348,9 @@ class IntQuantizer(object):
         if stat_id is not None:
             delta, offset, bits, per_channel = self._clipping_params_from_stats(tensor, stat_id, clip_type)
             if per_channel:
-                return ops.quantize1(tensor, delta, offset, self.num_bits, bits=bits, layout=self._nchw_layout(tensor),
-                                     bias=bias, out=self._out(tensor))
+                return self._quantize1(tensor, delta, offset, bits=bits, layout=self._nchw_layout(tensor), bias=bias)
+            if self._bca is not None and tensor.dim() == 4:
+                return self._quantize1(tensor, delta, offset, bias=bias)   # one parameter set, per-channel correction
             if bias is not None:
                 tensor = tensor.add_(bias.view(1, -1, 1, 1)) if self.inplace else tensor + bias.view(1, -1, 1, 1)
             return ops.quantize1(tensor, delta, offset, self.num_bits, out=self._out(tensor))
@@ -343,10 +384,16 @@ class IntQuantizer(object):
                 min_ = 0.0
             delta = np.float32(max_) - np.float32(min_)
             preserve_zero = bool((np.float32(min_) + delta) > 0 and min_ < 0)
-            return ops.float2gemmlowp(tensor, float(delta), min_, self.num_bits, self.int_exp, preserve_zero, None,
-                                      out=self._out(tensor)) if delta > 0 else tensor
+            if delta > 0:
+                if self._bca is not None and tensor.dim() == 4:
+                    return self.bias_correction_torch(tensor, ops.float2gemmlowp(tensor, float(delta), min_, self.num_bits,
+                                                                                 self.int_exp, preserve_zero, None), bool(self._bca))
+                return ops.float2gemmlowp(tensor, float(delta), min_, self.num_bits, self.int_exp, preserve_zero, None,
+                                          out=self._out(tensor))
+            return torch.relu_(tensor) if (self._relu_follows and self.inplace) else (torch.relu(tensor) if self._relu_follows else tensor)
         avg = ("activation" in tag and "classifier" not in tag)
-        kw = dict(range_mode=L.RANGE_MINMAX, leaf=L.LEAF_COMPILED, num_bits=self.num_bits, positive=self._positive())
+        kw = dict(range_mode=L.RANGE_MINMAX, leaf=L.LEAF_COMPILED, num_bits=self.num_bits, positive=self._positive(),
+                  relu_passthrough=self._relu_follows)
         if bias is not None:
             kw.update(bias=bias, bias_period=tensor.shape[2] * tensor.shape[3])
         if weight_correction is not None and any(weight_correction):
@@ -380,8 +427,7 @@ class IntQuantizer(object):
                 return (mx - mn).contiguous(), mn.contiguous(), bits
 
             delta, offset, bits = self._cached(key, build)
-            return ops.quantize1(tensor, delta, offset, self.num_bits, bits=bits, layout=layout, bias=bias,
-                                 out=self._out(tensor))
+            return self._quantize1(tensor, delta, offset, bits=bits, layout=layout, bias=bias)
         if min_ is None and max_ is None:
             hist = self._hist(tensor)
             res = self._fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
@@ -434,9 +480,59 @@ class IntQuantizer(object):
         return res
 
     # mid-tread "bin allocation" quantizer, int_quantizer.py:147-225
+    # `-me` on the mid-tread grid (int_quantizer.py:216-221): the grid is signed, clamped to per-channel and generally
+    # FRACTIONAL bounds c_min / c_max, and the reference runs torch.unique over the float grid of all channels together -
+    # so every channel's clamp bounds are symbols of their own.  The channels-last kernel histograms the integers and
+    # counts the elements sitting on a bound per channel; the symbol table is assembled from those (a few thousand entries).
+    MT_HIST_BINS, MT_HIST_OFFSET = 8192, 4096
+
+    @staticmethod
+    def mid_tread_entropy_from_hist(hist, offset, clamped, c_min, c_max):
+        dev = hist.device
+        values = torch.cat([torch.arange(hist.numel(), device=dev, dtype=torch.float32) - float(offset),
+                            c_min.reshape(-1).float(), c_max.reshape(-1).float()])
+        counts = torch.cat([hist.double(), clamped[:, 0].double(), clamped[:, 1].double()])
+        keep = counts > 0
+        values, counts = values[keep], counts[keep]
+        _, inv = torch.unique(values, return_inverse=True)           # equal floats are ONE symbol, as for torch.unique
+        merged = torch.zeros(int(inv.max()) + 1 if inv.numel() else 0, dtype=torch.float64, device=dev).scatter_add_(0, inv, counts)
+        p = (merged / merged.sum()).float()
+        return -(p * torch.log2(p)).sum()
+
+    def _mid_tread_entropy_torch(self, rows2d, target, clip, sym):
+        """The same measurement with stock torch ops on a [R, K] view (weights, non-channels-last activations: small or
+        rare tensors; the arithmetic follows int_quantizer.py:185-221 step by step)."""
+        t = rows2d
+        omega = self.get_omega(t.std(-1), target_bins=(2 ** target)).round()
+        if clip:
+            am = t.new_tensor(self.get_alpha_mult(omega, sym=sym))
+            mu = t.mean(dim=-1)
+            b = torch.mean(torch.abs(t - mu.unsqueeze(-1)), dim=-1)
+            rng = (2 * am * b) if sym else (torch.max(mu, mu.new_tensor([0.])) + am * b)
+        else:
+            rng = (t.max(-1)[0] - t.min(-1)[0]) if sym else t.max(-1)[0]
+        step = torch.where(omega > 0, rng / omega, t.new_tensor([np.finfo(np.float32).max]))
+        grid = (t / step.unsqueeze(-1)).round_()
+        if clip:
+            mu_q = mu / step if sym else torch.max(mu, mu.new_tensor([0.])) / step
+            c_max = mu_q + (omega / 2 if sym else omega)
+            c_min = (mu_q - omega / 2) if sym else t.new_tensor([0])
+            grid = torch.max(torch.min(grid, c_max.unsqueeze(-1)), c_min.unsqueeze(-1))
+        counts = torch.unique(grid.flatten(), return_counts=True)[1].float()
+        p = counts / counts.sum()
+        return -(p * torch.log2(p)).sum()
+
+    def _log_mt_entropy(self, entropy, id, meter, numel):
+        self.last_entropy = entropy
+        if self.logger is not None:
+            self.logger.log_metric(id + ".entropy", entropy.item(), step="auto", meterId=meter, weight=numel)
+
     def mid_tread_quantize_weights_per_channel(self, tensor, id, weight_correction=None):
         rows = tensor.shape[0]
         bc, vc = weight_correction if weight_correction is not None else (False, False)
+        if self.measure_entropy:
+            self._log_mt_entropy(self._mid_tread_entropy_torch(tensor.reshape(rows, -1), self.bit_alloc_target_weight, False, True),
+                                 id, "avg.entropy.weight", tensor.numel())
         return self._fused(tensor, (1, rows, tensor.numel() // rows), leaf=L.LEAF_MIDTREAD, positive=False,
                          mt_target=self.bit_alloc_target_weight, mt_clip=False, bias_corr=bc, var_corr=vc)
 
@@ -449,9 +545,24 @@ class IntQuantizer(object):
                          mt_target=self.bit_alloc_target_act, mt_clip=True, out=self._out(tensor))
 
     def mid_tread_quantize_activation_per_channel(self, tensor, id, bias=None):
-        return self._fused(tensor, self._nchw_layout(tensor), leaf=L.LEAF_MIDTREAD, positive=self._positive(),
-                         mt_target=self.bit_alloc_target_act, mt_clip=True, bias=bias, out=self._out(tensor),
-                         channels_last=self._channels_last(tensor))
+        layout = self._nchw_layout(tensor)
+        kw = dict(leaf=L.LEAF_MIDTREAD, positive=self._positive(), mt_target=self.bit_alloc_target_act, mt_clip=True, bias=bias,
+                  out=self._out(tensor), channels_last=self._channels_last(tensor))
+        if not self.measure_entropy:
+            return self._fused(tensor, layout, **kw)
+        if kw["channels_last"]:
+            hist = torch.zeros(self.MT_HIST_BINS, dtype=torch.int64, device=tensor.device)
+            clamped = torch.zeros((layout[1], 2), dtype=torch.int64, device=tensor.device)
+            res, st = ops.fused(tensor, layout, want_stats=True, hist=hist, hist_offset=self.MT_HIST_OFFSET, hist_clamped=clamped, **kw)
+            self.last_stats = st
+            entropy = self.mid_tread_entropy_from_hist(hist, self.MT_HIST_OFFSET, clamped, st[:, 9], st[:, 10])
+        else:
+            x = tensor if bias is None else tensor + bias.view(1, -1, 1, 1)
+            entropy = self._mid_tread_entropy_torch(x.transpose(0, 1).reshape(layout[1], -1), self.bit_alloc_target_act, True,
+                                                    not self._positive())
+            res = self._fused(tensor, layout, **kw)
+        self._log_mt_entropy(entropy, id, "avg.entropy.act", tensor.numel())
+        return res
 
     def mid_tread_quantization(self, tensor, id, target, clip=False, sym=True):
         """[R, K] view, int_quantizer.py:185-225.  Returns (quantized, None) like the reference without entropy."""

@@ -143,13 +143,40 @@ def _identity_forward(x):
 
 
 def _relu_forward_skipping(relu):
-    """forward of an nn.ReLU that returns tensors tagged non-negative by the quantization hook untouched."""
+    """forward of an nn.ReLU that returns tensors tagged non-negative by the quantizer untouched.  The tag is the tensor's
+    version counter at tagging time, so any in-place modification in between (``out += identity``) voids it."""
     orig = type(relu).forward
 
     def forward(x):
-        if getattr(x, "_fq_nonneg", False):
+        if getattr(x, "_fq_nonneg", None) == x._version:
             return x
         return orig(relu, x)
+
+    return forward
+
+
+def _residual_block_forward(block, bottleneck):
+    """forward of a torchvision BasicBlock / Bottleneck (torchvision/models/resnet.py) with the closing
+    ``out += identity; out = relu(out)`` as ONE kernel (ops.add_relu_, SURVEY.md 8f rank 4: the elementwise surroundings of
+    the hooked convolutions were 20 % of a step's kernel time).  Everything else goes through the block's own modules, so
+    the quantization hooks fire exactly as before; results are bit-identical."""
+    from . import ops
+
+    def forward(x):
+        identity = x
+        out = block.relu(block.bn1(block.conv1(x)))
+        if bottleneck:
+            out = block.relu(block.bn2(block.conv2(out)))
+            out = block.bn3(block.conv3(out))
+        else:
+            out = block.bn2(block.conv2(out))
+        if block.downsample is not None:
+            identity = block.downsample(x)
+        if (out.is_cuda and out.dtype == torch.float32 and identity.dtype == torch.float32 and out.shape == identity.shape
+                and out.stride() == identity.stride() and ops._dense(out) and not out.requires_grad):
+            return ops.add_relu_(out, identity)
+        out += identity
+        return block.relu(out)
 
     return forward
 
@@ -185,8 +212,9 @@ class QuantizationManagerInference(object):
         # a half-range / force-positive quantization returns values >= 0 (offset 0 -> zero point 0): the ReLU that
         # follows it is the identity, so the hooked ReLU modules skip the pass over tensors tagged by the conv hook
         self.skip_redundant_relu = self._native
-        # activation bias correction needs the un-quantized tensor after the quantizer ran
-        self.inplace_activations = self._native and not (self.stats_mode == "use" and args.bias_corr_act)
+        # the `out += identity; relu` that closes a torchvision ResNet block runs as one fused kernel
+        self.fuse_residual_relu = self._native
+        self.inplace_activations = self._native
         # offline statistics (inference_quantization_manager.py:299-318)
         self.stats_manager = None
         self._sm_tensor = self._sm_channel = None
@@ -326,6 +354,15 @@ class QuantizationManagerInference(object):
     def attach(self, model):
         """Register the forward hooks.  Modules built outside ``enable()`` get ids in ``model.modules()`` order."""
         fallback = {cls: count(0) for cls in _STAMPED}
+        if self.fuse_residual_relu and self.enabled and self.stats_mode != "collect":
+            try:
+                from torchvision.models.resnet import BasicBlock, Bottleneck
+            except ImportError:  # pragma: no cover
+                BasicBlock = Bottleneck = ()
+            for m in model.modules():
+                if type(m) in (BasicBlock, Bottleneck) and type(getattr(m, "relu", None)) is nn.ReLU:
+                    m.forward = _residual_block_forward(m, type(m) is Bottleneck)
+                    self._patched.append(m)
         for m in model.modules():
             if self.skip_redundant_relu and self.enabled and type(m) is nn.ReLU and self.stats_mode != "collect":
                 m.forward = _relu_forward_skipping(m)
@@ -342,10 +379,12 @@ class QuantizationManagerInference(object):
                 self._patched.append(m)
                 continue
             if cls is nn.Conv2d and self.fuse_conv_bias and self.enabled and m.bias is not None:
-                # the convolution runs bias-free; the (folded-BN) bias is added inside the fused quantization kernel
-                m._fq_bias = m.bias.data
+                # the convolution runs bias-free; the (folded-BN) bias is added inside the fused quantization kernel.  The
+                # vector stays with the module as a (non-persistent) BUFFER, so .to() / .cuda() / DataParallel replicas
+                # carry it along; detach() puts the parameter back, on whatever device the module lives by then.
                 m._fq_bias_param = m.bias
                 m.bias = None
+                m.register_buffer("_fq_bias", m._fq_bias_param.data, persistent=False)
                 self._debiased.append(m)
             hook = {nn.Conv2d: self._conv_hook, nn.Linear: self._linear_hook, nn.MaxPool2d: self._maxpool_hook,
                     nn.AvgPool2d: self._avgpool_hook, nn.BatchNorm2d: self._bn_hook}[cls]
@@ -360,8 +399,12 @@ class QuantizationManagerInference(object):
             m.__dict__.pop("forward", None)
         self._patched = []
         for m in self._debiased:
-            m.bias = m._fq_bias_param
-            del m._fq_bias, m._fq_bias_param
+            param = m._fq_bias_param
+            param.data = m._fq_bias.data   # follows the module if it moved / changed dtype while attached
+            del m._buffers["_fq_bias"]
+            m._non_persistent_buffers_set.discard("_fq_bias")
+            del m._fq_bias_param
+            m.bias = param
         self._debiased = []
 
     def _stat_id(self, activation_id):
@@ -379,29 +422,13 @@ class QuantizationManagerInference(object):
         extra = {} if bias is None else {"bias": bias}
         half_range = hasattr(m, "before_relu")
         if self.stats_mode == "use" and self.bcorr_act:
-            ref = out if bias is None else out + bias.view(1, -1, 1, 1)  # the un-quantized activation
-            out_q = self.quantize_instant(ref, activation_id, tag, stat_id=activation_id, half_range=half_range,
-                                          verbose=self.verbose)
-            return self._activation_bias_correction(ref, out_q, half_range or self.fused_relu)
-        res = self.quantize_instant(out, activation_id, tag, stat_id=self._stat_id(activation_id), half_range=half_range,
-                                    verbose=self.verbose, **extra)
+            # `-bca` (:180-196): the correction runs inside the quantizer's given-parameter launch
+            return self.quantize_instant(out, activation_id, tag, stat_id=activation_id, half_range=half_range,
+                                         verbose=self.verbose, bias_correct=bool(half_range or self.fused_relu), **extra)
         if self.skip_redundant_relu and (half_range or self.fused_relu) and tag == "activation" and not self.bcorr_act:
-            res._fq_nonneg = True  # range starts at 0 with zero point 0: every value is q * scale >= 0
-        return res
-
-    @staticmethod
-    def _activation_bias_correction(out, out_q, relu_first):
-        """``-bca`` (inference_quantization_manager.py:180-196): per channel, the difference of the sums of the
-        (rectified) activation and its quantized version, divided by the number of positive entries, is added back
-        where the quantized activation is positive.  Reductions over (N, H, W) directly on NCHW (no transposes)."""
-        if relu_first:
-            out = torch.nn.functional.relu(out)
-        dims = (0, 2, 3)
-        q_bias = out.sum(dims) - out_q.sum(dims)
-        count = (out > 0).sum(dims).to(q_bias.dtype)
-        q_bias = q_bias / (count + 1e-8)
-        out_q += (out_q > 0).to(out_q.dtype) * q_bias.view(1, -1, 1, 1)
-        return out_q
+            extra["relu_follows"] = True   # the quantizer tags the result _fq_nonneg; the hooked ReLU then returns it untouched
+        return self.quantize_instant(out, activation_id, tag, stat_id=self._stat_id(activation_id), half_range=half_range,
+                                     verbose=self.verbose, **extra)
 
     def _linear_hook(self, m, inputs, out):
         if not self.enabled:

@@ -184,11 +184,50 @@ def quantize1(x, delta, offset, num_bits, bits=None, layout=None, want_grid=Fals
     return (out, grid) if want_grid else out
 
 
+def quantize1_bca(x, delta, offset, num_bits, bits=None, bias=None, relu_first=False, out=None, want_qbias=False):
+    """C ABI fqb200_quantize1_bca: given-parameter quantization of a channels-last [N, C, H, W] activation with the
+    reference's activation bias correction (`-bca`, inference_quantization_manager.py:180-196) in the same launch.
+    ``x`` must satisfy ``cl_eligible``.  Returns the corrected quantized tensor (and the [C] corrections)."""
+    _require_cuda_f32(x, "tensor")
+    if not cl_eligible(x):
+        raise ValueError("quantize1_bca needs a channels-last activation with C % 4 == 0, C <= 2048")
+    lib = L.load()
+    dev = x.device
+    n, c = x.shape[0], x.shape[1]
+    inner = x.numel() // (n * c)
+    delta = torch.as_tensor(delta, dtype=torch.float32, device=dev).contiguous()
+    offset = torch.as_tensor(offset, dtype=torch.float32, device=dev).contiguous()
+    per_group = delta.numel() > 1 or bits is not None
+    if per_group:
+        delta = delta.reshape(-1).expand(c).contiguous() if delta.numel() == 1 else delta
+        offset = offset.reshape(-1).expand(c).contiguous() if offset.numel() == 1 else offset
+    if bits is not None:
+        bits = torch.as_tensor(bits, dtype=torch.float32, device=dev).contiguous()
+    if bias is not None:
+        _require_cuda_f32(bias, "bias")
+        bias = bias.contiguous()
+    kout, uout = _resolve_out(x, out)
+    qb = torch.empty(c, dtype=torch.float32, device=dev) if want_qbias else None
+    d = L.Desc()
+    d.outer, d.groups, d.inner, d.num_bits, d.channels_last = n, c, inner, 8, 1
+    with torch.cuda.device(dev):
+        stream = _stream_handle(dev)
+        ws = _workspace(dev, stream, lib.fqb200_workspace_bytes(ctypes.byref(d)))
+        with _Timed("C", x.numel(), 12, "%dx%dx%d" % (n, c, inner)):
+            L.check(lib.fqb200_quantize1_bca(x.data_ptr(), kout.data_ptr(), n, c, inner, delta.data_ptr(), offset.data_ptr(),
+                                             bits.data_ptr() if bits is not None else None, int(per_group), int(num_bits),
+                                             bias.data_ptr() if bias is not None else None, int(bool(relu_first)),
+                                             qb.data_ptr() if qb is not None else None, ws.data_ptr(), ws.numel(), stream))
+    res = _finish_out(kout, uout)
+    return (res, qb) if want_qbias else res
+
+
 def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH, num_bits=8,
           positive=False, solve_f64=False, clip_k=0.0, bit_alloc=False, bit_alloc_prior=L.PRIOR_STD,
           bit_alloc_round=True, bit_alloc_target=None, mt_target=0.0, mt_clip=False, bias_corr=False,
           var_corr=False, stats_only=False, want_stats=False, out=None, bias=None, bias_period=0, hist=None,
-          channels_last=False, any_dense_format=False, debug_stamps=None):
+          channels_last=False, any_dense_format=False, debug_stamps=None, relu_passthrough=False, hist_offset=0,
+          hist_clamped=None):
     """C ABI fqb200_fused: statistics -> parameters -> quantize/dequantize in one launch.
 
     Returns ``out`` (or ``(out, stats)`` with ``want_stats``; ``stats`` alone with ``stats_only``), where
@@ -228,13 +267,20 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
     else:
         d.bias = None
         d.bias_period = 0
+    d.hist_bins, d.hist_offset, d.out_hist_clamped = 0, 0, None
     if hist is not None:
-        if hist.dtype != torch.int64 or hist.numel() != 256 or not hist.is_cuda or not hist.is_contiguous():
-            raise ValueError("hist must be a contiguous CUDA int64 tensor of 256 counters")
+        if hist.dtype != torch.int64 or not hist.is_cuda or not hist.is_contiguous() or not (1 <= hist.numel() <= 8192):
+            raise ValueError("hist must be a contiguous CUDA int64 tensor of at most 8192 counters")
         d.out_hist = hist.data_ptr()
+        d.hist_bins, d.hist_offset = hist.numel(), int(hist_offset)
+        if hist_clamped is not None:
+            if hist_clamped.dtype != torch.int64 or not hist_clamped.is_cuda or hist_clamped.numel() != 2 * groups:
+                raise ValueError("hist_clamped must be a CUDA int64 tensor [groups, 2]")
+            d.out_hist_clamped = hist_clamped.data_ptr()
     else:
         d.out_hist = None
     d.debug_stamps = debug_stamps.data_ptr() if debug_stamps is not None else None
+    d.relu_passthrough = int(bool(relu_passthrough))
     stats = None
     if want_stats or stats_only:
         stats = torch.zeros((groups, L.STATS_STRIDE), dtype=torch.float32, device=dev)
@@ -261,6 +307,18 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
         return stats
     out = _finish_out(kout, uout)
     return (out, stats) if want_stats else out
+
+
+def add_relu_(a, b):
+    """``a += b; relu_(a)`` in one pass (C ABI fqb200_add_relu, 12 instead of 20 bytes per element).  Both tensors must be
+    dense with identical strides (any memory format); returns ``a``.  Bit-identical to the two torch ops."""
+    _require_cuda_f32(a, "a")
+    _require_cuda_f32(b, "b")
+    if a.shape != b.shape or a.stride() != b.stride() or not _dense(a):
+        raise ValueError("add_relu_ needs two dense tensors of identical shape and strides")
+    with torch.cuda.device(a.device), _Timed("E", a.numel(), 12):
+        L.check(L.load().fqb200_add_relu(a.data_ptr(), b.data_ptr(), a.data_ptr(), a.numel(), _stream_handle(a.device)))
+    return a
 
 
 def _test_division(a, b):

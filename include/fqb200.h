@@ -113,9 +113,19 @@ typedef struct fqb200_desc {
                           needs groups % 4 == 0 and groups <= 2048.  Sums of different CTAs meet in float64 atomics:
                           statistics are reproducible to fp32 rounding, not bit for bit.  The standard deviation comes
                           from the first pass (shifted sums; SURVEY.md 8d "single-pass" option). */
-  unsigned long long* out_hist; /* optional device array of 256 counters: the launch ADDS the histogram of the integer
-                          grid q (torch leaf: q in [0, 255]) to it - what the reference's `-me` entropy measurement
-                          needs (utils/entropy.py:6-17 on output.int(), int_quantizer.py:586-587) without torch.unique. */
+  unsigned long long* out_hist; /* optional device array of hist_bins counters: the launch ADDS the histogram of the integer
+                          grid q to it (bin = clamp(q + hist_offset, 0, hist_bins - 1)) - what the reference's `-me`
+                          entropy measurement needs (utils/entropy.py:6-17; int_quantizer.py:586-587, :216-221) without
+                          torch.unique over the tensor.  Torch leaf: q in [0, 255], hist_bins 256, hist_offset 0.
+                          Mid-tread leaf (channels_last only): q is clamped to per-channel, generally fractional bounds;
+                          elements ON a bound are counted in out_hist_clamped instead. */
+  int32_t hist_bins;   /* 0 = 256; at most 8192 (channels_last), 256 otherwise */
+  int32_t hist_offset; /* added to q before binning (mid-tread grids are signed) */
+  unsigned long long* out_hist_clamped; /* mid-tread: optional [groups][2] counters, elements on c_min / c_max of the group */
+  int32_t relu_passthrough; /* 1: the caller has fused the ReLU that follows this quantizer away (a positive range starts at
+                          zero with zero point 0, so the quantized tensor is >= 0 already).  The one case where that is
+                          not true - the compiled leaf handing its input back because the range is empty (range <= 0,
+                          gemmlowp.cu:31-32) - then returns max(x, 0) instead of x, so quantizer + ReLU stay exact. */
   unsigned long long* debug_stamps; /* diagnostics, NULL = off: device array of 16 counters that receives %globaltimer
                           (ns) at the phase boundaries of this launch (slot 0: start, 1 / 5: statistics phases combined,
                           4 / 8: past the grid barriers, 7: parameters ready, 9: apply done; tools/phasebench.py) */
@@ -161,6 +171,25 @@ int fqb200_float2gemmlowp(const float* in, float* out, int64_t n, float range, f
 int fqb200_quantize1(const float* in, float* out, float* grid, int64_t outer, int64_t groups, int64_t inner,
                      const float* delta, const float* offset, const float* bits, int per_group, int num_bits,
                      const float* bias, int channels_last, void* stream);
+
+/*
+ * `-bca` - a3 with the activation bias correction of Conv2dWithId.forward (inference_quantization_manager.py:180-196) in the
+ * same launch: y = quantize1(x + bias); per group q_bias = (sum r - sum y) / (#(r > 0) + 1e-8), r = x + bias (rectified
+ * first when relu_first, i.e. when a ReLU follows the convolution); out = y + q_bias where y > 0.  The tensor must be
+ * channels-last ([outer][inner][groups] in memory, groups % 4 == 0, groups <= 2048).  Optional out_qbias receives the
+ * `groups` corrections.  Workspace as for fqb200_fused (fqb200_workspace_bytes of any channels_last descriptor with the
+ * same `groups`).  `out` may alias `in`.
+ */
+int fqb200_quantize1_bca(const float* in, float* out, int64_t outer, int64_t groups, int64_t inner, const float* delta,
+                         const float* offset, const float* bits, int per_group, int num_bits, const float* bias, int relu_first,
+                         float* out_qbias, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * out[i] = max(a[i] + b[i], 0) - the residual add + ReLU between two hooked convolutions of a ResNet block (the call
+ * sites' surroundings, SURVEY.md 8f rank 4: torchvision's `out += identity; out = relu(out)`), one pass instead of two
+ * torch kernels; bit-identical to them.  `out` may alias `a` or `b`.
+ */
+int fqb200_add_relu(const float* a, const float* b, float* out, int64_t n, void* stream);
 
 /*
  * a4/a5/a6/a11/a12(+a7-a10, a13) - statistics -> parameters -> quantize-dequantize (-> weight

@@ -33,6 +33,11 @@ def available():
     return os.path.exists(_MARKER) and ext_path() is not None
 
 
+def python_available():
+    """True when the reference's Python path is staged (enough for the CPU legs)."""
+    return os.path.exists(_MARKER)
+
+
 def load_extension():
     """The reference's own compiled ``int_quantization`` module (kernels/int_quantization.cpp + gemmlowp.cu)."""
     if "ext" not in _state:
@@ -130,6 +135,47 @@ class LeafSpy(object):
     def __exit__(self, *exc):
         del self.q.__dict__["__gemmlowpQuantize1__"]
         del self.q.__dict__["__gemmlowpQuantize__"]
+
+
+def cpu_extension():
+    """Stand-in for the compiled ``int_quantization`` module on hosts without a GPU: the oracle's plain-C restatement of
+    kernels/gemmlowp.cu (oracle/fq_leaf.c).  Used by the CPU legs of bench.py and by the fixture generators."""
+    from oracle import fq_oracle as O
+    stub = types.ModuleType("int_quantization")
+    stub.float2gemmlowp = lambda t, d, o, b, ie, tz, noise: O.float2gemmlowp(t, float(d), float(o), b, ie, tz, None)
+    return stub
+
+
+class cpu_mode(object):
+    """Run the staged reference on CPU tensors: ``IntQuantizer.__gemmlowpQuantize__`` allocates its noise tensor with
+    ``torch.cuda.FloatTensor`` (int_quantizer.py:610) and utils/absorb_bn.py:19-20 hard-codes ``.cuda()``; inside this
+    context the former goes to the C restatement of the kernel (same preserve_zero rule) and the latter is a no-op when no
+    GPU is present.  Every other executed line is the reference's."""
+
+    def __enter__(self):
+        import torch
+        ns = load(extension=cpu_extension()) if "ns" not in _state else _state["ns"]
+        set_extension(cpu_extension())
+        self._orig_leaf = ns.IntQuantizer.__gemmlowpQuantize__
+        ext = ns.iq.int_quantization
+
+        def leaf_cpu(q, tensor, delta, offset):
+            preserve_zero = q.enforce_true_zero and (offset + delta) > 0 and offset < 0
+            return ext.float2gemmlowp(tensor.contiguous(), delta, offset, q.num_bits, q.int_exp, bool(preserve_zero), None)
+
+        ns.IntQuantizer.__gemmlowpQuantize__ = leaf_cpu
+        self._orig_cuda = torch.Tensor.cuda
+        if not torch.cuda.is_available():
+            torch.Tensor.cuda = lambda t, *a, **k: t
+        return ns
+
+    def __exit__(self, *exc):
+        import torch
+        ns = _state["ns"]
+        ns.IntQuantizer.__gemmlowpQuantize__ = self._orig_leaf
+        torch.Tensor.cuda = self._orig_cuda
+        if ext_path() is not None and torch.cuda.is_available():
+            set_extension(load_extension())
 
 
 def reset_reference_singletons():

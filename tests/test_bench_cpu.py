@@ -26,10 +26,24 @@ def test_reference_arm_prints_the_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "resnet50_w4a4_images_per_s" and line["unit"] == "images/s"
     assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    # the reference's own Python when build() staged it (oracle/_ref/pyref), else the oracle port
+    from oracle import ref_live
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_live.python_available() else "port")
+    assert line["cpu_baseline"]["value"] == line["value"]
     assert line["cpu_baseline"]["cores"] >= 1 and "images" in line["cpu_baseline"]["sample"]
+    assert 0.0 < line["cpu_baseline"]["quant_share_of_step"] < 1.0
+    assert "configs[2]" in line["config"]["workload"] and line["config"]["steps_requested"] == 1
     assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0
+
+
+def test_metric_and_workload_follow_the_config():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-batch", "1", "--config", "resnet18_w4a4"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["metric"] == "resnet18_w4a4_images_per_s" and "resnet18_w4a4" in line["config"]["workload"]
+    assert len(out.stdout.strip().splitlines()) == 1   # ONE line on stdout
 
 
 def test_reference_arm_other_ranks_exit_quietly():

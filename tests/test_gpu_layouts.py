@@ -127,3 +127,32 @@ def test_leaves_with_strided_out(fq, c):
             out2 = torch.empty_like(x, memory_format=torch.channels_last if out_cl else torch.contiguous_format)
             got2 = ops.float2gemmlowp(xin, 5.0, -2.0, 4, False, True, out=out2)
             assert got2.data_ptr() == out2.data_ptr() and torch.equal(got2, want_leaf), (xin_cl, out_cl)
+
+
+@pytest.mark.parametrize("c,relu_first,with_bits", [(64, True, True), (96, False, True), (256, True, False), (2048, True, True), (8, False, False)])
+def test_bias_corrected_quantization_matches_the_torch_formulation(fq, c, relu_first, with_bits):
+    """`-bca` (inference_quantization_manager.py:180-196) inside the given-parameter launch vs the same correction with
+    stock torch ops on top of our plain mode-A output: identical quantized values, corrections equal up to the fp32
+    summation order of the torch reductions."""
+    from cnn_quantization_b200 import ops
+    from cnn_quantization_b200.int_quantizer import IntQuantizer
+    n, hw = (16, 14) if c < 2048 else (8, 7)
+    g = torch.Generator(device="cuda").manual_seed(c)
+    x = torch.randn(n, c, hw, hw, device="cuda", generator=g) * 2 + 0.5
+    bias = torch.randn(c, device="cuda", generator=g) * 0.3
+    delta = torch.rand(c, device="cuda", generator=g) * 4 + 2
+    offset = torch.zeros(c, device="cuda") if relu_first else -torch.rand(c, device="cuda", generator=g) * 2
+    bits = torch.randint(2, 5, (c,), device="cuda", generator=g).float() if with_bits else None
+    xcl = x.contiguous(memory_format=torch.channels_last)
+    got, qb = ops.quantize1_bca(xcl, delta, offset, 4, bits=bits, bias=bias, relu_first=relu_first, want_qbias=True)
+    ref_in = x + bias.view(1, -1, 1, 1)
+    plain = ops.quantize1(ref_in, delta, offset, 4, bits=bits, layout=(n, c, hw * hw))
+    r = torch.relu(ref_in) if relu_first else ref_in
+    qb_ref = (r.double().sum((0, 2, 3)) - plain.double().sum((0, 2, 3))) / ((r > 0).sum((0, 2, 3)).double() + 1e-8)
+    scale = float(delta.max()) / 15
+    assert float((qb.double() - qb_ref).abs().max()) <= 1e-4 * scale + 1e-6
+    want = plain + (plain > 0).float() * qb.view(1, -1, 1, 1)
+    assert torch.equal(got, want)
+    # through the quantizer (stat tables), in place, on an NCHW tensor too
+    want_torch = IntQuantizer.bias_correction_torch(ref_in, plain.clone(), relu_first)
+    assert float((got - want_torch).abs().max()) <= 2e-4 * scale + 1e-6

@@ -88,15 +88,68 @@ def test_every_baseline_config_runs_and_quantizes(config):
     ops.profile_reset(enable=False)
     qm.detach()
     assert torch.isfinite(y).all()
-    expected = {"resnet50": 55, "resnet101": 106, "vgg16": 21, "resnet18": 22}[pipeline.CONFIGS[config]["arch"]]
+    arch = pipeline.CONFIGS[config]["arch"]
+    expected = {"resnet50": 55, "resnet101": 106, "vgg16": 21, "resnet18": 22}[arch]
+    blocks = {"resnet50": 16, "resnet101": 33, "vgg16": 0, "resnet18": 8}[arch]
     assert len(qm.calls) == expected
-    assert prof["launches"] == expected  # exactly one kernel launch per hooked tensor
+    quant = sum(v["launches"] for k, v in prof["modes"].items() if k != "E")
+    assert quant == expected  # exactly one kernel launch per hooked tensor
+    assert prof["modes"].get("E", {"launches": 0})["launches"] == blocks  # + one fused add+ReLU per residual block
+
+
+def test_bias_buffer_follows_the_module_and_detach_restores_it():
+    """ADVICE (round 1, medium): the fused conv bias must survive .to() / state_dict() while attached."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from cnn_quantization_b200 import pipeline
+    model, qm = pipeline.build_quantized_model("resnet18_w4a4", "cuda")
+    conv = model.layer1[0].conv1
+    assert conv.bias is None and conv._fq_bias.is_cuda
+    before = conv._fq_bias.clone()
+    model.cpu()
+    assert not conv._fq_bias.is_cuda           # the buffer moved with the module
+    model.cuda()
+    assert torch.equal(conv._fq_bias, before)
+    qm.detach()
+    assert conv.bias is not None and conv.bias.is_cuda and torch.equal(conv.bias.data, before)
+    assert "_fq_bias" not in dict(conv.named_buffers())
+
+
+def test_relu_is_not_skipped_after_an_inplace_modification():
+    """ADVICE (round 1, low): the non-negativity tag dies with any in-place op on the tensor."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from cnn_quantization_b200.manager import _relu_forward_skipping
+    relu = torch.nn.ReLU()
+    relu.forward = _relu_forward_skipping(relu)
+    x = torch.rand(8, device="cuda")
+    x._fq_nonneg = x._version
+    assert relu(x) is x
+    x -= 1.0
+    y = relu(x)
+    assert float(y.min()) >= 0.0
+
+
+def test_empty_positive_range_passthrough_is_rectified_when_the_relu_is_fused():
+    """ADVICE (round 1, low): compiled leaf, half range, every sample <= 0 -> the reference hands the input back and its
+    ReLU zeroes it; with the ReLU skipped the kernel's pass-through branch must do that."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import cnn_quantization_b200 as fq
+    from test_gpu_parity import params
+    x = -torch.rand(4, 8, 6, 6, device="cuda") - 0.1
+    q = fq.int_quantizer("int8", params())
+    q.half_range = True
+    y = q(x.clone(), "conv1_activation", "activation")                      # reference behaviour: input handed back
+    assert torch.equal(y, x)
+    y = q(x.clone(), "conv1_activation", "activation", relu_follows=True)   # fused ReLU: rectified, tagged
+    assert float(y.abs().max()) == 0.0 and y._fq_nonneg == y._version
 
 
 @pytest.mark.parametrize("config", ["resnet50_w4a4", "vgg16_w4a4", "resnet50_w8a8"])
 def test_pipeline_extensions_do_not_change_results(config):
-    """Conv-bias fusion, in-place activations and skipping the ReLU after a half-range quantization are exact
-    rewrites: switching them all off gives bit-identical logits."""
+    """Conv-bias fusion, in-place activations, skipping the ReLU after a half-range quantization and the fused residual
+    add + ReLU are exact rewrites: switching them all off gives bit-identical logits."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from cnn_quantization_b200 import manager as M, pipeline
@@ -108,7 +161,7 @@ def test_pipeline_extensions_do_not_change_results(config):
         args = M.make_args(**flags)
         qm = M.QuantizationManagerInference(args, M.get_params(args))
         if not native_extensions:
-            qm.fuse_conv_bias = qm.skip_redundant_relu = False
+            qm.fuse_conv_bias = qm.skip_redundant_relu = qm.fuse_residual_relu = False
             for q in list(qm.quantizers.values()) + [qm.quantizer_default]:
                 if hasattr(q, "inplace"):
                     q.inplace = False
@@ -151,7 +204,7 @@ def test_channels_last_pipeline_matches_nchw():
         prof = ops.profile_collect()
         ops.profile_reset(enable=False)
         qm.detach()
-        assert prof["launches"] == 55
+        assert prof["launches"] == 55 + 16   # 55 hooked tensors + 16 fused residual add + ReLU
     a, b = outs
     cos = float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b)))
     assert cos > 0.97, cos

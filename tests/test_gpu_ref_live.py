@@ -300,3 +300,50 @@ def test_dropin_alias_runs_the_unmodified_reference_manager(ref, config, min_cos
     _dump_report()
     assert cos >= min_cos, cos
     assert abs(np.linalg.norm(y) / np.linalg.norm(r) - 1) < 0.1
+
+
+class _Log(object):
+    def __init__(self):
+        self.rows = []
+
+    def log_metric(self, name, value, **kw):
+        self.rows.append((name, float(value), kw))
+
+
+@pytest.mark.parametrize("positive", [True, False])
+def test_mid_tread_entropy_vs_live_reference(ref, fq, positive):
+    """SURVEY 8(f) rank 3 / README.md:135-140 (`-mtq -me`): the average activation entropy of the mid-tread grid.  The
+    reference runs torch.unique over the float grid; ours histograms inside the apply phase (channels-last) or falls back
+    to torch ops (NCHW).  Same tensor, same logger call, entropies within 2e-3 bit."""
+    x = _activation(64, 64, 28, seed=4242)
+    if positive:
+        x = torch.relu(x)
+    over = dict(mtd_quant=True, measure_entropy=True, bit_alloc_target_act=5.3, bit_alloc_target_weight=5.3)
+    lr, lo = _Log(), _Log()
+    rq = ref.int_quantizer("int4", _params(logger=lr, **over))
+    rq.pcq_w, rq.force_positive = False, positive
+    want = rq(x, "conv3_activation", "activation")
+    q = fq.int_quantizer("int4", _params(logger=lo, **over))
+    q.pcq_w, q.force_positive = False, positive
+    got_cl = q(x.contiguous(memory_format=torch.channels_last), "conv3_activation", "activation")
+    got_nchw = q(x, "conv3_activation", "activation")
+    assert len(lr.rows) == 1 and len(lo.rows) == 2
+    name, e_ref, kw = lr.rows[0]
+    for (n2, e, kw2), got in zip(lo.rows, (got_cl, got_nchw)):
+        assert n2 == name == "conv3_activation.entropy" and kw2["meterId"] == kw["meterId"] == "avg.entropy.act"
+        assert kw2["weight"] == kw["weight"] == x.numel()
+        assert abs(e - e_ref) <= 2e-3, (e, e_ref)
+        bad = (got - want).abs() > 1e-5 * want.abs() + 1e-9
+        assert float(bad.float().mean()) <= 1e-3
+    REPORT["mid-tread entropy positive=%d" % positive] = {"reference_bits": e_ref, "ours_channels_last_bits": lo.rows[0][1],
+                                                          "ours_nchw_bits": lo.rows[1][1]}
+    _dump_report()
+    # weights: per-output-channel symmetric grid, min/max range
+    w = torch.randn(128, 64, 3, 3, device="cuda") * 0.05
+    lr, lo = _Log(), _Log()
+    rq = ref.int_quantizer("int4", _params(logger=lr, clipping="no", **over))
+    wq_ref = rq(w, "layer.weight", "weight")
+    q = fq.int_quantizer("int4", _params(logger=lo, clipping="no", **over))
+    wq = q(w, "layer.weight", "weight")
+    assert abs(lo.rows[0][1] - lr.rows[0][1]) <= 2e-3 and lo.rows[0][2]["meterId"] == "avg.entropy.weight"
+    assert float(((wq - wq_ref).abs() > 1e-5 * wq_ref.abs() + 1e-9).float().mean()) <= 2e-3
