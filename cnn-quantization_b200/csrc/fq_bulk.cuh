@@ -85,6 +85,8 @@ struct FlatGeo {
 struct StageMeta {
   unsigned start;  // first vector of the stage
   unsigned count;  // valid vectors; 0 = end of phase
+  unsigned tag;    // row-structured streams: row index | (last stage of its unit) << 31
+  unsigned pad;
 };
 
 struct BulkRing {
@@ -157,6 +159,7 @@ __device__ __forceinline__ void produce_phase(const FlatGeo& g, const float4* sr
       mbar_wait(smem_u32(&r.empty[pos.slot]), pos.parity ^ 1u);
       r.meta[pos.slot].start = start;
       r.meta[pos.slot].count = count;
+      r.meta[pos.slot].tag = 0u;
       const unsigned bar = smem_u32(&r.full[pos.slot]);
       mbar_arrive_expect_tx(bar, count * 16u);
       bulk_load(smem_u32(stage_base + pos.slot * kStageBytes), src + start, count * 16u, bar);
@@ -172,8 +175,63 @@ __device__ __forceinline__ void produce_phase(const FlatGeo& g, const float4* sr
   pos.next();
 }
 
+// Row-structured streams (per-sample statistics): `rows` rows of row_v vectors; a unit is a run of stages INSIDE one row
+// (the last stage of a row is short), so that per-row partial results can be combined at unit ends.
+struct RowsGeo {
+  unsigned rows, row_v;
+  unsigned stages_per_row;  // ceil(row_v / stage_v)
+  unsigned units_per_row;   // ceil(stages_per_row / unit_stages)
+};
+
+template <bool REV>
+__device__ __forceinline__ void produce_rows_phase(const FlatGeo& g, const RowsGeo& rg, const float4* src, unsigned* counter,
+                                                   const TicketPlan tp, BulkRing& r, unsigned char* stage_base, RingPos& pos) {
+  const unsigned total = g.units;  // rows * units_per_row
+  unsigned k = 0;
+  auto fetch = [&]() -> unsigned {
+    unsigned long long t;
+    if (k < tp.nstatic)
+      t = tp.first + static_cast<unsigned long long>(k) * tp.step;
+    else
+      t = static_cast<unsigned long long>(tp.dyn_base) + atomicAdd(counter, 1u);
+    ++k;
+    return t < total ? static_cast<unsigned>(t) : 0xffffffffu;
+  };
+  unsigned cur = fetch();
+  while (cur != 0xffffffffu) {
+    const unsigned nxt = fetch();
+    const unsigned u = REV ? total - 1u - cur : cur;
+    const unsigned row = u / rg.units_per_row;
+    const unsigned part = u - row * rg.units_per_row;
+    const unsigned s0 = part * g.unit_stages;
+    const unsigned s1 = min(s0 + g.unit_stages, rg.stages_per_row);
+    for (unsigned i = s0; i < s1; ++i) {
+      const unsigned st = REV ? s1 - 1u - (i - s0) : i;
+      const unsigned off = st * g.stage_v;
+      const unsigned start = row * rg.row_v + off;
+      const unsigned count = min(g.stage_v, rg.row_v - off);
+      mbar_wait(smem_u32(&r.empty[pos.slot]), pos.parity ^ 1u);
+      r.meta[pos.slot].start = start;
+      r.meta[pos.slot].count = count;
+      r.meta[pos.slot].tag = row | (i + 1u == s1 ? 0x80000000u : 0u);
+      const unsigned bar = smem_u32(&r.full[pos.slot]);
+      mbar_arrive_expect_tx(bar, count * 16u);
+      bulk_load(smem_u32(stage_base + pos.slot * kStageBytes), src + start, count * 16u, bar);
+      pos.next();
+    }
+    cur = nxt;
+  }
+  mbar_wait(smem_u32(&r.empty[pos.slot]), pos.parity ^ 1u);
+  r.meta[pos.slot].start = 0u;
+  r.meta[pos.slot].count = 0u;
+  r.meta[pos.slot].tag = 0u;
+  mbar_arrive(smem_u32(&r.full[pos.slot]));
+  pos.next();
+}
+
 // ---- consumer side (512 threads) -----------------------------------------------------------------------------------------
-// acc.consume(x, v) for every vector this thread owns (v = its index from the tensor base), until the end marker.
+// acc.consume(x, v) for every vector this thread owns (v = its index from the tensor base) and acc.stage_end(meta) once per
+// stage (where accumulators fold their fp32 partial sums into float64 every few stages), until the end marker.
 template <typename Acc>
 __device__ __forceinline__ void consume_phase(const FlatGeo& g, BulkRing& r, const unsigned char* stage_base, RingPos& pos,
                                               Acc& acc) {
@@ -204,6 +262,7 @@ __device__ __forceinline__ void consume_phase(const FlatGeo& g, BulkRing& r, con
         }
       }
     }
+    acc.stage_end(m);
     __syncwarp();
     if (lane0) mbar_arrive(smem_u32(&r.empty[pos.slot]));
     pos.next();

@@ -93,7 +93,7 @@ __device__ __forceinline__ void grid_exit_cl(GridSync* gs) {
 }
 
 // ---- per-phase accumulators ---------------------------------------------------------------------------------------------
-constexpr unsigned kClChunk = 8;  // vectors summed in fp32 before folding into float64
+constexpr unsigned kClChunkStages = (8 + kStageVec - 1) / kStageVec;  // stages (8 vectors) summed in fp32 before folding into float64
 
 // S1 runs on the RAW values (the bias is a per-channel constant): min / max of x + bias are (min x) + bias and
 // (max x) + bias exactly (rounding is monotone), and mean / std of fl(x + bias) equal mean(x) + bias / std(x) up to the
@@ -142,7 +142,9 @@ struct ClStats1 {
       fs[i] = __fadd_rn(fs[i], d);
       fq[i] = __fmaf_rn(d, d, fq[i]);
     }
-    if (++cnt == kClChunk) flush();
+  }
+  __device__ __forceinline__ void stage_end(const StageMeta&) {
+    if (++cnt == kClChunkStages) flush();
   }
 };
 
@@ -172,7 +174,9 @@ struct ClStats2 {
     const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) fa[i] = __fadd_rn(fa[i], fabsf(__fsub_rn(__fadd_rn(x[i], bias[i]), mu[i])));
-    if (++cnt == kClChunk) flush();
+  }
+  __device__ __forceinline__ void stage_end(const StageMeta&) {
+    if (++cnt == kClChunkStages) flush();
   }
 };
 
@@ -247,6 +251,7 @@ struct ClApply {
     else
       one<false>(v, off);
   }
+  __device__ __forceinline__ void stage_end(const StageMeta&) {}
 };
 
 // ---- CTA-wide combine of per-thread channel partials, then one atomic per channel into the replicated accumulators ------
@@ -398,6 +403,90 @@ __device__ __forceinline__ LeafParam cl_channel_param(const FusedArgs& A, const 
   return q;
 }
 
+// ---- the streaming phases as separate (non-inlined) functions: each gets the whole register budget for its hot loop ----
+struct ClCtx {
+  const FlatGeo* g;
+  BulkRing* ring;
+  unsigned char* stages;
+  unsigned char* cbuf;
+  RingPos pos;
+  ClView acc;
+  unsigned rep_base, c0;
+  bool active;
+};
+
+__device__ __noinline__ void cl_phase_s1(const FusedArgs& A, ClCtx& cx, float (&kshift)[4]) {
+  const FlatGeo& g = *cx.g;
+  ClStats1 s1;
+  s1.init(A, cx.c0, cx.active);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) kshift[i] = s1.k[i];
+  RingPos pos = cx.pos;
+  consume_phase(g, *cx.ring, cx.stages, pos, s1);
+  cx.pos = pos;
+  s1.flush();
+  if (blockIdx.x == 0) stamp(A, 13);
+  unsigned umn[4], umx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    umn[i] = ~enc_ordered(s1.mn[i]);
+    umx[i] = enc_ordered(s1.mx[i]);
+  }
+  const ClView& acc = cx.acc;
+  const unsigned rb = cx.rep_base;
+  auto umax = [](unsigned a, unsigned b) { return a > b ? a : b; };
+  cl_combine(cx.cbuf, g.cv, g.stride, umn, 0u, umax, [&](unsigned c, unsigned v) { red_max_u32(acc.amin_inv + rb + c, v); });
+  cl_combine(cx.cbuf, g.cv, g.stride, umx, 0u, umax, [&](unsigned c, unsigned v) { red_max_u32(acc.amax + rb + c, v); });
+  cl_combine(cx.cbuf, g.cv, g.stride, s1.s, 0.0, OpAdd(), [&](unsigned c, double v) { red_add_f64(acc.asum + rb + c, v); });
+  cl_combine(cx.cbuf, g.cv, g.stride, s1.q, 0.0, OpAdd(), [&](unsigned c, double v) { red_add_f64(acc.asq + rb + c, v); });
+}
+
+__device__ __noinline__ void cl_phase_s2(const FusedArgs& A, ClCtx& cx, const float (&mean)[4]) {
+  const FlatGeo& g = *cx.g;
+  ClStats2 s2;
+  s2.init(A, cx.c0, cx.active, mean);
+  RingPos pos = cx.pos;
+  consume_phase(g, *cx.ring, cx.stages, pos, s2);
+  cx.pos = pos;
+  s2.flush();
+  if (blockIdx.x == 0) stamp(A, 14);
+  const ClView& acc = cx.acc;
+  const unsigned rb = cx.rep_base;
+  cl_combine(cx.cbuf, g.cv, g.stride, s2.sa, 0.0, OpAdd(), [&](unsigned c, double v) { red_add_f64(acc.aabs + rb + c, v); });
+}
+
+template <int LEAF, bool HIST>
+__device__ __noinline__ void cl_phase_apply(const FusedArgs& A, ClCtx& cx, const LeafParam (&lp)[4], unsigned* hist) {
+  const FlatGeo& g = *cx.g;
+  const unsigned t = threadIdx.x;
+  if (HIST) {
+    for (unsigned i = t; i < kHistWords; i += kConsumers) hist[i] = 0u;
+    consumer_sync();
+  }
+  ClApply<LEAF, HIST> ap{A, hist};
+  ap.init(cx.c0, cx.active, lp);
+  RingPos pos = cx.pos;
+  consume_phase(g, *cx.ring, cx.stages, pos, ap);
+  cx.pos = pos;
+  if (HIST) {
+    consumer_sync();
+    const unsigned bins = static_cast<unsigned>(A.hist_bins);
+    const unsigned copies = max(1u, min(static_cast<unsigned>(kWarps), kHistWords / bins));
+    for (unsigned b = t; b < bins; b += kConsumers) {
+      unsigned long long cnt = 0;
+      for (unsigned w = 0; w < copies; ++w) cnt += hist[w * bins + b];
+      if (cnt) atomicAdd(A.hist + b, cnt);
+    }
+    if (LEAF == FQB200_LEAF_MIDTREAD && A.hist_clamped && cx.active) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (ap.nlo[i]) atomicAdd(A.hist_clamped + 2u * (cx.c0 + i), static_cast<unsigned long long>(ap.nlo[i]));
+        if (ap.nhi[i]) atomicAdd(A.hist_clamped + 2u * (cx.c0 + i) + 1u, static_cast<unsigned long long>(ap.nhi[i]));
+      }
+    }
+  }
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------------------------------
 // LEAF: torch or mid-tread.  DEV: phase S2 (the Laplace b) is needed.  HIST: histogram of the integer grid (`-me`).
 // Dynamic shared memory: [kStages stages][16 KB combine staging / parameter table][4 KB mean table][HIST: 16 KB histograms].
@@ -463,8 +552,6 @@ __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_kernel(const _
   const unsigned rep = A.nhwc_rep;
   const unsigned rep_base = (blockIdx.x % rep) * C;
   unsigned epoch = 0;
-  RingPos pos;
-  pos.init();
   if (blockIdx.x == 0) stamp(A, 0);
 
   // the bank the previous launch used: zero it for the next one (off the critical path)
@@ -478,27 +565,18 @@ __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_kernel(const _
   }
 
   // ---- S1
+  ClCtx cx;
+  cx.g = &g;
+  cx.ring = &ring;
+  cx.stages = stages;
+  cx.cbuf = cbuf;
+  cx.pos.init();
+  cx.acc = acc;
+  cx.rep_base = rep_base;
+  cx.c0 = c0;
+  cx.active = active;
   float kshift[4];
-  {
-    ClStats1 s1;
-    s1.init(A, c0, active);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) kshift[i] = s1.k[i];
-    consume_phase(g, ring, stages, pos, s1);
-    s1.flush();
-    if (blockIdx.x == 0) stamp(A, 13);
-    unsigned umn[4], umx[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      umn[i] = ~enc_ordered(s1.mn[i]);
-      umx[i] = enc_ordered(s1.mx[i]);
-    }
-    auto umax = [](unsigned a, unsigned b) { return a > b ? a : b; };
-    cl_combine(cbuf, cv, g.stride, umn, 0u, umax, [&](unsigned c, unsigned v) { red_max_u32(acc.amin_inv + rep_base + c, v); });
-    cl_combine(cbuf, cv, g.stride, umx, 0u, umax, [&](unsigned c, unsigned v) { red_max_u32(acc.amax + rep_base + c, v); });
-    cl_combine(cbuf, cv, g.stride, s1.s, 0.0, OpAdd(), [&](unsigned c, double v) { red_add_f64(acc.asum + rep_base + c, v); });
-    cl_combine(cbuf, cv, g.stride, s1.q, 0.0, OpAdd(), [&](unsigned c, double v) { red_add_f64(acc.asq + rep_base + c, v); });
-  }
+  cl_phase_s1(A, cx, kshift);
   if (blockIdx.x == 0) stamp(A, 1);
   grid_barrier_cl(A.sync, epoch);
   if (blockIdx.x == 0) stamp(A, 4);
@@ -526,12 +604,7 @@ __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_kernel(const _
 
   // ---- S2
   if constexpr (DEV) {
-    ClStats2 s2;
-    s2.init(A, c0, active, mean);
-    consume_phase(g, ring, stages, pos, s2);
-    s2.flush();
-    if (blockIdx.x == 0) stamp(A, 14);
-    cl_combine(cbuf, cv, g.stride, s2.sa, 0.0, OpAdd(), [&](unsigned c, double v) { red_add_f64(acc.aabs + rep_base + c, v); });
+    cl_phase_s2(A, cx, mean);
     if (blockIdx.x == 0) stamp(A, 5);
     grid_barrier_cl(A.sync, epoch);
     if (blockIdx.x == 0) stamp(A, 8);
@@ -561,30 +634,7 @@ __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_kernel(const _
 
   // ---- A
   if (!A.stats_only) {
-    if (HIST) {
-      for (unsigned i = t; i < kHistWords; i += kConsumers) hist[i] = 0u;
-      consumer_sync();
-    }
-    ClApply<LEAF, HIST> ap{A, hist};
-    ap.init(c0, active, lp);
-    consume_phase(g, ring, stages, pos, ap);
-    if (HIST) {
-      consumer_sync();
-      const unsigned bins = static_cast<unsigned>(A.hist_bins);
-      const unsigned copies = max(1u, min(static_cast<unsigned>(kWarps), kHistWords / bins));
-      for (unsigned b = t; b < bins; b += kConsumers) {
-        unsigned long long cnt = 0;
-        for (unsigned w = 0; w < copies; ++w) cnt += hist[w * bins + b];
-        if (cnt) atomicAdd(A.hist + b, cnt);
-      }
-      if (LEAF == FQB200_LEAF_MIDTREAD && A.hist_clamped && active) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (ap.nlo[i]) atomicAdd(A.hist_clamped + 2u * (c0 + i), static_cast<unsigned long long>(ap.nlo[i]));
-          if (ap.nhi[i]) atomicAdd(A.hist_clamped + 2u * (c0 + i) + 1u, static_cast<unsigned long long>(ap.nhi[i]));
-        }
-      }
-    }
+    cl_phase_apply<LEAF, HIST>(A, cx, lp, hist);
     if (blockIdx.x == 0) stamp(A, 9);
   }
   grid_exit_cl(A.sync);
@@ -620,6 +670,7 @@ struct ClGiven {
     else
       one<false>(v, off);
   }
+  __device__ __forceinline__ void stage_end(const StageMeta&) {}
 };
 
 template <bool GRID>
@@ -697,13 +748,15 @@ struct ClBca1 {
       fy[i] = __fadd_rn(fy[i], y);
       cnt[i] += rr > 0.f ? 1u : 0u;
     }
-    if (++n == kClChunk) flush();
   }
   __device__ __forceinline__ void consume(const float4& v, unsigned) {
     if (fast)
       one<true>(v);
     else
       one<false>(v);
+  }
+  __device__ __forceinline__ void stage_end(const StageMeta&) {
+    if (++n == kClChunkStages) flush();
   }
 };
 
@@ -734,6 +787,7 @@ struct ClBca2 {
     else
       one<false>(v, off);
   }
+  __device__ __forceinline__ void stage_end(const StageMeta&) {}
 };
 
 __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_bca_kernel(const __grid_constant__ FusedArgs A) {
@@ -831,6 +885,157 @@ __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_bca_kernel(con
     if (A.out_stats && blockIdx.x == 0 && t < cv) A.out_stats[c0 + i] = p2.qb[i];  // diagnostics: the correction applied
   }
   consume_phase(g, ring, stages, pos, p2);
+  grid_exit_cl(A.sync);
+}
+
+// ---- per-sample / per-tensor min-max ranges with the compiled-leaf arithmetic on the bulk engine -------------------------------
+// gemmlowpMinMaxQuantize (int_quantizer.py:361-379 + :605-614): every tensor of BASELINE configs[1] (W8A8) and the int8
+// pooling / classifier tensors of every other config.  Rows = samples (contiguous in NCHW and in channels-last memory);
+// S1: min / max of every row (units never straddle rows; one CTA-wide combine + two atomics per unit), grid barrier, then
+// EVERY CTA derives the one parameter set itself from the <= 4096 row results (scope GROUP_MEAN: batch average of the
+// per-sample min / max, :372; scope TENSOR / one row: global min / max), A: apply.  The optional per-channel bias (folded
+// BN) is a per-thread constant on channels-last memory, where a vector's channels are (index mod C/4).
+struct RowsStats {
+  const FusedArgs& A;
+  float* scratch;  // [2][kWarps] floats in shared memory
+  const ClView& acc;
+  float bias[4];
+  float mn, mx;
+  __device__ __forceinline__ void consume(const float4& v, unsigned) {
+    const float x0 = __fadd_rn(v.x, bias[0]), x1 = __fadd_rn(v.y, bias[1]), x2 = __fadd_rn(v.z, bias[2]), x3 = __fadd_rn(v.w, bias[3]);
+    mn = fminf(mn, fminf(fminf(x0, x1), fminf(x2, x3)));
+    mx = fmaxf(mx, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
+  }
+  __device__ __forceinline__ void stage_end(const StageMeta& m) {
+    if (!(m.tag & 0x80000000u)) return;  // CTA-uniform: the unit goes on
+    const float a = warp_reduce(mn, OpMin()), b = warp_reduce(mx, OpMax());
+    const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31u;
+    consumer_sync();
+    if (l == 0) {
+      scratch[w] = a;
+      scratch[kWarps + w] = b;
+    }
+    consumer_sync();
+    if (w == 0) {
+      float c = (l < kWarps) ? scratch[l] : INFINITY, d = (l < kWarps) ? scratch[kWarps + l] : -INFINITY;
+#pragma unroll
+      for (int o = kWarps / 2; o > 0; o >>= 1) {
+        c = fminf(c, __shfl_xor_sync(0xffffffffu, c, o));
+        d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
+      }
+      if (l == 0) {
+        const unsigned row = m.tag & 0x7fffffffu;
+        red_max_u32(acc.amin_inv + row, ~enc_ordered(c));
+        red_max_u32(acc.amax + row, enc_ordered(d));
+      }
+    }
+    mn = INFINITY;
+    mx = -INFINITY;
+  }
+};
+
+struct RowsApply {
+  const FusedArgs& A;
+  LeafParam q;
+  Divisor dv;
+  float bias[4];
+  template <bool FAST>
+  __device__ __forceinline__ void one(const float4& v, unsigned off) {
+    float gq;
+    float4 y;
+    y.x = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(v.x, bias[0]), q, dv, 0.f, gq);
+    y.y = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(v.y, bias[1]), q, dv, 0.f, gq);
+    y.z = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(v.z, bias[2]), q, dv, 0.f, gq);
+    y.w = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(v.w, bias[3]), q, dv, 0.f, gq);
+    st_tensor(reinterpret_cast<float4*>(A.out) + off, y);
+  }
+  __device__ __forceinline__ void consume(const float4& v, unsigned off) {
+    if (dv.fast)
+      one<true>(v, off);
+    else
+      one<false>(v, off);
+  }
+  __device__ __forceinline__ void stage_end(const StageMeta&) {}
+};
+
+__global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_rows_kernel(const __grid_constant__ FusedArgs A) {
+  extern __shared__ __align__(128) unsigned char fq_dyn[];
+  __shared__ BulkRing ring;
+  __shared__ LeaderSmem lsm;
+  __shared__ float scratch[2 * kWarps];
+  const FlatGeo& g = A.flat;
+  const RowsGeo& rg = A.rows;
+  const unsigned bank = ld_ws(&A.sync->launch_count) & 1u;
+  ring_init(ring);
+  if (threadIdx.x >= kConsumers) {
+    if (threadIdx.x == kConsumers) {
+      RingPos pos;
+      pos.init();
+      const float4* src = reinterpret_cast<const float4*>(A.in);
+      const TicketPlan all = {2u, blockIdx.x, gridDim.x, 2u * gridDim.x};
+      produce_rows_phase<false>(g, rg, src, &A.sync->unit_counter[0], all, ring, fq_dyn, pos);
+      if (!A.stats_only) produce_rows_phase<true>(g, rg, src, &A.sync->unit_counter[2], all, ring, fq_dyn, pos);
+    }
+    return;
+  }
+  const unsigned t = threadIdx.x;
+  const bool active = t < g.stride;
+  const unsigned c0 = active ? 4u * (t % g.cv) : 0u;
+  const ClView acc = cl_view(A, bank);
+  unsigned epoch = 0;
+  RingPos pos;
+  pos.init();
+  if (blockIdx.x == 0) stamp(A, 0);
+  if (blockIdx.x == gridDim.x - 1u) {  // zero the bank of the previous launch
+    const ClView other = cl_view(A, bank ^ 1u);
+    uint4* zu = reinterpret_cast<uint4*>(other.amin_inv);
+    uint4* zd = reinterpret_cast<uint4*>(other.asum);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (unsigned i = t; i < kAccU / 4u; i += kConsumers) zu[i] = z;
+    for (unsigned i = t; i < kAccD / 2u; i += kConsumers) zd[i] = z;
+  }
+  float bias[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) bias[i] = (A.bias && active) ? __ldg(A.bias + c0 + i) : 0.f;
+  {
+    RowsStats s1{A, scratch, acc, {bias[0], bias[1], bias[2], bias[3]}, INFINITY, -INFINITY};
+    consume_phase(g, ring, fq_dyn, pos, s1);
+  }
+  if (blockIdx.x == 0) stamp(A, 1);
+  grid_barrier_cl(A.sync, epoch);
+  if (blockIdx.x == 0) stamp(A, 4);
+  // the one parameter set, computed by every CTA from the row results
+  const unsigned R = rg.rows;
+  float mn, mx;
+  if (A.scope == FQB200_SCOPE_GROUP_MEAN) {
+    double smin = 0.0, smax = 0.0;
+    for (unsigned r = t; r < R; r += kConsumers) {
+      smin += static_cast<double>(dec_ordered(~ld_ws(acc.amin_inv + r)));
+      smax += static_cast<double>(dec_ordered(ld_ws(acc.amax + r)));
+    }
+    smin = block_reduce(smin, OpAdd(), lsm.d);
+    smax = block_reduce(smax, OpAdd(), lsm.d);
+    mn = static_cast<float>(smin / R);
+    mx = static_cast<float>(smax / R);
+  } else {
+    float lmin = INFINITY, lmax = -INFINITY;
+    for (unsigned r = t; r < R; r += kConsumers) {
+      lmin = fminf(lmin, dec_ordered(~ld_ws(acc.amin_inv + r)));
+      lmax = fmaxf(lmax, dec_ordered(ld_ws(acc.amax + r)));
+    }
+    mn = block_reduce(lmin, OpMin(), lsm.f);
+    mx = block_reduce(lmax, OpMax(), lsm.f);
+  }
+  float delta, offset;
+  solve_range(A, mn, mx, 0.f, 0.f, 0.f, static_cast<float>(A.num_bits), delta, offset);
+  const LeafParam q = make_leaf_param(FQB200_LEAF_COMPILED, delta, offset, static_cast<float>(A.num_bits), A.relu_passthrough != 0);
+  if (blockIdx.x == 0 && t == 0) export_stats(A, 0, mn, mx, 0.f, 0.f, 0.f, delta, offset, static_cast<float>(A.num_bits), q);
+  if (blockIdx.x == 0) stamp(A, 7);
+  if (!A.stats_only) {
+    RowsApply ap{A, q, make_divisor(q.a), {bias[0], bias[1], bias[2], bias[3]}};
+    consume_phase(g, ring, fq_dyn, pos, ap);
+    if (blockIdx.x == 0) stamp(A, 9);
+  }
   grid_exit_cl(A.sync);
 }
 

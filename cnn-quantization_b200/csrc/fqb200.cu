@@ -51,6 +51,7 @@ struct alignas(16) LeafParam {
 struct FusedArgs {
   Geometry geo;
   FlatGeo flat;        // channels-last / flat-stream kernels (fq_cl.cuh)
+  RowsGeo rows;        // ... row structure of the per-sample min-max kernel
   const float* in;
   float* out;
   const float* bias;   // optional per-group addend applied to x before everything else (folded-BN conv bias)
@@ -1217,6 +1218,7 @@ struct DeviceInfo {
   int resident = 0;        // CTAs of the cp.async-ring fused kernels (512 threads) that fit at once
   int resident_cl[2] = {0, 0};  // channels-last kernels without / with the histogram
   int resident_bca = 0;         // fq_cl_bca_kernel
+  int resident_rows = 0;        // fq_rows_kernel
 };
 constexpr int kMaxDevices = 64;
 DeviceInfo g_dev[kMaxDevices];
@@ -1333,6 +1335,14 @@ void init_device(int dev) {
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kBulkThreads, cl_smem(false));
     if (e != cudaSuccess || n < 1) return bad("bias-correction kernel setup", e);
     d.resident_bca = sms * n;
+  }
+  {
+    int n = 0;
+    const void* fn = reinterpret_cast<const void*>(fqb::fq_rows_kernel);
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cl_given_smem()));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kBulkThreads, cl_given_smem());
+    if (e != cudaSuccess || n < 1) return bad("row kernel setup", e);
+    d.resident_rows = sms * n;
   }
   const void* given[4] = {reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, false>),
                           reinterpret_cast<const void*>(fqb::fq_given_kernel<4, FQB200_LEAF_TORCH, true>),
@@ -1483,6 +1493,61 @@ int make_plan_flat(uint64_t elems, int64_t channels, int max_ctas, Plan* pl) {
   return FQB200_OK;
 }
 
+// row-structured plan (fq_rows_kernel): `rows` rows of `row_elems` contiguous floats; channel period `channels` as in
+// make_plan_flat (0: none).  Units are runs of stages inside one row.
+int make_plan_rows(uint64_t rows, uint64_t row_elems, int64_t channels, int max_ctas, Plan* pl, fqb::RowsGeo* rg) {
+  if (rows == 0 || row_elems == 0 || row_elems % 4 != 0 || rows > fqb::kMaxNhwcChannels)
+    return fail(FQB200_ERR_UNSUPPORTED, "row stream needs rows <= 4096 of a multiple of 4 elements%s");
+  const uint64_t row_v = row_elems / 4;
+  if (rows * row_v >= (1ULL << 32)) return fail(FQB200_ERR_UNSUPPORTED, "tensors of 2^32 vectors (64 GB) and more are not supported%s");
+  const uint64_t cv = channels > 0 ? static_cast<uint64_t>(channels) / 4 : 1;
+  if (channels > 0 && (!flat_eligible(channels) || row_v % cv != 0)) return fail(FQB200_ERR_UNSUPPORTED, "bias period does not fit the rows%s");
+  const uint64_t stride = (fqb::kConsumers / cv) * cv;
+  const uint64_t stage_v = static_cast<uint64_t>(fqb::kStageVec) * stride;
+  const uint64_t spr = (row_v + stage_v - 1) / stage_v;
+  const uint64_t ctas = static_cast<uint64_t>(max_ctas);
+  uint64_t unit_stages = rows * spr / (kUnitsPerCta * ctas);
+  if (unit_stages < 1) unit_stages = 1;
+  if (unit_stages > 64) unit_stages = 64;
+  if (unit_stages > spr) unit_stages = spr;
+  const uint64_t upr = (spr + unit_stages - 1) / unit_stages;
+  const uint64_t units = rows * upr;
+  if (units >= 0xfffffff0ULL) return fail(FQB200_ERR_UNSUPPORTED, "too many work units%s");
+  fqb::FlatGeo& g = pl->flat;
+  g.total_v = static_cast<unsigned>(rows * row_v);
+  g.stride = static_cast<unsigned>(stride);
+  g.stage_v = static_cast<unsigned>(stage_v);
+  g.n_stages = static_cast<unsigned>(rows * spr);
+  g.unit_stages = static_cast<unsigned>(unit_stages);
+  g.units = static_cast<unsigned>(units);
+  g.channels = static_cast<unsigned>(channels > 0 ? channels : 0);
+  g.cv = static_cast<unsigned>(cv);
+  rg->rows = static_cast<unsigned>(rows);
+  rg->row_v = static_cast<unsigned>(row_v);
+  rg->stages_per_row = static_cast<unsigned>(spr);
+  rg->units_per_row = static_cast<unsigned>(upr);
+  memset(&pl->geo, 0, sizeof(pl->geo));
+  pl->geo.channels = static_cast<unsigned>(rows);
+  pl->vec = 4;
+  pl->mode = 3;
+  pl->grid = static_cast<int>(units < ctas ? units : ctas);
+  return FQB200_OK;
+}
+
+// what fq_rows_kernel takes: one min/max parameter set from per-row (per-sample) statistics, compiled-leaf arithmetic
+bool rows_supported(const fqb200_desc* d, bool can_vec) {
+  if (d->leaf != FQB200_LEAF_COMPILED || d->range_mode != FQB200_RANGE_MINMAX || d->bias_corr || d->var_corr || d->channels_last ||
+      d->out_hist || !can_vec || d->outer != 1 || d->inner % 4 != 0 || d->groups > static_cast<int64_t>(fqb::kMaxNhwcChannels))
+    return false;
+  if (!(d->scope == FQB200_SCOPE_GROUP_MEAN || d->scope == FQB200_SCOPE_TENSOR || d->groups == 1)) return false;
+  if (d->bias) {  // only the channel-fastest form (bias_period = -C): a per-thread constant
+    if (d->bias_period >= 0) return false;
+    const int64_t c = -d->bias_period;
+    if (!flat_eligible(c) || d->inner % c != 0) return false;
+  }
+  return true;
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // workspace layout; returns total bytes, fills pointers when base != nullptr.  Partials: one slot per unit.
@@ -1622,6 +1687,15 @@ int fqb200_plan_info(const fqb200_desc* d, int64_t* out8) {
     out8[5] = pl.flat.stride; out8[6] = fqb::kStages; out8[7] = cl_needs_b(d) ? 3 : 2;
     return FQB200_OK;
   }
+  if (rows_supported(d, true)) {
+    fqb::RowsGeo rg;
+    rc = make_plan_rows(static_cast<uint64_t>(d->groups), static_cast<uint64_t>(d->inner), d->bias ? -d->bias_period : 0,
+                        di ? di->resident_rows : resident, &pl, &rg);
+    if (rc != FQB200_OK) return rc;
+    out8[0] = 3; out8[1] = pl.grid; out8[2] = pl.flat.units; out8[3] = pl.flat.unit_stages; out8[4] = pl.flat.stage_v;
+    out8[5] = pl.flat.stride; out8[6] = fqb::kStages; out8[7] = 2;
+    return FQB200_OK;
+  }
   rc = make_plan(d->outer, d->groups, d->inner, true, !(d->bias_corr || d->var_corr), resident, &pl);
   if (rc != FQB200_OK) return rc;
   out8[0] = pl.mode; out8[1] = pl.grid; out8[2] = pl.geo.units; out8[3] = pl.geo.parts; out8[4] = pl.geo.part_v;
@@ -1754,10 +1828,17 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   if (d->bias && d->bias_period <= 0 && d->scope == FQB200_SCOPE_GROUP_MEAN)
     return fail(FQB200_ERR_UNSUPPORTED, "a per-group bias needs groups = channels (scope GROUP or TENSOR); use bias_period%s");
   const bool can_vec = aligned16(in) && (d->stats_only || aligned16(out));
+  fqb::RowsGeo rows_geo;
+  memset(&rows_geo, 0, sizeof(rows_geo));
   if (d->channels_last) {
     if (!can_vec || !cl_supported(d))
       return fail(FQB200_ERR_UNSUPPORTED, "channels_last: per-channel torch / mid-tread leaves on 16-byte aligned tensors, C %% 4 == 0, C <= 2048%s");
     rc = make_plan_flat(static_cast<uint64_t>(d->outer) * d->groups * d->inner, d->groups, di->resident_cl[d->out_hist ? 1 : 0], &pl);
+  } else if (rows_supported(d, can_vec)) {
+    rc = make_plan_rows(static_cast<uint64_t>(d->groups), static_cast<uint64_t>(d->inner), d->bias ? -d->bias_period : 0,
+                        di->resident_rows, &pl, &rows_geo);
+  } else if (d->bias && d->bias_period < 0) {
+    return fail(FQB200_ERR_UNSUPPORTED, "a channel-fastest bias (bias_period < 0) needs the per-sample / per-tensor min-max layout%s");
   } else {
     rc = make_plan(d->outer, d->groups, d->inner, can_vec, !(d->bias_corr || d->var_corr), di->resident, &pl);
   }
@@ -1765,13 +1846,14 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   fqb::FusedArgs A;
   memset(&A, 0, sizeof(A));
   // per-unit partial slots; the channels-last kernels combine through the fixed accumulators instead
-  const uint64_t slots = (pl.mode == 2) ? 0 : static_cast<uint64_t>(pl.geo.parts) * pl.geo.channels;
+  const uint64_t slots = (pl.mode == 2 || pl.mode == 3) ? 0 : static_cast<uint64_t>(pl.geo.parts) * pl.geo.channels;
   const size_t need = carve(nullptr, slots, pl.geo.channels, nullptr);
   if (!workspace || workspace_bytes < need) return fail(FQB200_ERR_WORKSPACE, "workspace smaller than fqb200_workspace_bytes()%s");
   if (!aligned16(workspace)) return fail(FQB200_ERR_WORKSPACE, "workspace must be 16-byte aligned%s");
   carve(static_cast<char*>(workspace), slots, pl.geo.channels, &A);
   A.geo = pl.geo;
   A.flat = pl.flat;
+  A.rows = rows_geo;
   A.in = in;
   A.out = out;
   A.scope = d->scope;
@@ -1803,6 +1885,15 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   if (d->out_hist && (A.hist_bins > static_cast<int>(fqb::kHistWords) || (!d->channels_last && A.hist_bins != 256)))
     return fail(FQB200_ERR_UNSUPPORTED, "hist_bins: 256 (default), up to 8192 on channels-last tensors%s");
   A.bias_magic = 0;
+  if (pl.mode == 3) {
+    if (d->scope == FQB200_SCOPE_GROUP) A.scope = FQB200_SCOPE_TENSOR;  // one row
+    A.n_per_group = static_cast<double>(d->inner);
+    void* rargs[] = {&A};
+    cudaError_t re = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(fqb::fq_rows_kernel), dim3(pl.grid), dim3(fqb::kBulkThreads),
+                                                 rargs, cl_given_smem(), static_cast<cudaStream_t>(stream));
+    if (re != cudaSuccess) return fail(FQB200_ERR_CUDA, "cooperative launch fq_rows_kernel: %s", cudaGetErrorString(re));
+    return FQB200_OK;
+  }
   if (d->bias && d->bias_period > 0) {
     // bias indexed by the channel inside the row: needs whole vectors per channel and an exact magic division
     const uint64_t pv = static_cast<uint64_t>(d->bias_period) / pl.vec;

@@ -188,7 +188,11 @@ class IntQuantizer(object):
         if (self.clipping != "no" or not self.pcq_w) and self._pc_act(tensor) and tensor.shape[1] > 1:
             return True
         minmax = self.clipping == "no" and not self.pcq_w and not self._pc_act(tensor)
-        return bool(minmax and tensor.dim() == 4 and tensor.is_contiguous() and (tensor.shape[2] * tensor.shape[3]) % 4 == 0)
+        if not (minmax and tensor.dim() == 4):
+            return False
+        if tensor.is_contiguous():
+            return (tensor.shape[2] * tensor.shape[3]) % 4 == 0
+        return ops.cl_eligible(tensor)   # channels-last: the bias is a per-thread constant (bias_period = -C)
 
     @staticmethod
     def _dense(tensor):
@@ -394,14 +398,16 @@ class IntQuantizer(object):
         avg = ("activation" in tag and "classifier" not in tag)
         kw = dict(range_mode=L.RANGE_MINMAX, leaf=L.LEAF_COMPILED, num_bits=self.num_bits, positive=self._positive(),
                   relu_passthrough=self._relu_follows)
+        bias_cl = bias is not None and not tensor.is_contiguous()
         if bias is not None:
-            kw.update(bias=bias, bias_period=tensor.shape[2] * tensor.shape[3])
+            kw.update(bias=bias, bias_period=-tensor.shape[1] if bias_cl else tensor.shape[2] * tensor.shape[3])
         if weight_correction is not None and any(weight_correction):
             rows = tensor.shape[0]
             return self._fused(tensor, (1, rows, tensor.numel() // rows), scope=L.SCOPE_TENSOR,
                              bias_corr=weight_correction[0], var_corr=weight_correction[1], **kw)
         n = tensor.shape[0]
-        kw["any_dense_format"] = bias is None  # min / max and a scalar apply do not care about the order inside a sample
+        # min / max and a scalar apply do not care about the order inside a sample; a channels-last bias indexes that order
+        kw["any_dense_format"] = bias is None or bias_cl
         if avg:
             return self._fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_GROUP_MEAN, out=self._out(tensor), **kw)
         if bias is not None:

@@ -259,7 +259,7 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
     if bias is not None:
         _require_cuda_f32(bias, "bias")
         bias = bias.contiguous()
-        want = inner // bias_period if bias_period else groups
+        want = (inner // bias_period if bias_period > 0 else -bias_period) if bias_period else groups
         if bias.numel() != want:
             raise ValueError("bias must have %d elements" % want)
         d.bias = bias.data_ptr()

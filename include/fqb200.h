@@ -107,7 +107,8 @@ typedef struct fqb200_desc {
   int64_t bias_period; /* 0: bias[g] (groups are channels).  > 0: the row of a group holds inner / bias_period channels
                           of bias_period floats each and element i of the row gets bias[i / bias_period] - the
                           per-tensor and per-sample layouts of an NCHW activation (bias_period = H*W).  Needs
-                          bias_period % 4 == 0 on the 128-bit path. */
+                          bias_period % 4 == 0 on the 128-bit path.  < 0: element i of the row gets bias[i % -bias_period] -
+                          the same layouts of a CHANNELS-LAST activation (bias_period = -C; C % 4 == 0, C <= 2048). */
   int32_t channels_last; /* 1: the tensor is [outer][inner][groups] in memory (groups fastest), i.e. an NCHW-shaped
                           activation stored channels-last (NHWC).  Per-channel scope with the torch / mid-tread leaves;
                           needs groups % 4 == 0 and groups <= 2048.  Sums of different CTAs meet in float64 atomics:
@@ -139,7 +140,8 @@ const char* fqb200_last_error(void);
 int fqb200_resident_ctas(void);
 
 /* What a launch of `d` would look like on the current device (introspection for tools and tests), 8 values:
- * channels_last: {2, grid, units, stages per unit, vectors per stage, consumer stride, ring stages, phases};
+ * channels_last, and the per-sample / per-tensor min-max layouts ({3, ...}) on the bulk-copy engine:
+ *                {2, grid, units, stages per unit, vectors per stage, consumer stride, ring stages, phases};
  * otherwise:     {access mode 4|1|8, grid, units, parts per group, vectors per part, stride, ring depth, leader lanes}. */
 int fqb200_plan_info(const fqb200_desc* d, int64_t* out8);
 /* Self-test hook: fast[i] = the kernels' 3-instruction exact division a[i] / b[i], ieee[i] = IEEE a[i] / b[i]

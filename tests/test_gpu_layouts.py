@@ -156,3 +156,22 @@ def test_bias_corrected_quantization_matches_the_torch_formulation(fq, c, relu_f
     # through the quantizer (stat tables), in place, on an NCHW tensor too
     want_torch = IntQuantizer.bias_correction_torch(ref_in, plain.clone(), relu_first)
     assert float((got - want_torch).abs().max()) <= 2e-4 * scale + 1e-6
+
+
+@pytest.mark.parametrize("c", [64, 96, 2048])
+@pytest.mark.parametrize("tag,half_range", [("activation", True), ("activation", False), ("activation_classifier", False)])
+def test_per_sample_minmax_with_fused_bias_on_both_memory_formats(fq, c, tag, half_range):
+    """int8 min/max path (W8A8: every tensor) with the convolution bias added inside the launch: channels-last memory
+    (bias_period = -C, fq_rows_kernel) and NCHW memory (bias_period = H*W) against the un-fused `quantize(x + bias)`."""
+    n, hw = (8, 12) if c < 2048 else (4, 7)
+    if c == 2048:
+        hw = 8  # H*W % 4 == 0 for the NCHW bias_period path
+    x = _x(c, seed=9, n=n, hw=hw)
+    bias = torch.randn(c, device="cuda") * 0.5
+    q = fq.int_quantizer("int8", params())
+    q.half_range = half_range
+    want = q((x + bias.view(1, -1, 1, 1)).contiguous(), "conv1_activation", tag)
+    for cl in (False, True):
+        xin = x.clone().contiguous(memory_format=torch.channels_last) if cl else x.clone()
+        got = q(xin, "conv1_activation", tag, bias=bias)
+        assert torch.equal(got, want), (cl, float((got - want).abs().max()))
