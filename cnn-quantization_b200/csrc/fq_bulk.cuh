@@ -29,6 +29,10 @@ constexpr int kConsumerWarps = kConsumers / 32;
 constexpr int kStageVec = FQB_STAGE_VEC;         // vectors per consumer thread per stage
 constexpr int kStages = FQB_STAGES;              // ring depth
 constexpr unsigned kStageBytes = kStageVec * kConsumers * 16u;
+#ifndef FQB_BULK_SPLIT
+#define FQB_BULK_SPLIT 1
+#endif
+constexpr unsigned kBulkSplit = FQB_BULK_SPLIT;  // bulk copies per stage (all complete on the stage's one mbarrier)
 
 // consumer-only CTA barrier (the producer warp never joins): named barrier 1 over the 512 consumer threads.  The
 // 512-thread kernels of fq_device.cuh can use it as well (there it is equivalent to __syncthreads()).
@@ -60,10 +64,19 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   }
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on `bar`.  bytes % 16 == 0, both addresses 16-byte aligned.
-__device__ __forceinline__ void bulk_load(unsigned dst_smem, const void* src, unsigned bytes, unsigned bar) {
+__device__ __forceinline__ void bulk_load_one(unsigned dst_smem, const void* src, unsigned bytes, unsigned bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned dst_smem, const void* src, unsigned bytes, unsigned bar) {
+  if (kBulkSplit == 1u) {
+    bulk_load_one(dst_smem, src, bytes, bar);
+    return;
+  }
+  constexpr unsigned piece = kStageBytes / kBulkSplit;
+  for (unsigned off = 0; off < bytes; off += piece)
+    bulk_load_one(dst_smem + off, static_cast<const unsigned char*>(src) + off, min(piece, bytes - off), bar);
 }
 
 // ---- geometry of a flat stream ---------------------------------------------------------------------------------------
@@ -146,9 +159,11 @@ __device__ __forceinline__ void produce_phase(const FlatGeo& g, const float4* sr
     ++k;
     return t < total ? static_cast<unsigned>(t) : 0xffffffffu;
   };
+  // two tickets ahead: the atomic's round trip (~1 us under contention) must not sit in front of a unit's loads
   unsigned cur = fetch();
+  unsigned nxt = (cur != 0xffffffffu) ? fetch() : 0xffffffffu;
   while (cur != 0xffffffffu) {
-    const unsigned nxt = fetch();  // the reply is only needed after this unit's stages have been issued
+    const unsigned nxt2 = (nxt != 0xffffffffu) ? fetch() : 0xffffffffu;
     const unsigned u = REV ? total - 1u - cur : cur;
     const unsigned g0 = u * g.unit_stages;
     const unsigned g1 = min(g0 + g.unit_stages, g.n_stages);
@@ -166,6 +181,7 @@ __device__ __forceinline__ void produce_phase(const FlatGeo& g, const float4* sr
       pos.next();
     }
     cur = nxt;
+    nxt = nxt2;
   }
   // end-of-phase marker
   mbar_wait(smem_u32(&r.empty[pos.slot]), pos.parity ^ 1u);
@@ -198,8 +214,9 @@ __device__ __forceinline__ void produce_rows_phase(const FlatGeo& g, const RowsG
     return t < total ? static_cast<unsigned>(t) : 0xffffffffu;
   };
   unsigned cur = fetch();
+  unsigned nxt = (cur != 0xffffffffu) ? fetch() : 0xffffffffu;
   while (cur != 0xffffffffu) {
-    const unsigned nxt = fetch();
+    const unsigned nxt2 = (nxt != 0xffffffffu) ? fetch() : 0xffffffffu;
     const unsigned u = REV ? total - 1u - cur : cur;
     const unsigned row = u / rg.units_per_row;
     const unsigned part = u - row * rg.units_per_row;
@@ -220,6 +237,7 @@ __device__ __forceinline__ void produce_rows_phase(const FlatGeo& g, const RowsG
       pos.next();
     }
     cur = nxt;
+    nxt = nxt2;
   }
   mbar_wait(smem_u32(&r.empty[pos.slot]), pos.parity ^ 1u);
   r.meta[pos.slot].start = 0u;

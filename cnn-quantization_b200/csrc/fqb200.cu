@@ -1473,7 +1473,7 @@ int make_plan_flat(uint64_t elems, int64_t channels, int max_ctas, Plan* pl) {
   const uint64_t n_stages = (total_v + stage_v - 1) / stage_v;
   const uint64_t ctas = static_cast<uint64_t>(max_ctas);
   uint64_t unit_stages = n_stages / (kUnitsPerCta * ctas);
-  if (unit_stages < 1) unit_stages = 1;
+  if (unit_stages < 2) unit_stages = 2;   // a ticket (one atomic round trip) per >= 32 KB
   if (unit_stages > 64) unit_stages = 64;
   const uint64_t units = (n_stages + unit_stages - 1) / unit_stages;
   fqb::FlatGeo& g = pl->flat;

@@ -3,11 +3,12 @@
 same mutable attributes, same method names), routed to the fused sm_100a kernels in ``libfqb200.so``.
 
 Where the reference runs ~10 elementwise kernels, several reductions, up to 6 transposed copies and O(C)
-host synchronisations per hooked tensor, every dispatch target below is ONE cooperative kernel launch on the
-native NCHW layout and never reads anything back to the host.
+host synchronisations per hooked tensor, every dispatch target below is ONE kernel launch on the tensor's own
+memory (contiguous NCHW or channels-last) and never reads anything back to the host.
 
-Scope: on-the-fly statistics (``stat_id is None``).  Offline statistics (``-sm use``),
-KLD thresholds and entropy measurement are the "next" rows and raise ``NotImplementedError`` here.
+Scope: on-the-fly statistics, offline statistics (``-sm use``: parameters solved once per layer,
+then one apply-only launch), entropy measurement (``-me``, torch and mid-tread grids) and the activation bias
+correction (``-bca``).  Outside the path and raising ``NotImplementedError``: KLD thresholds (``-kld``), ``mix`` clipping.
 """
 import math
 

@@ -7,8 +7,8 @@ Run in the build container only (the GPU box has no /root/reference):
 
 The reference has no tests or golden vectors of its own, so the fixtures are the
 reference's *outputs*: its pure-PyTorch hot path (int_quantizer.py) executed on CPU tensors with a
-stub `int_quantization` module (the compiled leaf needs a GPU; its fixtures come from
-make_golden_gpu.py).  Inputs are drawn from numpy RandomState (stable across versions) and stored
+stub `int_quantization` module (the compiled leaf needs a GPU: it is compared live with the reference's own extension
+on the B200, tests/test_gpu_ref_ext.py and tests/test_gpu_ref_live.py).  Inputs are drawn from numpy RandomState (stable across versions) and stored
 in the fixture next to the outputs.  Nothing here is imported by the product or by the GPU tests.
 """
 import json

@@ -97,7 +97,7 @@ def test_memory_format_and_inplace_do_not_change_results(fq, c, mode):
     # Kernels that consume the NHWC memory as it is sum in a different order than on NCHW memory (and the channels-last
     # kernels combine CTAs with float64 atomics): statistics agree to fp32 rounding, so a vanishing fraction of elements
     # may land one step away.  Everything else must be bit-identical.
-    native_nhwc = c % 4 == 0 and 512 % (c // 4) == 0 and "pc" in mode and "use" not in mode
+    native_nhwc = c % 4 == 0 and c >= 4 and "pc" in mode and "use" not in mode
     order_free = mode == "laplace_per_tensor"
     for key, y in outs.items():
         if key[0] == "nhwc" and (native_nhwc or order_free):

@@ -22,7 +22,8 @@ import torch
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-FLIP_FRAC = 2e-4     # tier (ii) bound on the fraction of elements that may land one step away
+FLIP_FRAC = 5e-6     # tier (ii) bound on the fraction of elements that may land one step away (measured: <= 1.6e-7)
+FLIP_FRAC_MODEL = 5e-5  # ... layer by layer inside a model, incl. the compiled leaf's round-half-away grid (measured: <= 6.3e-6)
 PARAM_RTOL = 1e-5    # north_star: parameters / outputs within 1e-5 relative
 REPORT = {}
 
@@ -191,7 +192,7 @@ def test_int8_minmax_tensors_vs_live_reference(ref, fq, case):
             worst = float(((got - want).abs() / step).max())
             REPORT["int8 %s %s half_range=%d" % (case, fmt, half_range)] = {"flip_fraction": frac, "worst_steps": worst}
             _dump_report()
-            assert frac <= FLIP_FRAC and worst <= 1.01, (case, fmt, frac, worst)
+            assert frac <= FLIP_FRAC_MODEL and worst <= 1.01, (case, fmt, frac, worst)
 
 
 @pytest.mark.parametrize("arch", ["resnet50", "resnet101"])
@@ -269,7 +270,7 @@ def test_layerwise_differential_vs_live_reference(ref, fq, config, batch, channe
         "worst_layer": max(rows, key=lambda r: r[3])[0]}
     _dump_report()
     for id, tag, shape, frac, dmax, span, levels in rows:
-        assert frac <= FLIP_FRAC, (id, tag, shape, frac)
+        assert frac <= FLIP_FRAC_MODEL, (id, tag, shape, frac)
         assert dmax <= span / 2 + 1e-6, (id, tag, shape, dmax, span)   # flips are single grid steps, never garbage
 
 

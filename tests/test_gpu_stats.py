@@ -100,5 +100,5 @@ def test_use_mode_is_single_pass(need_gpu):
     prof = ops.profile_collect()
     ops.profile_reset(enable=False)
     qm.detach()
-    assert set(prof["modes"]) == {"A"}, prof["modes"].keys()
+    assert set(prof["modes"]) - {"E"} == {"A"}, prof["modes"].keys()   # "E": the fused residual add + ReLU of the 8 blocks
     assert prof["modes"]["A"]["launches"] == 22

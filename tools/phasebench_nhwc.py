@@ -12,11 +12,13 @@ order = [(0, "start"), (13, "S1 streamed"), (1, "S1 combined"), (2, "L1 begin"),
          (9, "apply done")]
 shapes = [(512, 64, 56), (512, 256, 14), (512, 128, 28), (512, 1024, 14), (512, 2048, 7), (512, 512, 7), (512, 512, 14),
           (128, 64, 56), (128, 256, 14), (128, 512, 7), (128, 1024, 14), (128, 256, 56)]
+cl_only = "--cl-only" in sys.argv
+sys.argv = [a for a in sys.argv if a != "--cl-only"]
 if len(sys.argv) > 3:
     v = [int(a) for a in sys.argv[1:]]
     shapes = [tuple(v[i:i + 3]) for i in range(0, len(v), 3)]
 for (n, c, hw) in shapes:
-    for cl in (False, True):
+    for cl in ((True,) if cl_only else (False, True)):
         x = torch.randn(n, c, hw, hw, device="cuda")
         if cl:
             x = x.contiguous(memory_format=torch.channels_last)
