@@ -26,6 +26,10 @@ constexpr int kConsumerWarps = kConsumers / 32;
 #ifndef FQB_STAGES
 #define FQB_STAGES 5
 #endif
+#ifndef FQB_BULK_CTAS
+#define FQB_BULK_CTAS 2
+#endif
+constexpr int kBulkCtasPerSm = FQB_BULK_CTAS;    // resident CTAs per SM of the bulk-ring kernels
 constexpr int kStageVec = FQB_STAGE_VEC;         // vectors per consumer thread per stage
 constexpr int kStages = FQB_STAGES;              // ring depth
 constexpr unsigned kStageBytes = kStageVec * kConsumers * 16u;

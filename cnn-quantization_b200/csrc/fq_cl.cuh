@@ -62,22 +62,21 @@ __device__ __forceinline__ void red_max_u32(unsigned* p, unsigned v) {
 
 // plain grid barrier over the consumer threads of every CTA: the last CTA to arrive releases the others
 // Split in two so that a CTA can do useful (instruction-cache warming) work between posting its arrival and waiting.
+// Memory ordering: release / acquire at GPU scope on the arrival counter and the release word (cumulative over the CTA
+// barrier in front), NOT __threadfence(): that is fence.sc.gpu, and a sequentially-consistent fence issued while the other
+// CTAs stream at full bandwidth was measured at ~10 us (round-2 stamps: "aux: iterations" -> "aux solved").
 __device__ __noinline__ void grid_arrive_cl(GridSync* gs, unsigned& epoch) {
   ++epoch;
   consumer_sync();
   if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned prev = atomicAdd(&gs->arrive, 1u);
-    if (prev + 1u == epoch * gridDim.x) {
-      __threadfence();
-      st_release_u32(&gs->release, epoch);
-    }
+    unsigned prev;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&gs->arrive) : "memory");
+    if (prev + 1u == epoch * gridDim.x) st_release_u32(&gs->release, epoch);
   }
 }
 __device__ __noinline__ void grid_wait_cl(GridSync* gs, unsigned epoch) {
   if (threadIdx.x == 0) {
     while (ld_acquire_u32(&gs->release) < epoch) __nanosleep(32);
-    __threadfence();
   }
   consumer_sync();
 }
@@ -308,18 +307,23 @@ __device__ __noinline__ void cl_combine_add_f64(unsigned char* buf, unsigned cv,
 }
 
 // mean (float64) of channel c (of x + bias) from the S1 accumulators: k + bias + S / n
+// sum over the (<= 8) replicas of one accumulator entry: all loads issued before the first add (they are L2 round trips
+// of ~1 us while the other CTAs stream)
+template <typename T, typename Op>
+__device__ __forceinline__ T cl_rep_reduce(const T* p, unsigned rep, unsigned C, unsigned c, T identity, Op op) {
+  T v[8];
+#pragma unroll
+  for (unsigned r = 0; r < 8u; ++r) v[r] = (r < rep) ? ld_ws(p + r * C + c) : identity;
+  return op(op(op(v[0], v[1]), op(v[2], v[3])), op(op(v[4], v[5]), op(v[6], v[7])));
+}
 __device__ __forceinline__ double cl_mean(const ClView& acc, unsigned rep, unsigned C, unsigned c, float k, float bias, double n) {
-  double s = 0.0;
-  for (unsigned r = 0; r < rep; ++r) s += ld_ws(acc.asum + r * C + c);
+  const double s = cl_rep_reduce(acc.asum, rep, C, c, 0.0, OpAdd());
   return static_cast<double>(k) + static_cast<double>(bias) + s / n;
 }
 // unbiased std of channel c: sqrt((Q - S^2 / n) / (n - 1))
 __device__ __forceinline__ float cl_std(const ClView& acc, unsigned rep, unsigned C, unsigned c, double n) {
-  double s = 0.0, q = 0.0;
-  for (unsigned r = 0; r < rep; ++r) {
-    s += ld_ws(acc.asum + r * C + c);
-    q += ld_ws(acc.asq + r * C + c);
-  }
+  const double s = cl_rep_reduce(acc.asum, rep, C, c, 0.0, OpAdd());
+  const double q = cl_rep_reduce(acc.asq, rep, C, c, 0.0, OpAdd());
   double m2 = q - s * s / n;
   if (m2 < 0.0) m2 = 0.0;
   return static_cast<float>(sqrt(m2 / (n - 1.0)));
@@ -366,7 +370,8 @@ __device__ __forceinline__ LeafParam mid_tread_param(const FusedArgs& A, float o
 // `dry`: same code on synthetic priors, nothing published - CTA 0 runs it once at kernel start, while the other CTAs
 // stream S1, so that the real run after barrier 1 finds its instructions in the SM's cache (cold, this function was
 // 12 - 15 us of latency, round-2 stamps; it sits on the critical path of the small layers).
-__device__ __noinline__ void cl_solve_aux(const FusedArgs& A, const ClView& acc, LeaderSmem& sm, unsigned tag, bool have_b, bool dry) {
+__device__ __noinline__ void cl_solve_aux(const FusedArgs& A, const ClView& acc, LeaderSmem& sm, unsigned tag, bool have_b, bool dry,
+                                          bool publish) {
   const unsigned C = A.flat.channels;
   const double n = A.n_per_group;
   const bool prior_b = (A.leaf != FQB200_LEAF_MIDTREAD) && A.prior == FQB200_PRIOR_B;
@@ -374,15 +379,14 @@ __device__ __noinline__ void cl_solve_aux(const FusedArgs& A, const ClView& acc,
     if (dry) {
       (prior_b ? A.gb : A.gstd)[c] = 0.5f + 0.03125f * static_cast<float>(c & 63u);
     } else if (prior_b) {
-      double sa = 0.0;
-      if (have_b)
-        for (unsigned r = 0; r < A.nhwc_rep; ++r) sa += ld_ws(acc.aabs + r * C + c);
+      const double sa = have_b ? cl_rep_reduce(acc.aabs, A.nhwc_rep, C, c, 0.0, OpAdd()) : 0.0;
       A.gb[c] = static_cast<float>(sa / n);
     } else {
       A.gstd[c] = cl_std(acc, A.nhwc_rep, C, c, n);
     }
   }
   consumer_sync();
+  if (!dry) stamp(A, 10);
   if (A.leaf == FQB200_LEAF_MIDTREAD) {
     double local = 0.0;
     for (unsigned c = threadIdx.x; c < C; c += kConsumers) {
@@ -397,10 +401,9 @@ __device__ __noinline__ void cl_solve_aux(const FusedArgs& A, const ClView& acc,
     solve_bit_alloc(A, sm);
   }
   consumer_sync();
-  if (!dry && threadIdx.x == 0) {
-    __threadfence();
-    st_release_u32(&A.sync->aux_ready, tag);
-  }
+  // `publish`: the result is needed before this CTA reaches another grid barrier (no S2 phase to hide behind); otherwise
+  // CTA 0's arrival at barrier 2 (release) publishes A.gbits along with everything else
+  if (!dry && publish && threadIdx.x == 0) st_release_u32(&A.sync->aux_ready, tag);
 }
 
 // leaf parameters of channel c from the reduced accumulators (what the leader section of the NCHW kernel computes, here for
@@ -411,13 +414,10 @@ __device__ __noinline__ void cl_solve_aux(const FusedArgs& A, const ClView& acc,
 template <int LEAF, bool DEV>
 __device__ __noinline__ LeafParam cl_channel_param(const FusedArgs& A, const ClView& acc, unsigned rep, unsigned C, unsigned c,
                                                    float mu, double n, bool alloc, bool do_export) {
-  unsigned lo = 0u, hi = 0u;
-  double sa = 0.0;
-  for (unsigned r = 0; r < rep; ++r) {
-    lo = max(lo, ld_ws(acc.amin_inv + r * C + c));
-    hi = max(hi, ld_ws(acc.amax + r * C + c));
-    if (DEV) sa += ld_ws(acc.aabs + r * C + c);
-  }
+  auto umax = [](unsigned a, unsigned b) { return a > b ? a : b; };
+  const unsigned lo = cl_rep_reduce(acc.amin_inv, rep, C, c, 0u, umax);
+  const unsigned hi = cl_rep_reduce(acc.amax, rep, C, c, 0u, umax);
+  const double sa = DEV ? cl_rep_reduce(acc.aabs, rep, C, c, 0.0, OpAdd()) : 0.0;
   const float cb = A.bias ? __ldg(A.bias + c) : 0.f;  // S1 ran on the raw values: min / max shift by the bias exactly
   const float mn = __fadd_rn(dec_ordered(~lo), cb), mx = __fadd_rn(dec_ordered(hi), cb);
   const float b = DEV ? static_cast<float>(sa / n) : 0.f;
@@ -470,8 +470,11 @@ __device__ __noinline__ void cl_phase_s1(const FusedArgs& A, ClCtx& cx, float (&
   const ClView& acc = cx.acc;
   const unsigned rb = cx.rep_base;
   cl_combine_max_u32(cx.cbuf, g.cv, g.stride, umn, acc.amin_inv + rb);
+  if (blockIdx.x == 0) stamp(A, 2);
   cl_combine_max_u32(cx.cbuf, g.cv, g.stride, umx, acc.amax + rb);
+  if (blockIdx.x == 0) stamp(A, 3);
   cl_combine_add_f64(cx.cbuf, g.cv, g.stride, s1.s, acc.asum + rb);
+  if (blockIdx.x == 0) stamp(A, 6);
   cl_combine_add_f64(cx.cbuf, g.cv, g.stride, s1.q, acc.asq + rb);
 }
 
@@ -529,7 +532,7 @@ constexpr unsigned kClTableChannels = 1024;                          // channel 
 constexpr unsigned kClCombineBytes = kClStagingBytes + kClTableChannels * 4u;
 
 template <int LEAF, bool DEV, bool HIST>
-__global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_kernel(const __grid_constant__ FusedArgs A) {
+__global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_kernel(const __grid_constant__ FusedArgs A) {
   extern __shared__ __align__(128) unsigned char fq_dyn[];
   unsigned char* stages = fq_dyn;
   unsigned char* cbuf = fq_dyn + kStages * kStageBytes;
@@ -602,7 +605,7 @@ __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_kernel(const _
   }
 
   if (warm_in_s1 && blockIdx.x == 0) {
-    cl_solve_aux(A, acc, lsm, tag, false, true);
+    cl_solve_aux(A, acc, lsm, tag, false, true, false);
     if (t == 0) mbar_arrive(smem_u32(&warm_done));
   }
 
@@ -644,7 +647,7 @@ __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_kernel(const _
 
   // ---- the global solve, where it can overlap with S2
   if (alloc && !aux_needs_b && blockIdx.x == 0) {
-    cl_solve_aux(A, acc, lsm, tag, false, false);
+    cl_solve_aux(A, acc, lsm, tag, false, false, !solver_in_s2);
     stamp(A, 12);
     if (t == 0) mbar_arrive(smem_u32(&solver_done));
   }
@@ -655,9 +658,9 @@ __global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_kernel(const _
     if (blockIdx.x == 0) stamp(A, 5);
     grid_barrier_cl(A.sync, epoch);
     if (blockIdx.x == 0) stamp(A, 8);
-    if (aux_needs_b && blockIdx.x == 0) cl_solve_aux(A, acc, lsm, tag, true, false);
+    if (aux_needs_b && blockIdx.x == 0) cl_solve_aux(A, acc, lsm, tag, true, false, true);
   }
-  if (alloc) {  // published by CTA 0 (long ago when it overlapped with S2)
+  if (alloc && !solver_in_s2) {  // (overlapped with S2, CTA 0's arrival at barrier 2 has published the bit widths already)
     if (t == 0)
       while (ld_acquire_u32(&A.sync->aux_ready) != tag) __nanosleep(40);
     consumer_sync();
@@ -721,7 +724,7 @@ struct ClGiven {
 };
 
 template <bool GRID>
-__global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_given_kernel(const __grid_constant__ FusedArgs A) {
+__global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_given_kernel(const __grid_constant__ FusedArgs A) {
   extern __shared__ __align__(128) unsigned char fq_dyn[];
   __shared__ BulkRing ring;
   const FlatGeo& g = A.flat;
@@ -837,7 +840,7 @@ struct ClBca2 {
   __device__ __forceinline__ void stage_end(const StageMeta&) {}
 };
 
-__global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_cl_bca_kernel(const __grid_constant__ FusedArgs A) {
+__global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_bca_kernel(const __grid_constant__ FusedArgs A) {
   extern __shared__ __align__(128) unsigned char fq_dyn[];
   unsigned char* stages = fq_dyn;
   unsigned char* cbuf = fq_dyn + kStages * kStageBytes;
@@ -1005,7 +1008,7 @@ struct RowsApply {
   __device__ __forceinline__ void stage_end(const StageMeta&) {}
 };
 
-__global__ void __launch_bounds__(kBulkThreads, kCtasPerSm) fq_rows_kernel(const __grid_constant__ FusedArgs A) {
+__global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_rows_kernel(const __grid_constant__ FusedArgs A) {
   extern __shared__ __align__(128) unsigned char fq_dyn[];
   __shared__ BulkRing ring;
   __shared__ LeaderSmem lsm;

@@ -227,6 +227,7 @@ __device__ __noinline__ void solve_bit_alloc(const FusedArgs& A, LeaderSmem& sm)
     half_gap = __fmul_rn(__fsub_rn(goal, mean), 0.5f);
     m += static_cast<double>(half_gap);
   }
+  stamp(A, 11);
   if (in_regs) {
 #pragma unroll
     for (unsigned k = 0; k < kRegGroups; ++k) {
@@ -1318,9 +1319,18 @@ void init_device(int dev) {
         const size_t smem = cl_smem(hist != 0);
         e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fqb::kBulkThreads, smem);
+        if (e != cudaSuccess && hist) {  // the histogram variant may not fit next to an enlarged ring (development builds)
+          (void)cudaGetLastError();
+          n = 0;
+          e = cudaSuccess;
+        }
         if (e != cudaSuccess) return bad("channels-last kernel setup", e);
         if (n < worst) worst = n;
       }
+    if (worst < 1 && hist) {
+      d.resident_cl[1] = 0;
+      continue;
+    }
     if (worst < 1) {
       d.rc = FQB200_ERR_CUDA;
       snprintf(d.err, sizeof(d.err), "channels-last kernel does not fit on an SM");
@@ -1825,7 +1835,7 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   rc = get_device(&di);
   if (rc != FQB200_OK) return rc;
   Plan pl;
-  if (d->bias && d->bias_period <= 0 && d->scope == FQB200_SCOPE_GROUP_MEAN)
+  if (d->bias && d->bias_period == 0 && d->scope == FQB200_SCOPE_GROUP_MEAN)
     return fail(FQB200_ERR_UNSUPPORTED, "a per-group bias needs groups = channels (scope GROUP or TENSOR); use bias_period%s");
   const bool can_vec = aligned16(in) && (d->stats_only || aligned16(out));
   fqb::RowsGeo rows_geo;

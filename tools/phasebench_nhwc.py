@@ -7,8 +7,8 @@ import cnn_quantization_b200 as fq
 from cnn_quantization_b200 import _lib as L
 buf = torch.zeros(16, dtype=torch.int64, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-order = [(0, "start"), (13, "S1 streamed"), (1, "S1 combined"), (2, "L1 begin"), (3, "L1 end"), (4, "past barrier 1"),
-         (12, "aux solved"), (14, "S2 streamed"), (5, "S2 combined"), (6, "L2 begin"), (7, "params ready"), (8, "past barrier 2"),
+order = [(0, "start"), (13, "S1 streamed"), (2, "comb min"), (3, "comb max"), (6, "comb S"), (1, "S1 combined"), (4, "past barrier 1"),
+         (10, "aux: std"), (15, "aux: pow+sum"), (11, "aux: iterations"), (12, "aux solved"), (14, "S2 streamed"), (5, "S2 combined"), (7, "params ready"), (8, "past barrier 2"),
          (9, "apply done")]
 shapes = [(512, 64, 56), (512, 256, 14), (512, 128, 28), (512, 1024, 14), (512, 2048, 7), (512, 512, 7), (512, 512, 14),
           (128, 64, 56), (128, 256, 14), (128, 512, 7), (128, 1024, 14), (128, 256, 56)]
