@@ -20,14 +20,17 @@ namespace fqb {
 constexpr int kConsumers = kThreads;             // 512 consumer threads (16 warps)
 constexpr int kBulkThreads = kConsumers + 32;    // + one producer warp
 constexpr int kConsumerWarps = kConsumers / 32;
+// Ring shape (round-2 A/B on the B200, profiles/README.md): ONE CTA per SM with six 32 KB stages beats two CTAs with
+// five 16 KB stages in every phase (S1 of a 411 MB tensor 74.5 vs 85.6 us, 103 MB launch 94 vs 115 us): a bulk request
+// should be large (8 KB stages: 126 us), and 148 CTAs halve the barrier arrivals, atomics and tickets.
 #ifndef FQB_STAGE_VEC
-#define FQB_STAGE_VEC 2
+#define FQB_STAGE_VEC 4
 #endif
 #ifndef FQB_STAGES
-#define FQB_STAGES 5
+#define FQB_STAGES 6
 #endif
 #ifndef FQB_BULK_CTAS
-#define FQB_BULK_CTAS 2
+#define FQB_BULK_CTAS 1
 #endif
 constexpr int kBulkCtasPerSm = FQB_BULK_CTAS;    // resident CTAs per SM of the bulk-ring kernels
 constexpr int kStageVec = FQB_STAGE_VEC;         // vectors per consumer thread per stage
@@ -110,25 +113,28 @@ struct BulkRing {
   alignas(8) unsigned long long full[kStages];
   alignas(8) unsigned long long empty[kStages];
   StageMeta meta[kStages];
+  unsigned nstages;  // stages in use (<= kStages; the histogram variants lend the last one to the histogram)
 };
 
 // position in the ring sequence: both sides count every stage AND every end-of-phase marker
 struct RingPos {
-  unsigned slot, parity;
-  __device__ __forceinline__ void init() {
+  unsigned slot, parity, n;
+  __device__ __forceinline__ void init(unsigned nstages = kStages) {
     slot = 0;
     parity = 0;
+    n = nstages;
   }
   __device__ __forceinline__ void next() {
-    if (++slot == static_cast<unsigned>(kStages)) {
+    if (++slot == n) {
       slot = 0;
       parity ^= 1u;
     }
   }
 };
 
-__device__ __forceinline__ void ring_init(BulkRing& r) {
+__device__ __forceinline__ void ring_init(BulkRing& r, unsigned nstages = kStages) {
   if (threadIdx.x == 0) {
+    r.nstages = nstages;
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       mbar_init(smem_u32(&r.full[s]), 1u);                 // the producer's arrive(.expect_tx)

@@ -193,6 +193,7 @@ struct ClStats2 {
 // per-channel, generally fractional bounds c_min / c_max (int_quantizer.py:207-214); elements sitting on a bound are
 // counted per channel (they are distinct symbols for torch.unique) instead of in the integer histogram.
 constexpr unsigned kHistWords = 8192;
+static_assert(kHistWords * 4u <= kStageBytes, "the histogram borrows one ring stage");
 
 template <int LEAF, bool HIST>
 struct ClApply {
@@ -265,24 +266,34 @@ struct ClApply {
 // buf: 16 KB of shared memory.  Threads sharing a column (t, t + cv, ...) are reduced by the column's owner items.  Code
 // that runs once per phase is cold in the instruction cache (round-2 stamps: ~1.5 us per inlined copy), so these are two
 // real functions, called for every array.
-__device__ __noinline__ void cl_combine_max_u32(unsigned char* buf, unsigned cv, unsigned stride, const unsigned (&v)[4], unsigned* dst) {
+// (min, max) pairs in one round: both are max-reductions of order-preserving encodings, staged as uint2
+__device__ __noinline__ void cl_combine_max_u32x2(unsigned char* buf, unsigned cv, unsigned stride, const unsigned (&v0)[4],
+                                                  const unsigned (&v1)[4], unsigned* dst0, unsigned* dst1) {
   if (cv == stride) {  // every active thread owns its column alone (C = 2048 with 512 threads): no staging
     if (threadIdx.x < stride) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) red_max_u32(dst + 4u * threadIdx.x + i, v[i]);
+      for (int i = 0; i < 4; ++i) {
+        red_max_u32(dst0 + 4u * threadIdx.x + i, v0[i]);
+        red_max_u32(dst1 + 4u * threadIdx.x + i, v1[i]);
+      }
     }
     return;
   }
-  unsigned* st = reinterpret_cast<unsigned*>(buf);  // [4][kConsumers]
+  uint2* st = reinterpret_cast<uint2*>(buf);  // [4][kConsumers]
   consumer_sync();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) st[i * kConsumers + threadIdx.x] = (threadIdx.x < stride) ? v[i] : 0u;
+  for (int i = 0; i < 4; ++i) st[i * kConsumers + threadIdx.x] = (threadIdx.x < stride) ? make_uint2(v0[i], v1[i]) : make_uint2(0u, 0u);
   consumer_sync();
   for (unsigned it = threadIdx.x; it < 4u * cv; it += kConsumers) {
     const unsigned col = it % cv, i = it / cv;
-    unsigned a = 0u;
-    for (unsigned t = col; t < stride; t += cv) a = max(a, st[i * kConsumers + t]);
-    red_max_u32(dst + 4u * col + i, a);
+    unsigned a = 0u, b = 0u;
+    for (unsigned t = col; t < stride; t += cv) {
+      const uint2 x = st[i * kConsumers + t];
+      a = max(a, x.x);
+      b = max(b, x.y);
+    }
+    red_max_u32(dst0 + 4u * col + i, a);
+    red_max_u32(dst1 + 4u * col + i, b);
   }
 }
 __device__ __noinline__ void cl_combine_add_f64(unsigned char* buf, unsigned cv, unsigned stride, const double (&v)[4], double* dst) {
@@ -469,9 +480,7 @@ __device__ __noinline__ void cl_phase_s1(const FusedArgs& A, ClCtx& cx, float (&
   }
   const ClView& acc = cx.acc;
   const unsigned rb = cx.rep_base;
-  cl_combine_max_u32(cx.cbuf, g.cv, g.stride, umn, acc.amin_inv + rb);
-  if (blockIdx.x == 0) stamp(A, 2);
-  cl_combine_max_u32(cx.cbuf, g.cv, g.stride, umx, acc.amax + rb);
+  cl_combine_max_u32x2(cx.cbuf, g.cv, g.stride, umn, umx, acc.amin_inv + rb, acc.amax + rb);
   if (blockIdx.x == 0) stamp(A, 3);
   cl_combine_add_f64(cx.cbuf, g.cv, g.stride, s1.s, acc.asum + rb);
   if (blockIdx.x == 0) stamp(A, 6);
@@ -526,7 +535,8 @@ __device__ __noinline__ void cl_phase_apply(const FusedArgs& A, ClCtx& cx, const
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------------
 // LEAF: torch or mid-tread.  DEV: phase S2 (the Laplace b) is needed.  HIST: histogram of the integer grid (`-me`).
-// Dynamic shared memory: [kStages stages][16 KB combine staging / parameter table][4 KB mean table][HIST: 16 KB histograms].
+// Dynamic shared memory: [kStages stages][16 KB combine staging / parameter table][4 KB mean table]; HIST: the last stage
+// holds the histograms and the ring runs with kStages - 1.
 constexpr unsigned kClStagingBytes = 4u * kConsumers * 8u;          // 16 KB
 constexpr unsigned kClTableChannels = 1024;                          // channel tables live in shared memory up to here
 constexpr unsigned kClCombineBytes = kClStagingBytes + kClTableChannels * 4u;
@@ -537,7 +547,7 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_kernel(con
   unsigned char* stages = fq_dyn;
   unsigned char* cbuf = fq_dyn + kStages * kStageBytes;
   float* tab_mean = reinterpret_cast<float*>(cbuf + kClStagingBytes);
-  unsigned* hist = reinterpret_cast<unsigned*>(cbuf + kClCombineBytes);
+  unsigned* hist = reinterpret_cast<unsigned*>(stages + (kStages - 1) * kStageBytes);  // HIST: the ring runs one stage short
   __shared__ BulkRing ring;
   __shared__ LeaderSmem lsm;
   __shared__ alignas(8) unsigned long long solver_done;  // mbarrier: CTA 0's consumers are back from the global solve
@@ -551,32 +561,37 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_kernel(con
   // CTA 0 computes the bit widths while the others stream S2: it takes no static S2 tickets and starts pulling dynamic
   // ones only when its consumers are back (it would sit on them otherwise)
   const bool solver_in_s2 = alloc && !aux_needs_b && DEV && gridDim.x > 1u;
-  // ... and, while the others stream S1, a dry run of that solve to pull its code into this SM's instruction cache
-  const bool warm_in_s1 = alloc && !aux_needs_b && gridDim.x > 1u;
-  __shared__ alignas(8) unsigned long long warm_done;
+  // the producer starts a phase's loads when the consumers are through the previous phase's combine: its reductions
+  // (a few thousand fire-and-forget atomics) queue behind 192 KB of bulk loads otherwise (round-2 stamps: 1.8 us per round)
+  __shared__ alignas(8) unsigned long long phase_go[2];
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&solver_done), 1u);
-    mbar_init(smem_u32(&warm_done), 1u);
+    mbar_init(smem_u32(&phase_go[0]), 1u);
+    mbar_init(smem_u32(&phase_go[1]), 1u);
   }
-  ring_init(ring);
+  const unsigned nstages = HIST ? kStages - 1u : kStages;  // the histogram lives in the last stage's memory
+  ring_init(ring, nstages);
 
   // ================================ producer warp ================================
   if (threadIdx.x >= kConsumers) {
     if (threadIdx.x == kConsumers) {
       RingPos pos;
-      pos.init();
+      pos.init(nstages);
       const float4* src = reinterpret_cast<const float4*>(A.in);
       const TicketPlan all = {2u, blockIdx.x, gridDim.x, 2u * gridDim.x};
-      // phases in which CTA 0's consumers are busy with the global solve: no static tickets for it, and its producer pulls
-      // dynamic ones only when they are back
+      // the phase in which CTA 0's consumers are busy with the global solve: no static tickets for it, and its producer
+      // pulls dynamic ones only when they are back
       const TicketPlan no0 = {blockIdx.x == 0 ? 0u : 2u, blockIdx.x - 1u, gridDim.x - 1u, 2u * (gridDim.x - 1u)};
-      if (warm_in_s1 && blockIdx.x == 0) mbar_wait(smem_u32(&warm_done), 0u);
-      produce_phase<false>(g, src, &A.sync->unit_counter[0], warm_in_s1 ? no0 : all, ring, stages, pos);
+      produce_phase<false>(g, src, &A.sync->unit_counter[0], all, ring, stages, pos);
       if (DEV) {
+        mbar_wait(smem_u32(&phase_go[0]), 0u);
         if (solver_in_s2 && blockIdx.x == 0) mbar_wait(smem_u32(&solver_done), 0u);
         produce_phase<true>(g, src, &A.sync->unit_counter[1], solver_in_s2 ? no0 : all, ring, stages, pos);
       }
-      if (!A.stats_only) produce_phase<!DEV>(g, src, &A.sync->unit_counter[2], all, ring, stages, pos);
+      if (!A.stats_only) {
+        mbar_wait(smem_u32(&phase_go[1]), 0u);
+        produce_phase<!DEV>(g, src, &A.sync->unit_counter[2], all, ring, stages, pos);
+      }
     }
     return;
   }
@@ -604,24 +619,20 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_kernel(con
     for (unsigned i = t; i < kAccD / 2u; i += kConsumers) zd[i] = z;
   }
 
-  if (warm_in_s1 && blockIdx.x == 0) {
-    cl_solve_aux(A, acc, lsm, tag, false, true, false);
-    if (t == 0) mbar_arrive(smem_u32(&warm_done));
-  }
-
   // ---- S1
   ClCtx cx;
   cx.g = &g;
   cx.ring = &ring;
   cx.stages = stages;
   cx.cbuf = cbuf;
-  cx.pos.init();
+  cx.pos.init(nstages);
   cx.acc = acc;
   cx.rep_base = rep_base;
   cx.c0 = c0;
   cx.active = active;
   float kshift[4];
   cl_phase_s1(A, cx, kshift);
+  if (t == 0) mbar_arrive(smem_u32(&phase_go[DEV ? 0 : 1]));
   if (blockIdx.x == 0) stamp(A, 1);
   grid_arrive_cl(A.sync, epoch);
   {  // instruction-cache warm-up of the parameter solve while the stragglers arrive
@@ -655,6 +666,7 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_kernel(con
   // ---- S2
   if constexpr (DEV) {
     cl_phase_s2(A, cx, mean);
+    if (t == 0) mbar_arrive(smem_u32(&phase_go[1]));
     if (blockIdx.x == 0) stamp(A, 5);
     grid_barrier_cl(A.sync, epoch);
     if (blockIdx.x == 0) stamp(A, 8);

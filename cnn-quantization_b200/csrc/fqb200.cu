@@ -1207,8 +1207,8 @@ const void* cl_kernel_ptr(int leaf, bool dev, bool hist) {
   return dev ? FQB_CL(FQB200_LEAF_TORCH, true, false) : FQB_CL(FQB200_LEAF_TORCH, false, false);
 #undef FQB_CL
 }
-size_t cl_smem(bool hist) {
-  return static_cast<size_t>(fqb::kStages) * fqb::kStageBytes + fqb::kClCombineBytes + (hist ? fqb::kHistWords * sizeof(unsigned) : 0u);
+size_t cl_smem(bool /*hist*/) {  // (the histogram variants borrow the last ring stage)
+  return static_cast<size_t>(fqb::kStages) * fqb::kStageBytes + fqb::kClCombineBytes;
 }
 size_t cl_given_smem() { return static_cast<size_t>(fqb::kStages) * fqb::kStageBytes; }
 

@@ -427,7 +427,10 @@ def test_channels_last_matches_nchw(fq, shape):
             y0, s0 = fq.ops.fused(x, lay, want_stats=True, bias=b, **kw)
             y1, s1 = fq.ops.fused(xcl, lay, want_stats=True, bias=b, channels_last=True, **kw)
             assert y1.is_contiguous(memory_format=torch.channels_last) and y1.shape == x.shape
-            assert torch.allclose(s0[:, :7], s1[:, :7], rtol=2e-6, atol=1e-6), (shape, kw)
+            # min, max, mean, delta, offset always; b / std where the range mode consumes them (the NCHW kernel leaves them
+            # at 0 when it skips its second pass, the channels-last kernel gets the std out of the first one)
+            cols = [0, 1, 2, 5, 6] + ([3, 4] if kw.get("range_mode") in (L.RANGE_LAPLACE, L.RANGE_GAUS) or "leaf" in kw else [])
+            assert torch.allclose(s0[:, cols], s1[:, cols], rtol=2e-6, atol=1e-6), (shape, kw)
             assert torch.equal(s0[:, 7], s1[:, 7])
             step = float(s0[:, 8].max()) + 1e-9
             frac, worst = fq_mismatch(y1.cpu().numpy(), y0.cpu().numpy(), step)
