@@ -263,61 +263,100 @@ struct ClApply {
 };
 
 // ---- CTA-wide combine of per-thread channel partials, then one reduction per channel into the replicated accumulators ----
-// buf: 16 KB of shared memory.  Threads sharing a column (t, t + cv, ...) are reduced by the column's owner items.  Code
-// that runs once per phase is cold in the instruction cache (round-2 stamps: ~1.5 us per inlined copy), so these are two
-// real functions, called for every array.
-// (min, max) pairs in one round: both are max-reductions of order-preserving encodings, staged as uint2
-__device__ __noinline__ void cl_combine_max_u32x2(unsigned char* buf, unsigned cv, unsigned stride, const unsigned (&v0)[4],
-                                                  const unsigned (&v1)[4], unsigned* dst0, unsigned* dst1) {
+// buf: 16 KB of shared memory.  Threads sharing a column (t, t + cv, ...) are reduced by the column's owner items
+// (item it -> column it % cv, channel-in-column it / cv; <= 4 items per thread since 4 * cv <= 2048).  The staging rounds
+// keep their results in registers and ALL the global reductions are issued at the very end: a CTA barrier behind a batch
+// of `red.global` waits for them (round-2 stamps: ~1.8 us per round with the reductions inside the rounds).
+constexpr unsigned kClItems = 4;
+
+template <typename T, typename Op>
+__device__ __forceinline__ void cl_stage_round(unsigned char* buf, unsigned cv, unsigned stride, const T (&v)[4], T identity, Op op,
+                                               T (&res)[kClItems]) {
+  T* st = reinterpret_cast<T*>(buf);  // [4][kConsumers]
+  consumer_sync();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) st[i * kConsumers + threadIdx.x] = (threadIdx.x < stride) ? v[i] : identity;
+  consumer_sync();
+#pragma unroll
+  for (unsigned k = 0; k < kClItems; ++k) {
+    const unsigned it = threadIdx.x + k * kConsumers;
+    T a = identity;
+    if (it < 4u * cv) {
+      const unsigned col = it % cv, i = it / cv;
+      for (unsigned t = col; t < stride; t += cv) a = op(a, st[i * kConsumers + t]);
+    }
+    res[k] = a;
+  }
+}
+
+// S1: (min, max) as one uint2 round, S and Q one round each, then the reductions
+__device__ __noinline__ void cl_combine_s1(unsigned char* buf, unsigned cv, unsigned stride, const unsigned (&umn)[4],
+                                           const unsigned (&umx)[4], const double (&s)[4], const double (&q)[4], unsigned* dmn,
+                                           unsigned* dmx, double* ds, double* dq) {
   if (cv == stride) {  // every active thread owns its column alone (C = 2048 with 512 threads): no staging
     if (threadIdx.x < stride) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        red_max_u32(dst0 + 4u * threadIdx.x + i, v0[i]);
-        red_max_u32(dst1 + 4u * threadIdx.x + i, v1[i]);
+        const unsigned c = 4u * threadIdx.x + i;
+        red_max_u32(dmn + c, umn[i]);
+        red_max_u32(dmx + c, umx[i]);
+        red_add_f64(ds + c, s[i]);
+        red_add_f64(dq + c, q[i]);
       }
     }
     return;
   }
-  uint2* st = reinterpret_cast<uint2*>(buf);  // [4][kConsumers]
-  consumer_sync();
+  uint2 mm[4], rmm[kClItems];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) st[i * kConsumers + threadIdx.x] = (threadIdx.x < stride) ? make_uint2(v0[i], v1[i]) : make_uint2(0u, 0u);
-  consumer_sync();
-  for (unsigned it = threadIdx.x; it < 4u * cv; it += kConsumers) {
-    const unsigned col = it % cv, i = it / cv;
-    unsigned a = 0u, b = 0u;
-    for (unsigned t = col; t < stride; t += cv) {
-      const uint2 x = st[i * kConsumers + t];
-      a = max(a, x.x);
-      b = max(b, x.y);
+  for (int i = 0; i < 4; ++i) mm[i] = make_uint2(umn[i], umx[i]);
+  auto max2 = [](uint2 a, uint2 b) { return make_uint2(a.x > b.x ? a.x : b.x, a.y > b.y ? a.y : b.y); };
+  double rs[kClItems], rq[kClItems];
+  cl_stage_round(buf, cv, stride, mm, make_uint2(0u, 0u), max2, rmm);
+  cl_stage_round(buf, cv, stride, s, 0.0, OpAdd(), rs);
+  cl_stage_round(buf, cv, stride, q, 0.0, OpAdd(), rq);
+#pragma unroll
+  for (unsigned k = 0; k < kClItems; ++k) {
+    const unsigned it = threadIdx.x + k * kConsumers;
+    if (it < 4u * cv) {
+      const unsigned c = 4u * (it % cv) + it / cv;
+      red_max_u32(dmn + c, rmm[k].x);
+      red_max_u32(dmx + c, rmm[k].y);
+      red_add_f64(ds + c, rs[k]);
+      red_add_f64(dq + c, rq[k]);
     }
-    red_max_u32(dst0 + 4u * col + i, a);
-    red_max_u32(dst1 + 4u * col + i, b);
   }
 }
-__device__ __noinline__ void cl_combine_add_f64(unsigned char* buf, unsigned cv, unsigned stride, const double (&v)[4], double* dst) {
+// up to three float64 sums (S2: one, `-bca`: three)
+__device__ __noinline__ void cl_combine_add_f64(unsigned char* buf, unsigned cv, unsigned stride, const double (&v0)[4], double* d0,
+                                                const double (&v1)[4], double* d1, const double (&v2)[4], double* d2) {
   if (cv == stride) {
     if (threadIdx.x < stride) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) red_add_f64(dst + 4u * threadIdx.x + i, v[i]);
+      for (int i = 0; i < 4; ++i) {
+        const unsigned c = 4u * threadIdx.x + i;
+        red_add_f64(d0 + c, v0[i]);
+        if (d1) red_add_f64(d1 + c, v1[i]);
+        if (d2) red_add_f64(d2 + c, v2[i]);
+      }
     }
     return;
   }
-  double* st = reinterpret_cast<double*>(buf);  // [4][kConsumers]
-  consumer_sync();
+  double r0[kClItems], r1[kClItems], r2[kClItems];
+  cl_stage_round(buf, cv, stride, v0, 0.0, OpAdd(), r0);
+  if (d1) cl_stage_round(buf, cv, stride, v1, 0.0, OpAdd(), r1);
+  if (d2) cl_stage_round(buf, cv, stride, v2, 0.0, OpAdd(), r2);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) st[i * kConsumers + threadIdx.x] = (threadIdx.x < stride) ? v[i] : 0.0;
-  consumer_sync();
-  for (unsigned it = threadIdx.x; it < 4u * cv; it += kConsumers) {
-    const unsigned col = it % cv, i = it / cv;
-    double a = 0.0;
-    for (unsigned t = col; t < stride; t += cv) a += st[i * kConsumers + t];
-    red_add_f64(dst + 4u * col + i, a);
+  for (unsigned k = 0; k < kClItems; ++k) {
+    const unsigned it = threadIdx.x + k * kConsumers;
+    if (it < 4u * cv) {
+      const unsigned c = 4u * (it % cv) + it / cv;
+      red_add_f64(d0 + c, r0[k]);
+      if (d1) red_add_f64(d1 + c, r1[k]);
+      if (d2) red_add_f64(d2 + c, r2[k]);
+    }
   }
 }
 
-// mean (float64) of channel c (of x + bias) from the S1 accumulators: k + bias + S / n
 // sum over the (<= 8) replicas of one accumulator entry: all loads issued before the first add (they are L2 round trips
 // of ~1 us while the other CTAs stream)
 template <typename T, typename Op>
@@ -378,9 +417,8 @@ __device__ __forceinline__ LeafParam mid_tread_param(const FusedArgs& A, float o
 // CTA 0, all consumer threads: the one computation that needs every channel - per-channel bit widths (int_quantizer.py:
 // 381-407) or mid-tread bin counts (:128-135) from the per-channel std (prior 'gaus') or b (prior 'laplace') - into
 // A.gbits, then the aux_ready flag.
-// `dry`: same code on synthetic priors, nothing published - CTA 0 runs it once at kernel start, while the other CTAs
-// stream S1, so that the real run after barrier 1 finds its instructions in the SM's cache (cold, this function was
-// 12 - 15 us of latency, round-2 stamps; it sits on the critical path of the small layers).
+// (`dry`: same code on synthetic priors, nothing published - an instruction-cache warm-up that was tried and dropped: the
+// CTA that runs it becomes the straggler of the phase it overlaps with.)
 __device__ __noinline__ void cl_solve_aux(const FusedArgs& A, const ClView& acc, LeaderSmem& sm, unsigned tag, bool have_b, bool dry,
                                           bool publish) {
   const unsigned C = A.flat.channels;
@@ -420,8 +458,6 @@ __device__ __noinline__ void cl_solve_aux(const FusedArgs& A, const ClView& acc,
 // leaf parameters of channel c from the reduced accumulators (what the leader section of the NCHW kernel computes, here for
 // one channel at a time): min / max / b over the replicas, std when a range mode or the export needs it, the channel's bit
 // width (or mid-tread bin count) published by CTA 0, then int_quantizer.py:284-300 + :557-572 (or :185-214).
-// One real function per kernel variant: every CTA also calls it once, on whatever the accumulators hold, between posting
-// its arrival at barrier 1 and waiting there - so that after the LAST barrier its instructions are in the cache.
 template <int LEAF, bool DEV>
 __device__ __noinline__ LeafParam cl_channel_param(const FusedArgs& A, const ClView& acc, unsigned rep, unsigned C, unsigned c,
                                                    float mu, double n, bool alloc, bool do_export) {
@@ -480,11 +516,7 @@ __device__ __noinline__ void cl_phase_s1(const FusedArgs& A, ClCtx& cx, float (&
   }
   const ClView& acc = cx.acc;
   const unsigned rb = cx.rep_base;
-  cl_combine_max_u32x2(cx.cbuf, g.cv, g.stride, umn, umx, acc.amin_inv + rb, acc.amax + rb);
-  if (blockIdx.x == 0) stamp(A, 3);
-  cl_combine_add_f64(cx.cbuf, g.cv, g.stride, s1.s, acc.asum + rb);
-  if (blockIdx.x == 0) stamp(A, 6);
-  cl_combine_add_f64(cx.cbuf, g.cv, g.stride, s1.q, acc.asq + rb);
+  cl_combine_s1(cx.cbuf, g.cv, g.stride, umn, umx, s1.s, s1.q, acc.amin_inv + rb, acc.amax + rb, acc.asum + rb, acc.asq + rb);
 }
 
 __device__ __noinline__ void cl_phase_s2(const FusedArgs& A, ClCtx& cx, const float (&mean)[4]) {
@@ -498,7 +530,7 @@ __device__ __noinline__ void cl_phase_s2(const FusedArgs& A, ClCtx& cx, const fl
   if (blockIdx.x == 0) stamp(A, 14);
   const ClView& acc = cx.acc;
   const unsigned rb = cx.rep_base;
-  cl_combine_add_f64(cx.cbuf, g.cv, g.stride, s2.sa, acc.aabs + rb);
+  cl_combine_add_f64(cx.cbuf, g.cv, g.stride, s2.sa, acc.aabs + rb, s2.sa, nullptr, s2.sa, nullptr);
 }
 
 template <int LEAF, bool HIST>
@@ -634,12 +666,7 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_kernel(con
   cl_phase_s1(A, cx, kshift);
   if (t == 0) mbar_arrive(smem_u32(&phase_go[DEV ? 0 : 1]));
   if (blockIdx.x == 0) stamp(A, 1);
-  grid_arrive_cl(A.sync, epoch);
-  {  // instruction-cache warm-up of the parameter solve while the stragglers arrive
-    const LeafParam w = cl_channel_param<LEAF, DEV>(A, acc, rep, C, t % C, 0.25f, n, false, false);
-    if (w.a == -1.2345e-30f) lsm.f[0] = w.b;  // never true: keeps the call
-  }
-  grid_wait_cl(A.sync, epoch);
+  grid_barrier_cl(A.sync, epoch);
   if (blockIdx.x == 0) stamp(A, 4);
 
   // ---- the mean of every channel: each accumulator value is read once per CTA
@@ -911,9 +938,7 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_bca_kernel
   double dc[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) dc[i] = static_cast<double>(p1.cnt[i]);
-  cl_combine_add_f64(cbuf, cv, g.stride, p1.sr, acc.asum + rep_base);
-  cl_combine_add_f64(cbuf, cv, g.stride, p1.sy, acc.asq + rep_base);
-  cl_combine_add_f64(cbuf, cv, g.stride, dc, acc.aabs + rep_base);
+  cl_combine_add_f64(cbuf, cv, g.stride, p1.sr, acc.asum + rep_base, p1.sy, acc.asq + rep_base, dc, acc.aabs + rep_base);
   grid_barrier_cl(A.sync, epoch);
   // q_bias of every channel, each accumulator value read once per CTA (table in shared memory; direct when cv == stride)
   auto qbias_of = [&](unsigned c) {
