@@ -19,7 +19,7 @@ STAT_COLUMNS = ("min", "max", "mean", "b", "std", "delta", "offset", "bits", "sc
 # every symbol include/fqb200.h declares (tests check the export table against this)
 SYMBOLS = ("fqb200_abi_version", "fqb200_last_error", "fqb200_resident_ctas", "fqb200_plan_info",
            "fqb200_selftest_division", "fqb200_workspace_bytes", "fqb200_workspace_init", "fqb200_float2gemmlowp",
-           "fqb200_quantize1", "fqb200_quantize1_bca", "fqb200_fused", "fqb200_add_relu")
+           "fqb200_quantize1", "fqb200_quantize1_bca", "fqb200_fused", "fqb200_add_relu", "fqb200_maxpool2d_nhwc")
 ABI_VERSION = 2
 
 
@@ -81,6 +81,8 @@ def load():
     lib.fqb200_fused.argtypes = [ctypes.POINTER(Desc), vp, vp, vp, ctypes.c_size_t, vp]
     lib.fqb200_quantize1_bca.restype = i32
     lib.fqb200_quantize1_bca.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, i32, i32, vp, i32, vp, vp, ctypes.c_size_t, vp]
+    lib.fqb200_maxpool2d_nhwc.restype = i32
+    lib.fqb200_maxpool2d_nhwc.argtypes = [vp, vp, i64, i64, i64, i64, i32, i32, i32, i32, i32, i32, vp]
     lib.fqb200_add_relu.restype = i32
     lib.fqb200_add_relu.argtypes = [vp, vp, vp, i64, vp]
     lib.fqb200_selftest_division.restype = i32

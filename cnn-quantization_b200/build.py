@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfqb200.so")
 SOURCES = [os.path.join(CSRC, "fqb200.cu")]
-HEADERS = [os.path.join(CSRC, "fq_device.cuh"), os.path.join(os.path.dirname(HERE), "include", "fqb200.h")]
+HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [
+    os.path.join(os.path.dirname(HERE), "include", "fqb200.h")]
 
 # -fmad=false: the reference's arithmetic is a chain of separately rounded fp32 torch ops; the kernels spell out
 # every fused multiply-add they want (__fmaf_rn) and must not get any other.  No fast-math anywhere.

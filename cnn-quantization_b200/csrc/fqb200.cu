@@ -1170,6 +1170,51 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
   }
 }
 
+// Max pooling on channels-last memory ([N][H][W][C], C % 4 == 0): the operator in front of the `activation_pooling`
+// quantization call site (MaxPool2dWithId.forward, inference_quantization_manager.py:58-74).  torch's NHWC kernel runs at
+// ~1.8 TB/s on the 1.6 GB ResNet stem activation (5 % of a step, 17 % of a VGG-16 step, profiles/README.md round 2); this
+// one is a plain gather of k*k 128-bit vectors per output vector - neighbouring windows overlap in L1 / L2 - with torch's
+// NaN rule (a NaN in the window wins).  Results are bit-identical (max is exact).
+struct PoolArgs {
+  const float* in;
+  float* out;
+  unsigned n, h, w, cv, oh, ow;
+  int kh, kw, sh, sw, ph, pw;
+  unsigned long long total;  // output vectors
+};
+__global__ void __launch_bounds__(256, 4) fq_maxpool_nhwc_kernel(const __grid_constant__ PoolArgs P) {
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  const float4* in = reinterpret_cast<const float4*>(P.in);
+  float4* out = reinterpret_cast<float4*>(P.out);
+  auto upd = [](float& m, float v) { m = (v > m || v != v) ? v : m; };
+  for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < P.total; i += stride) {
+    const unsigned c = static_cast<unsigned>(i % P.cv);
+    unsigned long long r = i / P.cv;
+    const unsigned ow = static_cast<unsigned>(r % P.ow);
+    r /= P.ow;
+    const unsigned oh = static_cast<unsigned>(r % P.oh);
+    const unsigned n = static_cast<unsigned>(r / P.oh);
+    const int h0 = static_cast<int>(oh) * P.sh - P.ph, w0 = static_cast<int>(ow) * P.sw - P.pw;
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dy = 0; dy < P.kh; ++dy) {
+      const int y = h0 + dy;
+      if (y < 0 || y >= static_cast<int>(P.h)) continue;
+      const float4* row = in + (static_cast<unsigned long long>(n) * P.h + y) * P.w * P.cv + c;
+#pragma unroll 3
+      for (int dx = 0; dx < P.kw; ++dx) {
+        const int x = w0 + dx;
+        if (x < 0 || x >= static_cast<int>(P.w)) continue;
+        const float4 v = __ldg(row + static_cast<unsigned long long>(x) * P.cv);
+        upd(m.x, v.x);
+        upd(m.y, v.y);
+        upd(m.z, v.z);
+        upd(m.w, v.w);
+      }
+    }
+    __stcs(out + i, m);
+  }
+}
+
 // test hook: q[i] = div_exact(a[i], b[i]) next to IEEE a[i]/b[i]
 __global__ void fq_divtest_kernel(const float* a, const float* b, float* fast, float* ieee, unsigned long long n) {
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
@@ -1980,6 +2025,34 @@ int fqb200_quantize1_bca(const float* in, float* out, int64_t outer, int64_t gro
   cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(fqb::fq_cl_bca_kernel), dim3(pl.grid),
                                               dim3(fqb::kBulkThreads), args, cl_smem(false), static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cooperative launch fq_cl_bca_kernel: %s", cudaGetErrorString(e));
+  return FQB200_OK;
+}
+
+int fqb200_maxpool2d_nhwc(const float* in, float* out, int64_t n, int64_t h, int64_t w, int64_t c, int kh, int kw, int sh, int sw,
+                          int ph, int pw, void* stream) {
+  g_err[0] = 0;
+  if (n < 0 || h <= 0 || w <= 0 || c <= 0 || kh <= 0 || kw <= 0 || sh <= 0 || sw <= 0 || ph < 0 || pw < 0 || 2 * ph > kh || 2 * pw > kw)
+    return fail(FQB200_ERR_INVALID, "bad pooling geometry%s");
+  if (n == 0) return FQB200_OK;
+  if (!in || !out) return fail(FQB200_ERR_INVALID, "null tensor pointer%s");
+  if (c % 4 != 0 || !aligned16(in) || !aligned16(out)) return fail(FQB200_ERR_UNSUPPORTED, "channels-last pooling needs C %% 4 == 0 and 16-byte aligned tensors%s");
+  const int64_t oh = (h + 2 * ph - kh) / sh + 1, ow = (w + 2 * pw - kw) / sw + 1;
+  if (oh <= 0 || ow <= 0 || h >= (1ll << 31) || w >= (1ll << 31) || n >= (1ll << 31)) return fail(FQB200_ERR_INVALID, "bad pooling geometry%s");
+  DeviceInfo* di = nullptr;
+  int rc = get_device(&di);
+  if (rc != FQB200_OK) return rc;
+  fqb::PoolArgs P;
+  P.in = in; P.out = out;
+  P.n = static_cast<unsigned>(n); P.h = static_cast<unsigned>(h); P.w = static_cast<unsigned>(w); P.cv = static_cast<unsigned>(c / 4);
+  P.oh = static_cast<unsigned>(oh); P.ow = static_cast<unsigned>(ow);
+  P.kh = kh; P.kw = kw; P.sh = sh; P.sw = sw; P.ph = ph; P.pw = pw;
+  P.total = static_cast<unsigned long long>(n) * oh * ow * (c / 4);
+  unsigned long long want = (P.total + 255ull) / 256ull;
+  const unsigned long long cap = static_cast<unsigned long long>(di->sms) * 32ull;
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  fqb::fq_maxpool_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "launch fq_maxpool_nhwc_kernel: %s", cudaGetErrorString(e));
   return FQB200_OK;
 }
 

@@ -321,6 +321,24 @@ def add_relu_(a, b):
     return a
 
 
+def maxpool2d_cl(x, kernel_size, stride, padding):
+    """``F.max_pool2d(x, kernel_size, stride, padding)`` for a channels-last fp32 activation with C % 4 == 0 (C ABI
+    fqb200_maxpool2d_nhwc); the result is channels-last as well.  Bit-identical to torch."""
+    _require_cuda_f32(x, "input")
+    if x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last) or x.shape[1] % 4 != 0:
+        raise ValueError("maxpool2d_cl needs a channels-last [N, C, H, W] tensor with C % 4 == 0")
+    kh, kw = (kernel_size, kernel_size) if isinstance(kernel_size, int) else kernel_size
+    sh, sw = (stride, stride) if isinstance(stride, int) else stride
+    ph, pw = (padding, padding) if isinstance(padding, int) else padding
+    n, c, h, w = x.shape
+    oh, ow = (h + 2 * ph - kh) // sh + 1, (w + 2 * pw - kw) // sw + 1
+    out = torch.empty((n, c, oh, ow), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device), _Timed("P", out.numel(), 4 + 4 * sh * sw):
+        L.check(L.load().fqb200_maxpool2d_nhwc(x.data_ptr(), out.data_ptr(), n, h, w, c, kh, kw, sh, sw, ph, pw,
+                                               _stream_handle(x.device)))
+    return out
+
+
 def _test_division(a, b):
     """(fast, ieee) quotients from the device: the 3-instruction exact division next to __fdiv_rn."""
     lib = L.load()

@@ -187,6 +187,15 @@ int fqb200_quantize1_bca(const float* in, float* out, int64_t outer, int64_t gro
                          float* out_qbias, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Max pooling of a channels-last activation ([n][h][w][c] in memory, c % 4 == 0; dilation 1, floor mode) - the operator in
+ * front of the `activation_pooling` quantization call site (MaxPool2dWithId.forward, inference_quantization_manager.py:
+ * 58-74).  out is [n][oh][ow][c], oh = (h + 2 ph - kh) / sh + 1.  Bit-identical to torch.nn.functional.max_pool2d
+ * (NaN in a window wins).
+ */
+int fqb200_maxpool2d_nhwc(const float* in, float* out, int64_t n, int64_t h, int64_t w, int64_t c, int kh, int kw, int sh, int sw,
+                          int ph, int pw, void* stream);
+
+/*
  * out[i] = max(a[i] + b[i], 0) - the residual add + ReLU between two hooked convolutions of a ResNet block (the call
  * sites' surroundings, SURVEY.md 8f rank 4: torchvision's `out += identity; out = relu(out)`), one pass instead of two
  * torch kernels; bit-identical to them.  `out` may alias `a` or `b`.

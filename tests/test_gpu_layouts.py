@@ -175,3 +175,17 @@ def test_per_sample_minmax_with_fused_bias_on_both_memory_formats(fq, c, tag, ha
         xin = x.clone().contiguous(memory_format=torch.channels_last) if cl else x.clone()
         got = q(xin, "conv1_activation", tag, bias=bias)
         assert torch.equal(got, want), (cl, float((got - want).abs().max()))
+
+
+@pytest.mark.parametrize("shape,k,s,p", [((4, 64, 56, 56), 3, 2, 1), ((2, 8, 7, 9), 2, 2, 0), ((3, 128, 14, 14), 3, 1, 1), ((2, 64, 32, 32), 2, 2, 0),
+                                         ((1, 4, 5, 5), 3, 2, 1)])
+def test_channels_last_maxpool_is_bit_identical_to_torch(fq, shape, k, s, p):
+    from cnn_quantization_b200 import ops
+    x = torch.randn(*shape, device="cuda").contiguous(memory_format=torch.channels_last)
+    x[0, 1, 2, 3] = float("nan")
+    x[-1, 0, 0, 0] = float("inf")
+    want = torch.nn.functional.max_pool2d(x, k, s, p)
+    got = ops.maxpool2d_cl(x, k, s, p)
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(torch.nan_to_num(got, nan=123.0), torch.nan_to_num(want, nan=123.0))
+    assert torch.equal(torch.isnan(got), torch.isnan(want))

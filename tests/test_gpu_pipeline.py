@@ -92,7 +92,7 @@ def test_every_baseline_config_runs_and_quantizes(config):
     expected = {"resnet50": 55, "resnet101": 106, "vgg16": 21, "resnet18": 22}[arch]
     blocks = {"resnet50": 16, "resnet101": 33, "vgg16": 0, "resnet18": 8}[arch]
     assert len(qm.calls) == expected
-    quant = sum(v["launches"] for k, v in prof["modes"].items() if k != "E")
+    quant = sum(v["launches"] for k, v in prof["modes"].items() if k not in ("E", "P"))
     assert quant == expected  # exactly one kernel launch per hooked tensor
     assert prof["modes"].get("E", {"launches": 0})["launches"] == blocks  # + one fused add+ReLU per residual block
 
@@ -161,7 +161,7 @@ def test_pipeline_extensions_do_not_change_results(config):
         args = M.make_args(**flags)
         qm = M.QuantizationManagerInference(args, M.get_params(args))
         if not native_extensions:
-            qm.fuse_conv_bias = qm.skip_redundant_relu = qm.fuse_residual_relu = False
+            qm.fuse_conv_bias = qm.skip_redundant_relu = qm.fuse_residual_relu = qm.fast_maxpool = False
             for q in list(qm.quantizers.values()) + [qm.quantizer_default]:
                 if hasattr(q, "inplace"):
                     q.inplace = False
@@ -204,7 +204,8 @@ def test_channels_last_pipeline_matches_nchw():
         prof = ops.profile_collect()
         ops.profile_reset(enable=False)
         qm.detach()
-        assert prof["launches"] == 55 + 16   # 55 hooked tensors + 16 fused residual add + ReLU
+        # 55 hooked tensors + 16 fused residual add + ReLU (+ the max pooling, on channels-last memory)
+        assert prof["launches"] == 55 + 16 + (1 if cl else 0)
     a, b = outs
     cos = float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b)))
     assert cos > 0.97, cos
