@@ -419,6 +419,12 @@ def run_fqb200(args):
                          "note": "algorithmic bytes = the reference computation's passes (SURVEY.md 8d); the channels-last "
                                  "kernel gets the std out of the first pass and small tensors stay L2-resident, so a layout "
                                  "can legitimately read above 1.0"},
+            "roofline_fused_block_epilogue": (lambda r: None if not r else {
+                "kernel": "%s mode D + residual add + ReLU of the block (16 of the 53 mode-D tensors of a step)" % kernel,
+                "algorithmic_bytes_per_elem": 20, "launches": r["launches"], "avg_launch_ms": r["ms"] / max(r["launches"], 1),
+                "achieved": (r["bytes"] / 1e9) / (r["ms"] / 1e3) if r["ms"] else None, "unit": "GB/s",
+                "frac": (r["bytes"] / 1e9) / (r["ms"] / 1e3) / peak if r["ms"] else None,
+                "note": "replaces a separate 12 B/element add+ReLU pass: 16 + 12 = 28 B/element become 20"})(prof["modes"].get("Dr")),
             "quant": {"gelem_per_s": quant_elems / (quant_ms / 1e3) / 1e9 if quant_ms else None,
                       "ms_per_step": quant_ms / args.steps, "share_of_step": quant_ms / ms,
                       "modes": {k: {"launches": v["launches"], "ms": v["ms"], "GBps": (v["bytes"] / 1e9) / (v["ms"] / 1e3) if v["ms"] else None}

@@ -42,6 +42,7 @@ class Desc(ctypes.Structure):
         ("hist_bins", ctypes.c_int32), ("hist_offset", ctypes.c_int32),
         ("out_hist_clamped", ctypes.c_void_p),
         ("relu_passthrough", ctypes.c_int32),
+        ("residual", ctypes.c_void_p), ("residual_relu", ctypes.c_int32),
         ("debug_stamps", ctypes.c_void_p),
     ]
 

@@ -247,6 +247,15 @@ struct ClApply {
       dv.fast = FAST;
       y[i] = leaf_apply<LEAF, FAST>(__fadd_rn(x[i], bias[i]), q[i], dv, 0.f, gq[i]);
     }
+    if (A.residual) {  // launch-uniform: the residual add (+ ReLU) that closes a ResNet block, on the quantized values
+      const float4 r = ld_tensor(reinterpret_cast<const float4*>(A.residual) + off);
+      const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        y[i] = __fadd_rn(y[i], rr[i]);
+        if (A.residual_relu) y[i] = y[i] < 0.f ? 0.f : y[i];
+      }
+    }
     st_tensor(reinterpret_cast<float4*>(A.out) + off, make_float4(y[0], y[1], y[2], y[3]));
     if (HIST) {
 #pragma unroll

@@ -54,6 +54,8 @@ struct FusedArgs {
   RowsGeo rows;        // ... row structure of the per-sample min-max kernel
   const float* in;
   float* out;
+  const float* residual;  // channels-last kernel: optional tensor added to the quantized values (fqb200_desc.residual)
+  int residual_relu;      // ... followed by max(., 0)
   const float* bias;   // optional per-group addend applied to x before everything else (folded-BN conv bias)
   unsigned long long bias_magic;  // 0: bias[g];  else ceil(2^40 / period_v): bias[(j * magic) >> 40], j = column in vectors
                                   // (per-tensor / per-sample layouts, where a row holds C channels of period_v vectors each)
@@ -1928,6 +1930,10 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   A.var_corr = d->var_corr;
   A.stats_only = d->stats_only;
   A.relu_passthrough = d->relu_passthrough;
+  A.residual = d->residual;
+  A.residual_relu = d->residual_relu;
+  if (d->residual && (!d->channels_last || d->stats_only || !aligned16(d->residual)))
+    return fail(FQB200_ERR_UNSUPPORTED, "residual: channels-last apply launches, 16-byte aligned%s");
   A.out_stats = d->out_stats;
   A.bias = d->bias;
   A.hist = d->out_hist;
@@ -1969,8 +1975,12 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
     A.nhwc_rep = r < 1u ? 1u : (r > 8u ? 8u : r);
     A.need_dev = cl_needs_b(d) ? 1 : 0;
     const bool hist = d->out_hist != nullptr;
+#ifdef FQB_PLAIN_LAUNCH  // development A/B only: what the cooperative launch itself costs
+    e = cudaLaunchKernel(cl_kernel_ptr(d->leaf, A.need_dev != 0, hist), dim3(pl.grid), dim3(fqb::kBulkThreads), args, cl_smem(hist), st);
+#else
     e = cudaLaunchCooperativeKernel(cl_kernel_ptr(d->leaf, A.need_dev != 0, hist), dim3(pl.grid), dim3(fqb::kBulkThreads), args,
                                     cl_smem(hist), st);
+#endif
     if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cooperative launch fq_cl_kernel: %s", cudaGetErrorString(e));
     return FQB200_OK;
   }

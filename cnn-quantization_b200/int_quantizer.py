@@ -105,16 +105,21 @@ class IntQuantizer(object):
         self.last_stats = None
         self._relu_follows = False
         self._bca = None
+        self._residual, self._residual_used = None, False
 
     # ------------------------------------------------------------------------------------------
     # dispatch (int_quantizer.py:92-122)
     # ------------------------------------------------------------------------------------------
     def __call__(self, tensor, id, tag="", stat_id=None, override_att=None, weight_correction=None, bias=None,
-                 relu_follows=False, bias_correct=None):
+                 relu_follows=False, bias_correct=None, residual=None):
         """Extensions used by this package's manager (all default to the reference behaviour):
         ``bias_correct`` (None = off, else the "ReLU follows" flag of the call site): the activation bias correction of
         Conv2dWithId.forward (`-bca`, inference_quantization_manager.py:180-196) is applied by the quantizer itself - inside
         the given-parameter launch for channels-last tensors;
+        ``residual``: the block input a ResNet block adds to this (its last convolution's) quantized output before the
+        closing ReLU; where the launch can take it (per-channel quantization of a channels-last tensor with on-the-fly
+        statistics) ``max(quantize(x) + residual, 0)`` is computed in the apply phase and the result is tagged
+        ``_fq_residual_fused``; otherwise the operand is ignored and the caller adds it itself;
         ``relu_follows``: the caller will skip the ReLU that follows when the result is tagged ``_fq_nonneg`` - set on
         every result of a positive (half-range / force-positive) range, where offset 0 gives zero point 0 and every value
         is q * scale >= 0; the compiled leaf's empty-range pass-through then returns max(x, 0) (fqb200_desc.relu_passthrough);
@@ -127,6 +132,7 @@ class IntQuantizer(object):
             setattr(self, override_att[0], override_att[1])
         self._relu_follows = bool(relu_follows) and self._positive()
         self._bca = bias_correct
+        self._residual, self._residual_used = residual, False
         try:
             self._unsupported(stat_id)
             if bias is not None and not self._bias_fusable(tensor):
@@ -156,8 +162,12 @@ class IntQuantizer(object):
                 setattr(self, override_att[0], orig_att)
         if self._relu_follows and isinstance(res, torch.Tensor):
             res._fq_nonneg = res._version   # void as soon as somebody modifies the tensor in place
+        if self._residual_used:
+            res._fq_residual_fused = True
+            res._fq_nonneg = res._version   # the fused epilogue ends with the ReLU
         self._relu_follows = False
         self._bca = None
+        self._residual, self._residual_used = None, False
         return res
 
     def __repr__(self):
@@ -270,6 +280,15 @@ class IntQuantizer(object):
         ref = tensor if bias is None else tensor + bias.view(1, -1, 1, 1)
         return self.bias_correction_torch(ref, ops.quantize1(ref, delta, offset, self.num_bits, bits=bits, layout=layout), relu_first)
 
+    def _residual_kw(self, tensor, channels_last):
+        """kwargs of the fused block epilogue when this launch can take it."""
+        r = self._residual
+        if (r is None or not channels_last or self.measure_entropy or r.shape != tensor.shape or r.stride() != tensor.stride()
+                or r.dtype != torch.float32 or r.device != tensor.device):
+            return {}
+        self._residual_used = True
+        return dict(residual=r, residual_relu=True)
+
     def _fused(self, tensor, layout, **kw):
         """ops.fused, keeping the exported statistics table when ``export_stats`` is set."""
         if not self.export_stats:
@@ -366,7 +385,8 @@ class IntQuantizer(object):
                             leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(),
                             bit_alloc=self.bit_alloc_act, bit_alloc_prior=self._prior(),
                             bit_alloc_round=self.bit_alloc_round, bit_alloc_target=self.bit_alloc_target_act,
-                            bias=bias, out=self._out(tensor), hist=hist, channels_last=self._channels_last(tensor))
+                            bias=bias, out=self._out(tensor), hist=hist, channels_last=self._channels_last(tensor),
+                            **self._residual_kw(tensor, self._channels_last(tensor)))
             self._log_entropy(hist, id, "avg.entropy.act", tensor.numel())
             return res
         return self._fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
@@ -441,7 +461,7 @@ class IntQuantizer(object):
                             num_bits=self.num_bits, positive=self._positive(), bit_alloc=self.bit_alloc_act,
                             bit_alloc_prior=self._prior(), bit_alloc_round=self.bit_alloc_round,
                             bit_alloc_target=self.bit_alloc_target_act, bias=bias, out=self._out(tensor), hist=hist,
-                            channels_last=self._channels_last(tensor))
+                            channels_last=self._channels_last(tensor), **self._residual_kw(tensor, self._channels_last(tensor)))
             self._log_entropy(hist, id, "avg.entropy.act", tensor.numel())
             return res
         if bias is not None:

@@ -173,22 +173,35 @@ def _maxpool_forward(pool):
     return forward
 
 
-def _residual_block_forward(block, bottleneck):
+def _residual_block_forward(block, bottleneck, manager):
     """forward of a torchvision BasicBlock / Bottleneck (torchvision/models/resnet.py) with the closing
     ``out += identity; out = relu(out)`` as ONE kernel (ops.add_relu_, SURVEY.md 8f rank 4: the elementwise surroundings of
     the hooked convolutions were 20 % of a step's kernel time).  Everything else goes through the block's own modules, so
     the quantization hooks fire exactly as before; results are bit-identical."""
     from . import ops
 
+    last_conv, last_bn = (block.conv3, block.bn3) if bottleneck else (block.conv2, block.bn2)
+
     def forward(x):
         identity = x
         out = block.relu(block.bn1(block.conv1(x)))
         if bottleneck:
             out = block.relu(block.bn2(block.conv2(out)))
-            out = block.bn3(block.conv3(out))
-        else:
-            out = block.bn2(block.conv2(out))
-        if block.downsample is not None:
+        # The shortcut depends on x only: computing it BEFORE the last convolution (torchvision does it after) lets the
+        # launch that quantizes that convolution's output take it as an operand and finish the block -
+        # max(quantize(conv) + identity, 0) - in its apply phase, when the folded BN behind the convolution is the
+        # identity.  The set of quantize_instant calls is unchanged; the shortcut's call moves one position forward.
+        early = (manager.fuse_residual_into_quant and manager.enabled and manager.bn_folding and hasattr(last_bn, "absorbed")
+                 and x.is_cuda and x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last))
+        if early:
+            if block.downsample is not None:
+                identity = block.downsample(x)
+            last_conv._fq_residual = identity
+        out = last_bn(last_conv(out))
+        last_conv.__dict__.pop("_fq_residual", None)
+        if getattr(out, "_fq_residual_fused", False):
+            return out
+        if not early and block.downsample is not None:
             identity = block.downsample(x)
         if (out.is_cuda and out.dtype == torch.float32 and identity.dtype == torch.float32 and out.shape == identity.shape
                 and out.stride() == identity.stride() and ops._dense(out) and not out.requires_grad):
@@ -232,6 +245,9 @@ class QuantizationManagerInference(object):
         self.skip_redundant_relu = self._native
         # the `out += identity; relu` that closes a torchvision ResNet block runs as one fused kernel
         self.fuse_residual_relu = self._native
+        # ... and, where the quantization launch of the block's last convolution can take the shortcut as an operand, inside
+        # that launch (channels-last per-channel activations with on-the-fly statistics)
+        self.fuse_residual_into_quant = self._native
         # channels-last max pooling in front of the `activation_pooling` call site runs on this package's kernel
         self.fast_maxpool = self._native
         self.inplace_activations = self._native
@@ -381,7 +397,7 @@ class QuantizationManagerInference(object):
                 BasicBlock = Bottleneck = ()
             for m in model.modules():
                 if type(m) in (BasicBlock, Bottleneck) and type(getattr(m, "relu", None)) is nn.ReLU:
-                    m.forward = _residual_block_forward(m, type(m) is Bottleneck)
+                    m.forward = _residual_block_forward(m, type(m) is Bottleneck, self)
                     self._patched.append(m)
         for m in model.modules():
             if self.fast_maxpool and self.enabled and type(m) is nn.MaxPool2d:
@@ -450,6 +466,9 @@ class QuantizationManagerInference(object):
                                          verbose=self.verbose, bias_correct=bool(half_range or self.fused_relu), **extra)
         if self.skip_redundant_relu and (half_range or self.fused_relu) and tag == "activation" and not self.bcorr_act:
             extra["relu_follows"] = True   # the quantizer tags the result _fq_nonneg; the hooked ReLU then returns it untouched
+        residual = m.__dict__.get("_fq_residual")
+        if residual is not None and self._native and tag == "activation":
+            extra["residual"] = residual
         return self.quantize_instant(out, activation_id, tag, stat_id=self._stat_id(activation_id), half_range=half_range,
                                      verbose=self.verbose, **extra)
 

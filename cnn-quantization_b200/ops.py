@@ -227,7 +227,7 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
           bit_alloc_round=True, bit_alloc_target=None, mt_target=0.0, mt_clip=False, bias_corr=False,
           var_corr=False, stats_only=False, want_stats=False, out=None, bias=None, bias_period=0, hist=None,
           channels_last=False, any_dense_format=False, debug_stamps=None, relu_passthrough=False, hist_offset=0,
-          hist_clamped=None):
+          hist_clamped=None, residual=None, residual_relu=False):
     """C ABI fqb200_fused: statistics -> parameters -> quantize/dequantize in one launch.
 
     Returns ``out`` (or ``(out, stats)`` with ``want_stats``; ``stats`` alone with ``stats_only``), where
@@ -281,6 +281,12 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
         d.out_hist = None
     d.debug_stamps = debug_stamps.data_ptr() if debug_stamps is not None else None
     d.relu_passthrough = int(bool(relu_passthrough))
+    d.residual, d.residual_relu = None, 0
+    if residual is not None:
+        _require_cuda_f32(residual, "residual")
+        if not channels_last or residual.shape != x.shape or residual.stride() != x.stride():
+            raise ValueError("residual needs channels_last=True and a tensor with the input's shape and strides")
+        d.residual, d.residual_relu = residual.data_ptr(), int(bool(residual_relu))
     stats = None
     if want_stats or stats_only:
         stats = torch.zeros((groups, L.STATS_STRIDE), dtype=torch.float32, device=dev)
@@ -300,6 +306,8 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
                     (bit_alloc and num_bits <= 4 and scope == L.SCOPE_GROUP))
         mode = "S" if stats_only else ("D" if two_pass else "B")
         bpe = (8 if two_pass else 4) + (0 if stats_only else 8)
+        if residual is not None:   # + the residual read of the fused block epilogue (the write is the apply's own)
+            mode, bpe = mode + "r", bpe + 4
         with _Timed(mode, x.numel(), bpe, "%dx%dx%d" % (outer, groups, inner)):
             L.check(lib.fqb200_fused(ctypes.byref(d), x.data_ptr(), kout.data_ptr() if kout is not None else None,
                                      ws.data_ptr(), ws.numel(), stream))

@@ -189,3 +189,35 @@ def test_channels_last_maxpool_is_bit_identical_to_torch(fq, shape, k, s, p):
     assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
     assert torch.equal(torch.nan_to_num(got, nan=123.0), torch.nan_to_num(want, nan=123.0))
     assert torch.equal(torch.isnan(got), torch.isnan(want))
+
+
+@pytest.mark.parametrize("c", [64, 96, 2048])
+def test_residual_epilogue_in_the_quantization_launch(fq, c):
+    """max(quantize(x + bias) + residual, 0) in the apply phase == the same launch without the operand, then torch's add and
+    ReLU (statistics of two launches differ in the last bits of their atomically combined sums: a vanishing fraction of
+    elements may sit one grid step apart)."""
+    from cnn_quantization_b200 import _lib as L, ops
+    n, hw = (8, 14) if c < 2048 else (4, 7)
+    x = _x(c, seed=21, n=n, hw=hw).contiguous(memory_format=torch.channels_last)
+    r = torch.randn_like(x)
+    bias = torch.randn(c, device="cuda") * 0.2
+    kw = dict(range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True, channels_last=True, bias=bias)
+    base = ops.fused(x, (n, c, hw * hw), **kw)
+    got = ops.fused(x, (n, c, hw * hw), residual=r, residual_relu=True, **kw)
+    want = torch.relu(base + r)
+    frac, _ = fq_mismatch(got.cpu().numpy(), want.cpu().numpy())
+    assert frac <= 2e-3 and float(got.min()) >= 0.0
+    got2 = ops.fused(x, (n, c, hw * hw), residual=r, residual_relu=False, **kw)
+    frac, _ = fq_mismatch(got2.cpu().numpy(), (base + r).cpu().numpy())
+    assert frac <= 2e-3
+    # in place (what the manager does) and through the quantizer: tagged, non-negative
+    q = fq.int_quantizer("int4", params(clipping="laplace", pcq_act=True, bit_alloc_act=True))
+    q.inplace = True
+    xin = x.clone()
+    y = q(xin, "conv3_activation", "activation", bias=bias, residual=r)
+    assert y.data_ptr() == xin.data_ptr() and getattr(y, "_fq_residual_fused", False) and y._fq_nonneg == y._version
+    frac, _ = fq_mismatch(y.cpu().numpy(), want.cpu().numpy())
+    assert frac <= 2e-3
+    # an NCHW tensor cannot take the operand: ignored, not tagged
+    y = q(x.contiguous().clone(), "conv3_activation", "activation", bias=bias, residual=r.contiguous())
+    assert not getattr(y, "_fq_residual_fused", False)

@@ -5,9 +5,9 @@ set -e
 cd "$(dirname "$0")/.."
 for v in "$@"; do
   set -- $v
-  out=tools/_variants/libfqb200_v$1_k$2_s$3_c${4:-2}.so
+  out=tools/_variants/libfqb200_v$1_k$2_s$3_c${4:-1}${5:+_$5}.so
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -shared -Xcompiler -fPIC \
-    -DFQB_STAGE_VEC=$1 -DFQB_STAGES=$2 -DFQB_BULK_SPLIT=$3 -DFQB_BULK_CTAS=${4:-2} -o $out cnn-quantization_b200/csrc/fqb200.cu &
+    -DFQB_STAGE_VEC=$1 -DFQB_STAGES=$2 -DFQB_BULK_SPLIT=$3 -DFQB_BULK_CTAS=${4:-1} ${5:+-D$5} -o $out cnn-quantization_b200/csrc/fqb200.cu &
 done
 wait
 ls -la tools/_variants
