@@ -155,9 +155,22 @@ struct TicketPlan {
   unsigned dyn_base;   // units dealt statically over the whole grid
 };
 
-template <bool REV>
+// PAIR: a second tensor of the same shape (`src2`, the residual of a fused block epilogue) rides along: the stage holds
+// stage_v vectors of src in its lower half and the same vectors of src2 in its upper half (g is then half_geo()).
+constexpr unsigned kPairOffset = kStageBytes / 2u;
+
+__device__ __forceinline__ FlatGeo half_geo(const FlatGeo& g) {
+  FlatGeo h = g;
+  h.stage_v = (kStageVec / 2u) * g.stride;
+  h.n_stages = (g.total_v + h.stage_v - 1u) / h.stage_v;
+  h.unit_stages = 2u * g.unit_stages;  // the units (and the tickets) stay the same
+  return h;
+}
+
+template <bool REV, bool PAIR = false>
 __device__ __forceinline__ void produce_phase(const FlatGeo& g, const float4* src, unsigned* counter, const TicketPlan tp,
-                                              BulkRing& r, unsigned char* stage_base, RingPos& pos) {
+                                              BulkRing& r, unsigned char* stage_base, RingPos& pos,
+                                              const float4* src2 = nullptr) {
   const unsigned total = g.units;
   unsigned k = 0;
   auto fetch = [&]() -> unsigned {
@@ -186,8 +199,9 @@ __device__ __forceinline__ void produce_phase(const FlatGeo& g, const float4* sr
       r.meta[pos.slot].count = count;
       r.meta[pos.slot].tag = 0u;
       const unsigned bar = smem_u32(&r.full[pos.slot]);
-      mbar_arrive_expect_tx(bar, count * 16u);
+      mbar_arrive_expect_tx(bar, PAIR ? count * 32u : count * 16u);
       bulk_load(smem_u32(stage_base + pos.slot * kStageBytes), src + start, count * 16u, bar);
+      if (PAIR) bulk_load(smem_u32(stage_base + pos.slot * kStageBytes + kPairOffset), src2 + start, count * 16u, bar);
       pos.next();
     }
     cur = nxt;
@@ -287,6 +301,51 @@ __device__ __forceinline__ void consume_phase(const FlatGeo& g, BulkRing& r, con
           float4 x;
           lds_vec(addr + i * step, x);
           acc.consume(x, m.start + idx);
+        }
+      }
+    }
+    acc.stage_end(m);
+    __syncwarp();
+    if (lane0) mbar_arrive(smem_u32(&r.empty[pos.slot]));
+    pos.next();
+    if (m.count == 0u) break;
+  }
+}
+
+// PAIR streams (see produce_phase): acc.consume2(x, r, v) with r the vector of the second tensor at the same index.
+template <typename Acc>
+__device__ __forceinline__ void consume_pair_phase(const FlatGeo& g, BulkRing& r, const unsigned char* stage_base, RingPos& pos,
+                                                   Acc& acc) {
+  static_assert(kStageVec % 2u == 0u, "a pair stage is split in two halves");
+  constexpr int kHalf = kStageVec / 2;
+  const unsigned t = threadIdx.x;
+  const bool lane0 = (t & 31u) == 0u;
+  const unsigned my = smem_u32(stage_base) + t * 16u;
+  const unsigned step = g.stride * 16u;
+  for (;;) {
+    mbar_wait(smem_u32(&r.full[pos.slot]), pos.parity);
+    const StageMeta m = r.meta[pos.slot];
+    const unsigned addr = my + pos.slot * kStageBytes;
+    if (m.count == g.stage_v) {
+      if (t < g.stride) {
+        float4 x[kHalf], y[kHalf];
+#pragma unroll
+        for (int i = 0; i < kHalf; ++i) {
+          lds_vec(addr + i * step, x[i]);
+          lds_vec(addr + kPairOffset + i * step, y[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < kHalf; ++i) acc.consume2(x[i], y[i], m.start + t + i * g.stride);
+      }
+    } else if (m.count != 0u) {
+#pragma unroll
+      for (int i = 0; i < kHalf; ++i) {
+        const unsigned idx = t + i * g.stride;
+        if (t < g.stride && idx < m.count) {
+          float4 x, y;
+          lds_vec(addr + i * step, x);
+          lds_vec(addr + kPairOffset + i * step, y);
+          acc.consume2(x, y, m.start + idx);
         }
       }
     }

@@ -235,8 +235,8 @@ struct ClApply {
       atomicAdd(hist + hbase + static_cast<unsigned>(v), 1u);
     }
   }
-  template <bool FAST>
-  __device__ __forceinline__ void one(const float4& v, unsigned off) {
+  template <bool FAST, bool PAIR>
+  __device__ __forceinline__ void one(const float4& v, const float4& rv, unsigned off) {
     const float x[4] = {v.x, v.y, v.z, v.w};
     float y[4], gq[4];
 #pragma unroll
@@ -247,9 +247,8 @@ struct ClApply {
       dv.fast = FAST;
       y[i] = leaf_apply<LEAF, FAST>(__fadd_rn(x[i], bias[i]), q[i], dv, 0.f, gq[i]);
     }
-    if (A.residual) {  // launch-uniform: the residual add (+ ReLU) that closes a ResNet block, on the quantized values
-      const float4 r = ld_tensor(reinterpret_cast<const float4*>(A.residual) + off);
-      const float rr[4] = {r.x, r.y, r.z, r.w};
+    if (PAIR) {  // the residual add (+ ReLU) that closes a ResNet block, on the quantized values
+      const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         y[i] = __fadd_rn(y[i], rr[i]);
@@ -264,9 +263,16 @@ struct ClApply {
   }
   __device__ __forceinline__ void consume(const float4& v, unsigned off) {
     if (fast)
-      one<true>(v, off);
+      one<true, false>(v, v, off);
     else
-      one<false>(v, off);
+      one<false, false>(v, v, off);
+  }
+  // the residual comes through the ring next to x (consume_pair_phase)
+  __device__ __forceinline__ void consume2(const float4& v, const float4& rv, unsigned off) {
+    if (fast)
+      one<true, true>(v, rv, off);
+    else
+      one<false, true>(v, rv, off);
   }
   __device__ __forceinline__ void stage_end(const StageMeta&) {}
 };
@@ -553,7 +559,12 @@ __device__ __noinline__ void cl_phase_apply(const FusedArgs& A, ClCtx& cx, const
   ClApply<LEAF, HIST> ap{A, hist};
   ap.init(cx.c0, cx.active, lp);
   RingPos pos = cx.pos;
-  consume_phase(g, *cx.ring, cx.stages, pos, ap);
+  if (A.residual) {
+    const FlatGeo h = half_geo(g);
+    consume_pair_phase(h, *cx.ring, cx.stages, pos, ap);
+  } else {
+    consume_phase(g, *cx.ring, cx.stages, pos, ap);
+  }
   cx.pos = pos;
   if (HIST) {
     consumer_sync();
@@ -631,7 +642,11 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_kernel(con
       }
       if (!A.stats_only) {
         mbar_wait(smem_u32(&phase_go[1]), 0u);
-        produce_phase<!DEV>(g, src, &A.sync->unit_counter[2], all, ring, stages, pos);
+        if (A.residual)
+          produce_phase<!DEV, true>(half_geo(g), src, &A.sync->unit_counter[2], all, ring, stages, pos,
+                                    reinterpret_cast<const float4*>(A.residual));
+        else
+          produce_phase<!DEV>(g, src, &A.sync->unit_counter[2], all, ring, stages, pos);
       }
     }
     return;
