@@ -823,6 +823,71 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_given_kern
   consume_phase(g, ring, fq_dyn, pos, ap);
 }
 
+// ---- a1, the drop-in of the reference's compiled kernel (kernels/gemmlowp.cu:8-45), on the bulk-copy ring -------------------
+// One parameter set, compiled-leaf arithmetic (roundf), optional noise tensor: it rides through the ring next to x (pair
+// stages).  Ordinary launch, static round-robin units.
+struct LeafBulkArgs {
+  FlatGeo flat;
+  const float* in;
+  float* out;
+  const float* noise;
+  LeafParam q;
+};
+
+template <bool NOISE>
+struct LeafBulk {
+  const LeafBulkArgs& A;
+  Divisor dv;
+  template <bool FAST>
+  __device__ __forceinline__ void one(const float4& v, const float4& nz, unsigned off) {
+    float gq;
+    float4 y;
+    y.x = leaf_apply<FQB200_LEAF_COMPILED, FAST, NOISE>(v.x, A.q, dv, NOISE ? nz.x : 0.f, gq);
+    y.y = leaf_apply<FQB200_LEAF_COMPILED, FAST, NOISE>(v.y, A.q, dv, NOISE ? nz.y : 0.f, gq);
+    y.z = leaf_apply<FQB200_LEAF_COMPILED, FAST, NOISE>(v.z, A.q, dv, NOISE ? nz.z : 0.f, gq);
+    y.w = leaf_apply<FQB200_LEAF_COMPILED, FAST, NOISE>(v.w, A.q, dv, NOISE ? nz.w : 0.f, gq);
+    st_tensor(reinterpret_cast<float4*>(A.out) + off, y);
+  }
+  __device__ __forceinline__ void consume(const float4& v, unsigned off) {
+    if (dv.fast)
+      one<true>(v, v, off);
+    else
+      one<false>(v, v, off);
+  }
+  __device__ __forceinline__ void consume2(const float4& v, const float4& nz, unsigned off) {
+    if (dv.fast)
+      one<true>(v, nz, off);
+    else
+      one<false>(v, nz, off);
+  }
+  __device__ __forceinline__ void stage_end(const StageMeta&) {}
+};
+
+template <bool NOISE>
+__global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_leaf_bulk_kernel(const __grid_constant__ LeafBulkArgs A) {
+  extern __shared__ __align__(128) unsigned char fq_dyn[];
+  __shared__ BulkRing ring;
+  const FlatGeo g = NOISE ? half_geo(A.flat) : A.flat;
+  ring_init(ring);
+  if (threadIdx.x >= kConsumers) {
+    if (threadIdx.x == kConsumers) {
+      RingPos pos;
+      pos.init();
+      const TicketPlan tp = {0xffffffffu, blockIdx.x, gridDim.x, 0u};
+      produce_phase<false, NOISE>(g, reinterpret_cast<const float4*>(A.in), nullptr, tp, ring, fq_dyn, pos,
+                                  reinterpret_cast<const float4*>(A.noise));
+    }
+    return;
+  }
+  LeafBulk<NOISE> ap{A, make_divisor(A.q.a)};
+  RingPos pos;
+  pos.init();
+  if (NOISE)
+    consume_pair_phase(g, ring, fq_dyn, pos, ap);
+  else
+    consume_phase(g, ring, fq_dyn, pos, ap);
+}
+
 // ---- `-bca`: given-parameter quantization with activation bias correction (inference_quantization_manager.py:180-196) -----
 // Per channel: q_bias = (sum r - sum y) / (#(r > 0) + 1e-8) with y the quantized activation and r the activation itself
 // (rectified first when a ReLU follows), added back where y > 0.  Two passes over x (both recompute y), one write:

@@ -1410,6 +1410,12 @@ void init_device(int dev) {
                              static_cast<int>(i < 2 ? dyn_smem(4) : cl_given_smem()));
     if (e != cudaSuccess) return bad("given-parameter kernel setup", e);
   }
+  const void* leafb[2] = {reinterpret_cast<const void*>(fqb::fq_leaf_bulk_kernel<false>),
+                          reinterpret_cast<const void*>(fqb::fq_leaf_bulk_kernel<true>)};
+  for (int i = 0; i < 2; ++i) {
+    e = cudaFuncSetAttribute(leafb[i], cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cl_given_smem()));
+    if (e != cudaSuccess) return bad("a1 bulk kernel setup", e);
+  }
   // mid-tread table (int_quantizer.py:41-51): omega grid = 5 decades x 20 steps, leading 0
   double om[fqb::kTable], al[fqb::kTable];
   om[0] = 0.0;
@@ -1789,6 +1795,23 @@ int fqb200_float2gemmlowp(const float* in, float* out, int64_t n, float range, f
   q.c = static_cast<float>(qmax_i);
   q.flags = enforce_true_zero ? fqb::FLAG_TRUE_ZERO : 0;
   const bool vec = (n % 4 == 0) && aligned16(in) && aligned16(out) && (!noise || aligned16(noise));
+  // the streaming case (16-byte aligned, a multiple of 4 elements, at least a few stages per SM): bulk-copy ring
+  if (vec && static_cast<uint64_t>(n) >= (1ull << 20) && static_cast<uint64_t>(n) / 4 < (1ull << 32)) {
+    Plan pl;
+    rc = make_plan_flat(static_cast<uint64_t>(n), 0, di->resident_cl[0] * 2, &pl);
+    if (rc != FQB200_OK) return rc;
+    fqb::LeafBulkArgs B;
+    B.flat = pl.flat;
+    B.in = in;
+    B.out = out;
+    B.noise = noise;
+    B.q = q;
+    if (noise) fqb::fq_leaf_bulk_kernel<true><<<pl.grid, fqb::kBulkThreads, cl_given_smem(), st>>>(B);
+    else       fqb::fq_leaf_bulk_kernel<false><<<pl.grid, fqb::kBulkThreads, cl_given_smem(), st>>>(B);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "launch fq_leaf_bulk_kernel: %s", cudaGetErrorString(e));
+    return FQB200_OK;
+  }
   const unsigned long long nvec = vec ? static_cast<unsigned long long>(n / 4) : static_cast<unsigned long long>(n);
   unsigned long long want = (nvec + fqb::kThreads * 4ull - 1) / (fqb::kThreads * 4ull);
   const unsigned long long cap = static_cast<unsigned long long>(di->resident) * 2ull;

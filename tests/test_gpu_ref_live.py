@@ -251,6 +251,7 @@ def test_layerwise_differential_vs_live_reference(ref, fq, config, batch, channe
     orig = qm.quantize_instant
 
     boundary = []   # (layer, channel, our bits, reference bits): bit-allocation rounding-boundary cases, see below
+    fused_blocks = []   # layers whose launch also did the block's residual add + ReLU
 
     def spy(tensor, id, tag="", stat_id=None, half_range=False, override_att=None, verbose=False, **extra):
         from oracle.ref_live import LeafSpy
@@ -263,6 +264,11 @@ def test_layerwise_differential_vs_live_reference(ref, fq, config, batch, channe
         rq.half_range = half_range
         with LeafSpy(rq) as leaf:
             want = rq(ref_in, id, tag)
+        if getattr(out, "_fq_residual_fused", False):
+            # the block's residual add + ReLU ran inside our quantization launch: apply the block's own two torch ops
+            # (torchvision Bottleneck.forward: out += identity; out = relu(out)) to the reference's quantized tensor
+            fused_blocks.append(id)
+            want = torch.relu(want + extra["residual"])
         tol = 1e-5 * torch.maximum(out.abs(), want.abs()) + 1e-9
         diff = (out - want).abs()
         bad = diff > tol
@@ -296,6 +302,7 @@ def test_layerwise_differential_vs_live_reference(ref, fq, config, batch, channe
         "hooked_tensors": len(rows), "worst_flip_fraction": worst,
         "mean_flip_fraction": sum(r[3] for r in rows) / len(rows),
         "worst_layer": max(rows, key=lambda r: r[3])[0],
+        "launches_with_fused_block_epilogue": len(fused_blocks),
         "bit_allocation_boundary_channels": ["%s ch %d: %g vs %g bits" % b for b in boundary]}
     _dump_report()
     for id, tag, shape, frac, dmax, span, levels in rows:
