@@ -268,8 +268,11 @@ def test_layerwise_differential_vs_live_reference(ref, fq, config, batch, channe
             # the block's residual add + ReLU ran inside our quantization launch: apply the block's own two torch ops
             # (torchvision Bottleneck.forward: out += identity; out = relu(out)) to the reference's quantized tensor
             fused_blocks.append(id)
+            mag = torch.maximum(want.abs(), extra["residual"].abs())   # the sum cancels: tolerance on the operands' scale
             want = torch.relu(want + extra["residual"])
-        tol = 1e-5 * torch.maximum(out.abs(), want.abs()) + 1e-9
+        else:
+            mag = want.abs()
+        tol = 1e-5 * torch.maximum(out.abs(), mag) + 1e-9
         diff = (out - want).abs()
         bad = diff > tol
         # Per-channel bit allocation rounds log2(bins): where the reference's value sits within fp32 rounding of x.5 its
