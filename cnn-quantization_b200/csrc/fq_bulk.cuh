@@ -223,9 +223,18 @@ struct RowsGeo {
   unsigned units_per_row;   // ceil(stages_per_row / unit_stages)
 };
 
-template <bool REV>
+// the row geometry of pair stages (g = half_geo() of the launch's geometry): the units stay the same
+__device__ __forceinline__ RowsGeo half_rows(const FlatGeo& h, const RowsGeo& rg) {
+  RowsGeo r = rg;
+  r.stages_per_row = (rg.row_v + h.stage_v - 1u) / h.stage_v;
+  r.units_per_row = (r.stages_per_row + h.unit_stages - 1u) / h.unit_stages;
+  return r;
+}
+
+template <bool REV, bool PAIR = false>
 __device__ __forceinline__ void produce_rows_phase(const FlatGeo& g, const RowsGeo& rg, const float4* src, unsigned* counter,
-                                                   const TicketPlan tp, BulkRing& r, unsigned char* stage_base, RingPos& pos) {
+                                                   const TicketPlan tp, BulkRing& r, unsigned char* stage_base, RingPos& pos,
+                                                   const float4* src2 = nullptr) {
   const unsigned total = g.units;  // rows * units_per_row
   unsigned k = 0;
   auto fetch = [&]() -> unsigned {
@@ -256,8 +265,9 @@ __device__ __forceinline__ void produce_rows_phase(const FlatGeo& g, const RowsG
       r.meta[pos.slot].count = count;
       r.meta[pos.slot].tag = row | (i + 1u == s1 ? 0x80000000u : 0u);
       const unsigned bar = smem_u32(&r.full[pos.slot]);
-      mbar_arrive_expect_tx(bar, count * 16u);
+      mbar_arrive_expect_tx(bar, PAIR ? count * 32u : count * 16u);
       bulk_load(smem_u32(stage_base + pos.slot * kStageBytes), src + start, count * 16u, bar);
+      if (PAIR) bulk_load(smem_u32(stage_base + pos.slot * kStageBytes + kPairOffset), src2 + start, count * 16u, bar);
       pos.next();
     }
     cur = nxt;

@@ -1115,21 +1115,39 @@ struct RowsApply {
   LeafParam q;
   Divisor dv;
   float bias[4];
-  template <bool FAST>
-  __device__ __forceinline__ void one(const float4& v, unsigned off) {
+  template <bool FAST, bool PAIR>
+  __device__ __forceinline__ void one(const float4& v, const float4& r, unsigned off) {
     float gq;
     float4 y;
     y.x = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(v.x, bias[0]), q, dv, 0.f, gq);
     y.y = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(v.y, bias[1]), q, dv, 0.f, gq);
     y.z = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(v.z, bias[2]), q, dv, 0.f, gq);
     y.w = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(v.w, bias[3]), q, dv, 0.f, gq);
+    if (PAIR) {  // the residual add (+ ReLU) that closes a ResNet block, on the quantized values
+      y.x = __fadd_rn(y.x, r.x);
+      y.y = __fadd_rn(y.y, r.y);
+      y.z = __fadd_rn(y.z, r.z);
+      y.w = __fadd_rn(y.w, r.w);
+      if (A.residual_relu) {
+        y.x = y.x < 0.f ? 0.f : y.x;
+        y.y = y.y < 0.f ? 0.f : y.y;
+        y.z = y.z < 0.f ? 0.f : y.z;
+        y.w = y.w < 0.f ? 0.f : y.w;
+      }
+    }
     st_tensor(reinterpret_cast<float4*>(A.out) + off, y);
   }
   __device__ __forceinline__ void consume(const float4& v, unsigned off) {
     if (dv.fast)
-      one<true>(v, off);
+      one<true, false>(v, v, off);
     else
-      one<false>(v, off);
+      one<false, false>(v, v, off);
+  }
+  __device__ __forceinline__ void consume2(const float4& v, const float4& r, unsigned off) {
+    if (dv.fast)
+      one<true, true>(v, r, off);
+    else
+      one<false, true>(v, r, off);
   }
   __device__ __forceinline__ void stage_end(const StageMeta&) {}
 };
@@ -1150,7 +1168,15 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_rows_kernel(c
       const float4* src = reinterpret_cast<const float4*>(A.in);
       const TicketPlan all = {2u, blockIdx.x, gridDim.x, 2u * gridDim.x};
       produce_rows_phase<false>(g, rg, src, &A.sync->unit_counter[0], all, ring, fq_dyn, pos);
-      if (!A.stats_only) produce_rows_phase<true>(g, rg, src, &A.sync->unit_counter[2], all, ring, fq_dyn, pos);
+      if (!A.stats_only) {
+        if (A.residual) {
+          const FlatGeo h = half_geo(g);
+          produce_rows_phase<true, true>(h, half_rows(h, rg), src, &A.sync->unit_counter[2], all, ring, fq_dyn, pos,
+                                         reinterpret_cast<const float4*>(A.residual));
+        } else {
+          produce_rows_phase<true>(g, rg, src, &A.sync->unit_counter[2], all, ring, fq_dyn, pos);
+        }
+      }
     }
     return;
   }
@@ -1209,7 +1235,10 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_rows_kernel(c
   if (blockIdx.x == 0) stamp(A, 7);
   if (!A.stats_only) {
     RowsApply ap{A, q, make_divisor(q.a), {bias[0], bias[1], bias[2], bias[3]}};
-    consume_phase(g, ring, fq_dyn, pos, ap);
+    if (A.residual)
+      consume_pair_phase(half_geo(g), ring, fq_dyn, pos, ap);
+    else
+      consume_phase(g, ring, fq_dyn, pos, ap);
     if (blockIdx.x == 0) stamp(A, 9);
   }
   grid_exit_cl(A.sync);

@@ -1955,8 +1955,8 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   A.relu_passthrough = d->relu_passthrough;
   A.residual = d->residual;
   A.residual_relu = d->residual_relu;
-  if (d->residual && (!d->channels_last || d->stats_only || !aligned16(d->residual)))
-    return fail(FQB200_ERR_UNSUPPORTED, "residual: channels-last apply launches, 16-byte aligned%s");
+  if (d->residual && ((!d->channels_last && pl.mode != 3) || d->stats_only || !aligned16(d->residual)))
+    return fail(FQB200_ERR_UNSUPPORTED, "residual: channels-last or per-sample / per-tensor min-max apply launches, 16-byte aligned%s");
   A.out_stats = d->out_stats;
   A.bias = d->bias;
   A.hist = d->out_hist;

@@ -280,11 +280,20 @@ class IntQuantizer(object):
         ref = tensor if bias is None else tensor + bias.view(1, -1, 1, 1)
         return self.bias_correction_torch(ref, ops.quantize1(ref, delta, offset, self.num_bits, bits=bits, layout=layout), relu_first)
 
-    def _residual_kw(self, tensor, channels_last):
-        """kwargs of the fused block epilogue when this launch can take it."""
+    def _residual_kw(self, tensor, channels_last, rows=False):
+        """kwargs of the fused block epilogue when this launch can take it: the channels-last per-channel kernel, or
+        (``rows``) the per-sample / per-tensor min-max kernel, which takes any dense order."""
         r = self._residual
-        if (r is None or not channels_last or self.measure_entropy or r.shape != tensor.shape or r.stride() != tensor.stride()
+        if (r is None or self.measure_entropy or r.shape != tensor.shape or r.stride() != tensor.stride()
                 or r.dtype != torch.float32 or r.device != tensor.device):
+            return {}
+        if rows:
+            n = tensor.shape[0]
+            dense = tensor.is_contiguous() or (tensor.dim() == 4 and tensor.is_contiguous(memory_format=torch.channels_last))
+            if not (dense and tensor.dim() == 4 and n <= 4096 and (tensor.numel() // n) % 4 == 0
+                    and tensor.data_ptr() % 16 == 0 and r.data_ptr() % 16 == 0):
+                return {}
+        elif not channels_last:
             return {}
         self._residual_used = True
         return dict(residual=r, residual_relu=True)
@@ -428,13 +437,16 @@ class IntQuantizer(object):
                              bias_corr=weight_correction[0], var_corr=weight_correction[1], **kw)
         n = tensor.shape[0]
         # min / max and a scalar apply do not care about the order inside a sample; a channels-last bias indexes that order
+        # (these are the launches of the row kernel, which can also take the block's residual)
         kw["any_dense_format"] = bias is None or bias_cl
         if avg:
-            return self._fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_GROUP_MEAN, out=self._out(tensor), **kw)
+            return self._fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_GROUP_MEAN, out=self._out(tensor), **kw,
+                               **self._residual_kw(tensor, False, rows=kw["any_dense_format"]))
         if bias is not None:
             # rows = samples so that the channel of an element is its column / (H*W); the global min / max is the
             # min / max of the per-row ones (scope TENSOR): identical to the flat per-tensor reduction
-            return self._fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_TENSOR, out=self._out(tensor), **kw)
+            return self._fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_TENSOR, out=self._out(tensor), **kw,
+                               **self._residual_kw(tensor, False, rows=kw["any_dense_format"]))
         return self._fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, out=self._out(tensor), **kw)
 
     def gemmlowpQuantizeActivationPerChannel(self, tensor, id, tag="", stat_id=None, min_=None, max_=None, bias=None):

@@ -284,8 +284,8 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
     d.residual, d.residual_relu = None, 0
     if residual is not None:
         _require_cuda_f32(residual, "residual")
-        if not channels_last or residual.shape != x.shape or residual.stride() != x.stride():
-            raise ValueError("residual needs channels_last=True and a tensor with the input's shape and strides")
+        if residual.shape != x.shape or residual.stride() != x.stride():
+            raise ValueError("residual needs a tensor with the input's shape and strides")
         d.residual, d.residual_relu = residual.data_ptr(), int(bool(residual_relu))
     stats = None
     if want_stats or stats_only:

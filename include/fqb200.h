@@ -127,7 +127,8 @@ typedef struct fqb200_desc {
                           zero with zero point 0, so the quantized tensor is >= 0 already).  The one case where that is
                           not true - the compiled leaf handing its input back because the range is empty (range <= 0,
                           gemmlowp.cu:31-32) - then returns max(x, 0) instead of x, so quantizer + ReLU stay exact. */
-  const float* residual; /* channels_last only, NULL = none: a tensor of the same shape and memory order that is ADDED to the
+  const float* residual; /* channels_last launches and the per-sample / per-tensor min-max launches on the compiled leaf
+                          (outer = 1, rows = samples); NULL = none: a tensor of the same shape and memory order that is ADDED to the
                           quantized values in the apply phase, out = quantize(x + bias) + residual, and with residual_relu
                           followed by max(., 0): the `out += identity; out = relu(out)` that closes a ResNet block
                           (torchvision resnet.py), fused into the launch that quantizes the block's last convolution

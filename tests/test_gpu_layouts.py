@@ -221,3 +221,49 @@ def test_residual_epilogue_in_the_quantization_launch(fq, c):
     # an NCHW tensor cannot take the operand: ignored, not tagged
     y = q(x.contiguous().clone(), "conv3_activation", "activation", bias=bias, residual=r.contiguous())
     assert not getattr(y, "_fq_residual_fused", False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cl", [False, True])
+@pytest.mark.parametrize("shape", [(8, 64, 14, 14), (3, 24, 10, 10), (16, 256, 28, 28)])
+def test_residual_epilogue_in_the_per_sample_minmax_launch(fq, shape, cl):
+    """int8 path (configs[1]): max(quantize(x + bias) + residual, 0) inside the per-sample min/max launch is exactly the
+    launch without the operand followed by torch's add and ReLU (min / max are order-independent: bit-equal)."""
+    from cnn_quantization_b200 import _lib as L, ops
+    n, c, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(31)
+    x = torch.randn(shape, device="cuda", generator=g) * 1.7 + 0.2
+    r = torch.randn(shape, device="cuda", generator=g)
+    if cl:
+        x, r = x.contiguous(memory_format=torch.channels_last), r.contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(c, device="cuda", generator=g) * 0.2
+    for use_bias in (False, True):
+        kw = dict(range_mode=L.RANGE_MINMAX, leaf=L.LEAF_COMPILED, num_bits=8, scope=L.SCOPE_GROUP_MEAN, any_dense_format=True)
+        if use_bias:
+            kw.update(bias=bias, bias_period=-c if cl else h * w)
+        lay = (1, n, c * h * w)
+        base = ops.fused(x, lay, **kw)
+        if use_bias and not cl:
+            # a per-channel bias on NCHW memory is not a per-thread constant: that launch is the round-1 kernel, no operand
+            with pytest.raises(fq._lib.FqError):
+                ops.fused(x, lay, residual=r, residual_relu=True, **kw)
+            continue
+        got = ops.fused(x, lay, residual=r, residual_relu=True, **kw)
+        assert got.stride() == x.stride()
+        assert torch.equal(got, torch.relu(base + r))
+        got = ops.fused(x, lay, residual=r, residual_relu=False, **kw)
+        assert torch.equal(got, base + r)
+    # through the quantizer, in place: tagged
+    q = fq.int_quantizer("int8", params())
+    q.inplace = True
+    xin = x.clone()
+    want = torch.relu(q(x.clone(), "conv3_activation", "activation", bias=bias) + r)
+    y = q(xin, "conv3_activation", "activation", bias=bias, residual=r)
+    assert y.data_ptr() == xin.data_ptr() and getattr(y, "_fq_residual_fused", False) == cl   # NCHW + bias: not fused
+    if not cl:
+        y = torch.relu(y + r)
+    assert torch.equal(y, want)
+    # a residual in another memory order is ignored, not tagged
+    other = r.contiguous() if cl else r.contiguous(memory_format=torch.channels_last)
+    y = q(x.clone(), "conv3_activation", "activation", bias=bias, residual=other)
+    assert not getattr(y, "_fq_residual_fused", False)

@@ -94,7 +94,12 @@ def test_every_baseline_config_runs_and_quantizes(config):
     assert len(qm.calls) == expected
     quant = sum(v["launches"] for k, v in prof["modes"].items() if k not in ("E", "P"))
     assert quant == expected  # exactly one kernel launch per hooked tensor
-    assert prof["modes"].get("E", {"launches": 0})["launches"] == blocks  # + one fused add+ReLU per residual block
+    # + per residual block either one fused add+ReLU kernel ("E") or - where the launch of the block's last convolution
+    # can take the shortcut as an operand (int8 per-sample min/max and per-channel Laplace, both on channels-last) -
+    # nothing at all: that launch's mode carries an "r"
+    fused = sum(v["launches"] for k, v in prof["modes"].items() if k.endswith("r"))
+    assert prof["modes"].get("E", {"launches": 0})["launches"] + fused == blocks
+    assert fused == 0   # NCHW input here; the channels-last census is test_channels_last_pipeline_matches_nchw
 
 
 def test_bias_buffer_follows_the_module_and_detach_restores_it():
@@ -186,6 +191,30 @@ def test_pipeline_extensions_do_not_change_results(config):
 
     a, b = run(True), run(False)
     assert torch.equal(a, b)
+
+
+def test_int8_channels_last_block_epilogue_is_exact():
+    """configs[1] on channels-last memory: the 16 block epilogues run inside the per-sample min/max launches ("Br") and
+    the logits are bit-identical to the run that keeps them as separate add + ReLU kernels."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from cnn_quantization_b200 import ops, pipeline
+    x, _ = pipeline.synthetic_batch(4, seed=9, hw=64)
+    xin = x.cuda().contiguous(memory_format=torch.channels_last)
+    outs = []
+    for fuse in (True, False):
+        model, qm = pipeline.build_quantized_model("resnet50_w8a8", "cuda", channels_last=True)
+        qm.fuse_residual_into_quant = fuse
+        ops.profile_reset(enable=True)
+        with torch.no_grad():
+            outs.append(model(xin.clone()))
+        prof = ops.profile_collect()
+        ops.profile_reset(enable=False)
+        qm.detach()
+        fused = sum(v["launches"] for k, v in prof["modes"].items() if k.endswith("r"))
+        assert fused == (16 if fuse else 0)
+        assert prof["modes"].get("E", {"launches": 0})["launches"] == (0 if fuse else 16)
+    assert torch.equal(outs[0], outs[1])
 
 
 def test_channels_last_pipeline_matches_nchw():
