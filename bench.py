@@ -389,7 +389,9 @@ def run_fqb200(args):
         # more read, 20 B/element).  Both are launches of ONE kernel: the headline roofline covers all of them, "parts"
         # splits it.
         dom_mode = "D" if "D" in prof["modes"] else "B"
-        parts = {k: prof["modes"][k] for k in (dom_mode, dom_mode + "r") if k in prof["modes"]}
+        # (mode "S": the statistics-only launches of the shortcut convolutions of down-sampling blocks, 8 B/element; their
+        # apply happens inside the "Dr" launch that consumes them)
+        parts = {k: prof["modes"][k] for k in (dom_mode, dom_mode + "r", "S") if k in prof["modes"]}
         dom = {f: sum(v[f] for v in parts.values()) for f in ("launches", "elems", "ms", "bytes")}
         achieved = (dom["bytes"] / 1e9) / (dom["ms"] / 1e3) if dom["ms"] > 0 else 0.0
         traffic, traffic_src = NCU_TRAFFIC_BYTES_PER_LAUNCH.get(
@@ -418,7 +420,7 @@ def run_fqb200(args):
                          "peak_source": peak_src, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, DRAM read + write)",
                          "traffic_source": traffic_src, "launches": dom["launches"],
                          "algorithmic_bytes_per_launch": dom["bytes"] / max(dom["launches"], 1),
-                         "algorithmic_bytes_per_elem": {"D": 16, "B": 12, "Dr": 20, "Br": 16},
+                         "algorithmic_bytes_per_elem": {"D": 16, "B": 12, "Dr": 20, "Br": 16, "S": "8 (mode D) / 4 (mode B)"},
                          "avg_launch_ms": dom["ms"] / max(dom["launches"], 1),
                          "parts": {k: {"launches": v["launches"], "avg_launch_ms": v["ms"] / max(v["launches"], 1),
                                        "algorithmic_bytes_per_launch": v["bytes"] / max(v["launches"], 1),
@@ -502,7 +504,7 @@ def secondary(args, dev, config, batch, channels_last, mode, barrier, peak=None)
     qm.detach()
     del model, qm, x
     torch.cuda.empty_cache()
-    ps = [prof["modes"][k] for k in (mode, mode + "r") if k in prof["modes"]]  # "r": + the block's residual add + ReLU
+    ps = [prof["modes"][k] for k in (mode, mode + "r", "S") if k in prof["modes"]]  # "r": + the block's residual add + ReLU; "S": statistics only
     b = {f: sum(v[f] for v in ps) for f in ("bytes", "ms", "launches")}
     gbs = (b["bytes"] / 1e9) / (b["ms"] / 1e3) if b["ms"] else None
     quant_ms = sum(m["ms"] for m in prof["modes"].values()) / 3

@@ -20,7 +20,7 @@ STAT_COLUMNS = ("min", "max", "mean", "b", "std", "delta", "offset", "bits", "sc
 SYMBOLS = ("fqb200_abi_version", "fqb200_last_error", "fqb200_resident_ctas", "fqb200_plan_info",
            "fqb200_selftest_division", "fqb200_workspace_bytes", "fqb200_workspace_init", "fqb200_float2gemmlowp",
            "fqb200_quantize1", "fqb200_quantize1_bca", "fqb200_fused", "fqb200_add_relu", "fqb200_maxpool2d_nhwc")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Desc(ctypes.Structure):
@@ -43,6 +43,7 @@ class Desc(ctypes.Structure):
         ("out_hist_clamped", ctypes.c_void_p),
         ("relu_passthrough", ctypes.c_int32),
         ("residual", ctypes.c_void_p), ("residual_relu", ctypes.c_int32),
+        ("residual_stats", ctypes.c_void_p), ("residual_bias", ctypes.c_void_p),
         ("debug_stamps", ctypes.c_void_p),
     ]
 

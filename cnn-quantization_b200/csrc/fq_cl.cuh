@@ -204,8 +204,33 @@ struct ClApply {
   unsigned nlo[4], nhi[4];  // HIST, mid-tread: elements on the lower / upper clamp bound of each channel
   unsigned hbase;           // this warp's replica
   bool fast;
+  // the residual operand of the fused block epilogue, when it is quantized on the fly (fqb200_desc.residual_stats)
+  LeafParam rq[4];
+  float rr[4], rbias[4];
+  bool rquant;
   __device__ __forceinline__ void init(unsigned c0, bool active, const LeafParam (&lp)[4]) {
     fast = true;
+    rquant = A.residual != nullptr && A.residual_stats != nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      rq[i].a = 1.f;
+      rq[i].b = 0.f;
+      rq[i].c = 0.f;
+      rq[i].flags = 0;
+      rr[i] = 1.f;
+      rbias[i] = 0.f;
+      if (rquant && active) {
+        const float* row = A.residual_stats + static_cast<size_t>(c0 + i) * FQB200_STATS_STRIDE;
+        rq[i].a = __ldg(row + 8);
+        rq[i].b = __ldg(row + 9);
+        rq[i].c = __ldg(row + 10);
+        rq[i].flags = static_cast<int>(__ldg(row + 11));
+        const Divisor dr = make_divisor(rq[i].a);
+        rr[i] = dr.r;
+        fast = fast && dr.fast;
+        if (A.residual_bias) rbias[i] = __ldg(A.residual_bias + c0 + i);
+      }
+    }
     const unsigned copies = max(1u, min(static_cast<unsigned>(kWarps), kHistWords / static_cast<unsigned>(max(A.hist_bins, 1))));
     hbase = ((threadIdx.x >> 5) % copies) * static_cast<unsigned>(A.hist_bins);
 #pragma unroll
@@ -235,7 +260,7 @@ struct ClApply {
       atomicAdd(hist + hbase + static_cast<unsigned>(v), 1u);
     }
   }
-  template <bool FAST, bool PAIR>
+  template <bool FAST, bool PAIR, bool RQ = false>
   __device__ __forceinline__ void one(const float4& v, const float4& rv, unsigned off) {
     const float x[4] = {v.x, v.y, v.z, v.w};
     float y[4], gq[4];
@@ -248,10 +273,21 @@ struct ClApply {
       y[i] = leaf_apply<LEAF, FAST>(__fadd_rn(x[i], bias[i]), q[i], dv, 0.f, gq[i]);
     }
     if (PAIR) {  // the residual add (+ ReLU) that closes a ResNet block, on the quantized values
-      const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+      float res[4] = {rv.x, rv.y, rv.z, rv.w};
+      if (RQ) {  // the shortcut of a down-sampling block arrives raw: quantize it with its own parameters first
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          Divisor dr;
+          dr.s = rq[i].a;
+          dr.r = rr[i];
+          dr.fast = FAST;
+          float g2;
+          res[i] = leaf_apply<LEAF, FAST>(__fadd_rn(res[i], rbias[i]), rq[i], dr, 0.f, g2);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        y[i] = __fadd_rn(y[i], rr[i]);
+        y[i] = __fadd_rn(y[i], res[i]);
         if (A.residual_relu) y[i] = y[i] < 0.f ? 0.f : y[i];
       }
     }
@@ -269,10 +305,16 @@ struct ClApply {
   }
   // the residual comes through the ring next to x (consume_pair_phase)
   __device__ __forceinline__ void consume2(const float4& v, const float4& rv, unsigned off) {
-    if (fast)
+    if (rquant) {
+      if (fast)
+        one<true, true, true>(v, rv, off);
+      else
+        one<false, true, true>(v, rv, off);
+    } else if (fast) {
       one<true, true>(v, rv, off);
-    else
+    } else {
       one<false, true>(v, rv, off);
+    }
   }
   __device__ __forceinline__ void stage_end(const StageMeta&) {}
 };
@@ -1115,10 +1157,44 @@ struct RowsApply {
   LeafParam q;
   Divisor dv;
   float bias[4];
+  // the residual operand, when it is quantized on the fly (fqb200_desc.residual_stats: one row, compiled leaf)
+  LeafParam rq;
+  Divisor rdv;
+  float rbias[4];
+  bool rquant;
+  __device__ __forceinline__ void init_residual(unsigned c0, bool active) {
+    rquant = A.residual != nullptr && A.residual_stats != nullptr;
+    rq.a = 1.f;
+    rq.b = 0.f;
+    rq.c = 0.f;
+    rq.flags = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rbias[i] = 0.f;
+    if (rquant) {
+      rq.a = __ldg(A.residual_stats + 8);
+      rq.b = __ldg(A.residual_stats + 9);
+      rq.c = __ldg(A.residual_stats + 10);
+      rq.flags = static_cast<int>(__ldg(A.residual_stats + 11));
+      if (A.residual_bias && active) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rbias[i] = __ldg(A.residual_bias + c0 + i);
+      }
+    }
+    rdv = make_divisor(rq.a);
+    if (rquant && !rdv.fast) dv.fast = false;  // one flag selects the division for both operands
+    rdv.fast = dv.fast;
+  }
   template <bool FAST, bool PAIR>
-  __device__ __forceinline__ void one(const float4& v, const float4& r, unsigned off) {
+  __device__ __forceinline__ void one(const float4& v, const float4& r0, unsigned off) {
     float gq;
     float4 y;
+    float4 r = r0;
+    if (PAIR && rquant) {
+      r.x = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(r0.x, rbias[0]), rq, rdv, 0.f, gq);
+      r.y = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(r0.y, rbias[1]), rq, rdv, 0.f, gq);
+      r.z = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(r0.z, rbias[2]), rq, rdv, 0.f, gq);
+      r.w = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(r0.w, rbias[3]), rq, rdv, 0.f, gq);
+    }
     y.x = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(v.x, bias[0]), q, dv, 0.f, gq);
     y.y = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(v.y, bias[1]), q, dv, 0.f, gq);
     y.z = leaf_apply<FQB200_LEAF_COMPILED, FAST>(__fadd_rn(v.z, bias[2]), q, dv, 0.f, gq);
@@ -1235,6 +1311,7 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_rows_kernel(c
   if (blockIdx.x == 0) stamp(A, 7);
   if (!A.stats_only) {
     RowsApply ap{A, q, make_divisor(q.a), {bias[0], bias[1], bias[2], bias[3]}};
+    ap.init_residual(c0, active);
     if (A.residual)
       consume_pair_phase(half_geo(g), ring, fq_dyn, pos, ap);
     else

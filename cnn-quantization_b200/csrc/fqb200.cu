@@ -56,6 +56,8 @@ struct FusedArgs {
   float* out;
   const float* residual;  // channels-last kernel: optional tensor added to the quantized values (fqb200_desc.residual)
   int residual_relu;      // ... followed by max(., 0)
+  const float* residual_stats;  // ... quantized on the fly with the parameters of this exported table first
+  const float* residual_bias;   // ... after this bias has been added to it
   const float* bias;   // optional per-group addend applied to x before everything else (folded-BN conv bias)
   unsigned long long bias_magic;  // 0: bias[g];  else ceil(2^40 / period_v): bias[(j * magic) >> 40], j = column in vectors
                                   // (per-tensor / per-sample layouts, where a row holds C channels of period_v vectors each)
@@ -1955,6 +1957,12 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   A.relu_passthrough = d->relu_passthrough;
   A.residual = d->residual;
   A.residual_relu = d->residual_relu;
+  A.residual_stats = d->residual_stats;
+  A.residual_bias = d->residual_bias;
+  if ((d->residual_stats || d->residual_bias) && !d->residual)
+    return fail(FQB200_ERR_INVALID, "residual_stats / residual_bias without a residual%s");
+  if (d->residual_bias && !d->residual_stats)
+    return fail(FQB200_ERR_INVALID, "residual_bias needs residual_stats (a bias on a plain addend can be folded by the caller)%s");
   if (d->residual && ((!d->channels_last && pl.mode != 3) || d->stats_only || !aligned16(d->residual)))
     return fail(FQB200_ERR_UNSUPPORTED, "residual: channels-last or per-sample / per-tensor min-max apply launches, 16-byte aligned%s");
   A.out_stats = d->out_stats;

@@ -106,12 +106,13 @@ class IntQuantizer(object):
         self._relu_follows = False
         self._bca = None
         self._residual, self._residual_used = None, False
+        self._defer, self._deferred = False, None
 
     # ------------------------------------------------------------------------------------------
     # dispatch (int_quantizer.py:92-122)
     # ------------------------------------------------------------------------------------------
     def __call__(self, tensor, id, tag="", stat_id=None, override_att=None, weight_correction=None, bias=None,
-                 relu_follows=False, bias_correct=None, residual=None):
+                 relu_follows=False, bias_correct=None, residual=None, defer=False):
         """Extensions used by this package's manager (all default to the reference behaviour):
         ``bias_correct`` (None = off, else the "ReLU follows" flag of the call site): the activation bias correction of
         Conv2dWithId.forward (`-bca`, inference_quantization_manager.py:180-196) is applied by the quantizer itself - inside
@@ -120,6 +121,11 @@ class IntQuantizer(object):
         closing ReLU; where the launch can take it (per-channel quantization of a channels-last tensor with on-the-fly
         statistics) ``max(quantize(x) + residual, 0)`` is computed in the apply phase and the result is tagged
         ``_fq_residual_fused``; otherwise the operand is ignored and the caller adds it itself;
+        ``defer``: this tensor is only ever used as the ``residual`` of another call (the shortcut of a down-sampling
+        ResNet block): where both launches can do it, only the statistics phases run now (8 instead of 16 B/element); the
+        tensor comes back UNQUANTIZED, tagged ``_fq_deferred = (parameter table, bias)``, and the call that takes it as
+        ``residual`` quantizes it on the fly in its apply phase.  The caller must finish a deferred tensor itself
+        (call again without ``defer``) when that other call did not fuse;
         ``relu_follows``: the caller will skip the ReLU that follows when the result is tagged ``_fq_nonneg`` - set on
         every result of a positive (half-range / force-positive) range, where offset 0 gives zero point 0 and every value
         is q * scale >= 0; the compiled leaf's empty-range pass-through then returns max(x, 0) (fqb200_desc.relu_passthrough);
@@ -133,6 +139,7 @@ class IntQuantizer(object):
         self._relu_follows = bool(relu_follows) and self._positive()
         self._bca = bias_correct
         self._residual, self._residual_used = residual, False
+        self._defer, self._deferred = bool(defer), None
         try:
             self._unsupported(stat_id)
             if bias is not None and not self._bias_fusable(tensor):
@@ -165,6 +172,9 @@ class IntQuantizer(object):
         if self._residual_used:
             res._fq_residual_fused = True
             res._fq_nonneg = res._version   # the fused epilogue ends with the ReLU
+        if self._deferred is not None:
+            res._fq_deferred = self._deferred
+        self._defer, self._deferred = False, None
         self._relu_follows = False
         self._bca = None
         self._residual, self._residual_used = None, False
@@ -280,7 +290,7 @@ class IntQuantizer(object):
         ref = tensor if bias is None else tensor + bias.view(1, -1, 1, 1)
         return self.bias_correction_torch(ref, ops.quantize1(ref, delta, offset, self.num_bits, bits=bits, layout=layout), relu_first)
 
-    def _residual_kw(self, tensor, channels_last, rows=False):
+    def _residual_kw(self, tensor, channels_last, rows=False, bias=None):
         """kwargs of the fused block epilogue when this launch can take it: the channels-last per-channel kernel, or
         (``rows``) the per-sample / per-tensor min-max kernel, which takes any dense order."""
         r = self._residual
@@ -295,8 +305,37 @@ class IntQuantizer(object):
                 return {}
         elif not channels_last:
             return {}
+        kw = dict(residual=r, residual_relu=True)
+        deferred = getattr(r, "_fq_deferred", None)
+        if deferred is not None:   # the shortcut arrives raw, with its parameter table: quantized in our apply phase
+            stats, rbias = deferred
+            if (rbias is None) != (bias is None) or (rbias is not None and rbias.numel() != bias.numel()) or self.mtd_quant:
+                return {}
+            kw.update(residual_stats=stats, residual_bias=rbias)
         self._residual_used = True
-        return dict(residual=r, residual_relu=True)
+        return kw
+
+    def _launch(self, tensor, layout, channels_last=False, rows=False, **kw):
+        """One fused launch of the activation paths that can end a ResNet block: deferred (statistics only, see
+        ``__call__``), with the block epilogue (``residual``), or plain."""
+        if self._defer and kw.get("hist") is None and self._can_defer(tensor, channels_last, rows):
+            skw = {k: v for k, v in kw.items() if k not in ("out", "hist")}
+            stats = ops.fused(tensor, layout, stats_only=True, channels_last=channels_last, **skw)
+            if self.export_stats:
+                self.last_stats = stats
+            self._deferred = (stats, kw.get("bias"))
+            return tensor
+        return self._fused(tensor, layout, channels_last=channels_last, **kw,
+                           **self._residual_kw(tensor, channels_last, rows=rows, bias=kw.get("bias")))
+
+    def _can_defer(self, tensor, channels_last, rows):
+        if self.measure_entropy or self.mtd_quant or tensor.dim() != 4 or tensor.dtype != torch.float32:
+            return False
+        if rows:
+            n = tensor.shape[0]
+            dense = tensor.is_contiguous() or tensor.is_contiguous(memory_format=torch.channels_last)
+            return dense and n <= 4096 and (tensor.numel() // n) % 4 == 0 and tensor.data_ptr() % 16 == 0
+        return bool(channels_last)
 
     def _fused(self, tensor, layout, **kw):
         """ops.fused, keeping the exported statistics table when ``export_stats`` is set."""
@@ -390,12 +429,12 @@ class IntQuantizer(object):
         mode, k = self._range_mode(clip_type)
         if self._pc_act(tensor) and tensor.shape[1] > 1:
             hist = self._hist(tensor)  # the reference measures entropy in gemmlowpQuantizeActivationPerChannel (:442-445)
-            res = self._fused(tensor, self._nchw_layout(tensor), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
-                            leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(),
-                            bit_alloc=self.bit_alloc_act, bit_alloc_prior=self._prior(),
-                            bit_alloc_round=self.bit_alloc_round, bit_alloc_target=self.bit_alloc_target_act,
-                            bias=bias, out=self._out(tensor), hist=hist, channels_last=self._channels_last(tensor),
-                            **self._residual_kw(tensor, self._channels_last(tensor)))
+            res = self._launch(tensor, self._nchw_layout(tensor), channels_last=self._channels_last(tensor),
+                               scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
+                               leaf=L.LEAF_TORCH, num_bits=self.num_bits, positive=self._positive(),
+                               bit_alloc=self.bit_alloc_act, bit_alloc_prior=self._prior(),
+                               bit_alloc_round=self.bit_alloc_round, bit_alloc_target=self.bit_alloc_target_act,
+                               bias=bias, out=self._out(tensor), hist=hist)
             self._log_entropy(hist, id, "avg.entropy.act", tensor.numel())
             return res
         return self._fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, range_mode=mode, clip_k=k,
@@ -440,13 +479,13 @@ class IntQuantizer(object):
         # (these are the launches of the row kernel, which can also take the block's residual)
         kw["any_dense_format"] = bias is None or bias_cl
         if avg:
-            return self._fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_GROUP_MEAN, out=self._out(tensor), **kw,
-                               **self._residual_kw(tensor, False, rows=kw["any_dense_format"]))
+            return self._launch(tensor, (1, n, tensor.numel() // n), rows=kw["any_dense_format"], scope=L.SCOPE_GROUP_MEAN,
+                                out=self._out(tensor), **kw)
         if bias is not None:
             # rows = samples so that the channel of an element is its column / (H*W); the global min / max is the
             # min / max of the per-row ones (scope TENSOR): identical to the flat per-tensor reduction
-            return self._fused(tensor, (1, n, tensor.numel() // n), scope=L.SCOPE_TENSOR, out=self._out(tensor), **kw,
-                               **self._residual_kw(tensor, False, rows=kw["any_dense_format"]))
+            return self._launch(tensor, (1, n, tensor.numel() // n), rows=kw["any_dense_format"], scope=L.SCOPE_TENSOR,
+                                out=self._out(tensor), **kw)
         return self._fused(tensor, (1, 1, tensor.numel()), scope=L.SCOPE_GROUP, out=self._out(tensor), **kw)
 
     def gemmlowpQuantizeActivationPerChannel(self, tensor, id, tag="", stat_id=None, min_=None, max_=None, bias=None):
@@ -469,11 +508,11 @@ class IntQuantizer(object):
             return self._quantize1(tensor, delta, offset, bits=bits, layout=layout, bias=bias)
         if min_ is None and max_ is None:
             hist = self._hist(tensor)
-            res = self._fused(tensor, layout, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
-                            num_bits=self.num_bits, positive=self._positive(), bit_alloc=self.bit_alloc_act,
-                            bit_alloc_prior=self._prior(), bit_alloc_round=self.bit_alloc_round,
-                            bit_alloc_target=self.bit_alloc_target_act, bias=bias, out=self._out(tensor), hist=hist,
-                            channels_last=self._channels_last(tensor), **self._residual_kw(tensor, self._channels_last(tensor)))
+            res = self._launch(tensor, layout, channels_last=self._channels_last(tensor),
+                               scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.LEAF_TORCH,
+                               num_bits=self.num_bits, positive=self._positive(), bit_alloc=self.bit_alloc_act,
+                               bit_alloc_prior=self._prior(), bit_alloc_round=self.bit_alloc_round,
+                               bit_alloc_target=self.bit_alloc_target_act, bias=bias, out=self._out(tensor), hist=hist)
             self._log_entropy(hist, id, "avg.entropy.act", tensor.numel())
             return res
         if bias is not None:

@@ -195,12 +195,25 @@ def _residual_block_forward(block, bottleneck, manager):
                  and x.is_cuda and x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last))
         if early:
             if block.downsample is not None:
-                identity = block.downsample(x)
+                # ... and the shortcut convolution's output is used by that launch only: its own launch can stop after
+                # the statistics phases and hand over raw tensor + parameter table (IntQuantizer ``defer``)
+                ds = block.downsample
+                ds_conv = ds[0] if (manager.defer_shortcut and isinstance(ds, nn.Sequential) and len(ds) == 2
+                                    and isinstance(ds[0], nn.Conv2d) and hasattr(ds[1], "absorbed")) else None
+                if ds_conv is not None:
+                    ds_conv._fq_defer = True
+                try:
+                    identity = ds(x)
+                finally:
+                    if ds_conv is not None:
+                        ds_conv.__dict__.pop("_fq_defer", None)
             last_conv._fq_residual = identity
         out = last_bn(last_conv(out))
         last_conv.__dict__.pop("_fq_residual", None)
         if getattr(out, "_fq_residual_fused", False):
             return out
+        if getattr(identity, "_fq_deferred", None) is not None:
+            identity = manager.finish_deferred(identity)   # the launch above could not take it: quantize it now
         if not early and block.downsample is not None:
             identity = block.downsample(x)
         if (out.is_cuda and out.dtype == torch.float32 and identity.dtype == torch.float32 and out.shape == identity.shape
@@ -248,6 +261,8 @@ class QuantizationManagerInference(object):
         # ... and, where the quantization launch of the block's last convolution can take the shortcut as an operand, inside
         # that launch (channels-last per-channel activations with on-the-fly statistics)
         self.fuse_residual_into_quant = self._native
+        # ... and the shortcut convolution of a down-sampling block runs statistics-only, quantized on the fly there
+        self.defer_shortcut = self._native
         # channels-last max pooling in front of the `activation_pooling` call site runs on this package's kernel
         self.fast_maxpool = self._native
         self.inplace_activations = self._native
@@ -469,8 +484,23 @@ class QuantizationManagerInference(object):
         residual = m.__dict__.get("_fq_residual")
         if residual is not None and self._native and tag == "activation":
             extra["residual"] = residual
+        if m.__dict__.get("_fq_defer") and self._native and tag == "activation" and self.stats_mode != "use":
+            res = self.quantize_instant(out, activation_id, tag, stat_id=None, half_range=half_range, verbose=self.verbose,
+                                        defer=True, **extra)
+            if getattr(res, "_fq_deferred", None) is not None:
+                res._fq_redo = (activation_id, tag, half_range, extra)
+            return res
         return self.quantize_instant(out, activation_id, tag, stat_id=self._stat_id(activation_id), half_range=half_range,
                                      verbose=self.verbose, **extra)
+
+    def finish_deferred(self, tensor):
+        """Quantize a tensor whose launch was deferred (IntQuantizer ``defer``) after all: the call that should have taken
+        it as its residual did not fuse.  Same quantizer, same arguments; not recorded as a second call."""
+        activation_id, tag, half_range, extra = tensor._fq_redo
+        del tensor._fq_deferred, tensor._fq_redo
+        q = self.get_quantizer(tag)
+        q.half_range = half_range
+        return q(tensor, activation_id, tag, None, None, **extra)
 
     def _linear_hook(self, m, inputs, out):
         if not self.enabled:

@@ -227,7 +227,7 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
           bit_alloc_round=True, bit_alloc_target=None, mt_target=0.0, mt_clip=False, bias_corr=False,
           var_corr=False, stats_only=False, want_stats=False, out=None, bias=None, bias_period=0, hist=None,
           channels_last=False, any_dense_format=False, debug_stamps=None, relu_passthrough=False, hist_offset=0,
-          hist_clamped=None, residual=None, residual_relu=False):
+          hist_clamped=None, residual=None, residual_relu=False, residual_stats=None, residual_bias=None):
     """C ABI fqb200_fused: statistics -> parameters -> quantize/dequantize in one launch.
 
     Returns ``out`` (or ``(out, stats)`` with ``want_stats``; ``stats`` alone with ``stats_only``), where
@@ -287,6 +287,21 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
         if residual.shape != x.shape or residual.stride() != x.stride():
             raise ValueError("residual needs a tensor with the input's shape and strides")
         d.residual, d.residual_relu = residual.data_ptr(), int(bool(residual_relu))
+    d.residual_stats, d.residual_bias = None, None
+    if residual_stats is not None:
+        # the [groups, 12] table a stats_only launch exported for the residual tensor: it is quantized on the fly
+        if residual is None or residual_stats.dtype != torch.float32 or not residual_stats.is_cuda or not residual_stats.is_contiguous() \
+                or residual_stats.dim() != 2 or residual_stats.shape[1] != L.STATS_STRIDE:
+            raise ValueError("residual_stats: the contiguous CUDA [groups, %d] table of a stats_only launch, with a residual" % L.STATS_STRIDE)
+        d.residual_stats = residual_stats.data_ptr()
+        if residual_bias is not None:
+            _require_cuda_f32(residual_bias, "residual_bias")
+            residual_bias = residual_bias.contiguous()
+            if bias is None or residual_bias.numel() != bias.numel():
+                raise ValueError("residual_bias must have the form of `bias`")
+            d.residual_bias = residual_bias.data_ptr()
+    elif residual_bias is not None:
+        raise ValueError("residual_bias needs residual_stats")
     stats = None
     if want_stats or stats_only:
         stats = torch.zeros((groups, L.STATS_STRIDE), dtype=torch.float32, device=dev)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FQB200_ABI_VERSION 2
+#define FQB200_ABI_VERSION 3
 
 /* ---- return codes ------------------------------------------------------------------------- */
 #define FQB200_OK 0
@@ -134,6 +134,14 @@ typedef struct fqb200_desc {
                           (torchvision resnet.py), fused into the launch that quantizes the block's last convolution
                           (8 B/element less traffic than a separate add + ReLU pass).  Must not alias `out`. */
   int32_t residual_relu;
+  const float* residual_stats; /* NULL: the residual is added as it is.  Else the [groups][FQB200_STATS_STRIDE] table
+                          (channels_last) or the one row (per-sample / per-tensor min-max) that a stats_only launch with the
+                          same leaf exported for the residual tensor: the residual is QUANTIZED with those parameters on the
+                          fly (columns scale, zero_point, qmax, flags) before the add - the shortcut branch of a
+                          down-sampling ResNet block never makes a round trip through memory as a quantized tensor
+                          (stats_only 8 B/element + 4 B/element here instead of 16 + 4) */
+  const float* residual_bias; /* optional bias of the residual tensor, added before its quantization; same form as `bias`
+                          (per channel; channel-fastest on the min-max launches) */
   unsigned long long* debug_stamps; /* diagnostics, NULL = off: device array of 16 counters that receives %globaltimer
                           (ns) at the phase boundaries of this launch (slot 0: start, 1 / 5: statistics phases combined,
                           4 / 8: past the grid barriers, 7: parameters ready, 9: apply done; tools/phasebench.py) */

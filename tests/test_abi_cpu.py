@@ -37,15 +37,16 @@ def test_library_exports_every_declared_symbol(lib):
     # ... and nothing else: no undeclared hooks ride along in the shipped library (round-1 VERDICT, boundary hygiene)
     ours = sorted(s for s in exported if s.startswith("fqb"))
     assert ours == declared, sorted(set(ours) - set(declared))
-    assert lib.fqb200_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.fqb200_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_desc_struct_layout_matches_header():
     from cnn_quantization_b200 import _lib
     # compile a one-liner against the header and compare sizeof / offsetof with the ctypes mirror
-    code = ('#include <stdio.h>\n#include <stddef.h>\n#include "fqb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", '
+    code = ('#include <stdio.h>\n#include <stddef.h>\n#include "fqb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", '
             'sizeof(fqb200_desc), offsetof(fqb200_desc, clip_k), offsetof(fqb200_desc, mt_target), '
-            'offsetof(fqb200_desc, out_stats), offsetof(fqb200_desc, channels_last), offsetof(fqb200_desc, debug_stamps));'
+            'offsetof(fqb200_desc, out_stats), offsetof(fqb200_desc, channels_last), offsetof(fqb200_desc, residual_stats), '
+            'offsetof(fqb200_desc, debug_stamps));'
             'return 0;}\n')
     exe = os.path.join(ROOT, "oracle", "_build", "abi_probe")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
@@ -53,7 +54,7 @@ def test_desc_struct_layout_matches_header():
     got = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     D = _lib.Desc
     assert got == [ctypes.sizeof(D), D.clip_k.offset, D.mt_target.offset, D.out_stats.offset, D.channels_last.offset,
-                   D.debug_stamps.offset]
+                   D.residual_stats.offset, D.debug_stamps.offset]
 
 
 def test_argument_validation_without_gpu(lib):

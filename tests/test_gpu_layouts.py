@@ -267,3 +267,60 @@ def test_residual_epilogue_in_the_per_sample_minmax_launch(fq, shape, cl):
     other = r.contiguous() if cl else r.contiguous(memory_format=torch.channels_last)
     y = q(x.clone(), "conv3_activation", "activation", bias=bias, residual=other)
     assert not getattr(y, "_fq_residual_fused", False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", [64, 96, 256])
+def test_deferred_shortcut_is_quantized_on_the_fly_per_channel(fq, c):
+    """The shortcut of a down-sampling block: a stats_only launch exports its parameter table, the launch of the block's
+    last convolution quantizes the raw shortcut with it in its apply phase.  Same result as quantizing it separately."""
+    from cnn_quantization_b200 import _lib as L, ops
+    n, hw = 8, 14
+    x = _x(c, seed=41, n=n, hw=hw).contiguous(memory_format=torch.channels_last)
+    r = (_x(c, seed=42, n=n, hw=hw) * 0.7 - 0.1).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(c, device="cuda") * 0.2
+    rbias = torch.randn(c, device="cuda") * 0.2
+    kw = dict(range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True, channels_last=True)
+    lay = (n, c, hw * hw)
+    qx = ops.fused(x, lay, bias=bias, **kw)
+    qr = ops.fused(r, lay, bias=rbias, **kw)
+    stats = ops.fused(r, lay, bias=rbias, stats_only=True, **kw)
+    got = ops.fused(x, lay, bias=bias, residual=r, residual_relu=True, residual_stats=stats, residual_bias=rbias, **kw)
+    frac, _ = fq_mismatch(got.cpu().numpy(), torch.relu(qx + qr).cpu().numpy())
+    assert frac <= 2e-3
+    # through the quantizer: defer hands the tensor back untouched with its table; the second call fuses
+    q = fq.int_quantizer("int4", params(clipping="laplace", pcq_act=True, bit_alloc_act=True))
+    q.inplace = True
+    r2 = r.clone()
+    d = q(r2, "conv4_activation", "activation", bias=rbias, defer=True)
+    assert d is r2 and torch.equal(d, r) and d._fq_deferred[0].shape == (c, 12)
+    y = q(x.clone(), "conv3_activation", "activation", bias=bias, residual=d)
+    assert getattr(y, "_fq_residual_fused", False)
+    frac, _ = fq_mismatch(y.cpu().numpy(), torch.relu(qx + qr).cpu().numpy())
+    assert frac <= 2e-3
+    # NCHW tensors are not deferred: quantized right away
+    d = q(r.contiguous().clone(), "conv4_activation", "activation", bias=rbias, defer=True)
+    assert getattr(d, "_fq_deferred", None) is None
+    frac, _ = fq_mismatch(d.cpu().numpy(), qr.cpu().numpy())
+    assert frac <= 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cl", [False, True])
+def test_deferred_shortcut_is_quantized_on_the_fly_int8(fq, cl):
+    from cnn_quantization_b200 import _lib as L, ops
+    shape = (8, 64, 14, 14)
+    g = torch.Generator(device="cuda").manual_seed(51)
+    x = torch.randn(shape, device="cuda", generator=g) * 1.7 + 0.2
+    r = torch.randn(shape, device="cuda", generator=g) * 0.6 - 0.3
+    if cl:
+        x, r = x.contiguous(memory_format=torch.channels_last), r.contiguous(memory_format=torch.channels_last)
+    q = fq.int_quantizer("int8", params())
+    bias = torch.randn(64, device="cuda", generator=g) * 0.2 if cl else None   # a per-channel bias needs channels-last here
+    rbias = torch.randn(64, device="cuda", generator=g) * 0.2 if cl else None
+    want = torch.relu(q(x.clone(), "a", "activation", bias=bias) + q(r.clone(), "b", "activation", bias=rbias))
+    d = q(r.clone(), "b", "activation", bias=rbias, defer=True)
+    assert torch.equal(d, r) and d._fq_deferred[0].shape[1] == 12
+    y = q(x.clone(), "a", "activation", bias=bias, residual=d)
+    assert getattr(y, "_fq_residual_fused", False)
+    assert torch.equal(y, want)

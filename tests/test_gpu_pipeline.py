@@ -201,20 +201,30 @@ def test_int8_channels_last_block_epilogue_is_exact():
     from cnn_quantization_b200 import ops, pipeline
     x, _ = pipeline.synthetic_batch(4, seed=9, hw=64)
     xin = x.cuda().contiguous(memory_format=torch.channels_last)
+    from cnn_quantization_b200.int_quantizer import IntQuantizer
     outs = []
-    for fuse in (True, False):
+    # (block epilogue in the launch, shortcut of the 4 down-sampling blocks deferred, the launch refuses the operand)
+    for fuse, defer, refuse in ((True, True, False), (True, False, False), (False, False, False), (True, True, True)):
         model, qm = pipeline.build_quantized_model("resnet50_w8a8", "cuda", channels_last=True)
-        qm.fuse_residual_into_quant = fuse
-        ops.profile_reset(enable=True)
-        with torch.no_grad():
-            outs.append(model(xin.clone()))
-        prof = ops.profile_collect()
-        ops.profile_reset(enable=False)
-        qm.detach()
+        qm.fuse_residual_into_quant, qm.defer_shortcut = fuse, defer
+        keep = IntQuantizer._residual_kw
+        if refuse:   # the fallback: a deferred shortcut is quantized after all (manager.finish_deferred), then add + ReLU
+            IntQuantizer._residual_kw = lambda self, *a, **k: {}
+        try:
+            ops.profile_reset(enable=True)
+            with torch.no_grad():
+                outs.append(model(xin.clone()))
+            prof = ops.profile_collect()
+        finally:
+            IntQuantizer._residual_kw = keep
+            ops.profile_reset(enable=False)
+            qm.detach()
         fused = sum(v["launches"] for k, v in prof["modes"].items() if k.endswith("r"))
-        assert fused == (16 if fuse else 0)
-        assert prof["modes"].get("E", {"launches": 0})["launches"] == (0 if fuse else 16)
-    assert torch.equal(outs[0], outs[1])
+        assert fused == (16 if fuse and not refuse else 0)
+        assert prof["modes"].get("E", {"launches": 0})["launches"] == (0 if fuse and not refuse else 16)
+        assert prof["modes"].get("S", {"launches": 0})["launches"] == (4 if defer else 0)
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)
 
 
 def test_channels_last_pipeline_matches_nchw():
@@ -238,6 +248,7 @@ def test_channels_last_pipeline_matches_nchw():
         assert prof["launches"] == (55 + 1 if cl else 55 + 16)
         if cl:
             assert sum(v["launches"] for k, v in prof["modes"].items() if k.endswith("r")) == 16
+            assert prof["modes"]["S"]["launches"] == 4   # the shortcut convolutions of the 4 down-sampling blocks: statistics only
     a, b = outs
     cos = float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b)))
     assert cos > 0.97, cos
