@@ -391,7 +391,7 @@ def run_fqb200(args):
         dom_mode = "D" if "D" in prof["modes"] else "B"
         # (mode "S": the statistics-only launches of the shortcut convolutions of down-sampling blocks, 8 B/element; their
         # apply happens inside the "Dr" launch that consumes them)
-        parts = {k: prof["modes"][k] for k in (dom_mode, dom_mode + "r", "S") if k in prof["modes"]}
+        parts = {k: prof["modes"][k] for k in (dom_mode, dom_mode + "r", dom_mode + "p", "S") if k in prof["modes"]}
         dom = {f: sum(v[f] for v in parts.values()) for f in ("launches", "elems", "ms", "bytes")}
         achieved = (dom["bytes"] / 1e9) / (dom["ms"] / 1e3) if dom["ms"] > 0 else 0.0
         traffic, traffic_src = NCU_TRAFFIC_BYTES_PER_LAUNCH.get(
@@ -420,7 +420,7 @@ def run_fqb200(args):
                          "peak_source": peak_src, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, DRAM read + write)",
                          "traffic_source": traffic_src, "launches": dom["launches"],
                          "algorithmic_bytes_per_launch": dom["bytes"] / max(dom["launches"], 1),
-                         "algorithmic_bytes_per_elem": {"D": 16, "B": 12, "Dr": 20, "Br": 16, "S": "8 (mode D) / 4 (mode B)"},
+                         "algorithmic_bytes_per_elem": {"D": 16, "B": 12, "Dr": 20, "Br": 16, "Dp": 13, "S": "8 (mode D) / 4 (mode B)"},
                          "avg_launch_ms": dom["ms"] / max(dom["launches"], 1),
                          "parts": {k: {"launches": v["launches"], "avg_launch_ms": v["ms"] / max(v["launches"], 1),
                                        "algorithmic_bytes_per_launch": v["bytes"] / max(v["launches"], 1),
@@ -504,14 +504,16 @@ def secondary(args, dev, config, batch, channels_last, mode, barrier, peak=None)
     qm.detach()
     del model, qm, x
     torch.cuda.empty_cache()
-    ps = [prof["modes"][k] for k in (mode, mode + "r", "S") if k in prof["modes"]]  # "r": + the block's residual add + ReLU; "S": statistics only
+    ps = [prof["modes"][k] for k in (mode, mode + "r", mode + "p", "S") if k in prof["modes"]]
+    # "r": + the block's residual add + ReLU (4 B/element more); "p": + the 2x2 max pooling behind the convolution (13 B/element:
+    # the apply phase writes a quarter); "S": statistics only (8)
     b = {f: sum(v[f] for v in ps) for f in ("bytes", "ms", "launches")}
     gbs = (b["bytes"] / 1e9) / (b["ms"] / 1e3) if b["ms"] else None
     quant_ms = sum(m["ms"] for m in prof["modes"].values()) / 3
     return {"workload": workload_string(config, batch), "memory_format": "channels_last" if channels_last else "nchw",
             "metric": metric_name(config), "value": batch / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": 3,
             "quant_ms_per_step": quant_ms,
-            "roofline": {"kernel": "fused kernel mode %s (+ residual epilogue launches: 4 B/element more)" % mode,
+            "roofline": {"kernel": "fused kernel mode %s (+ the r / p / S variants of its launches)" % mode,
                          "algorithmic_bytes_per_elem": {"D": 16, "B": 12}[mode],
                          "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak if gbs else None,
                          "launches": b["launches"]}}

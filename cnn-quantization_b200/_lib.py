@@ -44,6 +44,7 @@ class Desc(ctypes.Structure):
         ("relu_passthrough", ctypes.c_int32),
         ("residual", ctypes.c_void_p), ("residual_relu", ctypes.c_int32),
         ("residual_stats", ctypes.c_void_p), ("residual_bias", ctypes.c_void_p),
+        ("pool", ctypes.c_int32), ("pool_h", ctypes.c_int64), ("pool_w", ctypes.c_int64), ("pool_out", ctypes.c_void_p),
         ("debug_stamps", ctypes.c_void_p),
     ]
 

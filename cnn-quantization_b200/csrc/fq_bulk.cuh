@@ -281,6 +281,100 @@ __device__ __forceinline__ void produce_rows_phase(const FlatGeo& g, const RowsG
   pos.next();
 }
 
+// ---- 2x2 / stride-2 max pooling inside the apply phase (channels-last) -------------------------------------------------------
+// A TILE is two vertically adjacent input rows x `wt` pixels (wt even, wt * cv <= 1024 vectors): the two row pieces are two
+// contiguous runs of the stream and land in the two halves of a stage (pair layout); thread o < (wt / 2) * cv produces output
+// vector o of the tile: pixel pair j = o / cv, channel column o % cv (the same four channels the thread holds in the
+// statistics phases, since the stride of those is a multiple of cv).  Units are runs of `unit_tiles` tiles.
+struct PoolGeo {
+  unsigned h, w;           // input rows / pixels per row
+  unsigned wt;             // tile width in pixels
+  unsigned tiles_per_row;  // w / wt
+  unsigned row_pairs;      // h / 2 (a last odd row is dropped, like torch's floor mode)
+  unsigned tiles;          // n * row_pairs * tiles_per_row
+  unsigned unit_tiles, units;
+  unsigned ow;             // w / 2
+};
+
+__device__ __forceinline__ void produce_pool_phase(const FlatGeo& g, const PoolGeo& pg, const float4* src, unsigned* counter,
+                                                   const TicketPlan tp, BulkRing& r, unsigned char* stage_base, RingPos& pos) {
+  const unsigned total = pg.units;
+  unsigned k = 0;
+  auto fetch = [&]() -> unsigned {
+    unsigned long long t;
+    if (k < tp.nstatic)
+      t = tp.first + static_cast<unsigned long long>(k) * tp.step;
+    else
+      t = static_cast<unsigned long long>(tp.dyn_base) + atomicAdd(counter, 1u);
+    ++k;
+    return t < total ? static_cast<unsigned>(t) : 0xffffffffu;
+  };
+  const unsigned row_v = pg.w * g.cv;      // vectors per input row
+  const unsigned count = pg.wt * g.cv;     // vectors per row piece
+  const unsigned per_img = pg.row_pairs * pg.tiles_per_row;
+  unsigned cur = fetch();
+  unsigned nxt = (cur != 0xffffffffu) ? fetch() : 0xffffffffu;
+  while (cur != 0xffffffffu) {
+    const unsigned nxt2 = (nxt != 0xffffffffu) ? fetch() : 0xffffffffu;
+    const unsigned t0 = cur * pg.unit_tiles;
+    const unsigned t1 = min(t0 + pg.unit_tiles, pg.tiles);
+    for (unsigned tile = t0; tile < t1; ++tile) {
+      const unsigned n = tile / per_img;
+      const unsigned rem = tile - n * per_img;
+      const unsigned hp = rem / pg.tiles_per_row;
+      const unsigned wi = rem - hp * pg.tiles_per_row;
+      const unsigned a = (n * pg.h + 2u * hp) * row_v + wi * count;   // < total_v < 2^32
+      const unsigned o = ((n * pg.row_pairs + hp) * pg.ow + wi * (pg.wt / 2u)) * g.cv;
+      mbar_wait(smem_u32(&r.empty[pos.slot]), pos.parity ^ 1u);
+      r.meta[pos.slot].start = o;      // first OUTPUT vector of the tile
+      r.meta[pos.slot].count = count;
+      r.meta[pos.slot].tag = 0u;
+      const unsigned bar = smem_u32(&r.full[pos.slot]);
+      mbar_arrive_expect_tx(bar, count * 32u);
+      bulk_load(smem_u32(stage_base + pos.slot * kStageBytes), src + a, count * 16u, bar);
+      bulk_load(smem_u32(stage_base + pos.slot * kStageBytes + kPairOffset), src + a + row_v, count * 16u, bar);
+      pos.next();
+    }
+    cur = nxt;
+    nxt = nxt2;
+  }
+  mbar_wait(smem_u32(&r.empty[pos.slot]), pos.parity ^ 1u);
+  r.meta[pos.slot].start = 0u;
+  r.meta[pos.slot].count = 0u;
+  r.meta[pos.slot].tag = 0u;
+  mbar_arrive(smem_u32(&r.full[pos.slot]));
+  pos.next();
+}
+
+// acc.pooled(a0, a1, b0, b1, out_vector) for the one output vector this thread owns in every tile
+template <typename Acc>
+__device__ __forceinline__ void consume_pool_phase(const FlatGeo& g, const PoolGeo& pg, BulkRing& r, const unsigned char* stage_base,
+                                                   RingPos& pos, Acc& acc) {
+  const unsigned t = threadIdx.x;
+  const bool lane0 = (t & 31u) == 0u;
+  const bool mine = t < (pg.wt / 2u) * g.cv;
+  const unsigned j = t / g.cv, col = t - j * g.cv;
+  const unsigned my = smem_u32(stage_base) + ((2u * j) * g.cv + col) * 16u;
+  const unsigned nxt = g.cv * 16u;
+  for (;;) {
+    mbar_wait(smem_u32(&r.full[pos.slot]), pos.parity);
+    const StageMeta m = r.meta[pos.slot];
+    if (m.count != 0u && mine) {
+      const unsigned addr = my + pos.slot * kStageBytes;
+      float4 a0, a1, b0, b1;
+      lds_vec(addr, a0);
+      lds_vec(addr + nxt, a1);
+      lds_vec(addr + kPairOffset, b0);
+      lds_vec(addr + kPairOffset + nxt, b1);
+      acc.pooled(a0, a1, b0, b1, m.start + t);
+    }
+    __syncwarp();
+    if (lane0) mbar_arrive(smem_u32(&r.empty[pos.slot]));
+    pos.next();
+    if (m.count == 0u) break;
+  }
+}
+
 // ---- consumer side (512 threads) -----------------------------------------------------------------------------------------
 // acc.consume(x, v) for every vector this thread owns (v = its index from the tensor base) and acc.stage_end(meta) once per
 // stage (where accumulators fold their fp32 partial sums into float64 every few stages), until the end marker.

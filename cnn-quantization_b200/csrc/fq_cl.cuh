@@ -303,6 +303,30 @@ struct ClApply {
     else
       one<false, false>(v, v, off);
   }
+  // 2x2 max pooling in front of the leaf (consume_pool_phase): the leaf is monotone, so quantize(max) == max(quantize);
+  // torch's NaN rule (a NaN in the window wins); the bias is a per-channel constant and commutes with the max as well
+  template <bool FAST>
+  __device__ __forceinline__ void pooled_one(const float4& a0, const float4& a1, const float4& b0, const float4& b1, unsigned off) {
+    auto mx = [](float p, float q) { return (q > p || q != q) ? q : p; };
+    const float m[4] = {mx(mx(mx(a0.x, a1.x), b0.x), b1.x), mx(mx(mx(a0.y, a1.y), b0.y), b1.y),
+                        mx(mx(mx(a0.z, a1.z), b0.z), b1.z), mx(mx(mx(a0.w, a1.w), b0.w), b1.w)};
+    float y[4], gq;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      Divisor dv;
+      dv.s = q[i].a;
+      dv.r = r[i];
+      dv.fast = FAST;
+      y[i] = leaf_apply<LEAF, FAST>(__fadd_rn(m[i], bias[i]), q[i], dv, 0.f, gq);
+    }
+    st_tensor(reinterpret_cast<float4*>(A.pool_out) + off, make_float4(y[0], y[1], y[2], y[3]));
+  }
+  __device__ __forceinline__ void pooled(const float4& a0, const float4& a1, const float4& b0, const float4& b1, unsigned off) {
+    if (fast)
+      pooled_one<true>(a0, a1, b0, b1, off);
+    else
+      pooled_one<false>(a0, a1, b0, b1, off);
+  }
   // the residual comes through the ring next to x (consume_pair_phase)
   __device__ __forceinline__ void consume2(const float4& v, const float4& rv, unsigned off) {
     if (rquant) {
@@ -601,7 +625,9 @@ __device__ __noinline__ void cl_phase_apply(const FusedArgs& A, ClCtx& cx, const
   ClApply<LEAF, HIST> ap{A, hist};
   ap.init(cx.c0, cx.active, lp);
   RingPos pos = cx.pos;
-  if (A.residual) {
+  if (A.pool.tiles) {
+    consume_pool_phase(g, A.pool, *cx.ring, cx.stages, pos, ap);
+  } else if (A.residual) {
     const FlatGeo h = half_geo(g);
     consume_pair_phase(h, *cx.ring, cx.stages, pos, ap);
   } else {
@@ -684,7 +710,9 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_kernel(con
       }
       if (!A.stats_only) {
         mbar_wait(smem_u32(&phase_go[1]), 0u);
-        if (A.residual)
+        if (A.pool.tiles)
+          produce_pool_phase(g, A.pool, src, &A.sync->unit_counter[2], all, ring, stages, pos);
+        else if (A.residual)
           produce_phase<!DEV, true>(half_geo(g), src, &A.sync->unit_counter[2], all, ring, stages, pos,
                                     reinterpret_cast<const float4*>(A.residual));
         else

@@ -56,6 +56,8 @@ struct FusedArgs {
   float* out;
   const float* residual;  // channels-last kernel: optional tensor added to the quantized values (fqb200_desc.residual)
   int residual_relu;      // ... followed by max(., 0)
+  PoolGeo pool;           // channels-last kernel: 2x2 / stride-2 max pooling inside the apply phase (pool.tiles != 0) ...
+  float* pool_out;        // ... into this [N][H/2][W/2][C] tensor (`out` is not written)
   const float* residual_stats;  // ... quantized on the fly with the parameters of this exported table first
   const float* residual_bias;   // ... after this bias has been added to it
   const float* bias;   // optional per-group addend applied to x before everything else (folded-BN conv bias)
@@ -1901,7 +1903,7 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   if (rc != FQB200_OK) return rc;
   if (d->outer == 0 || d->groups == 0 || d->inner == 0) return FQB200_OK;
   if (!in) return fail(FQB200_ERR_INVALID, "null input%s");
-  if (!out && !d->stats_only) return fail(FQB200_ERR_INVALID, "null output%s");
+  if (!out && !d->stats_only && !d->pool) return fail(FQB200_ERR_INVALID, "null output%s");
   if (d->stats_only && !d->out_stats) return fail(FQB200_ERR_INVALID, "stats_only needs out_stats%s");
   DeviceInfo* di = nullptr;
   rc = get_device(&di);
@@ -1909,7 +1911,7 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   Plan pl;
   if (d->bias && d->bias_period == 0 && d->scope == FQB200_SCOPE_GROUP_MEAN)
     return fail(FQB200_ERR_UNSUPPORTED, "a per-group bias needs groups = channels (scope GROUP or TENSOR); use bias_period%s");
-  const bool can_vec = aligned16(in) && (d->stats_only || aligned16(out));
+  const bool can_vec = aligned16(in) && (d->stats_only || d->pool || aligned16(out));
   fqb::RowsGeo rows_geo;
   memset(&rows_geo, 0, sizeof(rows_geo));
   if (d->channels_last) {
@@ -1965,6 +1967,38 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
     return fail(FQB200_ERR_INVALID, "residual_bias needs residual_stats (a bias on a plain addend can be folded by the caller)%s");
   if (d->residual && ((!d->channels_last && pl.mode != 3) || d->stats_only || !aligned16(d->residual)))
     return fail(FQB200_ERR_UNSUPPORTED, "residual: channels-last or per-sample / per-tensor min-max apply launches, 16-byte aligned%s");
+  memset(&A.pool, 0, sizeof(A.pool));
+  A.pool_out = nullptr;
+  if (d->pool) {
+    if (d->pool != 2 || !d->channels_last || d->stats_only || d->residual || d->out_hist || !d->pool_out || !aligned16(d->pool_out))
+      return fail(FQB200_ERR_UNSUPPORTED, "pool: 2 (2x2 stride 2) on channels-last apply launches without residual / histogram, 16-byte aligned pool_out%s");
+    const int64_t h = d->pool_h, w = d->pool_w;
+    if (h < 2 || w < 2 || w % 2 != 0 || h * w != d->inner)
+      return fail(FQB200_ERR_UNSUPPORTED, "pool: pool_h * pool_w must be `inner`, W even%s");
+    const unsigned cv = pl.flat.cv, half_v = fqb::kStageVec * fqb::kConsumers / 2u;
+    unsigned wt = 0;
+    for (int64_t cand = w; cand >= 2; cand -= 2)
+      if (w % cand == 0 && static_cast<uint64_t>(cand) * cv <= half_v && static_cast<uint64_t>(cand / 2) * cv <= pl.flat.stride) {
+        wt = static_cast<unsigned>(cand);
+        break;
+      }
+    if (!wt) return fail(FQB200_ERR_UNSUPPORTED, "pool: no tile width fits%s");
+    const uint64_t tiles = static_cast<uint64_t>(d->outer) * static_cast<uint64_t>(h / 2) * static_cast<uint64_t>(w / wt);
+    if (tiles >= 0xfffffff0ull) return fail(FQB200_ERR_UNSUPPORTED, "pool: too many tiles%s");
+    uint64_t unit_tiles = tiles / (kUnitsPerCta * static_cast<uint64_t>(pl.grid));
+    if (unit_tiles < 2) unit_tiles = 2;
+    if (unit_tiles > 64) unit_tiles = 64;
+    A.pool.h = static_cast<unsigned>(h);
+    A.pool.w = static_cast<unsigned>(w);
+    A.pool.wt = wt;
+    A.pool.tiles_per_row = static_cast<unsigned>(w / wt);
+    A.pool.row_pairs = static_cast<unsigned>(h / 2);
+    A.pool.tiles = static_cast<unsigned>(tiles);
+    A.pool.unit_tiles = static_cast<unsigned>(unit_tiles);
+    A.pool.units = static_cast<unsigned>((tiles + unit_tiles - 1) / unit_tiles);
+    A.pool.ow = static_cast<unsigned>(w / 2);
+    A.pool_out = d->pool_out;
+  }
   A.out_stats = d->out_stats;
   A.bias = d->bias;
   A.hist = d->out_hist;

@@ -107,12 +107,13 @@ class IntQuantizer(object):
         self._bca = None
         self._residual, self._residual_used = None, False
         self._defer, self._deferred = False, None
+        self._pool, self._pooled = None, False
 
     # ------------------------------------------------------------------------------------------
     # dispatch (int_quantizer.py:92-122)
     # ------------------------------------------------------------------------------------------
     def __call__(self, tensor, id, tag="", stat_id=None, override_att=None, weight_correction=None, bias=None,
-                 relu_follows=False, bias_correct=None, residual=None, defer=False):
+                 relu_follows=False, bias_correct=None, residual=None, defer=False, pool=None):
         """Extensions used by this package's manager (all default to the reference behaviour):
         ``bias_correct`` (None = off, else the "ReLU follows" flag of the call site): the activation bias correction of
         Conv2dWithId.forward (`-bca`, inference_quantization_manager.py:180-196) is applied by the quantizer itself - inside
@@ -126,6 +127,10 @@ class IntQuantizer(object):
         tensor comes back UNQUANTIZED, tagged ``_fq_deferred = (parameter table, bias)``, and the call that takes it as
         ``residual`` quantizes it on the fly in its apply phase.  The caller must finish a deferred tensor itself
         (call again without ``defer``) when that other call did not fuse;
+        ``pool=(2, 2)`` / ``(2, 2, "direct")``: a 2x2 / stride-2 max pooling (floor mode, no padding) is the only consumer of
+        the result - directly, or behind a ReLU that this call's ``relu_follows`` lets the caller skip: where the launch can do it
+        (per-channel quantization of a channels-last tensor with an even width) the POOLED quantized tensor comes back,
+        tagged ``_fq_pooled`` - the leaf is monotone, so pooling first is bit-identical - and the caller skips its pooling;
         ``relu_follows``: the caller will skip the ReLU that follows when the result is tagged ``_fq_nonneg`` - set on
         every result of a positive (half-range / force-positive) range, where offset 0 gives zero point 0 and every value
         is q * scale >= 0; the compiled leaf's empty-range pass-through then returns max(x, 0) (fqb200_desc.relu_passthrough);
@@ -140,6 +145,7 @@ class IntQuantizer(object):
         self._bca = bias_correct
         self._residual, self._residual_used = residual, False
         self._defer, self._deferred = bool(defer), None
+        self._pool, self._pooled = (tuple(pool) if pool is not None else None), False
         try:
             self._unsupported(stat_id)
             if bias is not None and not self._bias_fusable(tensor):
@@ -174,7 +180,10 @@ class IntQuantizer(object):
             res._fq_nonneg = res._version   # the fused epilogue ends with the ReLU
         if self._deferred is not None:
             res._fq_deferred = self._deferred
+        if self._pooled:
+            res._fq_pooled = True
         self._defer, self._deferred = False, None
+        self._pool, self._pooled = None, False
         self._relu_follows = False
         self._bca = None
         self._residual, self._residual_used = None, False
@@ -325,6 +334,13 @@ class IntQuantizer(object):
                 self.last_stats = stats
             self._deferred = (stats, kw.get("bias"))
             return tensor
+        # (a ReLU between quantizer and pooling must be one the caller is going to skip: it has to hand the SAME tensor on)
+        if (self._pool is not None and self._pool[:2] == (2, 2) and (self._relu_follows or self._pool[2:] == ("direct",))
+                and channels_last and not rows and kw.get("hist") is None and self._residual is None and not self._defer
+                and tensor.dim() == 4 and tensor.shape[2] >= 2 and tensor.shape[3] >= 2 and tensor.shape[3] % 2 == 0):
+            kw.pop("out", None)   # only the pooled tensor is written
+            self._pooled = True
+            return self._fused(tensor, layout, channels_last=True, pool=(2, 2), **kw)
         return self._fused(tensor, layout, channels_last=channels_last, **kw,
                            **self._residual_kw(tensor, channels_last, rows=rows, bias=kw.get("bias")))
 

@@ -163,6 +163,12 @@ def _maxpool_forward(pool):
     orig = type(pool).forward
 
     def forward(x):
+        pending = pool.__dict__.pop("_fq_pending", False)
+        if getattr(x, "_fq_pooled", False):
+            del x._fq_pooled   # consumed: the tensor object lives on (the pooling call site quantizes it in place)
+            return x   # the quantization launch of the convolution in front has pooled already (IntQuantizer ``pool``)
+        if pending:
+            raise RuntimeError("a tensor pooled inside its quantization launch lost its tag on the way to %r" % (pool,))
         if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and not x.requires_grad and not pool.return_indices
                 and not pool.ceil_mode and pool.dilation in (1, (1, 1)) and x.shape[1] % 4 == 0 and not x.is_contiguous()
                 and x.is_contiguous(memory_format=torch.channels_last)):
@@ -263,6 +269,8 @@ class QuantizationManagerInference(object):
         self.fuse_residual_into_quant = self._native
         # ... and the shortcut convolution of a down-sampling block runs statistics-only, quantized on the fly there
         self.defer_shortcut = self._native
+        # a 2x2 / stride-2 max pooling behind a hooked convolution (+ skipped ReLU) runs inside that convolution's launch
+        self.fuse_pool_into_quant = self._native
         # channels-last max pooling in front of the `activation_pooling` call site runs on this package's kernel
         self.fast_maxpool = self._native
         self.inplace_activations = self._native
@@ -291,6 +299,7 @@ class QuantizationManagerInference(object):
         self.record = False
         self._hooks = []
         self._patched = []
+        self._pool_marked = []
         self._debiased = []
         self._orig_init = {}
         self._counters = {}
@@ -414,6 +423,24 @@ class QuantizationManagerInference(object):
                 if type(m) in (BasicBlock, Bottleneck) and type(getattr(m, "relu", None)) is nn.ReLU:
                     m.forward = _residual_block_forward(m, type(m) is Bottleneck, self)
                     self._patched.append(m)
+        if self.fuse_pool_into_quant and self.fast_maxpool and self.skip_redundant_relu and self.enabled and self.stats_mode == "no":
+            for seq in model.modules():
+                if not isinstance(seq, nn.Sequential):
+                    continue
+                kids = list(seq.children())
+                for i, conv in enumerate(kids):
+                    if type(conv) is not nn.Conv2d:
+                        continue
+                    nxt = kids[i + 1:i + 3]
+                    direct = len(nxt) >= 1 and type(nxt[0]) is nn.MaxPool2d
+                    pm = nxt[0] if direct else (nxt[1] if len(nxt) == 2 and type(nxt[0]) is nn.ReLU and type(nxt[1]) is nn.MaxPool2d else None)
+                    if pm is None:
+                        continue
+                    two = lambda v: (v, v) if isinstance(v, int) else tuple(v)
+                    if (two(pm.kernel_size) == (2, 2) and two(pm.stride if pm.stride is not None else pm.kernel_size) == (2, 2)
+                            and two(pm.padding) == (0, 0) and two(pm.dilation) == (1, 1) and not pm.ceil_mode and not pm.return_indices):
+                        conv._fq_pool_module = (pm, direct)
+                        self._pool_marked.append(conv)
         for m in model.modules():
             if self.fast_maxpool and self.enabled and type(m) is nn.MaxPool2d:
                 m.forward = _maxpool_forward(m)
@@ -452,6 +479,9 @@ class QuantizationManagerInference(object):
         for m in self._patched:
             m.__dict__.pop("forward", None)
         self._patched = []
+        for m in self._pool_marked:
+            m.__dict__.pop("_fq_pool_module", None)
+        self._pool_marked = []
         for m in self._debiased:
             param = m._fq_bias_param
             param.data = m._fq_bias.data   # follows the module if it moved / changed dtype while attached
@@ -484,6 +514,13 @@ class QuantizationManagerInference(object):
         residual = m.__dict__.get("_fq_residual")
         if residual is not None and self._native and tag == "activation":
             extra["residual"] = residual
+        pm = m.__dict__.get("_fq_pool_module")
+        if pm is not None and self._native and tag == "activation" and self.stats_mode == "no" and (pm[1] or extra.get("relu_follows")):
+            res = self.quantize_instant(out, activation_id, tag, stat_id=None, half_range=half_range, verbose=self.verbose,
+                                        pool=(2, 2, "direct") if pm[1] else (2, 2), **extra)
+            if getattr(res, "_fq_pooled", False):
+                pm[0]._fq_pending = True   # the pooling module must find the tag (it raises otherwise)
+            return res
         if m.__dict__.get("_fq_defer") and self._native and tag == "activation" and self.stats_mode != "use":
             res = self.quantize_instant(out, activation_id, tag, stat_id=None, half_range=half_range, verbose=self.verbose,
                                         defer=True, **extra)

@@ -227,7 +227,7 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
           bit_alloc_round=True, bit_alloc_target=None, mt_target=0.0, mt_clip=False, bias_corr=False,
           var_corr=False, stats_only=False, want_stats=False, out=None, bias=None, bias_period=0, hist=None,
           channels_last=False, any_dense_format=False, debug_stamps=None, relu_passthrough=False, hist_offset=0,
-          hist_clamped=None, residual=None, residual_relu=False, residual_stats=None, residual_bias=None):
+          hist_clamped=None, residual=None, residual_relu=False, residual_stats=None, residual_bias=None, pool=None):
     """C ABI fqb200_fused: statistics -> parameters -> quantize/dequantize in one launch.
 
     Returns ``out`` (or ``(out, stats)`` with ``want_stats``; ``stats`` alone with ``stats_only``), where
@@ -302,6 +302,15 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
             d.residual_bias = residual_bias.data_ptr()
     elif residual_bias is not None:
         raise ValueError("residual_bias needs residual_stats")
+    d.pool, d.pool_h, d.pool_w, d.pool_out = 0, 0, 0, None
+    pooled = None
+    if pool is not None:
+        # a 2x2 / stride-2 max pooling (floor mode) follows and is the only consumer: computed inside the apply phase
+        if tuple(pool) != (2, 2) or not channels_last or stats_only or residual is not None or hist is not None or x.shape[3] % 2:
+            raise ValueError("pool=(2, 2) needs a channels-last launch with an even W and no residual / histogram")
+        n_, c_, h_, w_ = x.shape
+        pooled = torch.empty((n_, c_, h_ // 2, w_ // 2), dtype=x.dtype, device=dev, memory_format=torch.channels_last)
+        d.pool, d.pool_h, d.pool_w, d.pool_out = 2, h_, w_, pooled.data_ptr()
     stats = None
     if want_stats or stats_only:
         stats = torch.zeros((groups, L.STATS_STRIDE), dtype=torch.float32, device=dev)
@@ -309,8 +318,9 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
     else:
         d.out_stats = None
     if x.numel() == 0:
-        return stats if stats_only else ((x.clone(), stats) if want_stats else x.clone())
-    kout, uout = (None, None) if stats_only else _resolve_out(x, out)
+        res = pooled if pooled is not None else x.clone()
+        return stats if stats_only else ((res, stats) if want_stats else res)
+    kout, uout = (None, None) if (stats_only or pooled is not None) else _resolve_out(x, out)
     with torch.cuda.device(dev):
         stream = _stream_handle(dev)
         need = lib.fqb200_workspace_bytes(ctypes.byref(d))
@@ -323,11 +333,15 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
         bpe = (8 if two_pass else 4) + (0 if stats_only else 8)
         if residual is not None:   # + the residual read of the fused block epilogue (the write is the apply's own)
             mode, bpe = mode + "r", bpe + 4
+        if pooled is not None:     # the apply phase reads x and writes a quarter of it
+            mode, bpe = mode + "p", bpe - 3
         with _Timed(mode, x.numel(), bpe, "%dx%dx%d" % (outer, groups, inner)):
             L.check(lib.fqb200_fused(ctypes.byref(d), x.data_ptr(), kout.data_ptr() if kout is not None else None,
                                      ws.data_ptr(), ws.numel(), stream))
     if stats_only:
         return stats
+    if pooled is not None:
+        return (pooled, stats) if want_stats else pooled
     out = _finish_out(kout, uout)
     return (out, stats) if want_stats else out
 

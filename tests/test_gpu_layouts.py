@@ -324,3 +324,50 @@ def test_deferred_shortcut_is_quantized_on_the_fly_int8(fq, cl):
     y = q(x.clone(), "a", "activation", bias=bias, residual=d)
     assert getattr(y, "_fq_residual_fused", False)
     assert torch.equal(y, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c,h,w", [(64, 14, 14), (96, 10, 12), (512, 7, 6), (2048, 4, 4), (128, 28, 56), (24, 9, 2)])
+def test_max_pooling_inside_the_quantization_launch(fq, c, h, w):
+    """fqb200_desc.pool: quantize + 2x2/stride-2 max pooling in one launch == the launch without it, then torch's pooling.
+    Per-channel min/max statistics are order-independent, so that case must be bit-equal; the Laplace case may differ in
+    the vanishing fraction of elements its atomically combined sums move by one grid step."""
+    import torch.nn.functional as F
+    from cnn_quantization_b200 import _lib as L, ops
+    n = 5
+    g = torch.Generator(device="cuda").manual_seed(c + h)
+    x = (torch.randn(n, c, h, w, device="cuda", generator=g) * 1.3 + 0.4).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(c, device="cuda", generator=g) * 0.2
+    lay = (n, c, h * w)
+    for kw, exact in ((dict(range_mode=L.RANGE_MINMAX, num_bits=4), True),
+                      (dict(range_mode=L.RANGE_MINMAX, num_bits=8, positive=True, bias=bias), True),
+                      (dict(range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True, bias=bias, positive=True), False)):
+        full = ops.fused(x, lay, channels_last=True, **kw)
+        got = ops.fused(x, lay, channels_last=True, pool=(2, 2), **kw)
+        want = F.max_pool2d(full, 2)
+        assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+        if exact:
+            assert torch.equal(got, want)
+        else:
+            frac, _ = fq_mismatch(got.cpu().numpy(), want.cpu().numpy())
+            assert frac <= 2e-3
+    # a NaN in a window wins, like torch's pooling
+    xn = x.clone()
+    xn[0, 1, 0, 1] = float("nan")
+    got = ops.fused(xn, lay, channels_last=True, pool=(2, 2), range_mode=L.RANGE_MINMAX, num_bits=4)
+    want = F.max_pool2d(ops.fused(xn, lay, channels_last=True, range_mode=L.RANGE_MINMAX, num_bits=4), 2)
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    with pytest.raises(ValueError):
+        ops.fused(x[..., :w - 1].contiguous(memory_format=torch.channels_last), (n, c, h * (w - 1)), channels_last=True, pool=(2, 2))
+    # through the quantizer: only behind a positive range (the ReLU in between is then skipped) or directly
+    q = fq.int_quantizer("int4", params(clipping="laplace", pcq_act=True, bit_alloc_act=True))
+    q.half_range = True
+    y = q(x.clone(), "conv1_activation", "activation", bias=bias, relu_follows=True, pool=(2, 2))
+    assert getattr(y, "_fq_pooled", False) and y.shape == (n, c, h // 2, w // 2) and y._fq_nonneg == y._version
+    q.half_range = False
+    y = q(x.clone(), "conv1_activation", "activation", bias=bias, relu_follows=True, pool=(2, 2))
+    assert not getattr(y, "_fq_pooled", False) and y.shape == x.shape
+    y = q(x.clone(), "conv1_activation", "activation", bias=bias, pool=(2, 2, "direct"))
+    assert getattr(y, "_fq_pooled", False)
+    y = q(x.contiguous().clone(), "conv1_activation", "activation", bias=bias, pool=(2, 2, "direct"))   # NCHW: not fused
+    assert not getattr(y, "_fq_pooled", False) and y.shape == x.shape

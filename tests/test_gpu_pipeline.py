@@ -193,6 +193,36 @@ def test_pipeline_extensions_do_not_change_results(config):
     assert torch.equal(a, b)
 
 
+def test_vgg_pooling_runs_inside_the_quantization_launches():
+    """VGG-16 W4A4 on channels-last memory: the five max poolings run inside the launches of the convolutions in front of
+    them ("Dp"), no pooling kernel is left, and the logits agree with the run that keeps them separate."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from cnn_quantization_b200 import ops, pipeline
+    x, _ = pipeline.synthetic_batch(4, seed=13, hw=64)
+    xin = x.cuda().contiguous(memory_format=torch.channels_last)
+    outs = []
+    for fuse in (True, False):
+        model, qm = pipeline.build_quantized_model("vgg16_w4a4", "cuda", channels_last=True)
+        if not fuse:
+            for m in model.modules():
+                m.__dict__.pop("_fq_pool_module", None)
+        qm.record = True
+        ops.profile_reset(enable=True)
+        with torch.no_grad():
+            outs.append(model(xin.clone()).float().cpu().numpy())
+        prof = ops.profile_collect()
+        ops.profile_reset(enable=False)
+        qm.detach()
+        assert len(qm.calls) == 21
+        pooled = sum(v["launches"] for k, v in prof["modes"].items() if k.endswith("p"))
+        assert pooled == (5 if fuse else 0)
+        assert prof["modes"].get("P", {"launches": 0})["launches"] == (0 if fuse else 5)
+    a, b = outs
+    cos = float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b)))
+    assert cos > 0.999, cos
+
+
 def test_int8_channels_last_block_epilogue_is_exact():
     """configs[1] on channels-last memory: the 16 block epilogues run inside the per-sample min/max launches ("Br") and
     the logits are bit-identical to the run that keeps them as separate add + ReLU kernels."""

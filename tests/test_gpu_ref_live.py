@@ -252,6 +252,7 @@ def test_layerwise_differential_vs_live_reference(ref, fq, config, batch, channe
 
     boundary = []   # (layer, channel, our bits, reference bits): bit-allocation rounding-boundary cases, see below
     fused_blocks = []   # layers whose launch also did the block's residual add + ReLU
+    pooled_layers = []  # layers whose launch also did the max pooling behind them
     deferred, deferred_used = {}, []   # shortcut convolutions quantized inside the launch of the block's last convolution
 
     def spy(tensor, id, tag="", stat_id=None, half_range=False, override_att=None, verbose=False, **extra):
@@ -281,6 +282,10 @@ def test_layerwise_differential_vs_live_reference(ref, fq, config, batch, channe
             deferred[id] = (out, want, excl)
             return out
         excl_res = []
+        if getattr(out, "_fq_pooled", False):
+            # the 2x2 max pooling behind this convolution ran inside our launch: pool the reference's quantized tensor
+            pooled_layers.append(id)
+            want = torch.nn.functional.max_pool2d(want, 2)
         if getattr(out, "_fq_residual_fused", False):
             # the block's residual add + ReLU ran inside our quantization launch: apply the block's own two torch ops
             # (torchvision Bottleneck.forward: out += identity; out = relu(out)) to the reference's quantized tensor
@@ -333,6 +338,7 @@ def test_layerwise_differential_vs_live_reference(ref, fq, config, batch, channe
         "mean_flip_fraction": sum(r[3] for r in rows) / len(rows),
         "worst_layer": max(rows, key=lambda r: r[3])[0],
         "launches_with_fused_block_epilogue": len(fused_blocks),
+        "launches_with_fused_max_pooling": len(pooled_layers),
         "shortcuts_quantized_inside_that_launch": len(deferred_used),
         "bit_allocation_boundary_channels": ["%s ch %d: %g vs %g bits" % b for b in boundary]}
     _dump_report()
