@@ -371,3 +371,51 @@ def test_max_pooling_inside_the_quantization_launch(fq, c, h, w):
     assert getattr(y, "_fq_pooled", False)
     y = q(x.contiguous().clone(), "conv1_activation", "activation", bias=bias, pool=(2, 2, "direct"))   # NCHW: not fused
     assert not getattr(y, "_fq_pooled", False) and y.shape == x.shape
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,variant", [((512, 256, 56, 56), "epilogue"), ((512, 256, 56, 56), "deferred"),
+                                           ((512, 2048, 7, 7), "deferred"), ((512, 64, 224, 224), "pool"),
+                                           ((512, 512, 14, 14), "pool"), ((512, 256, 56, 56), "int8 deferred")])
+def test_fused_variants_at_baseline_sizes(fq, shape, variant):
+    """BASELINE.json sizes (batch 512): the launches that carry a block epilogue, a deferred shortcut or the pooling are
+    the composition of the plain launch - which tests/test_gpu_ref_live.py pins against the live reference at these sizes -
+    with torch's add / ReLU / max_pool2d.  Multi-unit, multi-stage, 64-bit-offset paths of the pair / tile producers."""
+    import torch.nn.functional as F
+    from cnn_quantization_b200 import _lib as L, ops
+    n, c, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(h * c)
+    scale = torch.linspace(0.3, 2.5, c, device="cuda").view(1, c, 1, 1)
+    x = (torch.randn(shape, device="cuda", generator=g) * scale).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(c, device="cuda", generator=g) * 0.1
+    lay = (n, c, h * w)
+    if variant == "int8 deferred":
+        kw = dict(range_mode=L.RANGE_MINMAX, leaf=L.LEAF_COMPILED, num_bits=8, scope=L.SCOPE_GROUP_MEAN, any_dense_format=True,
+                  bias=bias, bias_period=-c)
+        lay = (1, n, c * h * w)
+    else:
+        kw = dict(range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True, channels_last=True, bias=bias)
+    if variant == "pool":
+        want = F.max_pool2d(ops.fused(x, lay, positive=True, **kw), 2)
+        got = ops.fused(x, lay, positive=True, pool=(2, 2), **kw)
+    else:
+        r = (torch.randn(shape, device="cuda", generator=g) * 0.8).contiguous(memory_format=torch.channels_last)
+        qx = ops.fused(x, lay, **kw)
+        if "deferred" in variant:
+            rbias = torch.randn(c, device="cuda", generator=g) * 0.1
+            kwr = dict(kw, bias=rbias)
+            qr = ops.fused(r, lay, **kwr)
+            stats = ops.fused(r, lay, stats_only=True, **kwr)
+            got = ops.fused(x, lay, residual=r, residual_relu=True, residual_stats=stats, residual_bias=rbias, **kw)
+            want = torch.relu_(qx.add_(qr))
+            del qr
+        else:
+            got = ops.fused(x, lay, residual=r, residual_relu=True, **kw)
+            want = torch.relu_(qx.add_(r))
+        del r
+    # (two launches combine their float64 sums in different orders: parameters agree to ~1e-7, values to a few ulps; a grid
+    # step is 1e-2 .. 1e-1 here, so anything beyond the tolerance is a real one-step difference)
+    bad = (got - want).abs() > 1e-5 * torch.maximum(got.abs(), want.abs()) + 2e-6
+    frac = float(bad.float().mean())
+    print("%s %s: fraction of elements that differ from the composition %.3g" % (variant, shape, frac))
+    assert frac <= (0.0 if variant == "int8 deferred" else 1e-4)
