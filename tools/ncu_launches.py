@@ -52,8 +52,11 @@ for k, (n, t, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 ours = sum(a[1] for k, a in agg.items() if k.startswith("fq_"))
 print("fq_* kernels: %.1f %% of the summed kernel time (%.3f ms of %.3f ms)" % (100 * ours / total, ours / 1e6, total / 1e6))
 if key:
+    pat = r"fq_cl_kernel<\(int\)0, \(bool\)1|fq_cl_kernel<0, true|fq_cl_kernel<0, 1"
+    if not key.endswith("/nhwc"):
+        pat += r"|fq_fused_kernel<4, 0, true|fq_fused_kernel<4, 0, 1"
     fused = [(m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)) for lid, m in launch.items()
-             if re.search(r"fq_cl_kernel<\(int\)0, \(bool\)1|fq_cl_kernel<0, true|fq_cl_kernel<0, 1|fq_fused_kernel<4, 0, true|fq_fused_kernel<4, 0, 1", names[lid])]
+             if re.search(pat, names[lid])]
     if fused:
         out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
         table = json.load(open(out)) if os.path.exists(out) else {}
