@@ -294,7 +294,114 @@ struct PoolGeo {
   unsigned tiles;          // n * row_pairs * tiles_per_row
   unsigned unit_tiles, units;
   unsigned ow;             // w / 2
+  unsigned kind;           // 2: 2x2 / stride 2 (above); 3: 3x3 / stride 2 / padding 1 (below)
 };
+
+// kind 3 (the ResNet stem): a tile is ONE output row x `wt` OUTPUT pixels; it needs the three input rows 2*oh-1 .. 2*oh+1
+// from input pixel 2*ow0-1 on, 2*wt+1 pixels each: three bulk copies into three regions of region_v = (2*wt+1)*cv vectors
+// (3 * region_v <= one stage).  The row above the image and the pixel left of it do not exist: those copies are skipped /
+// start one pixel later (at the same place in the region) and the tag tells the consumer (bit 0: top row present, bit 1:
+// left pixel present).  H and W are even, so the bottom row and the right pixel always exist.  Neighbouring tiles and rows
+// overlap by one pixel / one row: 1.5 reads per element, most of them L2 hits.
+constexpr unsigned kPoolTop = 1u, kPoolLeft = 2u;
+
+__device__ __forceinline__ void produce_pool3_phase(const FlatGeo& g, const PoolGeo& pg, const float4* src, unsigned* counter,
+                                                    const TicketPlan tp, BulkRing& r, unsigned char* stage_base, RingPos& pos) {
+  const unsigned total = pg.units;
+  unsigned k = 0;
+  auto fetch = [&]() -> unsigned {
+    unsigned long long t;
+    if (k < tp.nstatic)
+      t = tp.first + static_cast<unsigned long long>(k) * tp.step;
+    else
+      t = static_cast<unsigned long long>(tp.dyn_base) + atomicAdd(counter, 1u);
+    ++k;
+    return t < total ? static_cast<unsigned>(t) : 0xffffffffu;
+  };
+  const unsigned row_v = pg.w * g.cv;
+  const unsigned region_v = (2u * pg.wt + 1u) * g.cv;
+  const unsigned per_img = pg.row_pairs * pg.tiles_per_row;   // row_pairs = output rows
+  unsigned cur = fetch();
+  unsigned nxt = (cur != 0xffffffffu) ? fetch() : 0xffffffffu;
+  while (cur != 0xffffffffu) {
+    const unsigned nxt2 = (nxt != 0xffffffffu) ? fetch() : 0xffffffffu;
+    const unsigned t0 = cur * pg.unit_tiles;
+    const unsigned t1 = min(t0 + pg.unit_tiles, pg.tiles);
+    for (unsigned tile = t0; tile < t1; ++tile) {
+      const unsigned n = tile / per_img;
+      const unsigned rem = tile - n * per_img;
+      const unsigned oh = rem / pg.tiles_per_row;
+      const unsigned wi = rem - oh * pg.tiles_per_row;
+      const bool top = oh > 0u, left = wi > 0u;
+      const unsigned skip = left ? 0u : g.cv;                      // vectors of the missing left pixel
+      const unsigned count = region_v - skip;                       // vectors per row piece
+      // first vector of the middle row's piece (input row 2*oh, input pixel 2*wi*wt - 1, clipped)
+      const unsigned mid = (n * pg.h + 2u * oh) * row_v + (2u * wi * pg.wt) * g.cv - (left ? g.cv : 0u);
+      const unsigned o = ((n * pg.row_pairs + oh) * pg.ow + wi * pg.wt) * g.cv;
+      mbar_wait(smem_u32(&r.empty[pos.slot]), pos.parity ^ 1u);
+      r.meta[pos.slot].start = o;
+      r.meta[pos.slot].count = count;
+      r.meta[pos.slot].tag = (top ? kPoolTop : 0u) | (left ? kPoolLeft : 0u);
+      const unsigned bar = smem_u32(&r.full[pos.slot]);
+      mbar_arrive_expect_tx(bar, count * 16u * (top ? 3u : 2u));
+      const unsigned dst = smem_u32(stage_base + pos.slot * kStageBytes) + skip * 16u;
+      if (top) bulk_load(dst, src + mid - row_v, count * 16u, bar);
+      bulk_load(dst + region_v * 16u, src + mid, count * 16u, bar);
+      bulk_load(dst + 2u * region_v * 16u, src + mid + row_v, count * 16u, bar);
+      pos.next();
+    }
+    cur = nxt;
+    nxt = nxt2;
+  }
+  mbar_wait(smem_u32(&r.empty[pos.slot]), pos.parity ^ 1u);
+  r.meta[pos.slot].start = 0u;
+  r.meta[pos.slot].count = 0u;
+  r.meta[pos.slot].tag = 0u;
+  mbar_arrive(smem_u32(&r.full[pos.slot]));
+  pos.next();
+}
+
+// acc.pool_begin(); acc.pool_tap(v) for every tap of the window that exists, in torch's order (rows, then pixels);
+// acc.pool_end(out_vector)
+template <typename Acc>
+__device__ __forceinline__ void consume_pool3_phase(const FlatGeo& g, const PoolGeo& pg, BulkRing& r, const unsigned char* stage_base,
+                                                    RingPos& pos, Acc& acc) {
+  const unsigned t = threadIdx.x;
+  const bool lane0 = (t & 31u) == 0u;
+  const bool mine = t < pg.wt * g.cv;
+  const unsigned j = t / g.cv, col = t - j * g.cv;
+  const unsigned region = (2u * pg.wt + 1u) * g.cv * 16u;
+  const unsigned my = smem_u32(stage_base) + ((2u * j) * g.cv + col) * 16u;   // tap (dy = 0, dx = 0)
+  const unsigned nxt = g.cv * 16u;
+  for (;;) {
+    mbar_wait(smem_u32(&r.full[pos.slot]), pos.parity);
+    const StageMeta m = r.meta[pos.slot];
+    if (m.count != 0u && mine) {
+      const unsigned addr = my + pos.slot * kStageBytes;
+      const bool first = (j != 0u) || (m.tag & kPoolLeft);   // the window's left pixel exists
+      acc.pool_begin();
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        if (dy == 0 && !(m.tag & kPoolTop)) continue;
+        const unsigned row = addr + dy * region;
+        float4 v;
+        if (first) {
+          lds_vec(row, v);
+          acc.pool_tap(v);
+        }
+        lds_vec(row + nxt, v);
+        acc.pool_tap(v);
+        lds_vec(row + 2u * nxt, v);
+        acc.pool_tap(v);
+      }
+      acc.pool_end(m.start + t);
+    }
+    __syncwarp();
+    if (lane0) mbar_arrive(smem_u32(&r.empty[pos.slot]));
+    pos.next();
+    if (m.count == 0u) break;
+  }
+}
 
 __device__ __forceinline__ void produce_pool_phase(const FlatGeo& g, const PoolGeo& pg, const float4* src, unsigned* counter,
                                                    const TicketPlan tp, BulkRing& r, unsigned char* stage_base, RingPos& pos) {

@@ -327,6 +327,38 @@ struct ClApply {
     else
       pooled_one<false>(a0, a1, b0, b1, off);
   }
+  // the same tap by tap (consume_pool3_phase: windows at the image border have fewer taps)
+  float pm[4];
+  __device__ __forceinline__ void pool_begin() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pm[i] = -INFINITY;
+  }
+  __device__ __forceinline__ void pool_tap(const float4& v) {
+    auto mx = [](float p, float q) { return (q > p || q != q) ? q : p; };
+    pm[0] = mx(pm[0], v.x);
+    pm[1] = mx(pm[1], v.y);
+    pm[2] = mx(pm[2], v.z);
+    pm[3] = mx(pm[3], v.w);
+  }
+  template <bool FAST>
+  __device__ __forceinline__ void pool_end_one(unsigned off) {
+    float y[4], gq;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      Divisor dv;
+      dv.s = q[i].a;
+      dv.r = r[i];
+      dv.fast = FAST;
+      y[i] = leaf_apply<LEAF, FAST>(__fadd_rn(pm[i], bias[i]), q[i], dv, 0.f, gq);
+    }
+    st_tensor(reinterpret_cast<float4*>(A.pool_out) + off, make_float4(y[0], y[1], y[2], y[3]));
+  }
+  __device__ __forceinline__ void pool_end(unsigned off) {
+    if (fast)
+      pool_end_one<true>(off);
+    else
+      pool_end_one<false>(off);
+  }
   // the residual comes through the ring next to x (consume_pair_phase)
   __device__ __forceinline__ void consume2(const float4& v, const float4& rv, unsigned off) {
     if (rquant) {
@@ -626,7 +658,10 @@ __device__ __noinline__ void cl_phase_apply(const FusedArgs& A, ClCtx& cx, const
   ap.init(cx.c0, cx.active, lp);
   RingPos pos = cx.pos;
   if (A.pool.tiles) {
-    consume_pool_phase(g, A.pool, *cx.ring, cx.stages, pos, ap);
+    if (A.pool.kind == 3u)
+      consume_pool3_phase(g, A.pool, *cx.ring, cx.stages, pos, ap);
+    else
+      consume_pool_phase(g, A.pool, *cx.ring, cx.stages, pos, ap);
   } else if (A.residual) {
     const FlatGeo h = half_geo(g);
     consume_pair_phase(h, *cx.ring, cx.stages, pos, ap);
@@ -710,7 +745,9 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_kernel(con
       }
       if (!A.stats_only) {
         mbar_wait(smem_u32(&phase_go[1]), 0u);
-        if (A.pool.tiles)
+        if (A.pool.tiles && A.pool.kind == 3u)
+          produce_pool3_phase(g, A.pool, src, &A.sync->unit_counter[2], all, ring, stages, pos);
+        else if (A.pool.tiles)
           produce_pool_phase(g, A.pool, src, &A.sync->unit_counter[2], all, ring, stages, pos);
         else if (A.residual)
           produce_phase<!DEV, true>(half_geo(g), src, &A.sync->unit_counter[2], all, ring, stages, pos,

@@ -1970,20 +1970,33 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   memset(&A.pool, 0, sizeof(A.pool));
   A.pool_out = nullptr;
   if (d->pool) {
-    if (d->pool != 2 || !d->channels_last || d->stats_only || d->residual || d->out_hist || !d->pool_out || !aligned16(d->pool_out))
-      return fail(FQB200_ERR_UNSUPPORTED, "pool: 2 (2x2 stride 2) on channels-last apply launches without residual / histogram, 16-byte aligned pool_out%s");
+    if ((d->pool != 2 && d->pool != 3) || !d->channels_last || d->stats_only || d->residual || d->out_hist || !d->pool_out || !aligned16(d->pool_out))
+      return fail(FQB200_ERR_UNSUPPORTED, "pool: 2 (2x2 stride 2) or 3 (3x3 stride 2 padding 1) on channels-last apply launches without residual / histogram, 16-byte aligned pool_out%s");
     const int64_t h = d->pool_h, w = d->pool_w;
-    if (h < 2 || w < 2 || w % 2 != 0 || h * w != d->inner)
-      return fail(FQB200_ERR_UNSUPPORTED, "pool: pool_h * pool_w must be `inner`, W even%s");
-    const unsigned cv = pl.flat.cv, half_v = fqb::kStageVec * fqb::kConsumers / 2u;
+    if (h < 2 || w < 2 || w % 2 != 0 || h * w != d->inner || (d->pool == 3 && h % 2 != 0))
+      return fail(FQB200_ERR_UNSUPPORTED, "pool: pool_h * pool_w must be `inner`, W even (3x3: H even too)%s");
+    const unsigned cv = pl.flat.cv, stage_v = fqb::kStageVec * fqb::kConsumers;
     unsigned wt = 0;
-    for (int64_t cand = w; cand >= 2; cand -= 2)
-      if (w % cand == 0 && static_cast<uint64_t>(cand) * cv <= half_v && static_cast<uint64_t>(cand / 2) * cv <= pl.flat.stride) {
-        wt = static_cast<unsigned>(cand);
-        break;
-      }
+    uint64_t tiles = 0;
+    if (d->pool == 2) {
+      // tile = 2 rows x wt input pixels: two row pieces in the two halves of a stage, (wt / 2) * cv output vectors
+      for (int64_t cand = w; cand >= 2; cand -= 2)
+        if (w % cand == 0 && static_cast<uint64_t>(cand) * cv <= stage_v / 2u && static_cast<uint64_t>(cand / 2) * cv <= pl.flat.stride) {
+          wt = static_cast<unsigned>(cand);
+          break;
+        }
+      if (wt) tiles = static_cast<uint64_t>(d->outer) * static_cast<uint64_t>(h / 2) * static_cast<uint64_t>(w / wt);
+    } else {
+      // tile = 1 output row x wt output pixels: three row pieces of 2 * wt + 1 input pixels in three regions of a stage
+      const int64_t ow = w / 2;
+      for (int64_t cand = ow; cand >= 1; --cand)
+        if (ow % cand == 0 && 3ull * static_cast<uint64_t>(2 * cand + 1) * cv <= stage_v && static_cast<uint64_t>(cand) * cv <= pl.flat.stride) {
+          wt = static_cast<unsigned>(cand);
+          break;
+        }
+      if (wt) tiles = static_cast<uint64_t>(d->outer) * static_cast<uint64_t>(h / 2) * static_cast<uint64_t>(ow / wt);
+    }
     if (!wt) return fail(FQB200_ERR_UNSUPPORTED, "pool: no tile width fits%s");
-    const uint64_t tiles = static_cast<uint64_t>(d->outer) * static_cast<uint64_t>(h / 2) * static_cast<uint64_t>(w / wt);
     if (tiles >= 0xfffffff0ull) return fail(FQB200_ERR_UNSUPPORTED, "pool: too many tiles%s");
     uint64_t unit_tiles = tiles / (kUnitsPerCta * static_cast<uint64_t>(pl.grid));
     if (unit_tiles < 2) unit_tiles = 2;
@@ -1991,12 +2004,13 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
     A.pool.h = static_cast<unsigned>(h);
     A.pool.w = static_cast<unsigned>(w);
     A.pool.wt = wt;
-    A.pool.tiles_per_row = static_cast<unsigned>(w / wt);
+    A.pool.tiles_per_row = static_cast<unsigned>((d->pool == 2 ? w : w / 2) / wt);
     A.pool.row_pairs = static_cast<unsigned>(h / 2);
     A.pool.tiles = static_cast<unsigned>(tiles);
     A.pool.unit_tiles = static_cast<unsigned>(unit_tiles);
     A.pool.units = static_cast<unsigned>((tiles + unit_tiles - 1) / unit_tiles);
     A.pool.ow = static_cast<unsigned>(w / 2);
+    A.pool.kind = static_cast<unsigned>(d->pool);
     A.pool_out = d->pool_out;
   }
   A.out_stats = d->out_stats;

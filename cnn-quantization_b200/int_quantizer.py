@@ -127,8 +127,8 @@ class IntQuantizer(object):
         tensor comes back UNQUANTIZED, tagged ``_fq_deferred = (parameter table, bias)``, and the call that takes it as
         ``residual`` quantizes it on the fly in its apply phase.  The caller must finish a deferred tensor itself
         (call again without ``defer``) when that other call did not fuse;
-        ``pool=(2, 2)`` / ``(2, 2, "direct")``: a 2x2 / stride-2 max pooling (floor mode, no padding) is the only consumer of
-        the result - directly, or behind a ReLU that this call's ``relu_follows`` lets the caller skip: where the launch can do it
+        ``pool=(2, 2)`` / ``(2, 2, "direct")``: a 2x2 / stride-2 max pooling (floor mode, no padding) - or ``(3, 3)``: 3x3 /
+        stride 2 / padding 1 on even H and W, the ResNet stem - is the only consumer of the result - directly, or behind a ReLU that this call's ``relu_follows`` lets the caller skip: where the launch can do it
         (per-channel quantization of a channels-last tensor with an even width) the POOLED quantized tensor comes back,
         tagged ``_fq_pooled`` - the leaf is monotone, so pooling first is bit-identical - and the caller skips its pooling;
         ``relu_follows``: the caller will skip the ReLU that follows when the result is tagged ``_fq_nonneg`` - set on
@@ -181,7 +181,7 @@ class IntQuantizer(object):
         if self._deferred is not None:
             res._fq_deferred = self._deferred
         if self._pooled:
-            res._fq_pooled = True
+            res._fq_pooled = self._pooled   # 2 / 3: which pooling the launch has done
         self._defer, self._deferred = False, None
         self._pool, self._pooled = None, False
         self._relu_follows = False
@@ -335,12 +335,13 @@ class IntQuantizer(object):
             self._deferred = (stats, kw.get("bias"))
             return tensor
         # (a ReLU between quantizer and pooling must be one the caller is going to skip: it has to hand the SAME tensor on)
-        if (self._pool is not None and self._pool[:2] == (2, 2) and (self._relu_follows or self._pool[2:] == ("direct",))
+        if (self._pool is not None and self._pool[:2] in ((2, 2), (3, 3)) and (self._relu_follows or self._pool[2:] == ("direct",))
                 and channels_last and not rows and kw.get("hist") is None and self._residual is None and not self._defer
-                and tensor.dim() == 4 and tensor.shape[2] >= 2 and tensor.shape[3] >= 2 and tensor.shape[3] % 2 == 0):
+                and tensor.dim() == 4 and tensor.shape[2] >= 2 and tensor.shape[3] >= 2 and tensor.shape[3] % 2 == 0
+                and (self._pool[0] == 2 or (tensor.shape[2] % 2 == 0 and tensor.shape[1] <= 896))):   # 3x3: 9 * C/4 vectors per stage
             kw.pop("out", None)   # only the pooled tensor is written
-            self._pooled = True
-            return self._fused(tensor, layout, channels_last=True, pool=(2, 2), **kw)
+            self._pooled = self._pool[0]
+            return self._fused(tensor, layout, channels_last=True, pool=self._pool[:2], **kw)
         return self._fused(tensor, layout, channels_last=channels_last, **kw,
                            **self._residual_kw(tensor, channels_last, rows=rows, bias=kw.get("bias")))
 

@@ -424,23 +424,33 @@ class QuantizationManagerInference(object):
                     m.forward = _residual_block_forward(m, type(m) is Bottleneck, self)
                     self._patched.append(m)
         if self.fuse_pool_into_quant and self.fast_maxpool and self.skip_redundant_relu and self.enabled and self.stats_mode == "no":
+            two = lambda v: (v, v) if isinstance(v, int) else tuple(v)
+
+            def pool_kind(pm):
+                """2: 2x2 / stride 2; 3: 3x3 / stride 2 / padding 1; None: not a pooling the quantization launch can do"""
+                if type(pm) is not nn.MaxPool2d or two(pm.dilation) != (1, 1) or pm.ceil_mode or pm.return_indices:
+                    return None
+                geo = (two(pm.kernel_size), two(pm.stride if pm.stride is not None else pm.kernel_size), two(pm.padding))
+                return {((2, 2), (2, 2), (0, 0)): 2, ((3, 3), (2, 2), (1, 1)): 3}.get(geo)
+
+            def mark(conv, pm, direct):
+                if type(conv) is nn.Conv2d and pool_kind(pm) is not None:
+                    conv._fq_pool_module = (pm, direct, pool_kind(pm))
+                    self._pool_marked.append(conv)
+
             for seq in model.modules():
-                if not isinstance(seq, nn.Sequential):
-                    continue
-                kids = list(seq.children())
-                for i, conv in enumerate(kids):
-                    if type(conv) is not nn.Conv2d:
-                        continue
-                    nxt = kids[i + 1:i + 3]
-                    direct = len(nxt) >= 1 and type(nxt[0]) is nn.MaxPool2d
-                    pm = nxt[0] if direct else (nxt[1] if len(nxt) == 2 and type(nxt[0]) is nn.ReLU and type(nxt[1]) is nn.MaxPool2d else None)
-                    if pm is None:
-                        continue
-                    two = lambda v: (v, v) if isinstance(v, int) else tuple(v)
-                    if (two(pm.kernel_size) == (2, 2) and two(pm.stride if pm.stride is not None else pm.kernel_size) == (2, 2)
-                            and two(pm.padding) == (0, 0) and two(pm.dilation) == (1, 1) and not pm.ceil_mode and not pm.return_indices):
-                        conv._fq_pool_module = (pm, direct)
-                        self._pool_marked.append(conv)
+                if isinstance(seq, nn.Sequential):   # VGG: Conv2d, [ReLU,] MaxPool2d
+                    kids = list(seq.children())
+                    for i, conv in enumerate(kids):
+                        nxt = kids[i + 1:i + 3]
+                        if len(nxt) >= 1 and type(nxt[0]) is nn.MaxPool2d:
+                            mark(conv, nxt[0], True)
+                        elif len(nxt) == 2 and type(nxt[0]) is nn.ReLU and type(nxt[1]) is nn.MaxPool2d:
+                            mark(conv, nxt[1], False)
+                elif type(seq).__name__ == "ResNet" and all(hasattr(seq, a) for a in ("conv1", "bn1", "relu", "maxpool")):
+                    # torchvision ResNet._forward_impl: conv1 -> bn1 -> relu -> maxpool; bn1 must be folded away
+                    if self.bn_folding and hasattr(seq.bn1, "absorbed") and type(seq.relu) is nn.ReLU:
+                        mark(seq.conv1, seq.maxpool, False)
         for m in model.modules():
             if self.fast_maxpool and self.enabled and type(m) is nn.MaxPool2d:
                 m.forward = _maxpool_forward(m)
@@ -517,7 +527,7 @@ class QuantizationManagerInference(object):
         pm = m.__dict__.get("_fq_pool_module")
         if pm is not None and self._native and tag == "activation" and self.stats_mode == "no" and (pm[1] or extra.get("relu_follows")):
             res = self.quantize_instant(out, activation_id, tag, stat_id=None, half_range=half_range, verbose=self.verbose,
-                                        pool=(2, 2, "direct") if pm[1] else (2, 2), **extra)
+                                        pool=(pm[2], pm[2], "direct") if pm[1] else (pm[2], pm[2]), **extra)
             if getattr(res, "_fq_pooled", False):
                 pm[0]._fq_pending = True   # the pooling module must find the tag (it raises otherwise)
             return res

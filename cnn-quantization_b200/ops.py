@@ -306,11 +306,13 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
     pooled = None
     if pool is not None:
         # a 2x2 / stride-2 max pooling (floor mode) follows and is the only consumer: computed inside the apply phase
-        if tuple(pool) != (2, 2) or not channels_last or stats_only or residual is not None or hist is not None or x.shape[3] % 2:
-            raise ValueError("pool=(2, 2) needs a channels-last launch with an even W and no residual / histogram")
+        # ((3, 3): stride 2, padding 1, H and W even - the ResNet stem)
+        if (tuple(pool) not in ((2, 2), (3, 3)) or not channels_last or stats_only or residual is not None or hist is not None
+                or x.shape[3] % 2 or (tuple(pool) == (3, 3) and x.shape[2] % 2)):
+            raise ValueError("pool=(2, 2) / (3, 3) needs a channels-last launch with an even W (3x3: and H) and no residual / histogram")
         n_, c_, h_, w_ = x.shape
         pooled = torch.empty((n_, c_, h_ // 2, w_ // 2), dtype=x.dtype, device=dev, memory_format=torch.channels_last)
-        d.pool, d.pool_h, d.pool_w, d.pool_out = 2, h_, w_, pooled.data_ptr()
+        d.pool, d.pool_h, d.pool_w, d.pool_out = int(pool[0]), h_, w_, pooled.data_ptr()
     stats = None
     if want_stats or stats_only:
         stats = torch.zeros((groups, L.STATS_STRIDE), dtype=torch.float32, device=dev)
@@ -333,7 +335,7 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
         bpe = (8 if two_pass else 4) + (0 if stats_only else 8)
         if residual is not None:   # + the residual read of the fused block epilogue (the write is the apply's own)
             mode, bpe = mode + "r", bpe + 4
-        if pooled is not None:     # the apply phase reads x and writes a quarter of it
+        if pooled is not None:     # the apply phase reads x (3x3: rows twice, the second time mostly out of L2) and writes a quarter
             mode, bpe = mode + "p", bpe - 3
         with _Timed(mode, x.numel(), bpe, "%dx%dx%d" % (outer, groups, inner)):
             L.check(lib.fqb200_fused(ctypes.byref(d), x.data_ptr(), kout.data_ptr() if kout is not None else None,

@@ -142,12 +142,12 @@ typedef struct fqb200_desc {
                           (stats_only 8 B/element + 4 B/element here instead of 16 + 4) */
   const float* residual_bias; /* optional bias of the residual tensor, added before its quantization; same form as `bias`
                           (per channel; channel-fastest on the min-max launches) */
-  int32_t pool;           /* 0 = none; 2 = a 2x2 / stride-2 max pooling (floor mode, no padding) follows this quantizer and is its
-                          only consumer: channels_last launches compute it INSIDE the apply phase (the leaf is monotone:
+  int32_t pool;           /* 0 = none; 2 = a 2x2 / stride-2 max pooling (floor mode, no padding), 3 = a 3x3 / stride-2 / padding-1
+                          max pooling (H and W even: the ResNet stem) follows this quantizer and is its only consumer: channels_last launches compute it INSIDE the apply phase (the leaf is monotone:
                           quantize(max) == max(quantize), bit for bit) and write only the pooled tensor - `out` is not
                           touched; statistics are those of the full tensor.  Saves the write of the quantized tensor and
                           the pooling kernel's read: 8 of 21 B/element (VGG-16: every convolution in front of a pooling) */
-  int64_t pool_h, pool_w; /* the H and W behind `inner` = H * W (W even) */
+  int64_t pool_h, pool_w; /* the H and W behind `inner` = H * W (W even; pool = 3: H even too) */
   float* pool_out;        /* [outer][H/2][W/2][groups], 16-byte aligned */
   unsigned long long* debug_stamps; /* diagnostics, NULL = off: device array of 16 counters that receives %globaltimer
                           (ns) at the phase boundaries of this launch (slot 0: start, 1 / 5: statistics phases combined,

@@ -419,3 +419,53 @@ def test_fused_variants_at_baseline_sizes(fq, shape, variant):
     frac = float(bad.float().mean())
     print("%s %s: fraction of elements that differ from the composition %.3g" % (variant, shape, frac))
     assert frac <= (0.0 if variant == "int8 deferred" else 1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,c,h,w", [(3, 64, 16, 16), (2, 64, 112, 112), (5, 96, 10, 12), (4, 256, 6, 4), (7, 896, 2, 2),
+                                     (2, 12, 8, 30)])
+def test_stem_max_pooling_inside_the_quantization_launch(fq, n, c, h, w):
+    """fqb200_desc.pool = 3: the 3x3 / stride-2 / padding-1 pooling of the ResNet stem (overlapping windows, image borders)
+    inside the apply phase == the plain launch, then torch's pooling; bit-equal with order-independent statistics."""
+    import torch.nn.functional as F
+    from cnn_quantization_b200 import _lib as L, ops
+    g = torch.Generator(device="cuda").manual_seed(c + h + w)
+    x = (torch.randn(n, c, h, w, device="cuda", generator=g) * 1.3 + 0.4).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(c, device="cuda", generator=g) * 0.2
+    lay = (n, c, h * w)
+    for kw, exact in ((dict(range_mode=L.RANGE_MINMAX, num_bits=4), True),
+                      (dict(range_mode=L.RANGE_MINMAX, num_bits=8, positive=True, bias=bias), True),
+                      (dict(range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True, bias=bias, positive=True), False)):
+        got = ops.fused(x, lay, channels_last=True, pool=(3, 3), **kw)
+        want = F.max_pool2d(ops.fused(x, lay, channels_last=True, **kw), 3, 2, 1)
+        assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+        if exact:
+            assert torch.equal(got, want)
+        else:
+            frac, _ = fq_mismatch(got.cpu().numpy(), want.cpu().numpy())
+            assert frac <= 2e-3
+    xn = x.clone()
+    xn[0, 1, 0, 0] = float("nan")
+    xn[n - 1, 2, h - 1, w - 1] = float("nan")
+    got = ops.fused(xn, lay, channels_last=True, pool=(3, 3), range_mode=L.RANGE_MINMAX, num_bits=4)
+    want = F.max_pool2d(ops.fused(xn, lay, channels_last=True, range_mode=L.RANGE_MINMAX, num_bits=4), 3, 2, 1)
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    q = fq.int_quantizer("int4", params(clipping="laplace", pcq_act=True, bit_alloc_act=True))
+    q.half_range = True
+    y = q(x.clone(), "conv0_activation", "activation", bias=bias, relu_follows=True, pool=(3, 3))
+    assert getattr(y, "_fq_pooled", 0) == 3 and y.shape == (n, c, h // 2, w // 2)
+
+
+@pytest.mark.gpu
+def test_stem_pooling_at_baseline_size(fq):
+    """512x64x112x112 (the ResNet-50 stem at batch 512): fused == composition."""
+    import torch.nn.functional as F
+    from cnn_quantization_b200 import _lib as L, ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = (torch.randn(512, 64, 112, 112, device="cuda", generator=g) * torch.linspace(0.3, 2.5, 64, device="cuda").view(1, 64, 1, 1))
+    x = x.contiguous(memory_format=torch.channels_last)
+    kw = dict(range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True, channels_last=True, positive=True)
+    got = ops.fused(x, (512, 64, 112 * 112), pool=(3, 3), **kw)
+    want = F.max_pool2d(ops.fused(x, (512, 64, 112 * 112), **kw), 3, 2, 1)
+    bad = (got - want).abs() > 1e-5 * torch.maximum(got.abs(), want.abs()) + 2e-6
+    assert float(bad.float().mean()) <= 1e-4

@@ -285,7 +285,7 @@ def test_layerwise_differential_vs_live_reference(ref, fq, config, batch, channe
         if getattr(out, "_fq_pooled", False):
             # the 2x2 max pooling behind this convolution ran inside our launch: pool the reference's quantized tensor
             pooled_layers.append(id)
-            want = torch.nn.functional.max_pool2d(want, 2)
+            want = torch.nn.functional.max_pool2d(want, 2) if out._fq_pooled == 2 else torch.nn.functional.max_pool2d(want, 3, 2, 1)
         if getattr(out, "_fq_residual_fused", False):
             # the block's residual add + ReLU ran inside our quantization launch: apply the block's own two torch ops
             # (torchvision Bottleneck.forward: out += identity; out = relu(out)) to the reference's quantized tensor
