@@ -1291,6 +1291,43 @@ struct RowsApply {
       one<false, true>(v, r, off);
   }
   __device__ __forceinline__ void stage_end(const StageMeta&) {}
+  // max pooling in front of the (monotone) leaf, see ClApply
+  float pm[4];
+  __device__ __forceinline__ void pool_begin() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pm[i] = -INFINITY;
+  }
+  __device__ __forceinline__ void pool_tap(const float4& v) {
+    auto mx = [](float p, float q) { return (q > p || q != q) ? q : p; };
+    pm[0] = mx(pm[0], v.x);
+    pm[1] = mx(pm[1], v.y);
+    pm[2] = mx(pm[2], v.z);
+    pm[3] = mx(pm[3], v.w);
+  }
+  __device__ __forceinline__ void pool_end(unsigned off) {
+    float gq;
+    float4 y;
+    if (dv.fast) {
+      y.x = leaf_apply<FQB200_LEAF_COMPILED, true>(__fadd_rn(pm[0], bias[0]), q, dv, 0.f, gq);
+      y.y = leaf_apply<FQB200_LEAF_COMPILED, true>(__fadd_rn(pm[1], bias[1]), q, dv, 0.f, gq);
+      y.z = leaf_apply<FQB200_LEAF_COMPILED, true>(__fadd_rn(pm[2], bias[2]), q, dv, 0.f, gq);
+      y.w = leaf_apply<FQB200_LEAF_COMPILED, true>(__fadd_rn(pm[3], bias[3]), q, dv, 0.f, gq);
+    } else {
+      y.x = leaf_apply<FQB200_LEAF_COMPILED, false>(__fadd_rn(pm[0], bias[0]), q, dv, 0.f, gq);
+      y.y = leaf_apply<FQB200_LEAF_COMPILED, false>(__fadd_rn(pm[1], bias[1]), q, dv, 0.f, gq);
+      y.z = leaf_apply<FQB200_LEAF_COMPILED, false>(__fadd_rn(pm[2], bias[2]), q, dv, 0.f, gq);
+      y.w = leaf_apply<FQB200_LEAF_COMPILED, false>(__fadd_rn(pm[3], bias[3]), q, dv, 0.f, gq);
+    }
+    st_tensor(reinterpret_cast<float4*>(A.pool_out) + off, y);
+  }
+  __device__ __forceinline__ void pooled(const float4& a0, const float4& a1, const float4& b0, const float4& b1, unsigned off) {
+    pool_begin();
+    pool_tap(a0);
+    pool_tap(a1);
+    pool_tap(b0);
+    pool_tap(b1);
+    pool_end(off);
+  }
 };
 
 __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_rows_kernel(const __grid_constant__ FusedArgs A) {
@@ -1310,7 +1347,11 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_rows_kernel(c
       const TicketPlan all = {2u, blockIdx.x, gridDim.x, 2u * gridDim.x};
       produce_rows_phase<false>(g, rg, src, &A.sync->unit_counter[0], all, ring, fq_dyn, pos);
       if (!A.stats_only) {
-        if (A.residual) {
+        if (A.pool.tiles && A.pool.kind == 3u) {
+          produce_pool3_phase(g, A.pool, src, &A.sync->unit_counter[2], all, ring, fq_dyn, pos);
+        } else if (A.pool.tiles) {
+          produce_pool_phase(g, A.pool, src, &A.sync->unit_counter[2], all, ring, fq_dyn, pos);
+        } else if (A.residual) {
           const FlatGeo h = half_geo(g);
           produce_rows_phase<true, true>(h, half_rows(h, rg), src, &A.sync->unit_counter[2], all, ring, fq_dyn, pos,
                                          reinterpret_cast<const float4*>(A.residual));
@@ -1377,7 +1418,11 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_rows_kernel(c
   if (!A.stats_only) {
     RowsApply ap{A, q, make_divisor(q.a), {bias[0], bias[1], bias[2], bias[3]}};
     ap.init_residual(c0, active);
-    if (A.residual)
+    if (A.pool.tiles && A.pool.kind == 3u)
+      consume_pool3_phase(g, A.pool, ring, fq_dyn, pos, ap);
+    else if (A.pool.tiles)
+      consume_pool_phase(g, A.pool, ring, fq_dyn, pos, ap);
+    else if (A.residual)
       consume_pair_phase(half_geo(g), ring, fq_dyn, pos, ap);
     else
       consume_phase(g, ring, fq_dyn, pos, ap);

@@ -1970,11 +1970,17 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   memset(&A.pool, 0, sizeof(A.pool));
   A.pool_out = nullptr;
   if (d->pool) {
-    if ((d->pool != 2 && d->pool != 3) || !d->channels_last || d->stats_only || d->residual || d->out_hist || !d->pool_out || !aligned16(d->pool_out))
+    // channels-last per-channel launches, or the per-sample / per-tensor min-max launches (rows = samples) on channels-last
+    // memory, which know the channel count from their channel-fastest bias
+    const bool rows_cl = pl.mode == 3 && d->bias && d->bias_period < 0;
+    if ((d->pool != 2 && d->pool != 3) || !(d->channels_last || rows_cl) || d->stats_only || d->residual || d->out_hist || !d->pool_out ||
+        !aligned16(d->pool_out))
       return fail(FQB200_ERR_UNSUPPORTED, "pool: 2 (2x2 stride 2) or 3 (3x3 stride 2 padding 1) on channels-last apply launches without residual / histogram, 16-byte aligned pool_out%s");
     const int64_t h = d->pool_h, w = d->pool_w;
-    if (h < 2 || w < 2 || w % 2 != 0 || h * w != d->inner || (d->pool == 3 && h % 2 != 0))
-      return fail(FQB200_ERR_UNSUPPORTED, "pool: pool_h * pool_w must be `inner`, W even (3x3: H even too)%s");
+    const int64_t hw = rows_cl ? d->inner / -d->bias_period : d->inner;
+    const int64_t images = rows_cl ? d->groups : d->outer;
+    if (h < 2 || w < 2 || w % 2 != 0 || h * w != hw || (d->pool == 3 && h % 2 != 0))
+      return fail(FQB200_ERR_UNSUPPORTED, "pool: pool_h * pool_w must be H * W of the tensor, W even (3x3: H even too)%s");
     const unsigned cv = pl.flat.cv, stage_v = fqb::kStageVec * fqb::kConsumers;
     unsigned wt = 0;
     uint64_t tiles = 0;
@@ -1985,7 +1991,7 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
           wt = static_cast<unsigned>(cand);
           break;
         }
-      if (wt) tiles = static_cast<uint64_t>(d->outer) * static_cast<uint64_t>(h / 2) * static_cast<uint64_t>(w / wt);
+      if (wt) tiles = static_cast<uint64_t>(images) * static_cast<uint64_t>(h / 2) * static_cast<uint64_t>(w / wt);
     } else {
       // tile = 1 output row x wt output pixels: three row pieces of 2 * wt + 1 input pixels in three regions of a stage
       const int64_t ow = w / 2;
@@ -1994,7 +2000,7 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
           wt = static_cast<unsigned>(cand);
           break;
         }
-      if (wt) tiles = static_cast<uint64_t>(d->outer) * static_cast<uint64_t>(h / 2) * static_cast<uint64_t>(ow / wt);
+      if (wt) tiles = static_cast<uint64_t>(images) * static_cast<uint64_t>(h / 2) * static_cast<uint64_t>(ow / wt);
     }
     if (!wt) return fail(FQB200_ERR_UNSUPPORTED, "pool: no tile width fits%s");
     if (tiles >= 0xfffffff0ull) return fail(FQB200_ERR_UNSUPPORTED, "pool: too many tiles%s");

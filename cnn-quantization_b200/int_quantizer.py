@@ -336,12 +336,16 @@ class IntQuantizer(object):
             return tensor
         # (a ReLU between quantizer and pooling must be one the caller is going to skip: it has to hand the SAME tensor on)
         if (self._pool is not None and self._pool[:2] in ((2, 2), (3, 3)) and (self._relu_follows or self._pool[2:] == ("direct",))
-                and channels_last and not rows and kw.get("hist") is None and self._residual is None and not self._defer
+                and ((channels_last and not rows) or (rows and kw.get("bias") is not None and kw.get("bias_period", 0) < 0
+                                                      and tensor.dim() == 4 and not tensor.is_contiguous()
+                                                      and tensor.is_contiguous(memory_format=torch.channels_last)
+                                                      and tensor.shape[1] % 4 == 0 and tensor.shape[1] <= 2048))
+                and kw.get("hist") is None and self._residual is None and not self._defer
                 and tensor.dim() == 4 and tensor.shape[2] >= 2 and tensor.shape[3] >= 2 and tensor.shape[3] % 2 == 0
                 and (self._pool[0] == 2 or (tensor.shape[2] % 2 == 0 and tensor.shape[1] <= 896))):   # 3x3: 9 * C/4 vectors per stage
             kw.pop("out", None)   # only the pooled tensor is written
             self._pooled = self._pool[0]
-            return self._fused(tensor, layout, channels_last=True, pool=self._pool[:2], **kw)
+            return self._fused(tensor, layout, channels_last=channels_last, pool=self._pool[:2], **kw)
         return self._fused(tensor, layout, channels_last=channels_last, **kw,
                            **self._residual_kw(tensor, channels_last, rows=rows, bias=kw.get("bias")))
 

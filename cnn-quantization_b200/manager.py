@@ -214,8 +214,10 @@ def _residual_block_forward(block, bottleneck, manager):
                     if ds_conv is not None:
                         ds_conv.__dict__.pop("_fq_defer", None)
             last_conv._fq_residual = identity
-        out = last_bn(last_conv(out))
-        last_conv.__dict__.pop("_fq_residual", None)
+        try:
+            out = last_bn(last_conv(out))
+        finally:
+            last_conv.__dict__.pop("_fq_residual", None)
         if getattr(out, "_fq_residual_fused", False):
             return out
         if getattr(identity, "_fq_deferred", None) is not None:

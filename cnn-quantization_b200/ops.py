@@ -307,7 +307,10 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
     if pool is not None:
         # a 2x2 / stride-2 max pooling (floor mode) follows and is the only consumer: computed inside the apply phase
         # ((3, 3): stride 2, padding 1, H and W even - the ResNet stem)
-        if (tuple(pool) not in ((2, 2), (3, 3)) or not channels_last or stats_only or residual is not None or hist is not None
+        # (the per-sample / per-tensor min-max launches take it on channels-last memory when a channel-fastest bias tells
+        # them the channel count)
+        rows_cl = any_dense_format and is_cl and bias is not None and bias_period < 0
+        if (tuple(pool) not in ((2, 2), (3, 3)) or not (channels_last or rows_cl) or stats_only or residual is not None or hist is not None
                 or x.shape[3] % 2 or (tuple(pool) == (3, 3) and x.shape[2] % 2)):
             raise ValueError("pool=(2, 2) / (3, 3) needs a channels-last launch with an even W (3x3: and H) and no residual / histogram")
         n_, c_, h_, w_ = x.shape

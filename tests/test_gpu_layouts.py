@@ -469,3 +469,26 @@ def test_stem_pooling_at_baseline_size(fq):
     want = F.max_pool2d(ops.fused(x, (512, 64, 112 * 112), **kw), 3, 2, 1)
     bad = (got - want).abs() > 1e-5 * torch.maximum(got.abs(), want.abs()) + 2e-6
     assert float(bad.float().mean()) <= 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,shape", [(2, (6, 64, 14, 12)), (3, (6, 64, 16, 12)), (3, (3, 96, 8, 10)), (2, (2, 512, 6, 6))])
+def test_max_pooling_inside_the_int8_launch(fq, kind, shape):
+    """configs[1]: the per-sample min/max launch (compiled leaf) on channels-last memory pools in its apply phase too."""
+    import torch.nn.functional as F
+    from cnn_quantization_b200 import _lib as L, ops
+    n, c, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(kind * 100 + c)
+    x = (torch.randn(shape, device="cuda", generator=g) * 1.3 + 0.4).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(c, device="cuda", generator=g) * 0.2
+    kw = dict(range_mode=L.RANGE_MINMAX, leaf=L.LEAF_COMPILED, num_bits=8, scope=L.SCOPE_GROUP_MEAN, any_dense_format=True,
+              bias=bias, bias_period=-c, positive=True)
+    lay = (1, n, c * h * w)
+    full = ops.fused(x, lay, **kw)
+    got = ops.fused(x, lay, pool=(kind, kind), **kw)
+    want = F.max_pool2d(full, 2) if kind == 2 else F.max_pool2d(full, 3, 2, 1)
+    assert got.shape == want.shape and torch.equal(got, want)
+    q = fq.int_quantizer("int8", params())
+    q.half_range = True
+    y = q(x.clone(), "conv0_activation", "activation", bias=bias, relu_follows=True, pool=(kind, kind))
+    assert getattr(y, "_fq_pooled", 0) == kind and torch.equal(y, want)

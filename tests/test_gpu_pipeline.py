@@ -253,6 +253,7 @@ def test_int8_channels_last_block_epilogue_is_exact():
         assert fused == (16 if fuse and not refuse else 0)
         assert prof["modes"].get("E", {"launches": 0})["launches"] == (0 if fuse and not refuse else 16)
         assert prof["modes"].get("S", {"launches": 0})["launches"] == (4 if defer else 0)
+        assert sum(v["launches"] for k, v in prof["modes"].items() if k.endswith("p")) == 1 and "P" not in prof["modes"]   # the stem
     for o in outs[1:]:
         assert torch.equal(outs[0], o)
 
