@@ -2060,12 +2060,10 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
     A.nhwc_rep = r < 1u ? 1u : (r > 8u ? 8u : r);
     A.need_dev = cl_needs_b(d) ? 1 : 0;
     const bool hist = d->out_hist != nullptr;
-#ifdef FQB_PLAIN_LAUNCH  // development A/B only: what the cooperative launch itself costs
-    e = cudaLaunchKernel(cl_kernel_ptr(d->leaf, A.need_dev != 0, hist), dim3(pl.grid), dim3(fqb::kBulkThreads), args, cl_smem(hist), st);
-#else
+    // (A/B on the GPU, profiles/README.md round 2: an ordinary launch of the same grid is not faster; the cooperative one
+    // guarantees the co-residency the grid barriers need)
     e = cudaLaunchCooperativeKernel(cl_kernel_ptr(d->leaf, A.need_dev != 0, hist), dim3(pl.grid), dim3(fqb::kBulkThreads), args,
                                     cl_smem(hist), st);
-#endif
     if (e != cudaSuccess) return fail(FQB200_ERR_CUDA, "cooperative launch fq_cl_kernel: %s", cudaGetErrorString(e));
     return FQB200_OK;
   }

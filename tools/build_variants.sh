@@ -3,6 +3,7 @@
 #   tools/build_variants.sh "2 5 1 2" "4 6 1 1"      # each tuple = FQB_STAGE_VEC FQB_STAGES FQB_BULK_SPLIT FQB_BULK_CTAS
 set -e
 cd "$(dirname "$0")/.."
+mkdir -p tools/_variants   # git-ignored (*.so); delete them when done: they travel to the GPU box with every gpurun
 for v in "$@"; do
   set -- $v
   out=tools/_variants/libfqb200_v$1_k$2_s$3_c${4:-1}${5:+_$5}.so
