@@ -456,6 +456,10 @@ def run_fqb200(args):
             other = not args.channels_last
             line["channels_last_variant" if other else "nchw_variant"] = secondary(
                 args, dev, args.config, args.batch, other, "D", barrier, peak=peak)
+            try:
+                line["stats_use_variant"] = stats_use_variant(args, dev, barrier, peak)
+            except Exception as e:  # a diagnostic next to the headline: never fails the run
+                line["stats_use_variant"] = {"unavailable": repr(e)[:300]}
             line["kernel_bench"] = kernel_bench(torch, dev, peak)
             try:
                 line["gpu_baseline"] = gpu_baseline(torch, dev, peak)
@@ -476,6 +480,62 @@ def run_fqb200(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def stats_use_variant(args, dev, barrier, peak):
+    """SURVEY.md 8(f) rank 1, the reference README's best-accuracy recipe: `-sm collect` on two 32-image batches (twice,
+    like the reference: per-tensor and per-channel tables, written in the reference's CSV / pickle formats; two batches
+    because the reference's per-channel summary collapses the channels of a single-batch collection,
+    statistic_manager_perchannel.py:163-165), then `-sm use` - every activation is an apply-only launch (mode A,
+    8 B/element).  Reports the pipeline rate of the use mode."""
+    import shutil
+    import tempfile
+    import torch
+    from cnn_quantization_b200 import ops, pipeline
+    base = tempfile.mkdtemp(prefix="fq_stats_")
+    try:
+        flags = dict(pipeline.CONFIGS[args.config], stats_folder="bench", stats_base_dir=base)
+        xs, _ = pipeline.synthetic_batch(64, seed=11, channels_last=args.channels_last)
+        xs = xs.to(dev)
+        if args.channels_last:
+            xs = xs.contiguous(memory_format=torch.channels_last)
+        for pcq in (False, True):
+            model, qm = pipeline.build_quantized_model(dict(flags, stats_mode="collect", per_channel_quant_act=pcq), dev,
+                                                       channels_last=args.channels_last)
+            with torch.no_grad():
+                model(xs[:32])
+                model(xs[32:])
+            qm.__exit__()
+            del model, qm
+        model, qm = pipeline.build_quantized_model(dict(flags, stats_mode="use"), dev, channels_last=args.channels_last)
+        x, t = pipeline.synthetic_batch(args.batch, seed=7, channels_last=args.channels_last)
+        x, t = x.to(dev), t.to(dev)
+        if args.channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
+
+        def step():
+            with torch.no_grad():
+                pipeline.accuracy_counts(model(x), t)
+
+        for _ in range(3):
+            step()
+        ops.profile_reset(enable=True)
+        ms = timed_steps(torch, step, 3, barrier) / 3
+        prof = ops.profile_collect()
+        ops.profile_reset(enable=False)
+        qm.detach()
+        del model, qm, x
+        torch.cuda.empty_cache()
+        a = prof["modes"].get("A", {"bytes": 0, "ms": 0.0, "launches": 0})
+        gbs = (a["bytes"] / 1e9) / (a["ms"] / 1e3) if a["ms"] else None
+        return {"workload": workload_string(args.config, args.batch) + ", offline statistics (-sm use) collected on 2 x 32 images",
+                "metric": metric_name(args.config), "value": args.batch / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": 3,
+                "quant_ms_per_step": sum(m["ms"] for m in prof["modes"].values()) / 3,
+                "launches_per_step": {k: v["launches"] // 3 for k, v in prof["modes"].items()},
+                "roofline": {"kernel": "given-parameter launches (mode A)", "algorithmic_bytes_per_elem": 8, "achieved": gbs,
+                             "peak": peak, "unit": "GB/s", "frac": gbs / peak if gbs else None, "launches": a["launches"]}}
+    finally:
+        shutil.rmtree(base, ignore_errors=True)
 
 
 def secondary(args, dev, config, batch, channels_last, mode, barrier, peak=None):

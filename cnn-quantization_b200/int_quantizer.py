@@ -648,7 +648,7 @@ class IntQuantizer(object):
         kw = dict(leaf=L.LEAF_MIDTREAD, positive=self._positive(), mt_target=self.bit_alloc_target_act, mt_clip=True, bias=bias,
                   out=self._out(tensor), channels_last=self._channels_last(tensor))
         if not self.measure_entropy:
-            return self._fused(tensor, layout, **kw)
+            return self._launch(tensor, layout, **kw)   # the mid-tread leaf is monotone too: block epilogue / pooling apply
         if kw["channels_last"]:
             hist = torch.zeros(self.MT_HIST_BINS, dtype=torch.int64, device=tensor.device)
             clamped = torch.zeros((layout[1], 2), dtype=torch.int64, device=tensor.device)

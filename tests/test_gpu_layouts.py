@@ -341,7 +341,8 @@ def test_max_pooling_inside_the_quantization_launch(fq, c, h, w):
     lay = (n, c, h * w)
     for kw, exact in ((dict(range_mode=L.RANGE_MINMAX, num_bits=4), True),
                       (dict(range_mode=L.RANGE_MINMAX, num_bits=8, positive=True, bias=bias), True),
-                      (dict(range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True, bias=bias, positive=True), False)):
+                      (dict(range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True, bias=bias, positive=True), False),
+                      (dict(leaf=L.LEAF_MIDTREAD, mt_target=4.0, mt_clip=True, positive=True, bias=bias), False)):
         full = ops.fused(x, lay, channels_last=True, **kw)
         got = ops.fused(x, lay, channels_last=True, pool=(2, 2), **kw)
         want = F.max_pool2d(full, 2)

@@ -193,7 +193,8 @@ def test_pipeline_extensions_do_not_change_results(config):
     assert torch.equal(a, b)
 
 
-def test_vgg_pooling_runs_inside_the_quantization_launches():
+@pytest.mark.parametrize("config", ["vgg16_w4a4", "vgg16_w4a4_mtq"])
+def test_vgg_pooling_runs_inside_the_quantization_launches(config):
     """VGG-16 W4A4 on channels-last memory: the five max poolings run inside the launches of the convolutions in front of
     them ("Dp"), no pooling kernel is left, and the logits agree with the run that keeps them separate."""
     if not torch.cuda.is_available():
@@ -203,7 +204,7 @@ def test_vgg_pooling_runs_inside_the_quantization_launches():
     xin = x.cuda().contiguous(memory_format=torch.channels_last)
     outs = []
     for fuse in (True, False):
-        model, qm = pipeline.build_quantized_model("vgg16_w4a4", "cuda", channels_last=True)
+        model, qm = pipeline.build_quantized_model(config, "cuda", channels_last=True)
         if not fuse:
             for m in model.modules():
                 m.__dict__.pop("_fq_pool_module", None)
