@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("FQB200_LIB") or os.path.join(HERE, "libfqb200.so")  #
 
 OK, ERR_INVALID, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 SCOPE_GROUP, SCOPE_GROUP_MEAN, SCOPE_TENSOR = 0, 1, 2
-RANGE_MINMAX, RANGE_LAPLACE, RANGE_GAUS, RANGE_KSTD = 0, 1, 2, 3
+RANGE_MINMAX, RANGE_LAPLACE, RANGE_GAUS, RANGE_KSTD, RANGE_GIVEN = 0, 1, 2, 3, 4
 LEAF_TORCH, LEAF_COMPILED, LEAF_MIDTREAD = 0, 1, 2
 PRIOR_STD, PRIOR_B = 0, 1
 STATS_STRIDE = 12
@@ -45,6 +45,7 @@ class Desc(ctypes.Structure):
         ("residual", ctypes.c_void_p), ("residual_relu", ctypes.c_int32),
         ("residual_stats", ctypes.c_void_p), ("residual_bias", ctypes.c_void_p),
         ("pool", ctypes.c_int32), ("pool_h", ctypes.c_int64), ("pool_w", ctypes.c_int64), ("pool_out", ctypes.c_void_p),
+        ("given_delta", ctypes.c_void_p), ("given_offset", ctypes.c_void_p), ("given_bits", ctypes.c_void_p),
         ("debug_stamps", ctypes.c_void_p),
     ]
 

@@ -930,6 +930,55 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_given_kern
   consume_phase(g, ring, fq_dyn, pos, ap);
 }
 
+// ---- mode A with everything the apply phase can carry (FQB200_RANGE_GIVEN through fqb200_fused): bias, the block epilogue
+// (residual, raw or quantized on the fly), max pooling.  Same apply code as fq_cl_kernel (ClApply), no statistics, no barrier,
+// ordinary launch, static round-robin units.
+__global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_given_fused_kernel(const __grid_constant__ FusedArgs A) {
+  extern __shared__ __align__(128) unsigned char fq_dyn[];
+  __shared__ BulkRing ring;
+  const FlatGeo& g = A.flat;
+  ring_init(ring);
+  if (threadIdx.x >= kConsumers) {
+    if (threadIdx.x == kConsumers) {
+      RingPos pos;
+      pos.init();
+      const float4* src = reinterpret_cast<const float4*>(A.in);
+      const TicketPlan tp = {0xffffffffu, blockIdx.x, gridDim.x, 0u};
+      if (A.pool.tiles && A.pool.kind == 3u)
+        produce_pool3_phase(g, A.pool, src, nullptr, tp, ring, fq_dyn, pos);
+      else if (A.pool.tiles)
+        produce_pool_phase(g, A.pool, src, nullptr, tp, ring, fq_dyn, pos);
+      else if (A.residual)
+        produce_phase<false, true>(half_geo(g), src, nullptr, tp, ring, fq_dyn, pos, reinterpret_cast<const float4*>(A.residual));
+      else
+        produce_phase<false>(g, src, nullptr, tp, ring, fq_dyn, pos);
+    }
+    return;
+  }
+  const unsigned t = threadIdx.x;
+  const bool active = t < g.stride;
+  const unsigned c0 = active ? 4u * (t % g.cv) : 0u;
+  LeafParam lp[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const unsigned c = c0 + i;
+    const float bits = A.g_bits ? __ldg(A.g_bits + c) : static_cast<float>(A.num_bits);
+    lp[i] = make_leaf_param(FQB200_LEAF_TORCH, __ldg(A.g_delta + c), __ldg(A.g_offset + c), bits);
+  }
+  ClApply<FQB200_LEAF_TORCH, false> ap{A, nullptr};
+  ap.init(c0, active, lp);
+  RingPos pos;
+  pos.init();
+  if (A.pool.tiles && A.pool.kind == 3u)
+    consume_pool3_phase(g, A.pool, ring, fq_dyn, pos, ap);
+  else if (A.pool.tiles)
+    consume_pool_phase(g, A.pool, ring, fq_dyn, pos, ap);
+  else if (A.residual)
+    consume_pair_phase(half_geo(g), ring, fq_dyn, pos, ap);
+  else
+    consume_phase(g, ring, fq_dyn, pos, ap);
+}
+
 // ---- a1, the drop-in of the reference's compiled kernel (kernels/gemmlowp.cu:8-45), on the bulk-copy ring -------------------
 // One parameter set, compiled-leaf arithmetic (roundf), optional noise tensor: it rides through the ring next to x (pair
 // stages).  Ordinary launch, static round-robin units.

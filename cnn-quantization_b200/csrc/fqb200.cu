@@ -1414,6 +1414,9 @@ void init_device(int dev) {
                              static_cast<int>(i < 2 ? dyn_smem(4) : cl_given_smem()));
     if (e != cudaSuccess) return bad("given-parameter kernel setup", e);
   }
+  e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fqb::fq_cl_given_fused_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(cl_given_smem()));
+  if (e != cudaSuccess) return bad("given-parameter fused kernel setup", e);
   const void* leafb[2] = {reinterpret_cast<const void*>(fqb::fq_leaf_bulk_kernel<false>),
                           reinterpret_cast<const void*>(fqb::fq_leaf_bulk_kernel<true>)};
   for (int i = 0; i < 2; ++i) {
@@ -1671,7 +1674,11 @@ size_t carve(char* base, uint64_t slots, uint64_t groups, fqb::FusedArgs* A) {
 int check_desc(const fqb200_desc* d) {
   if (!d) return fail(FQB200_ERR_INVALID, "null descriptor%s");
   if (d->scope < FQB200_SCOPE_GROUP || d->scope > FQB200_SCOPE_TENSOR) return fail(FQB200_ERR_INVALID, "bad scope%s");
-  if (d->range_mode < FQB200_RANGE_MINMAX || d->range_mode > FQB200_RANGE_KSTD) return fail(FQB200_ERR_INVALID, "bad range_mode%s");
+  if (d->range_mode < FQB200_RANGE_MINMAX || d->range_mode > FQB200_RANGE_GIVEN) return fail(FQB200_ERR_INVALID, "bad range_mode%s");
+  if (d->range_mode == FQB200_RANGE_GIVEN &&
+      (!d->channels_last || d->leaf != FQB200_LEAF_TORCH || d->scope != FQB200_SCOPE_GROUP || d->stats_only || d->out_stats || d->out_hist ||
+       d->bias_corr || d->var_corr || d->bit_alloc || !d->given_delta || !d->given_offset))
+    return fail(FQB200_ERR_UNSUPPORTED, "RANGE_GIVEN: channels_last, torch leaf, scope GROUP, given_delta / given_offset, no statistics outputs%s");
   if (d->leaf < FQB200_LEAF_TORCH || d->leaf > FQB200_LEAF_MIDTREAD) return fail(FQB200_ERR_INVALID, "bad leaf%s");
   if (d->leaf != FQB200_LEAF_MIDTREAD && (d->num_bits < 1 || d->num_bits > 8))
     return fail(FQB200_ERR_INVALID, "num_bits must be in 1..8%s");
@@ -1712,6 +1719,7 @@ int fqb200_resident_ctas(void) {
 size_t fqb200_workspace_bytes(const fqb200_desc* d) {
   if (check_desc(d) != FQB200_OK) return 0;
   if (d->outer <= 0 || d->groups <= 0 || d->inner <= 0) return 256;
+  if (d->range_mode == FQB200_RANGE_GIVEN) return 256;  // not used by the launch; non-zero = "descriptor accepted"
   int resident = 148 * fqb::kCtasPerSm;  // without a device (build container) assume a B200
   DeviceInfo* di = nullptr;
   if (get_device(&di) == FQB200_OK) resident = di->resident;
@@ -1917,7 +1925,8 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   if (d->channels_last) {
     if (!can_vec || !cl_supported(d))
       return fail(FQB200_ERR_UNSUPPORTED, "channels_last: per-channel torch / mid-tread leaves on 16-byte aligned tensors, C %% 4 == 0, C <= 2048%s");
-    rc = make_plan_flat(static_cast<uint64_t>(d->outer) * d->groups * d->inner, d->groups, di->resident_cl[d->out_hist ? 1 : 0], &pl);
+    rc = make_plan_flat(static_cast<uint64_t>(d->outer) * d->groups * d->inner, d->groups,
+                        d->range_mode == FQB200_RANGE_GIVEN ? di->resident_cl[0] * 2 : di->resident_cl[d->out_hist ? 1 : 0], &pl);
   } else if (rows_supported(d, can_vec)) {
     rc = make_plan_rows(static_cast<uint64_t>(d->groups), static_cast<uint64_t>(d->inner), d->bias ? -d->bias_period : 0,
                         di->resident_rows, &pl, &rows_geo);
@@ -1931,10 +1940,13 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   memset(&A, 0, sizeof(A));
   // per-unit partial slots; the channels-last kernels combine through the fixed accumulators instead
   const uint64_t slots = (pl.mode == 2 || pl.mode == 3) ? 0 : static_cast<uint64_t>(pl.geo.parts) * pl.geo.channels;
-  const size_t need = carve(nullptr, slots, pl.geo.channels, nullptr);
-  if (!workspace || workspace_bytes < need) return fail(FQB200_ERR_WORKSPACE, "workspace smaller than fqb200_workspace_bytes()%s");
-  if (!aligned16(workspace)) return fail(FQB200_ERR_WORKSPACE, "workspace must be 16-byte aligned%s");
-  carve(static_cast<char*>(workspace), slots, pl.geo.channels, &A);
+  const bool given = d->range_mode == FQB200_RANGE_GIVEN;   // no statistics, no barrier: no workspace
+  if (!given) {
+    const size_t need = carve(nullptr, slots, pl.geo.channels, nullptr);
+    if (!workspace || workspace_bytes < need) return fail(FQB200_ERR_WORKSPACE, "workspace smaller than fqb200_workspace_bytes()%s");
+    if (!aligned16(workspace)) return fail(FQB200_ERR_WORKSPACE, "workspace must be 16-byte aligned%s");
+    carve(static_cast<char*>(workspace), slots, pl.geo.channels, &A);
+  }
   A.geo = pl.geo;
   A.flat = pl.flat;
   A.rows = rows_geo;
@@ -2031,6 +2043,16 @@ int fqb200_fused(const fqb200_desc* d, const float* in, float* out, void* worksp
   if (d->out_hist && (A.hist_bins > static_cast<int>(fqb::kHistWords) || (!d->channels_last && A.hist_bins != 256)))
     return fail(FQB200_ERR_UNSUPPORTED, "hist_bins: 256 (default), up to 8192 on channels-last tensors%s");
   A.bias_magic = 0;
+  if (given) {
+    A.g_delta = d->given_delta;
+    A.g_offset = d->given_offset;
+    A.g_bits = d->given_bits;
+    A.given_per_group = 1;
+    fqb::fq_cl_given_fused_kernel<<<pl.grid, fqb::kBulkThreads, cl_given_smem(), static_cast<cudaStream_t>(stream)>>>(A);
+    cudaError_t ge = cudaGetLastError();
+    if (ge != cudaSuccess) return fail(FQB200_ERR_CUDA, "launch fq_cl_given_fused_kernel: %s", cudaGetErrorString(ge));
+    return FQB200_OK;
+  }
   if (pl.mode == 3) {
     if (d->scope == FQB200_SCOPE_GROUP) A.scope = FQB200_SCOPE_TENSOR;  // one row
     A.n_per_group = static_cast<double>(d->inner);

@@ -288,6 +288,11 @@ class IntQuantizer(object):
     def _quantize1(self, tensor, delta, offset, bits=None, layout=None, bias=None):
         """Mode A launch; with ``bias_correct`` set the activation bias correction rides along."""
         if self._bca is None or tensor.dim() != 4:
+            if (layout is not None and (self._residual is not None or self._pool is not None) and ops.cl_eligible(tensor, layout)
+                    and torch.is_tensor(delta) and delta.numel() == layout[1] and not self.measure_entropy):
+                # the same leaf through the descriptor entry point, which can also finish a ResNet block / pool (`-sm use`)
+                return self._launch(tensor, layout, channels_last=True, range_mode=L.RANGE_GIVEN, leaf=L.LEAF_TORCH,
+                                    num_bits=min(self.num_bits, 8), given=(delta, offset, bits), bias=bias, out=self._out(tensor))
             return ops.quantize1(tensor, delta, offset, self.num_bits, bits=bits, layout=layout, bias=bias, out=self._out(tensor))
         relu_first = bool(self._bca)
         c = tensor.shape[1]
@@ -327,7 +332,7 @@ class IntQuantizer(object):
     def _launch(self, tensor, layout, channels_last=False, rows=False, **kw):
         """One fused launch of the activation paths that can end a ResNet block: deferred (statistics only, see
         ``__call__``), with the block epilogue (``residual``), or plain."""
-        if self._defer and kw.get("hist") is None and self._can_defer(tensor, channels_last, rows):
+        if self._defer and kw.get("hist") is None and kw.get("range_mode") != L.RANGE_GIVEN and self._can_defer(tensor, channels_last, rows):
             skw = {k: v for k, v in kw.items() if k not in ("out", "hist")}
             stats = ops.fused(tensor, layout, stats_only=True, channels_last=channels_last, **skw)
             if self.export_stats:

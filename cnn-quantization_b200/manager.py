@@ -425,7 +425,7 @@ class QuantizationManagerInference(object):
                 if type(m) in (BasicBlock, Bottleneck) and type(getattr(m, "relu", None)) is nn.ReLU:
                     m.forward = _residual_block_forward(m, type(m) is Bottleneck, self)
                     self._patched.append(m)
-        if self.fuse_pool_into_quant and self.fast_maxpool and self.skip_redundant_relu and self.enabled and self.stats_mode == "no":
+        if self.fuse_pool_into_quant and self.fast_maxpool and self.skip_redundant_relu and self.enabled and self.stats_mode in ("no", "use"):
             two = lambda v: (v, v) if isinstance(v, int) else tuple(v)
 
             def pool_kind(pm):
@@ -527,8 +527,8 @@ class QuantizationManagerInference(object):
         if residual is not None and self._native and tag == "activation":
             extra["residual"] = residual
         pm = m.__dict__.get("_fq_pool_module")
-        if pm is not None and self._native and tag == "activation" and self.stats_mode == "no" and (pm[1] or extra.get("relu_follows")):
-            res = self.quantize_instant(out, activation_id, tag, stat_id=None, half_range=half_range, verbose=self.verbose,
+        if pm is not None and self._native and tag == "activation" and (pm[1] or extra.get("relu_follows")):
+            res = self.quantize_instant(out, activation_id, tag, stat_id=self._stat_id(activation_id), half_range=half_range, verbose=self.verbose,
                                         pool=(pm[2], pm[2], "direct") if pm[1] else (pm[2], pm[2]), **extra)
             if getattr(res, "_fq_pooled", False):
                 pm[0]._fq_pending = True   # the pooling module must find the tag (it raises otherwise)

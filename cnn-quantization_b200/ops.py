@@ -227,7 +227,7 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
           bit_alloc_round=True, bit_alloc_target=None, mt_target=0.0, mt_clip=False, bias_corr=False,
           var_corr=False, stats_only=False, want_stats=False, out=None, bias=None, bias_period=0, hist=None,
           channels_last=False, any_dense_format=False, debug_stamps=None, relu_passthrough=False, hist_offset=0,
-          hist_clamped=None, residual=None, residual_relu=False, residual_stats=None, residual_bias=None, pool=None):
+          hist_clamped=None, residual=None, residual_relu=False, residual_stats=None, residual_bias=None, pool=None, given=None):
     """C ABI fqb200_fused: statistics -> parameters -> quantize/dequantize in one launch.
 
     Returns ``out`` (or ``(out, stats)`` with ``want_stats``; ``stats`` alone with ``stats_only``), where
@@ -302,6 +302,26 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
             d.residual_bias = residual_bias.data_ptr()
     elif residual_bias is not None:
         raise ValueError("residual_bias needs residual_stats")
+    d.given_delta, d.given_offset, d.given_bits = None, None, None
+    if range_mode == L.RANGE_GIVEN:
+        # parameters from the caller (`-sm use`): per-group delta / offset (/ bits) device vectors, no statistics phases
+        if given is None or not channels_last or stats_only or want_stats:
+            raise ValueError("RANGE_GIVEN needs given=(delta, offset, bits), channels_last=True and no statistics outputs")
+        gd, go, gb = given
+        keep = []
+        for name, v in (("delta", gd), ("offset", go), ("bits", gb)):
+            if v is None:
+                keep.append(None)
+                continue
+            _require_cuda_f32(v, "given " + name)
+            v = v.contiguous()
+            if v.numel() != groups:
+                raise ValueError("given %s must have %d elements" % (name, groups))
+            keep.append(v)
+        if keep[0] is None or keep[1] is None:
+            raise ValueError("RANGE_GIVEN needs delta and offset")
+        d.given_delta, d.given_offset = keep[0].data_ptr(), keep[1].data_ptr()
+        d.given_bits = keep[2].data_ptr() if keep[2] is not None else None
     d.pool, d.pool_h, d.pool_w, d.pool_out = 0, 0, 0, None
     pooled = None
     if pool is not None:
@@ -336,6 +356,8 @@ def fused(x, layout, *, scope=L.SCOPE_GROUP, range_mode=L.RANGE_MINMAX, leaf=L.L
                     (bit_alloc and num_bits <= 4 and scope == L.SCOPE_GROUP))
         mode = "S" if stats_only else ("D" if two_pass else "B")
         bpe = (8 if two_pass else 4) + (0 if stats_only else 8)
+        if range_mode == L.RANGE_GIVEN:
+            mode, bpe = "A", 8
         if residual is not None:   # + the residual read of the fused block epilogue (the write is the apply's own)
             mode, bpe = mode + "r", bpe + 4
         if pooled is not None:     # the apply phase reads x (3x3: rows twice, the second time mostly out of L2) and writes a quarter

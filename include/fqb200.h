@@ -54,6 +54,9 @@ extern "C" {
 #define FQB200_RANGE_LAPLACE 1 /* ACIQ Laplace: alpha = F[bits] * b          (int_quantizer.py:227-253) */
 #define FQB200_RANGE_GAUS 2    /* ACIQ Gauss:   alpha = F[bits] * std        (:255-264) */
 #define FQB200_RANGE_KSTD 3    /* alpha = clip_k * std ('2std')              (:266-275) */
+#define FQB200_RANGE_GIVEN 4   /* no statistics: per-group delta / offset (/ bits) from the caller (`-sm use`, the a3 leaf of
+                                  fqb200_quantize1) - through this descriptor so that the launch can also take bias,
+                                  residual (+ residual_stats) and pool; channels_last, torch leaf, scope GROUP only */
 /* which leaf arithmetic */
 #define FQB200_LEAF_TORCH 0    /* __gemmlowpQuantize1__: round-half-even, scale floor 1e-8, true zero */
 #define FQB200_LEAF_COMPILED 1 /* float2gemmlowp: roundf (half away), no floor, preserve_zero rule */
@@ -149,6 +152,9 @@ typedef struct fqb200_desc {
                           the pooling kernel's read: 8 of 21 B/element (VGG-16: every convolution in front of a pooling) */
   int64_t pool_h, pool_w; /* the H and W behind `inner` = H * W (W even; pool = 3: H even too) */
   float* pool_out;        /* [outer][H/2][W/2][groups], 16-byte aligned */
+  const float* given_delta;  /* FQB200_RANGE_GIVEN: [groups] device vectors (delta, offset as in fqb200_quantize1) ... */
+  const float* given_offset;
+  const float* given_bits;   /* ... and optional per-group bit widths (NULL: num_bits) */
   unsigned long long* debug_stamps; /* diagnostics, NULL = off: device array of 16 counters that receives %globaltimer
                           (ns) at the phase boundaries of this launch (slot 0: start, 1 / 5: statistics phases combined,
                           4 / 8: past the grid barriers, 7: parameters ready, 9: apply done; tools/phasebench.py) */

@@ -102,3 +102,61 @@ def test_use_mode_is_single_pass(need_gpu):
     qm.detach()
     assert set(prof["modes"]) - {"E"} == {"A"}, prof["modes"].keys()   # "E": the fused residual add + ReLU of the 8 blocks
     assert prof["modes"]["A"]["launches"] == 22
+
+
+def test_use_mode_on_channels_last_memory_finishes_the_blocks_in_the_launch(need_gpu):
+    """`-sm use` on a channels-last model: the given-parameter launch of a block's last convolution also does the block's
+    residual add + ReLU (FQB200_RANGE_GIVEN through fqb200_fused), and the stem's max pooling where the stem is 4-bit;
+    logits equal the NCHW run's (pure elementwise rewrites: bit-identical up to cuDNN's NHWC / NCHW convolution order)."""
+    from cnn_quantization_b200 import ops, pipeline
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = dict(arch="resnet18", stats_folder="resnet18", stats_base_dir=os.path.join(GOLD, "ref_stats"), stats_mode="use", **W4A4)
+    x = batches()[0].cuda()
+    outs = []
+    for cl, fuse in ((False, True), (True, True), (True, False)):
+        model, qm = pipeline.build_quantized_model(cfg, "cuda", channels_last=cl)
+        qm.fuse_residual_into_quant = fuse
+        xin = x.contiguous(memory_format=torch.channels_last) if cl else x
+        ops.profile_reset(enable=True)
+        with torch.no_grad():
+            outs.append(model(xin).float())
+        prof = ops.profile_collect()
+        ops.profile_reset(enable=False)
+        qm.detach()
+        fused = sum(v["launches"] for k, v in prof["modes"].items() if k.endswith("r"))
+        assert fused == (8 if cl and fuse else 0)
+        assert prof["modes"].get("E", {"launches": 0})["launches"] == (0 if cl and fuse else 8)
+        assert sum(v["launches"] for k, v in prof["modes"].items() if k[0] == "A") == 22
+    nchw, cl_fused, cl_plain = outs
+    assert torch.equal(cl_fused, cl_plain)   # given parameters: the epilogue in the launch is an exact rewrite
+    a, b = nchw.cpu().numpy(), cl_fused.cpu().numpy()   # cuDNN's NHWC / NCHW kernels sum in different orders: 4-bit grids flip
+    cos = float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b)))
+    assert cos > 0.97, cos
+
+
+def test_given_parameters_through_the_descriptor_entry_point(need_gpu):
+    """FQB200_RANGE_GIVEN == fqb200_quantize1 (bit-equal), with bias, block epilogue and pooling on top."""
+    import torch.nn.functional as F
+    from cnn_quantization_b200 import _lib as L, ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n, c, h, w = 6, 96, 12, 10
+    x = (torch.randn(n, c, h, w, device="cuda", generator=g) * 1.4).contiguous(memory_format=torch.channels_last)
+    r = torch.randn(n, c, h, w, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(c, device="cuda", generator=g) * 0.2
+    delta = torch.rand(c, device="cuda", generator=g) * 3 + 0.5
+    offset = -torch.rand(c, device="cuda", generator=g) * 1.5
+    bits = torch.randint(1, 7, (c,), device="cuda", generator=g).float()
+    lay = (n, c, h * w)
+    for bt in (None, bits):
+        base = ops.quantize1(x, delta, offset, 4, bits=bt, layout=lay, bias=bias)
+        kw = dict(channels_last=True, range_mode=L.RANGE_GIVEN, num_bits=4, given=(delta, offset, bt), bias=bias)
+        assert torch.equal(ops.fused(x, lay, **kw), base)
+        assert torch.equal(ops.fused(x, lay, residual=r, residual_relu=True, **kw), torch.relu(base + r))
+        assert torch.equal(ops.fused(x, lay, pool=(2, 2), **kw), F.max_pool2d(base, 2))
+        assert torch.equal(ops.fused(x, lay, pool=(3, 3), **kw), F.max_pool2d(base, 3, 2, 1))
+    y = x.clone()
+    out = ops.fused(y, lay, out=y, channels_last=True, range_mode=L.RANGE_GIVEN, num_bits=4, given=(delta, offset, None), bias=bias)
+    assert out.data_ptr() == y.data_ptr() and torch.equal(out, ops.quantize1(x, delta, offset, 4, layout=lay, bias=bias))
+    with pytest.raises(Exception):
+        ops.fused(x, lay, channels_last=True, range_mode=L.RANGE_GIVEN, num_bits=4)   # no parameters
