@@ -530,17 +530,13 @@ __device__ __forceinline__ LeafParam mid_tread_param(const FusedArgs& A, float o
 // CTA 0, all consumer threads: the one computation that needs every channel - per-channel bit widths (int_quantizer.py:
 // 381-407) or mid-tread bin counts (:128-135) from the per-channel std (prior 'gaus') or b (prior 'laplace') - into
 // A.gbits, then the aux_ready flag.
-// (`dry`: same code on synthetic priors, nothing published - an instruction-cache warm-up that was tried and dropped: the
-// CTA that runs it becomes the straggler of the phase it overlaps with.)
-__device__ __noinline__ void cl_solve_aux(const FusedArgs& A, const ClView& acc, LeaderSmem& sm, unsigned tag, bool have_b, bool dry,
+__device__ __noinline__ void cl_solve_aux(const FusedArgs& A, const ClView& acc, LeaderSmem& sm, unsigned tag, bool have_b,
                                           bool publish) {
   const unsigned C = A.flat.channels;
   const double n = A.n_per_group;
   const bool prior_b = (A.leaf != FQB200_LEAF_MIDTREAD) && A.prior == FQB200_PRIOR_B;
   for (unsigned c = threadIdx.x; c < C; c += kConsumers) {
-    if (dry) {
-      (prior_b ? A.gb : A.gstd)[c] = 0.5f + 0.03125f * static_cast<float>(c & 63u);
-    } else if (prior_b) {
+    if (prior_b) {
       const double sa = have_b ? cl_rep_reduce(acc.aabs, A.nhwc_rep, C, c, 0.0, OpAdd()) : 0.0;
       A.gb[c] = static_cast<float>(sa / n);
     } else {
@@ -548,7 +544,7 @@ __device__ __noinline__ void cl_solve_aux(const FusedArgs& A, const ClView& acc,
     }
   }
   consumer_sync();
-  if (!dry) stamp(A, 10);
+  stamp(A, 10);
   if (A.leaf == FQB200_LEAF_MIDTREAD) {
     double local = 0.0;
     for (unsigned c = threadIdx.x; c < C; c += kConsumers) {
@@ -565,7 +561,7 @@ __device__ __noinline__ void cl_solve_aux(const FusedArgs& A, const ClView& acc,
   consumer_sync();
   // `publish`: the result is needed before this CTA reaches another grid barrier (no S2 phase to hide behind); otherwise
   // CTA 0's arrival at barrier 2 (release) publishes A.gbits along with everything else
-  if (!dry && publish && threadIdx.x == 0) st_release_u32(&A.sync->aux_ready, tag);
+  if (publish && threadIdx.x == 0) st_release_u32(&A.sync->aux_ready, tag);
 }
 
 // leaf parameters of channel c from the reduced accumulators (what the leader section of the NCHW kernel computes, here for
@@ -816,7 +812,7 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_kernel(con
 
   // ---- the global solve, where it can overlap with S2
   if (alloc && !aux_needs_b && blockIdx.x == 0) {
-    cl_solve_aux(A, acc, lsm, tag, false, false, !solver_in_s2);
+    cl_solve_aux(A, acc, lsm, tag, false, !solver_in_s2);
     stamp(A, 12);
     if (t == 0) mbar_arrive(smem_u32(&solver_done));
   }
@@ -828,7 +824,7 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm) fq_cl_kernel(con
     if (blockIdx.x == 0) stamp(A, 5);
     grid_barrier_cl(A.sync, epoch);
     if (blockIdx.x == 0) stamp(A, 8);
-    if (aux_needs_b && blockIdx.x == 0) cl_solve_aux(A, acc, lsm, tag, true, false, true);
+    if (aux_needs_b && blockIdx.x == 0) cl_solve_aux(A, acc, lsm, tag, true, true);
   }
   if (alloc && !solver_in_s2) {  // (overlapped with S2, CTA 0's arrival at barrier 2 has published the bit widths already)
     if (t == 0)
