@@ -288,6 +288,12 @@ class IntQuantizer(object):
     def _quantize1(self, tensor, delta, offset, bits=None, layout=None, bias=None):
         """Mode A launch; with ``bias_correct`` set the activation bias correction rides along."""
         if self._bca is None or tensor.dim() != 4:
+            if (self._defer and layout is not None and ops.cl_eligible(tensor, layout) and torch.is_tensor(delta)
+                    and delta.numel() == layout[1] and not self.measure_entropy):
+                # `defer` with known parameters: nothing to launch at all - the call that takes the tensor as its residual
+                # gets the leaf parameters as the table a stats_only launch would have exported (columns 8..11)
+                self._deferred = (self._given_table(delta, offset, bits), bias)
+                return tensor
             if (layout is not None and (self._residual is not None or self._pool is not None) and ops.cl_eligible(tensor, layout)
                     and torch.is_tensor(delta) and delta.numel() == layout[1] and not self.measure_entropy):
                 # the same leaf through the descriptor entry point, which can also finish a ResNet block / pool (`-sm use`)
@@ -303,6 +309,23 @@ class IntQuantizer(object):
                                          out=x if (self.inplace or x is not tensor) else None)
         ref = tensor if bias is None else tensor + bias.view(1, -1, 1, 1)
         return self.bias_correction_torch(ref, ops.quantize1(ref, delta, offset, self.num_bits, bits=bits, layout=layout), relu_first)
+
+    def _given_table(self, delta, offset, bits):
+        """[C, 12] parameter table (``_lib.STAT_COLUMNS``) of the torch leaf for given per-channel (delta, offset, bits):
+        the arithmetic of int_quantizer.py:557-572 as the kernels do it (make_leaf_param), cached per parameter set."""
+        key = ("table", delta.data_ptr(), offset.data_ptr(), None if bits is None else bits.data_ptr(), self.num_bits)
+        hit = self._stat_cache.get(key)
+        if hit is not None and hit[0] is delta and hit[1] is offset and hit[2] is bits:
+            return hit[3]
+        b = bits if bits is not None else torch.full_like(delta, float(min(self.num_bits, 8)))
+        qmax = torch.pow(2.0, b) - 1.0
+        scale = torch.where(qmax > 0, delta / qmax, torch.zeros_like(delta)).clamp_min(1e-8)
+        zp = torch.round(0.0 - offset / scale)
+        table = torch.zeros((delta.numel(), L.STATS_STRIDE), dtype=torch.float32, device=delta.device)
+        table[:, 5], table[:, 6], table[:, 7] = delta, offset, b
+        table[:, 8], table[:, 9], table[:, 10], table[:, 11] = scale, zp, qmax, 2.0   # flags: FLAG_TRUE_ZERO
+        self._stat_cache[key] = (delta, offset, bits, table)   # the operands are kept alive with the entry
+        return table
 
     def _residual_kw(self, tensor, channels_last, rows=False, bias=None):
         """kwargs of the fused block epilogue when this launch can take it: the channels-last per-channel kernel, or

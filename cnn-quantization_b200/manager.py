@@ -533,9 +533,9 @@ class QuantizationManagerInference(object):
             if getattr(res, "_fq_pooled", False):
                 pm[0]._fq_pending = True   # the pooling module must find the tag (it raises otherwise)
             return res
-        if m.__dict__.get("_fq_defer") and self._native and tag == "activation" and self.stats_mode != "use":
-            res = self.quantize_instant(out, activation_id, tag, stat_id=None, half_range=half_range, verbose=self.verbose,
-                                        defer=True, **extra)
+        if m.__dict__.get("_fq_defer") and self._native and tag == "activation":
+            res = self.quantize_instant(out, activation_id, tag, stat_id=self._stat_id(activation_id), half_range=half_range,
+                                        verbose=self.verbose, defer=True, **extra)
             if getattr(res, "_fq_deferred", None) is not None:
                 res._fq_redo = (activation_id, tag, half_range, extra)
             return res
@@ -547,9 +547,11 @@ class QuantizationManagerInference(object):
         it as its residual did not fuse.  Same quantizer, same arguments; not recorded as a second call."""
         activation_id, tag, half_range, extra = tensor._fq_redo
         del tensor._fq_deferred, tensor._fq_redo
-        q = self.get_quantizer(tag)
+        stat_id = self._stat_id(activation_id)
+        ignore = stat_id is not None and any(l == stat_id for l in self.ignore_ids)
+        q = self.get_quantizer("ignored" if ignore else tag)
         q.half_range = half_range
-        return q(tensor, activation_id, tag, None, None, **extra)
+        return q(tensor, activation_id, tag, stat_id, None, **extra)
 
     def _linear_hook(self, m, inputs, out):
         if not self.enabled:

@@ -127,7 +127,8 @@ def test_use_mode_on_channels_last_memory_finishes_the_blocks_in_the_launch(need
         fused = sum(v["launches"] for k, v in prof["modes"].items() if k.endswith("r"))
         assert fused == (8 if cl and fuse else 0)
         assert prof["modes"].get("E", {"launches": 0})["launches"] == (0 if cl and fuse else 8)
-        assert sum(v["launches"] for k, v in prof["modes"].items() if k[0] == "A") == 22
+        # the shortcut convolutions of the 3 down-sampling blocks launch nothing at all: quantized inside the consuming launch
+        assert sum(v["launches"] for k, v in prof["modes"].items() if k[0] == "A") == (19 if cl and fuse else 22)
     nchw, cl_fused, cl_plain = outs
     assert torch.equal(cl_fused, cl_plain)   # given parameters: the epilogue in the launch is an exact rewrite
     a, b = nchw.cpu().numpy(), cl_fused.cpu().numpy()   # cuDNN's NHWC / NCHW kernels sum in different orders: 4-bit grids flip
