@@ -530,8 +530,9 @@ class QuantizationManagerInference(object):
         if pm is not None and self._native and tag == "activation" and (pm[1] or extra.get("relu_follows")):
             res = self.quantize_instant(out, activation_id, tag, stat_id=self._stat_id(activation_id), half_range=half_range, verbose=self.verbose,
                                         pool=(pm[2], pm[2], "direct") if pm[1] else (pm[2], pm[2]), **extra)
-            if getattr(res, "_fq_pooled", False):
-                pm[0]._fq_pending = True   # the pooling module must find the tag (it raises otherwise)
+            # the pooling module must find the tag when the launch has pooled (it raises otherwise); a stale flag of an
+            # aborted forward is overwritten here
+            pm[0]._fq_pending = bool(getattr(res, "_fq_pooled", False))
             return res
         if m.__dict__.get("_fq_defer") and self._native and tag == "activation":
             res = self.quantize_instant(out, activation_id, tag, stat_id=self._stat_id(activation_id), half_range=half_range,
