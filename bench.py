@@ -608,6 +608,7 @@ def kernel_bench(torch, dev, peak):
     o = -torch.rand(c, device=dev)
     bits = torch.full((c,), 4.0, device=dev)
     out, outcl = torch.empty_like(x), torch.empty_like(xcl)
+    rcl = torch.randn(n, c, hw, hw, device=dev).contiguous(memory_format=torch.channels_last)
     cases = [
         ("D_laplace_bitalloc_nhwc", 16, lambda: ops.fused(xcl, lay, range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True, out=outcl, channels_last=True)),
         ("D_laplace_bitalloc_nchw", 16, lambda: ops.fused(x, lay, range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True, out=out)),
@@ -617,6 +618,15 @@ def kernel_bench(torch, dev, peak):
         ("A_given_per_channel_nchw", 8, lambda: ops.quantize1(x, d, o, 4, bits=bits, layout=lay, out=out)),
         ("A_given_per_tensor", 8, lambda: ops.quantize1(x, d[:1], o[:1], 4, out=out)),
         ("a1_float2gemmlowp", 8, lambda: ops.float2gemmlowp(x, 7.0, -3.0, 8, False, True, None, out=out)),
+        # the launches that also finish what surrounds the convolution (bytes = what THIS launch has to move)
+        ("Dr_laplace_bitalloc_block_epilogue_nhwc", 20, lambda: ops.fused(xcl, lay, range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True,
+                                                                            out=outcl, channels_last=True, residual=rcl, residual_relu=True)),
+        ("S_statistics_only_nhwc", 8, lambda: ops.fused(xcl, lay, range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True,
+                                                          channels_last=True, stats_only=True)),
+        ("Dp_laplace_bitalloc_pool2x2_nhwc", 13, lambda: ops.fused(xcl, lay, range_mode=L.RANGE_LAPLACE, num_bits=4, bit_alloc=True,
+                                                                     channels_last=True, positive=True, pool=(2, 2))),
+        ("Ar_given_block_epilogue_nhwc", 12, lambda: ops.fused(xcl, lay, range_mode=L.RANGE_GIVEN, num_bits=4, given=(d, o, bits),
+                                                                 out=outcl, channels_last=True, residual=rcl, residual_relu=True)),
         ("torch_copy_reference_point", 8, lambda: out.copy_(x)),
     ]
     res = {"tensor": "512x64x56x56 fp32 (411 MB)", "l2": "flushed between repetitions (256 MB memset)", "reps": 5}
