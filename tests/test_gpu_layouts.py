@@ -493,3 +493,52 @@ def test_max_pooling_inside_the_int8_launch(fq, kind, shape):
     q.half_range = True
     y = q(x.clone(), "conv0_activation", "activation", bias=bias, relu_follows=True, pool=(kind, kind))
     assert getattr(y, "_fq_pooled", 0) == kind and torch.equal(y, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(24))
+def test_fused_variants_random_shapes(fq, seed):
+    """Seeded random geometries (channel counts with and without idle consumer threads, one-pixel-wide tiles, odd heights,
+    single images) through every fused variant; min/max statistics are order-independent, so everything must be bit-equal
+    to the composition of the plain launch with torch's ops."""
+    import torch.nn.functional as F
+    from cnn_quantization_b200 import _lib as L, ops
+    rs = np.random.RandomState(1000 + seed)
+    c = int(rs.choice([4, 8, 12, 20, 36, 64, 96, 100, 128, 192, 256, 384, 512, 640, 896, 1024, 2048]))
+    n = int(rs.randint(1, 7))
+    h = int(rs.randint(2, 19))
+    w = int(2 * rs.randint(1, 10))
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = (torch.randn(n, c, h, w, device="cuda", generator=g) * 1.5 + 0.3).contiguous(memory_format=torch.channels_last)
+    r = torch.randn(n, c, h, w, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(c, device="cuda", generator=g) * 0.2
+    rbias = torch.randn(c, device="cuda", generator=g) * 0.2
+    lay = (n, c, h * w)
+    kw = dict(range_mode=L.RANGE_MINMAX, num_bits=int(rs.choice([2, 4, 8])), channels_last=True, bias=bias,
+              positive=bool(rs.randint(0, 2)))
+    base = ops.fused(x, lay, **kw)
+    tag = (c, n, h, w, kw["num_bits"], kw["positive"])
+    assert torch.equal(ops.fused(x, lay, pool=(2, 2), **kw), F.max_pool2d(base, 2)), tag
+    if h % 2 == 0 and c <= 896:
+        assert torch.equal(ops.fused(x, lay, pool=(3, 3), **kw), F.max_pool2d(base, 3, 2, 1)), tag
+    assert torch.equal(ops.fused(x, lay, residual=r, residual_relu=True, **kw), torch.relu(base + r)), tag
+    kwr = dict(kw, bias=rbias)
+    stats = ops.fused(r, lay, stats_only=True, **kwr)
+    got = ops.fused(x, lay, residual=r, residual_relu=True, residual_stats=stats, residual_bias=rbias, **kw)
+    assert torch.equal(got, torch.relu(base + ops.fused(r, lay, **kwr))), tag
+    # the same with given parameters (mode A through the descriptor entry point)
+    st = ops.fused(x, lay, stats_only=True, **kw)
+    delta, offset = st[:, 5].contiguous(), st[:, 6].contiguous()
+    gk = dict(range_mode=L.RANGE_GIVEN, num_bits=kw["num_bits"], channels_last=True, bias=bias, given=(delta, offset, None))
+    assert torch.equal(ops.fused(x, lay, **gk), base), tag
+    assert torch.equal(ops.fused(x, lay, pool=(2, 2), **gk), F.max_pool2d(base, 2)), tag
+    assert torch.equal(ops.fused(x, lay, residual=r, residual_relu=True, **gk), torch.relu(base + r)), tag
+    # int8 per-sample min/max (row kernel) on the same memory
+    k8 = dict(range_mode=L.RANGE_MINMAX, leaf=L.LEAF_COMPILED, num_bits=8, scope=L.SCOPE_GROUP_MEAN, any_dense_format=True,
+              bias=bias, bias_period=-c, positive=kw["positive"])
+    lay8 = (1, n, c * h * w)
+    b8 = ops.fused(x, lay8, **k8)
+    assert torch.equal(ops.fused(x, lay8, residual=r, residual_relu=True, **k8), torch.relu(b8 + r)), tag
+    assert torch.equal(ops.fused(x, lay8, pool=(2, 2), **k8), F.max_pool2d(b8, 2)), tag
+    if h % 2 == 0 and c <= 896:
+        assert torch.equal(ops.fused(x, lay8, pool=(3, 3), **k8), F.max_pool2d(b8, 3, 2, 1)), tag
