@@ -542,3 +542,30 @@ def test_fused_variants_random_shapes(fq, seed):
     assert torch.equal(ops.fused(x, lay8, pool=(2, 2), **k8), F.max_pool2d(b8, 2)), tag
     if h % 2 == 0 and c <= 896:
         assert torch.equal(ops.fused(x, lay8, pool=(3, 3), **k8), F.max_pool2d(b8, 3, 2, 1)), tag
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", [64, 96, 512])
+def test_mid_tread_leaf_with_block_epilogue_and_pooling(fq, c):
+    """`-mtq`: the mid-tread leaf goes through the same apply code, so its launches take the block epilogue and the pooling
+    too (a vanishing fraction of elements may move by one step: statistics are combined in a different order)."""
+    import torch.nn.functional as F
+    from cnn_quantization_b200 import _lib as L, ops
+    n, h, w = 6, 12, 10
+    g = torch.Generator(device="cuda").manual_seed(c)
+    x = (torch.randn(n, c, h, w, device="cuda", generator=g) * 1.2).contiguous(memory_format=torch.channels_last)
+    r = torch.randn(n, c, h, w, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(c, device="cuda", generator=g) * 0.2
+    lay = (n, c, h * w)
+    for positive in (False, True):
+        kw = dict(leaf=L.LEAF_MIDTREAD, mt_target=4.0, mt_clip=True, positive=positive, bias=bias, channels_last=True)
+        base = ops.fused(x, lay, **kw)
+        frac, _ = fq_mismatch(ops.fused(x, lay, residual=r, residual_relu=True, **kw).cpu().numpy(), torch.relu(base + r).cpu().numpy())
+        assert frac <= 2e-3
+        frac, _ = fq_mismatch(ops.fused(x, lay, pool=(2, 2), **kw).cpu().numpy(), F.max_pool2d(base, 2).cpu().numpy())
+        assert frac <= 2e-3
+    q = fq.int_quantizer("int4", params(clipping="laplace", pcq_act=True, bit_alloc_act=True, mtd_quant=True, bit_alloc_target_act=4.0))
+    y = q(x.clone(), "conv3_activation", "activation", bias=bias, residual=r)
+    assert getattr(y, "_fq_residual_fused", False)
+    d = q(r.clone(), "conv4_activation", "activation", bias=bias, defer=True)   # mid-tread parameters are not a leaf table: not deferred
+    assert getattr(d, "_fq_deferred", None) is None
